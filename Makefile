@@ -1,0 +1,69 @@
+# Top-level build: the product library, the oracle, the test harnesses.
+#
+#   make            -> bjxa_b200/lib/libbjxa_b200.so  (CUDA sm_100a + host C)
+#   make oracle     -> oracle/_build, oracle/_ref     (test infrastructure)
+#   make emul       -> tests/_build/libxa_emul.so     (CPU single-stepper of
+#                                                      the tile code; tests only)
+#   make dropin     -> oracle/_ref/bjxa_dropin ...    (the reference's own CLI
+#                      and API test, compiled from /root/reference and linked
+#                      against OUR library: the drop-in acceptance binaries)
+
+NVCC     ?= nvcc
+CC       ?= gcc
+CXX      ?= g++
+ARCH     := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v $(XA_DEFS)
+CFLAGS   := -std=c99 -O2 -fPIC -Wall -Wextra -Wno-unused-parameter
+REFERENCE ?= /root/reference
+
+SRC      := bjxa_b200/csrc
+LIBDIR   := bjxa_b200/lib
+OBJDIR   := build
+LIB      := $(LIBDIR)/libbjxa_b200.so
+HDRS     := $(SRC)/xa_core.h $(SRC)/xa_tile.h $(SRC)/xa_plan.h include/bjxa.h include/bjxa_batch.h
+
+.PHONY: all lib oracle emul dropin clean
+all: lib
+
+lib: $(LIB)
+
+$(OBJDIR)/xa_kernels.o: $(SRC)/xa_kernels.cu $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c -o $@ $< 2> $(OBJDIR)/ptxas.log || (cat $(OBJDIR)/ptxas.log; false)
+
+$(OBJDIR)/bjxa_host.o: $(SRC)/bjxa_host.c include/bjxa.h include/bjxa_batch.h
+	@mkdir -p $(OBJDIR)
+	$(CC) $(CFLAGS) -c -o $@ $<
+
+$(LIB): $(OBJDIR)/xa_kernels.o $(OBJDIR)/bjxa_host.o $(SRC)/libbjxa.map
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJDIR)/xa_kernels.o $(OBJDIR)/bjxa_host.o \
+	    -Xlinker --version-script=$(SRC)/libbjxa.map -Xlinker -soname=libbjxa_b200.so \
+	    -cudart static -lpthread -ldl -lrt
+
+oracle:
+	$(MAKE) -s -C oracle all
+
+emul: tests/_build/libxa_emul.so
+
+tests/_build/libxa_emul.so: tests/emul/xa_emul.cc $(HDRS)
+	@mkdir -p tests/_build
+	$(CXX) -std=c++17 -O1 -g -fPIC -Wall -Wno-unknown-pragmas -shared -o $@ tests/emul/xa_emul.cc
+
+# The reference's CLI and API test, unmodified, against the product library.
+ifneq ($(wildcard $(REFERENCE)/src/bjxa.c),)
+REF_CLI  := $(REFERENCE)/src/bjxa.c $(REFERENCE)/src/bjxa_decode.c $(REFERENCE)/src/bjxa_encode.c
+REF_CF   := -std=c99 -D_POSIX_C_SOURCE=200809L -D_XOPEN_SOURCE=600 -O2 -Ioracle/_ref -I$(REFERENCE)/src
+DROPLINK := -L$(LIBDIR) -lbjxa_b200 -Wl,-rpath,'$$ORIGIN/../../$(LIBDIR)'
+dropin: lib oracle
+	$(CC) $(REF_CF) -o oracle/_ref/bjxa_dropin $(REF_CLI) $(DROPLINK)
+	$(CC) $(REF_CF) -DBJXA_SINGLE_PASS -o oracle/_ref/bjxa_dropin_single_pass $(REF_CLI) $(DROPLINK)
+	$(CC) $(REF_CF) -o oracle/_ref/test_api_dropin $(REFERENCE)/test/test_libbjxa_api.c $(DROPLINK)
+else
+dropin:
+	@echo "dropin: $(REFERENCE) not present; using prebuilt oracle/_ref binaries if any"
+endif
+
+clean:
+	rm -rf $(OBJDIR) $(LIBDIR) tests/_build
+	$(MAKE) -s -C oracle clean

@@ -1,9 +1,9 @@
 """ctypes binding of the libbjxa C ABI (include/bjxa.h).
 
 `BjxaLib(path)` binds the 19 public symbols of any libbjxa-compatible shared
-object: the product library (bjxa_b200/lib/libbjxa_b200.so) or -- in tests and
-the CPU baseline only -- the unmodified reference compiled to
-oracle/_ref/libbjxa_ref.so.  Names, argument order and error behaviour are the
+object: the product library (bjxa_b200/lib/libbjxa_b200.so), or -- from the
+tests and the CPU-baseline leg of the benchmark only -- a build of the
+unmodified reference library.  Names, argument order and error behaviour are the
 reference's (/root/reference/src/bjxa.h:36-65): every call returns what the C
 function returns and `BjxaLib.errno()` reads the C errno.
 """

@@ -1,0 +1,240 @@
+/*
+ * xa_core.h -- per-block arithmetic of the BandJAM XA transform, written once
+ * for the sm_100a kernels (xa_kernels.cu) and compilable by a host compiler so
+ * tests/emul can single-step the very same code on a CPU (test harness only;
+ * the product library has no CPU path).
+ *
+ * One "block" is 32 samples of one channel: 1 profile byte + 4*BITS payload
+ * bytes in, 32 int16 out (/root/reference/bjxa.5.rst:107-187).
+ *
+ * Representation used throughout: a code is held TOP-ALIGNED in a 32-bit
+ * register (x = code << (32-BITS), low bits zero).  The reference keeps it
+ * top-aligned in an int16 and shifts by `range` (src/libbjxa.c:296-339,558);
+ * with x = dst << 16 the same value is  x >> (16 + range)  (arithmetic).
+ */
+#ifndef XA_CORE_H
+#define XA_CORE_H
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define XA_HD __host__ __device__ __forceinline__
+#else
+#define XA_HD inline
+#endif
+
+namespace xa {
+
+constexpr int kBlockSamples = 32;
+
+XA_HD constexpr int block_bytes(int bits) { return 4 * bits + 1; }
+
+/* ---- funnel shift / byte permute with host twins ----------------------- */
+
+/* low 32 bits of ((hi:lo) >> sh), 0 <= sh <= 31 */
+XA_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh)
+{
+#if defined(__CUDA_ARCH__)
+	return __funnelshift_r(lo, hi, sh);
+#else
+	return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
+#endif
+}
+
+/* PRMT, default mode: result byte i = byte (sel >> 4i & 7) of the pair b:a */
+XA_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel)
+{
+#if defined(__CUDA_ARCH__)
+	return __byte_perm(a, b, sel);
+#else
+	uint64_t pair = ((uint64_t)b << 32) | a;
+	uint32_t r = 0;
+	for (int i = 0; i < 4; i++) {
+		uint32_t s = (sel >> (4 * i)) & 7u;
+		r |= (uint32_t)((pair >> (8 * s)) & 0xffu) << (8 * i);
+	}
+	return r;
+#endif
+}
+
+/* two int32 already inside int16 range -> one word, lo | hi << 16 */
+XA_HD uint32_t pack2(int lo, int hi)
+{
+	return byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410);
+}
+
+/* ---- profile byte ------------------------------------------------------ */
+
+/* K0, K1 scaled by 256 (src/libbjxa.c:525-531, bjxa.5.rst:123-129) */
+XA_HD int gain_k0(unsigned f)
+{
+	return f == 1 ? 240 : f == 2 ? 460 : f == 3 ? 392 : f == 4 ? 488 : 0;
+}
+XA_HD int gain_k1(unsigned f)
+{
+	return f == 2 ? -208 : f == 3 ? -220 : f == 4 ? -240 : 0;
+}
+
+/* How a block takes part in the decode schedule. */
+enum BlockKind {
+	kCut = 0,	/* filter 0: output does not depend on predictor state */
+	kChain = 1,	/* filter 1..4: needs the two previous samples */
+	kBad = 2	/* filter >= 5: EPROTO in the reference (libbjxa.c:550) */
+};
+
+XA_HD int block_kind(uint32_t profile)
+{
+	unsigned f = profile >> 4;
+	return f == 0 ? kCut : (f < 5 ? kChain : kBad);
+}
+
+/* ---- payload access ---------------------------------------------------- */
+
+/*
+ * A block's payload as BITS little-endian words, realigned from a byte
+ * address that is generally odd: `words` points at the 4-byte aligned word
+ * holding payload byte 0, `sh` = 8 * (address & 3).  Reads BITS+1 words.
+ */
+template <int BITS>
+XA_HD void load_payload(uint32_t (&pw)[BITS], const uint32_t *words, uint32_t sh)
+{
+	uint32_t prev = words[0];
+#pragma unroll
+	for (int i = 0; i < BITS; i++) {
+		uint32_t next = words[i + 1];
+		pw[i] = funnel_r(prev, next, sh);
+		prev = next;
+	}
+}
+
+/*
+ * Code n (0..31) of a block, top-aligned in 32 bits with zeros below.
+ * N must be a compile-time constant after unrolling.
+ *   4 bit: high nibble then low nibble of each byte   (libbjxa.c:296-297)
+ *   6 bit: four fields of a big-endian 24-bit group    (libbjxa.c:315-321)
+ *   8 bit: one byte                                    (libbjxa.c:339)
+ */
+template <int BITS>
+XA_HD int top_code(const uint32_t (&pw)[BITS], int n)
+{
+	if (BITS == 8) {
+		/* byte (n&3) of word n>>2 into byte 3, zeros elsewhere */
+		return (int)byte_perm(pw[n >> 2], 0u, (uint32_t)(((n & 3) << 12) | 0x0444));
+	} else if (BITS == 4) {
+		int byte = (n & 7) >> 1;
+		int pos = byte * 8 + ((n & 1) ? 0 : 4);	/* LSB of the nibble */
+		return (int)((pw[n >> 3] << (28 - pos)) & 0xf0000000u);
+	} else {
+		/* group g = n>>2 covers payload bytes 3g..3g+2 */
+		int b = 3 * (n >> 2);
+		int w = b >> 2, o = b & 3;
+		/* T = b0<<24 | b1<<16 | b2<<8 | junk */
+		uint32_t hi = (w + 1 < BITS) ? pw[w + 1] : 0u;
+		uint32_t sel = (uint32_t)(((o) << 12) | ((o + 1) << 8) | ((o + 2) << 4) | 0);
+		uint32_t t = byte_perm(pw[w], hi, sel);
+		return (int)((t << (6 * (n & 3))) & 0xfc000000u);
+	}
+}
+
+/* ---- one sample -------------------------------------------------------- */
+
+/* filter 0: the ranged code IS the sample (gain 0, and it cannot leave int16) */
+XA_HD int sample_cut(int x, int sh) { return x >> sh; }
+
+/*
+ * filters 1..4 (src/libbjxa.c:556-571):
+ *   sample = ranged + (p0*k0 + p1*k1) / 256   -- division truncates toward 0
+ *   clamp to int16; the CLAMPED value becomes the new state.
+ */
+XA_HD int sample_chain(int x, int sh, int k0, int k1, int &p0, int &p1)
+{
+	int g = p0 * k0 + p1 * k1;
+	/* truncating /256 as shift + sign fix-up: add 255 when g < 0 */
+	int q = (g + ((g >> 31) & 255)) >> 8;
+	int s = (x >> sh) + q;
+	s = s < -32768 ? -32768 : s;
+	s = s > 32767 ? 32767 : s;
+	p1 = p0;
+	p0 = s;
+	return s;
+}
+
+/* ---- whole blocks, results as 16 packed words (sample 2i | 2i+1 << 16) -- */
+
+template <int BITS>
+XA_HD void decode_block_cut(uint32_t (&out)[16], const uint32_t (&pw)[BITS],
+    uint32_t profile)
+{
+	const int sh = 16 + (int)(profile & 15u);
+#pragma unroll
+	for (int i = 0; i < 16; i++) {
+		int a = sample_cut(top_code<BITS>(pw, 2 * i), sh);
+		int b = sample_cut(top_code<BITS>(pw, 2 * i + 1), sh);
+		out[i] = pack2(a, b);
+	}
+}
+
+template <int BITS>
+XA_HD void decode_block_chain(uint32_t (&out)[16], const uint32_t (&pw)[BITS],
+    uint32_t profile, int &p0, int &p1)
+{
+	const int sh = 16 + (int)(profile & 15u);
+	const int k0 = gain_k0(profile >> 4), k1 = gain_k1(profile >> 4);
+#pragma unroll
+	for (int i = 0; i < 16; i++) {
+		int a = sample_chain(top_code<BITS>(pw, 2 * i), sh, k0, k1, p0, p1);
+		int b = sample_chain(top_code<BITS>(pw, 2 * i + 1), sh, k0, k1, p0, p1);
+		out[i] = pack2(a, b);
+	}
+}
+
+/* ---- encode: 32 int16 (16 packed words) -> 4*BITS payload bytes --------- */
+
+/*
+ * Keeps the top BITS bits of every sample (logical shift of the uint16 image,
+ * src/libbjxa.c:355-387) and packs MSB-first; result as BITS little-endian
+ * words, i.e. the payload's byte image.
+ */
+template <int BITS>
+XA_HD void deflate_block(uint32_t (&pw)[BITS], const uint32_t (&in)[16])
+{
+	if (BITS == 8) {
+#pragma unroll
+		for (int i = 0; i < 8; i++)	/* high bytes of 4 samples */
+			pw[i] = byte_perm(in[2 * i], in[2 * i + 1], 0x7531);
+	} else if (BITS == 4) {
+#pragma unroll
+		for (int i = 0; i < 4; i++) {
+			uint32_t w = 0;
+#pragma unroll
+			for (int b = 0; b < 4; b++) {
+				uint32_t pr = in[4 * i + b];	/* s0 | s1<<16 */
+				uint32_t byte = ((pr >> 8) & 0xf0u) | (pr >> 28);
+				w |= byte << (8 * b);
+			}
+			pw[i] = w;
+		}
+	} else {
+		/* 4 samples -> 24 bits big-endian -> 3 bytes; 8 groups -> 6 words */
+		uint32_t g[8];
+#pragma unroll
+		for (int i = 0; i < 8; i++) {
+			uint32_t a = in[2 * i], b = in[2 * i + 1];
+			uint32_t v = ((a >> 10) & 0x3fu) << 18 | (a >> 26) << 12 |
+			    ((b >> 10) & 0x3fu) << 6 | (b >> 26);
+			/* byte image b0,b1,b2 = v>>16, v>>8, v : as LE word */
+			g[i] = byte_perm(v, 0u, 0x4012);
+		}
+		/* concatenate eight 3-byte groups into six words */
+#pragma unroll
+		for (int k = 0; k < 2; k++) {
+			const uint32_t *q = g + 4 * k;
+			pw[3 * k + 0] = q[0] | (q[1] << 24);
+			pw[3 * k + 1] = (q[1] >> 8) | (q[2] << 16);
+			pw[3 * k + 2] = (q[2] >> 16) | (q[3] << 8);
+		}
+	}
+}
+
+} /* namespace xa */
+#endif

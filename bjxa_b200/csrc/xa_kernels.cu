@@ -1,0 +1,794 @@
+/*
+ * xa_kernels.cu -- sm_100a kernels and the device-resident batch layer
+ * (bjxa_plan_*, bjxa_gpu_* of include/bjxa_batch.h).
+ *
+ * Replaces the serial block loops of the reference
+ * (/root/reference/src/libbjxa.c:602-661 decode, :759-819 encode) with one
+ * launch per (bits, channels) class of a batch.  The tile algorithm is in
+ * xa_tile.h; this file adds what only exists on the GPU: the bulk-async
+ * (TMA, cp.async.bulk) load of a tile's contiguous source bytes into shared
+ * memory behind an mbarrier, the CTA barriers between phases, the atomic
+ * ticket that orders tiles, and the CUDA runtime plumbing.
+ *
+ * There is no CPU fallback: without a CUDA device every entry point fails
+ * with ENODEV.
+ */
+#include <cuda_runtime.h>
+
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/bjxa_batch.h"
+#include "xa_plan.h"
+
+using namespace xa;
+
+/* ---- PTX helpers: mbarrier + bulk async copy (Hopper/Blackwell) ---------- */
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+	return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+	/* make the init visible to the async proxy before any bulk copy uses it */
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+	    :: "r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "XA_WAIT_%=:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "@p bra XA_DONE_%=;\n"
+	    "bra XA_WAIT_%=;\n"
+	    "XA_DONE_%=:\n"
+	    "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+
+/* global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned;
+ * completion is signalled on the mbarrier as transaction bytes */
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src,
+    uint32_t bytes, uint32_t bar)
+{
+	asm volatile(
+	    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes"
+	    " [%0], [%1], %2, [%3];"
+	    :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+/* ---- kernels -------------------------------------------------------------- */
+
+template <int BITS, int CH>
+__global__ void __launch_bounds__(kDecThreads)
+xa_decode_kernel(const DecodeParams p)
+{
+	typedef DecTile<BITS, CH, kDecTBQ> Tile;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	typename Tile::Smem &sm = *reinterpret_cast<typename Tile::Smem *>(smem_raw);
+	const uint32_t tid = threadIdx.x;
+	const uint32_t bar = smem_u32(&sm.mbar);
+
+	if (tid == 0) {
+		sm.ticket = (uint32_t)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
+		mbar_init(bar, 1);
+	}
+	__syncthreads();
+
+	Tile t(p, sm, sm.ticket);
+	if (tid == 0) {
+		const uint32_t nb = t.bulk_bytes();
+		if (nb) {
+			mbar_expect_tx(bar, nb);
+			bulk_g2s(smem_u32(sm.in), p.src + t.a0, nb, bar);
+		} else {
+			mbar_arrive(bar);
+		}
+	}
+	t.load_tail(tid, kDecThreads);
+	mbar_wait(bar, 0);
+	__syncthreads();
+
+	t.phase_a(tid, kDecThreads);
+	__syncthreads();
+	t.phase_seed(tid, kDecThreads);
+
+	for (int cur = 0;; cur ^= 1) {
+		__syncthreads();
+		const int n = sm.n_live[cur];
+		if (n == 0)
+			break;
+		t.phase_round(tid, kDecThreads, cur, n);
+		__syncthreads();
+		if (tid == 0)
+			sm.n_live[cur] = 0;
+	}
+
+	t.phase_store(tid, kDecThreads);
+}
+
+template <int BITS, int CH>
+__global__ void __launch_bounds__(kEncThreads)
+xa_encode_kernel(const EncodeParams p)
+{
+	typedef EncTile<BITS, CH, kEncTBE> Tile;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	typename Tile::Smem &sm = *reinterpret_cast<typename Tile::Smem *>(smem_raw);
+	const uint32_t tid = threadIdx.x;
+	const uint32_t bar = smem_u32(&sm.mbar);
+
+	if (tid == 0)
+		mbar_init(bar, 1);
+	__syncthreads();
+
+	Tile t(p, sm, blockIdx.x);
+	if (tid == 0) {
+		const uint32_t nb = t.bulk_bytes();
+		if (nb) {
+			mbar_expect_tx(bar, nb);
+			bulk_g2s(smem_u32(sm.in), p.src + t.in0, nb, bar);
+		} else {
+			mbar_arrive(bar);
+		}
+	}
+	t.load_tail(tid, kEncThreads);
+	mbar_wait(bar, 0);
+	__syncthreads();
+
+	t.phase_pack(tid, kEncThreads);
+	__syncthreads();
+	t.phase_store(tid, kEncThreads);
+}
+
+/* ---- error mapping -------------------------------------------------------- */
+
+static int
+cuda_errno(cudaError_t e)
+{
+	switch (e) {
+	case cudaSuccess:
+		return 0;
+	case cudaErrorNoDevice:
+	case cudaErrorInsufficientDriver:
+	case cudaErrorInitializationError:
+	case cudaErrorInvalidDevice:
+	case cudaErrorDevicesUnavailable:
+	case cudaErrorSystemDriverMismatch:
+	case cudaErrorCompatNotSupportedOnDevice:
+		return ENODEV;
+	case cudaErrorMemoryAllocation:
+		return ENOMEM;
+	default:
+		return EIO;
+	}
+}
+
+#define XA_CUDA(call)					\
+	do {						\
+		cudaError_t e_ = (call);		\
+		if (e_ != cudaSuccess) {		\
+			(void)cudaGetLastError();	\
+			errno = cuda_errno(e_);		\
+			return (-1);			\
+		}					\
+	} while (0)
+
+#define XA_CUDA_NULL(call)				\
+	do {						\
+		cudaError_t e_ = (call);		\
+		if (e_ != cudaSuccess) {		\
+			(void)cudaGetLastError();	\
+			errno = cuda_errno(e_);		\
+			return (NULL);			\
+		}					\
+	} while (0)
+
+/* ---- device helpers ------------------------------------------------------- */
+
+extern "C" int
+bjxa_gpu_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		(void)cudaGetLastError();
+		return (0);
+	}
+	return (n);
+}
+
+extern "C" int
+bjxa_gpu_select(int device)
+{
+	XA_CUDA(cudaSetDevice(device));
+	return (0);
+}
+
+extern "C" void *
+bjxa_gpu_alloc(size_t bytes)
+{
+	void *p = NULL;
+	XA_CUDA_NULL(cudaMalloc(&p, bytes ? bytes : 16));
+	return (p);
+}
+
+extern "C" int
+bjxa_gpu_free(void *dptr)
+{
+	XA_CUDA(cudaFree(dptr));
+	return (0);
+}
+
+extern "C" void *
+bjxa_host_alloc(size_t bytes)
+{
+	void *p = NULL;
+	XA_CUDA_NULL(cudaMallocHost(&p, bytes ? bytes : 16));
+	return (p);
+}
+
+extern "C" int
+bjxa_host_free(void *hptr)
+{
+	XA_CUDA(cudaFreeHost(hptr));
+	return (0);
+}
+
+extern "C" int
+bjxa_gpu_upload(void *dptr, const void *hptr, size_t bytes)
+{
+	XA_CUDA(cudaMemcpy(dptr, hptr, bytes, cudaMemcpyHostToDevice));
+	return (0);
+}
+
+extern "C" int
+bjxa_gpu_download(void *hptr, const void *dptr, size_t bytes)
+{
+	XA_CUDA(cudaMemcpy(hptr, dptr, bytes, cudaMemcpyDeviceToHost));
+	return (0);
+}
+
+extern "C" int
+bjxa_gpu_sync(void *cuda_stream)
+{
+	XA_CUDA(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+	return (0);
+}
+
+/* ---- plans ---------------------------------------------------------------- */
+
+template <class T>
+struct DevBuf {
+	T *p;
+	size_t cap;
+	DevBuf() : p(NULL), cap(0) {}
+	int reserve(size_t n, bool zero)
+	{
+		if (n <= cap)
+			return 0;
+		if (p)
+			cudaFree(p);
+		p = NULL;
+		cap = 0;
+		size_t want = n + n / 4 + 16;
+		cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+		if (e != cudaSuccess) {
+			(void)cudaGetLastError();
+			return cuda_errno(e);
+		}
+		if (zero) {
+			e = cudaMemset(p, 0, want * sizeof(T));
+			if (e != cudaSuccess)
+				return cuda_errno(e);
+		}
+		cap = want;
+		return 0;
+	}
+	void release()
+	{
+		if (p)
+			cudaFree(p);
+		p = NULL;
+		cap = 0;
+	}
+};
+
+struct bjxa_plan {
+	uint32_t magic;
+#define BJXA_PLAN_MAGIC 0x706c414eu
+	HostPlan hp;
+	std::vector<bjxa_stream_desc_t> descs;
+	DevBuf<StreamDev> d_streams;
+	DevBuf<StreamRes> d_results;
+	DevBuf<uint32_t> d_first_bad;
+	DevBuf<TileEnt> d_tiles;
+	DevBuf<unsigned long long> d_carry;
+	DevBuf<unsigned long long> d_ticket;	/* one counter per bucket */
+	unsigned long long ticket_base[6];
+	uint32_t epoch;
+	/* last run */
+	bool ran;
+	uint8_t *last_dst;
+	const uint8_t *last_src;
+	uint64_t last_src_bytes;
+	cudaStream_t last_stream;
+	int launches;
+};
+
+static bool g_attr_done = false;
+
+template <int BITS, int CH>
+static cudaError_t
+set_attrs_one(void)
+{
+	cudaError_t e = cudaFuncSetAttribute(xa_decode_kernel<BITS, CH>,
+	    cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    (int)sizeof(DecSmem<BITS, CH, kDecTBQ>));
+	if (e != cudaSuccess)
+		return e;
+	return cudaFuncSetAttribute(xa_encode_kernel<BITS, CH>,
+	    cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    (int)sizeof(EncSmem<BITS, CH, kEncTBE>));
+}
+
+static cudaError_t
+set_attrs(void)
+{
+	/* per device in principle; the attribute is sticky per context */
+	static thread_local int done_dev = -1;
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess)
+		return e;
+	if (g_attr_done && done_dev == dev)
+		return cudaSuccess;
+	if ((e = set_attrs_one<4, 1>()) != cudaSuccess) return e;
+	if ((e = set_attrs_one<4, 2>()) != cudaSuccess) return e;
+	if ((e = set_attrs_one<6, 1>()) != cudaSuccess) return e;
+	if ((e = set_attrs_one<6, 2>()) != cudaSuccess) return e;
+	if ((e = set_attrs_one<8, 1>()) != cudaSuccess) return e;
+	if ((e = set_attrs_one<8, 2>()) != cudaSuccess) return e;
+	g_attr_done = true;
+	done_dev = dev;
+	return cudaSuccess;
+}
+
+static int
+plan_upload(bjxa_plan *pl)
+{
+	HostPlan &hp = pl->hp;
+	size_t n = hp.streams.size();
+	int rc;
+
+	if ((rc = pl->d_streams.reserve(n, false)) ||
+	    (rc = pl->d_results.reserve(n, false)) ||
+	    (rc = pl->d_first_bad.reserve(n, false)) ||
+	    (rc = pl->d_tiles.reserve(hp.tiles.size(), false)) ||
+	    (rc = pl->d_carry.reserve((size_t)hp.n_slots * 2, true)) ||
+	    (rc = pl->d_ticket.reserve(8, true))) {
+		errno = rc;
+		return (-1);
+	}
+	if (pl->d_ticket.cap && pl->ticket_base[0] == ~0ULL) {
+		/* fresh counter allocation */
+		memset(pl->ticket_base, 0, sizeof pl->ticket_base);
+	}
+	if (n)
+		XA_CUDA(cudaMemcpy(pl->d_streams.p, hp.streams.data(),
+		    n * sizeof(StreamDev), cudaMemcpyHostToDevice));
+	if (!hp.tiles.empty())
+		XA_CUDA(cudaMemcpy(pl->d_tiles.p, hp.tiles.data(),
+		    hp.tiles.size() * sizeof(TileEnt), cudaMemcpyHostToDevice));
+	return (0);
+}
+
+static int
+plan_build(bjxa_plan *pl, int kind, const bjxa_stream_desc_t *descs, size_t n)
+{
+	size_t bad = 0;
+
+	if (kind != BJXA_PLAN_DECODE && kind != BJXA_PLAN_ENCODE) {
+		errno = EINVAL;
+		return (-1);
+	}
+	if (descs == NULL && n != 0) {
+		errno = EFAULT;
+		return (-1);
+	}
+	int rc = build_plan(pl->hp, kind, descs, n, &bad);
+	if (rc) {
+		errno = rc;
+		return (-1);
+	}
+	pl->descs.assign(descs, descs + n);
+	pl->ran = false;
+	pl->launches = 0;
+	for (int b = 0; b < 6; b++)
+		if (pl->hp.tile_begin[b + 1] > pl->hp.tile_begin[b])
+			pl->launches++;
+	return (plan_upload(pl));
+}
+
+extern "C" bjxa_plan_t *
+bjxa_plan_create(int kind, const bjxa_stream_desc_t *descs, size_t n)
+{
+	if (bjxa_gpu_count() <= 0) {
+		errno = ENODEV;
+		return (NULL);
+	}
+	bjxa_plan *pl = new (std::nothrow) bjxa_plan();
+	if (pl == NULL) {
+		errno = ENOMEM;
+		return (NULL);
+	}
+	pl->magic = BJXA_PLAN_MAGIC;
+	pl->epoch = 0;
+	pl->ran = false;
+	pl->ticket_base[0] = ~0ULL;
+	if (plan_build(pl, kind, descs, n) < 0) {
+		int e = errno;
+		bjxa_plan_free(&pl);
+		errno = e;
+		return (NULL);
+	}
+	return (pl);
+}
+
+#define CHECK_PLAN(pl)							\
+	do {								\
+		if ((pl) == NULL) { errno = EFAULT; return (-1); }	\
+		if ((pl)->magic != BJXA_PLAN_MAGIC) { errno = EINVAL; return (-1); } \
+	} while (0)
+
+extern "C" int
+bjxa_plan_reset(bjxa_plan_t *pl, int kind, const bjxa_stream_desc_t *descs,
+    size_t n)
+{
+	CHECK_PLAN(pl);
+	if (pl->ran)
+		XA_CUDA(cudaStreamSynchronize(pl->last_stream));
+	return (plan_build(pl, kind, descs, n));
+}
+
+extern "C" int
+bjxa_plan_free(bjxa_plan_t **planp)
+{
+	if (planp == NULL) {
+		errno = EFAULT;
+		return (-1);
+	}
+	bjxa_plan *pl = *planp;
+	CHECK_PLAN(pl);
+	if (pl->ran)
+		(void)cudaStreamSynchronize(pl->last_stream);
+	pl->d_streams.release();
+	pl->d_results.release();
+	pl->d_first_bad.release();
+	pl->d_tiles.release();
+	pl->d_carry.release();
+	pl->d_ticket.release();
+	pl->magic = 0;
+	delete pl;
+	*planp = NULL;
+	return (0);
+}
+
+extern "C" int
+bjxa_plan_launches(const bjxa_plan_t *pl)
+{
+	CHECK_PLAN(pl);
+	return (pl->launches);
+}
+
+extern "C" int
+bjxa_plan_extent(const bjxa_plan_t *pl, uint64_t *src_bytes, uint64_t *dst_bytes)
+{
+	CHECK_PLAN(pl);
+	if (src_bytes)
+		*src_bytes = pl->hp.src_need;
+	if (dst_bytes)
+		*dst_bytes = pl->hp.dst_need;
+	return (0);
+}
+
+template <int BITS, int CH>
+static cudaError_t
+launch_decode(const DecodeParams &p, cudaStream_t st)
+{
+	xa_decode_kernel<BITS, CH><<<p.n_tiles, kDecThreads,
+	    sizeof(DecSmem<BITS, CH, kDecTBQ>), st>>>(p);
+	return cudaGetLastError();
+}
+
+template <int BITS, int CH>
+static cudaError_t
+launch_encode(const EncodeParams &p, cudaStream_t st)
+{
+	xa_encode_kernel<BITS, CH><<<p.n_tiles, kEncThreads,
+	    sizeof(EncSmem<BITS, CH, kEncTBE>), st>>>(p);
+	return cudaGetLastError();
+}
+
+extern "C" int
+bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
+    size_t src_bytes, void *cuda_stream)
+{
+	CHECK_PLAN(pl);
+	HostPlan &hp = pl->hp;
+	cudaStream_t st = (cudaStream_t)cuda_stream;
+
+	if (hp.tiles.empty()) {
+		pl->ran = true;
+		pl->last_stream = st;
+		pl->last_dst = (uint8_t *)dst;
+		pl->last_src = (const uint8_t *)src;
+		pl->last_src_bytes = src_bytes;
+		return (0);
+	}
+	if (dst == NULL || src == NULL) {
+		errno = EFAULT;
+		return (-1);
+	}
+	if (((uintptr_t)dst | (uintptr_t)src) & 15u) {
+		errno = EINVAL;
+		return (-1);
+	}
+	if (src_bytes < hp.src_need || dst_bytes < hp.dst_need) {
+		errno = ENOBUFS;
+		return (-1);
+	}
+	XA_CUDA(set_attrs());
+
+	size_t n = hp.streams.size();
+	pl->epoch++;
+	if (pl->epoch == 0) {		/* wrapped: mailboxes may hold stale tags */
+		XA_CUDA(cudaMemsetAsync(pl->d_carry.p, 0,
+		    pl->d_carry.cap * sizeof(unsigned long long), st));
+		pl->epoch = 1;
+	}
+	if (hp.kind == kKindDecode)
+		XA_CUDA(cudaMemsetAsync(pl->d_first_bad.p, 0xff, n * sizeof(uint32_t), st));
+
+	for (int b = 0; b < 6; b++) {
+		uint32_t t0 = hp.tile_begin[b], t1 = hp.tile_begin[b + 1];
+		if (t1 == t0)
+			continue;
+		cudaError_t e;
+		if (hp.kind == kKindDecode) {
+			DecodeParams p;
+			p.src = (const uint8_t *)src;
+			p.src_bytes = src_bytes;
+			p.dst = (uint8_t *)dst;
+			p.streams = pl->d_streams.p;
+			p.results = pl->d_results.p;
+			p.first_bad = pl->d_first_bad.p;
+			p.tiles = pl->d_tiles.p + t0;
+			p.n_tiles = t1 - t0;
+			p.carry = pl->d_carry.p;
+			p.ticket = pl->d_ticket.p + b;
+			p.ticket_base = pl->ticket_base[b];
+			p.epoch = pl->epoch;
+			pl->ticket_base[b] += p.n_tiles;
+			switch (b) {
+			case 0: e = launch_decode<4, 1>(p, st); break;
+			case 1: e = launch_decode<4, 2>(p, st); break;
+			case 2: e = launch_decode<6, 1>(p, st); break;
+			case 3: e = launch_decode<6, 2>(p, st); break;
+			case 4: e = launch_decode<8, 1>(p, st); break;
+			default: e = launch_decode<8, 2>(p, st); break;
+			}
+		} else {
+			EncodeParams p;
+			p.src = (const uint8_t *)src;
+			p.src_bytes = src_bytes;
+			p.dst = (uint8_t *)dst;
+			p.dst_bytes = dst_bytes;
+			p.streams = pl->d_streams.p;
+			p.tiles = pl->d_tiles.p + t0;
+			p.n_tiles = t1 - t0;
+			switch (b) {
+			case 0: e = launch_encode<4, 1>(p, st); break;
+			case 1: e = launch_encode<4, 2>(p, st); break;
+			case 2: e = launch_encode<6, 1>(p, st); break;
+			case 3: e = launch_encode<6, 2>(p, st); break;
+			case 4: e = launch_encode<8, 1>(p, st); break;
+			default: e = launch_encode<8, 2>(p, st); break;
+			}
+		}
+		XA_CUDA(e);
+	}
+	pl->ran = true;
+	pl->last_stream = st;
+	pl->last_dst = (uint8_t *)dst;
+	pl->last_src = (const uint8_t *)src;
+	pl->last_src_bytes = src_bytes;
+	return (0);
+}
+
+/*
+ * State of channel c after effective block `eb` (eb >= 0) of a decoded stream:
+ * the block's last two samples, read back from the PCM arena.
+ */
+static int
+state_from_pcm(const bjxa_plan *pl, const bjxa_stream_desc_t &d, uint32_t eb,
+    int16_t prev[2][2])
+{
+	int16_t tail[4];
+	unsigned ch = d.channels;
+	uint64_t off = d.pcm_off + (uint64_t)eb * 64u * ch + 60u * ch;
+
+	XA_CUDA(cudaMemcpy(tail, pl->last_dst + off, 4u * ch, cudaMemcpyDeviceToHost));
+	for (unsigned c = 0; c < ch; c++) {
+		prev[c][1] = tail[c];		/* sample 30 */
+		prev[c][0] = tail[ch + c];	/* sample 31 */
+	}
+	return (0);
+}
+
+/* the reference advances the LEFT channel before it meets a bad RIGHT block
+ * (libbjxa.c:633-643): redo that one pair on the device to get the state */
+static int
+left_state_after(const bjxa_plan *pl, const bjxa_stream_desc_t &d, uint32_t eb,
+    const int16_t before[2][2], int16_t left[2])
+{
+	bjxa_stream_desc_t one = d;
+	one.xa_off = d.xa_off + (uint64_t)eb * (uint64_t)(block_bytes(d.bits) * 2);
+	one.pcm_off = 0;
+	one.blocks = 1;
+	one.pcm_len = 128;
+	memcpy(one.prev, before, sizeof one.prev);
+
+	bjxa_plan_t *mini = bjxa_plan_create(BJXA_PLAN_DECODE, &one, 1);
+	if (mini == NULL)
+		return (-1);
+	void *scratch = bjxa_gpu_alloc(256);
+	int rc = -1;
+	if (scratch != NULL &&
+	    bjxa_plan_run(mini, scratch, 256, pl->last_src, pl->last_src_bytes,
+	    pl->last_stream) == 0 &&
+	    cudaStreamSynchronize(pl->last_stream) == cudaSuccess) {
+		StreamRes r;
+		if (cudaMemcpy(&r, mini->d_results.p, sizeof r,
+		    cudaMemcpyDeviceToHost) == cudaSuccess) {
+			left[0] = r.prev[0][0];
+			left[1] = r.prev[0][1];
+			rc = 0;
+		}
+	}
+	int e = errno;
+	if (scratch)
+		bjxa_gpu_free(scratch);
+	bjxa_plan_free(&mini);
+	if (rc < 0)
+		errno = e ? e : EIO;
+	return (rc);
+}
+
+extern "C" int
+bjxa_plan_fetch(bjxa_plan_t *pl, bjxa_stream_desc_t *out, size_t n)
+{
+	CHECK_PLAN(pl);
+	if (out == NULL && n != 0) {
+		errno = EFAULT;
+		return (-1);
+	}
+	if (!pl->ran || n != pl->descs.size()) {
+		errno = EINVAL;
+		return (-1);
+	}
+	XA_CUDA(cudaStreamSynchronize(pl->last_stream));
+	XA_CUDA(cudaGetLastError());
+
+	if (pl->hp.kind == kKindEncode) {
+		for (size_t i = 0; i < n; i++) {
+			out[i] = pl->descs[i];
+			out[i].done = out[i].blocks;
+			out[i].result = (int32_t)out[i].blocks;
+			out[i].error = 0;
+		}
+		return (0);
+	}
+
+	std::vector<StreamRes> res(n);
+	std::vector<uint32_t> bad(n);
+	if (n) {
+		XA_CUDA(cudaMemcpy(res.data(), pl->d_results.p, n * sizeof(StreamRes),
+		    cudaMemcpyDeviceToHost));
+		XA_CUDA(cudaMemcpy(bad.data(), pl->d_first_bad.p, n * sizeof(uint32_t),
+		    cudaMemcpyDeviceToHost));
+	}
+	for (size_t i = 0; i < n; i++) {
+		const bjxa_stream_desc_t &d = pl->descs[i];
+		out[i] = d;
+		if (d.blocks == 0) {
+			out[i].done = 0;
+			out[i].result = 0;
+			out[i].error = 0;
+			continue;
+		}
+		if (bad[i] == 0xffffffffu) {
+			memcpy(out[i].prev, res[i].prev, sizeof res[i].prev);
+			out[i].done = d.blocks;
+			out[i].result = (int32_t)d.blocks;
+			out[i].error = 0;
+			continue;
+		}
+		/* bad profile at block-channel bad[i] (libbjxa.c:550,634,642) */
+		uint32_t eb = bad[i] / d.channels, c = bad[i] % d.channels;
+		out[i].done = eb;
+		out[i].result = -1;
+		out[i].error = EPROTO;
+		if (eb > 0 && state_from_pcm(pl, d, eb - 1, out[i].prev) < 0)
+			return (-1);
+		if (c == 1) {
+			int16_t before[2][2], left[2];
+			memcpy(before, out[i].prev, sizeof before);
+			if (left_state_after(pl, d, eb, before, left) < 0)
+				return (-1);
+			out[i].prev[0][0] = left[0];
+			out[i].prev[0][1] = left[1];
+		}
+	}
+	return (0);
+}
+
+/* ---- sharding ------------------------------------------------------------- */
+
+extern "C" int
+bjxa_shard_range(const uint64_t *bytes, size_t n, int rank, int world,
+    size_t *first, size_t *count)
+{
+	if (first == NULL || count == NULL) {
+		errno = EFAULT;
+		return (-1);
+	}
+	if (world <= 0 || rank < 0 || rank >= world) {
+		errno = EINVAL;
+		return (-1);
+	}
+	size_t lo, hi;
+	if (bytes == NULL) {
+		lo = n * (size_t)rank / (size_t)world;
+		hi = n * ((size_t)rank + 1) / (size_t)world;
+	} else {
+		/* boundary k sits where the running total first reaches k/world */
+		long double total = 0;
+		for (size_t i = 0; i < n; i++)
+			total += (long double)bytes[i];
+		long double tlo = total * rank / world, thi = total * (rank + 1) / world;
+		long double run = 0;
+		lo = hi = n;
+		bool got_lo = false, got_hi = false;
+		for (size_t i = 0; i <= n; i++) {
+			if (!got_lo && run >= tlo) { lo = i; got_lo = true; }
+			if (!got_hi && run >= thi) { hi = i; got_hi = true; }
+			if (i < n)
+				run += (long double)bytes[i];
+		}
+		if (rank == world - 1)
+			hi = n;
+		if (rank == 0)
+			lo = 0;
+	}
+	*first = lo;
+	*count = hi - lo;
+	return (0);
+}

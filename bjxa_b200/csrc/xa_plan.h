@@ -1,0 +1,137 @@
+/*
+ * xa_plan.h -- host-side batch planning: turns a table of stream descriptors
+ * into per-(bits,channels) tile lists and the device records of xa_tile.h.
+ * Pure host C++ (no CUDA calls) so the same code feeds the sm_100a launcher
+ * (xa_kernels.cu) and the CPU single-stepper used by the tests (tests/emul).
+ *
+ * The reference has no counterpart: it walks one stream serially
+ * (/root/reference/src/libbjxa.c:629-658).  Here every stream is cut into
+ * tiles of TBE effective blocks; tiles are issued "time-major" (tile j of every
+ * stream before tile j+1 of any) so that concurrently resident CTAs work on
+ * different streams and a tile's predecessor in its stream has long finished
+ * when its carry is needed.
+ */
+#ifndef XA_PLAN_H
+#define XA_PLAN_H
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "xa_tile.h"
+
+/* public descriptor, see include/bjxa_batch.h */
+struct bjxa_stream_desc;
+
+namespace xa {
+
+/* tile geometry: block-channels per decode tile, effective blocks per encode tile */
+constexpr int kDecTBQ = 512;
+constexpr int kDecThreads = 128;
+constexpr int kEncTBE = 256;
+constexpr int kEncThreads = 128;
+
+enum { kKindDecode = 0, kKindEncode = 1 };
+
+XA_HD int bucket_of(int bits, int ch) { return (bits / 2 - 2) * 2 + (ch - 1); }
+XA_HD int bucket_bits(int b) { return 4 + 2 * (b / 2); }
+XA_HD int bucket_ch(int b) { return 1 + (b & 1); }
+
+struct HostPlan {
+	int kind;
+	std::vector<StreamDev> streams;
+	std::vector<uint8_t> bucket;		/* per stream */
+	std::vector<TileEnt> tiles;		/* all buckets, concatenated */
+	uint32_t tile_begin[7];			/* bucket b owns [b], [b+1]) */
+	uint32_t n_slots;
+	uint64_t src_need, dst_need;		/* arena bytes the batch touches */
+};
+
+/* effective blocks per tile for a stream with `ch` channels */
+inline uint32_t tile_blocks(int kind, int ch)
+{
+	return kind == kKindDecode ? (uint32_t)(kDecTBQ / ch) : (uint32_t)kEncTBE;
+}
+
+/*
+ * Validates the descriptors and builds the plan.  Returns 0, or an errno
+ * value (EINVAL) with *bad_index set to the offending stream.
+ */
+template <class Desc>
+inline int build_plan(HostPlan &hp, int kind, const Desc *d, size_t n,
+    size_t *bad_index)
+{
+	hp.kind = kind;
+	hp.streams.resize(n);
+	hp.bucket.resize(n);
+	hp.tiles.clear();
+	hp.n_slots = 0;
+	hp.src_need = hp.dst_need = 0;
+
+	std::vector<uint32_t> order[6];
+	for (size_t i = 0; i < n; i++) {
+		const Desc &s = d[i];
+		bool ok = (s.bits == 4 || s.bits == 6 || s.bits == 8) &&
+		    (s.channels == 1 || s.channels == 2) && (s.pcm_off % 16 == 0) &&
+		    (s.pcm_len % (2u * s.channels) == 0) &&
+		    (uint64_t)s.pcm_len <= (uint64_t)s.blocks * 64u * s.channels;
+		if (!ok) {
+			if (bad_index)
+				*bad_index = i;
+			return 22;	/* EINVAL */
+		}
+		StreamDev &sd = hp.streams[i];
+		std::memset(&sd, 0, sizeof sd);
+		sd.xa_off = s.xa_off;
+		sd.pcm_off = s.pcm_off;
+		sd.blocks = s.blocks;
+		sd.pcm_len = s.pcm_len;
+		std::memcpy(sd.prev, s.prev, sizeof sd.prev);
+		int b = bucket_of(s.bits, s.channels);
+		hp.bucket[i] = (uint8_t)b;
+		uint32_t tbe = tile_blocks(kind, s.channels);
+		uint32_t nt = (s.blocks + tbe - 1) / tbe;
+		sd.slot_base = hp.n_slots;
+		hp.n_slots += nt;
+		if (s.blocks) {
+			order[b].push_back((uint32_t)i);
+			uint64_t xa_end = s.xa_off + (uint64_t)s.blocks *
+			    (uint64_t)(block_bytes(s.bits) * s.channels);
+			uint64_t pcm_end = s.pcm_off + s.pcm_len;
+			uint64_t &src = kind == kKindDecode ? hp.src_need : hp.dst_need;
+			uint64_t &dst = kind == kKindDecode ? hp.dst_need : hp.src_need;
+			src = std::max(src, xa_end);
+			dst = std::max(dst, pcm_end);
+		}
+	}
+
+	for (int b = 0; b < 6; b++) {
+		hp.tile_begin[b] = (uint32_t)hp.tiles.size();
+		std::vector<uint32_t> &o = order[b];
+		if (o.empty())
+			continue;
+		uint32_t tbe = tile_blocks(kind, bucket_ch(b));
+		/* longest first: the streams still active at tile j are a prefix */
+		std::stable_sort(o.begin(), o.end(), [&](uint32_t x, uint32_t y) {
+			return hp.streams[x].blocks > hp.streams[y].blocks;
+		});
+		size_t active = o.size();
+		for (uint32_t j = 0; active > 0; j++) {
+			while (active > 0 &&
+			    (uint64_t)j * tbe >= hp.streams[o[active - 1]].blocks)
+				active--;
+			for (size_t k = 0; k < active; k++) {
+				TileEnt te;
+				te.stream = o[k];
+				te.first_eb = j * tbe;
+				hp.tiles.push_back(te);
+			}
+		}
+	}
+	hp.tile_begin[6] = (uint32_t)hp.tiles.size();
+	return 0;
+}
+
+} /* namespace xa */
+#endif

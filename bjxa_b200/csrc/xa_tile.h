@@ -1,0 +1,526 @@
+/*
+ * xa_tile.h -- the tile-level decode and encode algorithms.
+ *
+ * A "tile" is a run of consecutive effective blocks of ONE stream that one CTA
+ * stages in shared memory: contiguous XA bytes on one side, contiguous
+ * interleaved PCM on the other.  The code below is the per-thread body of each
+ * phase between two CTA barriers; xa_kernels.cu wraps the phases in the
+ * sm_100a kernel (bulk-async loads, mbarrier, __syncthreads), tests/emul wraps
+ * the same phases in plain loops to single-step them on a CPU (tests only).
+ *
+ * Decode schedule (replaces the serial block loop of
+ * /root/reference/src/libbjxa.c:629-658):
+ *   phase A   every filter-0 ("cut") block is decoded at once -- its output
+ *             does not depend on predictor state (k0 = k1 = 0,
+ *             libbjxa.c:526,559) -- one thread per block-channel;
+ *   rounds    blocks with filters 1..4 form chains behind a cut block; round r
+ *             decodes the r-th block of every chain in the tile, compacted so
+ *             that live chains fill whole warps; a chain's state is the last
+ *             two samples of the previous block, read back from the staged
+ *             output;
+ *   carry     a chain that crosses a tile boundary takes its state from the
+ *             previous tile of the stream through a 64-bit mailbox in global
+ *             memory (epoch-tagged, so no clearing between launches); tiles
+ *             are handed out by an atomic ticket in an order that puts every
+ *             tile after its predecessor, so waiting is deadlock-free;
+ *   store     staged PCM rows are interleaved (stereo) and written with
+ *             16-byte stores; the last block of a stream is truncated to the
+ *             PCM bytes owed (libbjxa.c:622-624,648).
+ */
+#ifndef XA_TILE_H
+#define XA_TILE_H
+
+#include "xa_core.h"
+
+namespace xa {
+
+/* ---- records shared by host and device --------------------------------- */
+
+struct StreamDev {		/* one stream of a batch, device resident */
+	uint64_t xa_off;	/* first XA block, bytes into the XA arena */
+	uint64_t pcm_off;	/* PCM, bytes into the PCM arena; multiple of 16 */
+	uint32_t blocks;	/* effective blocks to process */
+	uint32_t pcm_len;	/* PCM bytes owed (decode) / available (encode) */
+	uint32_t slot_base;	/* first carry mailbox of this stream */
+	uint32_t reserved;
+	int16_t  prev[2][2];	/* decode: predictor state on entry [ch][n-1,n-2] */
+};
+
+struct StreamRes {		/* decode results, device resident */
+	int16_t  prev[2][2];	/* predictor state after the last block */
+};
+
+struct TileEnt {
+	uint32_t stream;
+	uint32_t first_eb;	/* first effective block of the tile */
+};
+
+struct DecodeParams {
+	const uint8_t *src;	/* XA arena */
+	uint64_t src_bytes;
+	uint8_t *dst;		/* PCM arena */
+	const StreamDev *streams;
+	StreamRes *results;
+	uint32_t *first_bad;	/* per stream: lowest bad block-channel index */
+	const TileEnt *tiles;
+	uint32_t n_tiles;
+	unsigned long long *carry;	/* [slot][2] mailboxes */
+	unsigned long long *ticket;
+	unsigned long long ticket_base;
+	uint32_t epoch;
+};
+
+struct EncodeParams {
+	const uint8_t *src;	/* PCM arena */
+	uint64_t src_bytes;
+	uint8_t *dst;		/* XA arena */
+	uint64_t dst_bytes;
+	const StreamDev *streams;
+	const TileEnt *tiles;
+	uint32_t n_tiles;
+};
+
+/* ---- environment shims -------------------------------------------------- */
+
+#if defined(__CUDA_ARCH__)
+XA_HD int smem_inc(int *p) { return atomicAdd(p, 1); }
+XA_HD void global_min_u32(uint32_t *p, uint32_t v) { atomicMin(p, v); }
+XA_HD void mailbox_put(unsigned long long *p, unsigned long long v)
+{
+	asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+XA_HD unsigned long long mailbox_get(const unsigned long long *p, uint32_t epoch)
+{
+	unsigned long long v;
+	for (;;) {
+		asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+		if ((uint32_t)(v >> 32) == epoch)
+			return v;
+		__nanosleep(64);
+	}
+}
+#else
+XA_HD int smem_inc(int *p) { return (*p)++; }
+XA_HD void global_min_u32(uint32_t *p, uint32_t v) { if (v < *p) *p = v; }
+XA_HD void mailbox_put(unsigned long long *p, unsigned long long v) { *p = v; }
+XA_HD unsigned long long mailbox_get(const unsigned long long *p, uint32_t epoch)
+{
+	/* the emulator runs tiles in ticket order: the value must be there */
+	if ((uint32_t)(*p >> 32) != epoch)
+		__builtin_trap();
+	return *p;
+}
+#endif
+
+/* ---- decode -------------------------------------------------------------- */
+
+template <int BITS, int CH, int TBQ>
+struct DecSmem {
+	static constexpr int BS = block_bytes(BITS);
+	/* payload + up to 15 bytes of misalignment, in 16-byte units, plus one
+	 * unit of slack for load_payload's one-word over-read */
+	static constexpr int IN_BYTES = ((TBQ * BS + 15 + 15) / 16) * 16 + 16;
+
+	alignas(16) uint8_t in[IN_BYTES];
+	alignas(16) uint32_t out[TBQ * 16];	/* planar rows, 64 B each, swizzled */
+	uint8_t prof[TBQ];
+	uint16_t live[2][TBQ];
+	int n_live[2];
+	uint32_t ticket;
+	alignas(8) unsigned long long mbar;
+};
+
+template <int BITS, int CH, int TBQ>
+struct DecTile {
+	typedef DecSmem<BITS, CH, TBQ> Smem;
+	static constexpr int BS = block_bytes(BITS);
+	static constexpr int TBE = TBQ / CH;	/* effective blocks per tile */
+	static_assert(TBQ % CH == 0, "tile must hold whole effective blocks");
+
+	const DecodeParams &p;
+	Smem &sm;
+	uint32_t stream, first_eb, neb, nq;
+	uint64_t g0;		/* first source byte */
+	uint64_t a0;		/* g0 rounded down to 16 */
+	uint32_t in_off;	/* g0 - a0 */
+	uint32_t in_need;	/* bytes from a0 covering the tile's blocks */
+	uint64_t out0;		/* first destination byte */
+	uint32_t out_valid;	/* PCM bytes this tile owes */
+	uint32_t slot;
+	bool first_tile, last_tile;
+
+	XA_HD DecTile(const DecodeParams &p_, Smem &sm_, uint32_t ticket)
+	    : p(p_), sm(sm_)
+	{
+		const TileEnt te = p.tiles[ticket];
+		const StreamDev &s = p.streams[te.stream];
+		stream = te.stream;
+		first_eb = te.first_eb;
+		uint32_t rem = s.blocks - first_eb;
+		neb = rem < (uint32_t)TBE ? rem : (uint32_t)TBE;
+		nq = neb * CH;
+		g0 = s.xa_off + (uint64_t)first_eb * (BS * CH);
+		a0 = g0 & ~(uint64_t)15;
+		in_off = (uint32_t)(g0 - a0);
+		in_need = in_off + nq * BS;
+		uint64_t pcm_done = (uint64_t)first_eb * (64 * CH);
+		out0 = s.pcm_off + pcm_done;
+		uint64_t owed = s.pcm_len > pcm_done ? s.pcm_len - pcm_done : 0;
+		uint64_t full = (uint64_t)neb * (64 * CH);
+		out_valid = (uint32_t)(owed < full ? owed : full);
+		slot = s.slot_base + first_eb / TBE;
+		first_tile = first_eb == 0;
+		last_tile = first_eb + neb == s.blocks;
+	}
+
+	/* bytes the bulk-async engine can fetch: whole 16-byte units inside the arena */
+	XA_HD uint32_t bulk_bytes() const
+	{
+		uint64_t end = a0 + ((in_need + 15u) & ~15u);
+		uint64_t lim = p.src_bytes & ~(uint64_t)15;
+		if (end > lim)
+			end = lim > a0 ? lim : a0;
+		return (uint32_t)(end - a0);
+	}
+
+	/* bytes past bulk_bytes() fetched one by one (only at the arena's end) */
+	XA_HD void load_tail(uint32_t tid, uint32_t nt)
+	{
+		for (uint32_t i = bulk_bytes() + tid; i < in_need; i += nt)
+			sm.in[i] = p.src[a0 + i];
+	}
+
+	XA_HD static int row_word(uint32_t q, int chunk, int w)
+	{
+		return (int)(q * 16 + (uint32_t)((chunk ^ (int)((q >> 1) & 3u)) * 4 + w));
+	}
+
+	XA_HD void store_row(uint32_t q, const uint32_t (&o)[16])
+	{
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			uint32_t *d = &sm.out[row_word(q, j, 0)];
+#if defined(__CUDA_ARCH__)
+			*reinterpret_cast<uint4 *>(d) = make_uint4(o[4 * j], o[4 * j + 1],
+			    o[4 * j + 2], o[4 * j + 3]);
+#else
+			d[0] = o[4 * j]; d[1] = o[4 * j + 1];
+			d[2] = o[4 * j + 2]; d[3] = o[4 * j + 3];
+#endif
+		}
+	}
+
+	XA_HD void fetch_block(uint32_t q, uint32_t (&pw)[BITS]) const
+	{
+		uint32_t pay = in_off + q * BS + 1;	/* first payload byte */
+		const uint32_t *w = reinterpret_cast<const uint32_t *>(sm.in) + (pay >> 2);
+		load_payload<BITS>(pw, w, (pay & 3u) * 8u);
+	}
+
+	/* hand the channel's state to whoever continues it */
+	XA_HD void publish(uint32_t c, int p0, int p1)
+	{
+		if (last_tile) {
+			p.results[stream].prev[c][0] = (int16_t)p0;
+			p.results[stream].prev[c][1] = (int16_t)p1;
+		} else {
+			unsigned long long v = ((unsigned long long)p.epoch << 32) |
+			    ((unsigned long long)(uint16_t)p1 << 16) | (uint16_t)p0;
+			mailbox_put(&p.carry[(uint64_t)slot * 2 + c], v);
+		}
+	}
+
+	XA_HD void carried_in(uint32_t c, int &p0, int &p1) const
+	{
+		if (first_tile) {
+			p0 = p.streams[stream].prev[c][0];
+			p1 = p.streams[stream].prev[c][1];
+		} else {
+			unsigned long long v = mailbox_get(
+			    &p.carry[(uint64_t)(slot - 1) * 2 + c], p.epoch);
+			p0 = (int16_t)(uint16_t)v;
+			p1 = (int16_t)(uint16_t)(v >> 16);
+		}
+	}
+
+	/* phase A: profiles, cut blocks */
+	XA_HD void phase_a(uint32_t tid, uint32_t nt)
+	{
+		if (tid == 0) {
+			sm.n_live[0] = 0;
+			sm.n_live[1] = 0;
+		}
+		for (uint32_t q = tid; q < nq; q += nt) {
+			uint32_t prof = sm.in[in_off + q * BS];
+			sm.prof[q] = (uint8_t)prof;
+			int kind = block_kind(prof);
+			if (kind == kChain)
+				continue;
+			if (kind == kBad)
+				global_min_u32(&p.first_bad[stream], first_eb * CH + q);
+			/* a bad block is decoded as if it were a cut so that
+			 * nothing downstream waits for it; what lies at and after
+			 * it is not part of the result */
+			uint32_t pw[BITS], o[16];
+			fetch_block(q, pw);
+			decode_block_cut<BITS>(o, pw, prof);
+			store_row(q, o);
+			if (q + CH >= nq)
+				publish(q % CH, (int)(int16_t)(o[15] >> 16),
+				    (int)(int16_t)(o[15] & 0xffffu));
+		}
+	}
+
+	/* heads of chains: a chain block whose predecessor is not a chain block */
+	XA_HD void phase_seed(uint32_t tid, uint32_t nt)
+	{
+		for (uint32_t q = tid; q < nq; q += nt) {
+			if (block_kind(sm.prof[q]) != kChain)
+				continue;
+			if (q >= (uint32_t)CH && block_kind(sm.prof[q - CH]) == kChain)
+				continue;
+			sm.live[0][smem_inc(&sm.n_live[0])] = (uint16_t)q;
+		}
+	}
+
+	/* one round: the next block of every live chain */
+	XA_HD void phase_round(uint32_t tid, uint32_t nt, int cur, int n)
+	{
+		for (uint32_t i = tid; i < (uint32_t)n; i += nt) {
+			uint32_t q = sm.live[cur][i];
+			uint32_t prof = sm.prof[q];
+			int p0, p1;
+			if (q < (uint32_t)CH) {
+				carried_in(q, p0, p1);
+			} else {
+				uint32_t last = sm.out[row_word(q - CH, 3, 3)];
+				p0 = (int)(int16_t)(last >> 16);
+				p1 = (int)(int16_t)(last & 0xffffu);
+			}
+			uint32_t pw[BITS], o[16];
+			fetch_block(q, pw);
+			decode_block_chain<BITS>(o, pw, prof, p0, p1);
+			store_row(q, o);
+			if (q + CH >= nq)
+				publish(q % CH, p0, p1);
+			else if (block_kind(sm.prof[q + CH]) == kChain)
+				sm.live[cur ^ 1][smem_inc(&sm.n_live[cur ^ 1])] =
+				    (uint16_t)(q + CH);
+		}
+	}
+
+	/* staged rows -> interleaved PCM, 16 bytes per step */
+	XA_HD void phase_store(uint32_t tid, uint32_t nt)
+	{
+		uint8_t *dst = p.dst + out0;
+		const uint32_t nchunk = neb * (4 * CH);
+		for (uint32_t i = tid; i < nchunk; i += nt) {
+			uint32_t w0, w1, w2, w3;
+			if (CH == 1) {
+				uint32_t q = i >> 2;
+				int j = (int)(i & 3u);
+				const uint32_t *s = &sm.out[row_word(q, j, 0)];
+				w0 = s[0]; w1 = s[1]; w2 = s[2]; w3 = s[3];
+			} else {
+				uint32_t eb = i >> 3, jj = i & 7u;
+				int j = (int)(jj >> 1), h = (int)(jj & 1u) * 2;
+				const uint32_t *l = &sm.out[row_word(2 * eb, j, h)];
+				const uint32_t *r = &sm.out[row_word(2 * eb + 1, j, h)];
+				w0 = byte_perm(l[0], r[0], 0x5410);
+				w1 = byte_perm(l[0], r[0], 0x7632);
+				w2 = byte_perm(l[1], r[1], 0x5410);
+				w3 = byte_perm(l[1], r[1], 0x7632);
+			}
+			uint32_t boff = i * 16u;
+			if (boff + 16u <= out_valid) {
+#if defined(__CUDA_ARCH__)
+				*reinterpret_cast<uint4 *>(dst + boff) = make_uint4(w0, w1, w2, w3);
+#else
+				uint32_t *d = reinterpret_cast<uint32_t *>(dst + boff);
+				d[0] = w0; d[1] = w1; d[2] = w2; d[3] = w3;
+#endif
+			} else if (boff < out_valid) {
+				/* the truncated last block of a stream */
+				uint32_t w[4] = { w0, w1, w2, w3 };
+				uint16_t *d = reinterpret_cast<uint16_t *>(dst + boff);
+				uint32_t n16 = (out_valid - boff) / 2u;
+				for (uint32_t k = 0; k < n16; k++)
+					d[k] = (uint16_t)(w[k >> 1] >> (16u * (k & 1u)));
+			}
+		}
+	}
+};
+
+/* ---- encode -------------------------------------------------------------- */
+/*
+ * Reference-exact encoder (/root/reference/src/libbjxa.c:665-691,759-819):
+ * profile byte 0, top-bits truncation, zero-padded last block.  One thread per
+ * effective block: it reads 64*CH contiguous PCM bytes and produces CH
+ * consecutive XA blocks.
+ */
+
+template <int BITS, int CH, int TBE>
+struct EncSmem {
+	static constexpr int BS = block_bytes(BITS);
+	static constexpr int OUT_BYTES = ((TBE * CH * BS + 15 + 15) / 16) * 16 + 16;
+
+	alignas(16) uint8_t in[TBE * CH * 64 + 16];
+	alignas(16) uint8_t out[OUT_BYTES];
+	alignas(8) unsigned long long mbar;
+};
+
+template <int BITS, int CH, int TBE>
+struct EncTile {
+	typedef EncSmem<BITS, CH, TBE> Smem;
+	static constexpr int BS = block_bytes(BITS);
+
+	const EncodeParams &p;
+	Smem &sm;
+	uint32_t stream, first_eb, neb;
+	uint64_t in0;		/* first PCM byte (16-byte aligned) */
+	uint32_t in_valid;	/* PCM bytes that exist for this tile */
+	uint64_t o0, o1;	/* destination byte range */
+	uint64_t oa;		/* o0 rounded down to 16 */
+	uint32_t out_off;
+
+	XA_HD EncTile(const EncodeParams &p_, Smem &sm_, uint32_t tile)
+	    : p(p_), sm(sm_)
+	{
+		const TileEnt te = p.tiles[tile];
+		const StreamDev &s = p.streams[te.stream];
+		stream = te.stream;
+		first_eb = te.first_eb;
+		uint32_t rem = s.blocks - first_eb;
+		neb = rem < (uint32_t)TBE ? rem : (uint32_t)TBE;
+		uint64_t done = (uint64_t)first_eb * (64 * CH);
+		in0 = s.pcm_off + done;
+		uint64_t have = s.pcm_len > done ? s.pcm_len - done : 0;
+		uint64_t full = (uint64_t)neb * (64 * CH);
+		in_valid = (uint32_t)(have < full ? have : full);
+		o0 = s.xa_off + (uint64_t)first_eb * (BS * CH);
+		o1 = o0 + (uint64_t)neb * (BS * CH);
+		oa = o0 & ~(uint64_t)15;
+		out_off = (uint32_t)(o0 - oa);
+	}
+
+	XA_HD uint32_t bulk_bytes() const
+	{
+		uint64_t end = in0 + ((in_valid + 15u) & ~15u);
+		uint64_t lim = p.src_bytes & ~(uint64_t)15;
+		if (end > lim)
+			end = lim > in0 ? lim : in0;
+		return (uint32_t)(end - in0);
+	}
+
+	XA_HD void load_tail(uint32_t tid, uint32_t nt)
+	{
+		for (uint32_t i = bulk_bytes() + tid; i < in_valid; i += nt)
+			sm.in[i] = p.src[in0 + i];
+	}
+
+	/* write BS bytes (profile 0 + payload) at an arbitrary smem byte address */
+	XA_HD void put_block(uint32_t at, const uint32_t (&pw)[BITS])
+	{
+		/* the block as BITS+1 little-endian words: byte 0 = profile */
+		uint32_t sw[BITS + 2];
+		sw[0] = pw[0] << 8;
+#pragma unroll
+		for (int k = 1; k < BITS; k++)
+			sw[k] = funnel_r(pw[k - 1], pw[k], 24);
+		sw[BITS] = pw[BITS - 1] >> 24;
+		sw[BITS + 1] = 0;
+
+		const uint32_t d = at & 3u;
+		uint32_t *base = reinterpret_cast<uint32_t *>(sm.out) + (at >> 2);
+		uint8_t *bbase = sm.out + (at & ~3u);
+		const uint32_t sh = (4u - d) * 8u;	/* 32 when d == 0 */
+		uint32_t prev = 0;
+#pragma unroll
+		for (int j = 0; j < BITS + 2; j++) {
+			/* destination word j holds block bytes [4j-d, 4j-d+4) */
+			uint32_t cur = sw[j];
+			uint32_t v = d ? funnel_r(prev, cur, sh & 31u) : cur;
+			prev = cur;
+			int lo = 4 * j - (int)d;
+			if (lo >= BS)
+				break;
+			if (lo >= 0 && lo + 4 <= BS) {
+				base[j] = v;
+			} else {
+#pragma unroll
+				for (int b = 0; b < 4; b++)
+					if (lo + b >= 0 && lo + b < BS)
+						bbase[4 * j + b] = (uint8_t)(v >> (8 * b));
+			}
+		}
+	}
+
+	XA_HD void phase_pack(uint32_t tid, uint32_t nt)
+	{
+		const uint32_t *in32 = reinterpret_cast<const uint32_t *>(sm.in);
+		for (uint32_t eb = tid; eb < neb; eb += nt) {
+			/* frames of this block that exist (the rest are zero) */
+			uint32_t fr_have = in_valid / (2u * CH);
+			uint32_t fr0 = eb * 32u;
+			uint32_t fv = fr_have > fr0 ? fr_have - fr0 : 0u;
+			if (fv > 32u)
+				fv = 32u;
+#pragma unroll
+			for (int c = 0; c < CH; c++) {
+				uint32_t s16[16];
+#pragma unroll
+				for (int i = 0; i < 16; i++) {
+					uint32_t w;
+					if (CH == 1) {
+						w = in32[eb * 16u + i];
+					} else {
+						uint32_t f0 = in32[eb * 32u + 2 * i];
+						uint32_t f1 = in32[eb * 32u + 2 * i + 1];
+						w = byte_perm(f0, f1, c ? 0x7632 : 0x5410);
+					}
+					if (fv < 32u) {		/* zero-pad (libbjxa.c:686-690) */
+						if (2u * i >= fv)
+							w = 0;
+						else if (2u * i + 1 >= fv)
+							w &= 0xffffu;
+					}
+					s16[i] = w;
+				}
+				uint32_t pw[BITS];
+				deflate_block<BITS>(pw, s16);
+				put_block(out_off + (eb * CH + c) * BS, pw);
+			}
+		}
+	}
+
+	XA_HD void phase_store(uint32_t tid, uint32_t nt)
+	{
+		/* smem byte i mirrors global byte oa + i */
+		uint64_t v0 = (o0 + 15) & ~(uint64_t)15;	/* vector part */
+		uint64_t v1 = o1 & ~(uint64_t)15;
+		if (v0 > v1) {			/* tile smaller than one unit */
+			v0 = o1;
+			v1 = o1;
+		}
+		uint8_t *dst = p.dst;
+		uint32_t nvec = (uint32_t)((v1 - v0) >> 4);
+		for (uint32_t i = tid; i < nvec; i += nt) {
+			uint64_t g = v0 + (uint64_t)i * 16;
+			const uint32_t *s = reinterpret_cast<const uint32_t *>(sm.out + (g - oa));
+#if defined(__CUDA_ARCH__)
+			*reinterpret_cast<uint4 *>(dst + g) = *reinterpret_cast<const uint4 *>(s);
+#else
+			uint32_t *d = reinterpret_cast<uint32_t *>(dst + g);
+			d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+#endif
+		}
+		uint32_t head = (uint32_t)(v0 - o0), tail = (uint32_t)(o1 - v1);
+		for (uint32_t i = tid; i < head + tail; i += nt) {
+			uint64_t g = i < head ? o0 + i : v1 + (i - head);
+			dst[g] = sm.out[g - oa];
+		}
+	}
+};
+
+} /* namespace xa */
+#endif

@@ -1,0 +1,144 @@
+/*
+ * bjxa_batch.h -- additive batched C ABI of the B200-native libbjxa backend.
+ *
+ * Nothing in this header exists in the reference; it is what a binding (cgo,
+ * JNI, ctypes ...) uses to run MANY independent XA streams per GPU launch.
+ * Plain pointers and sizes only.  Every stream behaves exactly as if it had
+ * been passed alone to bjxa_decode() / bjxa_encode()
+ * (/root/reference/src/libbjxa.c:602-661, 759-819): same bytes, same per-stream
+ * return value, same errno, same codec-object bookkeeping.
+ *
+ * Three levels:
+ *   1. bjxa_batch_decode / bjxa_batch_encode  -- arrays of codec objects and
+ *      HOST buffers; the library stages, launches and copies back.
+ *   2. bjxa_plan_*   -- DEVICE-resident arenas + a table of stream
+ *      descriptors; nothing crosses PCIe in bjxa_plan_run().  This is the path
+ *      the throughput benchmark times.
+ *   3. bjxa_decoder_describe / _commit (and the encoder twins) -- glue between
+ *      the reference's codec objects and level 2.
+ *
+ * All functions return 0 (or a count) on success and -1 with errno on failure,
+ * like the rest of the API; they never print.  ENODEV: no usable CUDA device.
+ */
+#ifndef BJXA_BATCH_H
+#define BJXA_BATCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "bjxa.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- level 1: host buffers, one call per batch ------------------------- */
+
+/*
+ * For i in [0, n): results[i] = what bjxa_decode(decs[i], dsts[i], dst_lens[i],
+ * srcs[i], src_lens[i]) returns, errnos[i] = the errno it would leave (0 when
+ * results[i] >= 0).  Each decoder is updated exactly as the single call would
+ * (fmt->blocks, fmt->data_len_pcm, predictor state).  A codec may appear only
+ * once per batch.  Returns 0 when the batch ran (individual streams may still
+ * have failed), -1/errno when it could not run at all.
+ */
+int bjxa_batch_decode(bjxa_decoder_t *const *decs, void *const *dsts,
+    const size_t *dst_lens, const void *const *srcs, const size_t *src_lens,
+    int *results, int *errnos, size_t n);
+
+int bjxa_batch_encode(bjxa_encoder_t *const *encs, void *const *dsts,
+    const size_t *dst_lens, const void *const *srcs, const size_t *src_lens,
+    int *results, int *errnos, size_t n);
+
+/* ---- level 2: device-resident arenas ----------------------------------- */
+
+typedef struct bjxa_stream_desc {
+	uint64_t xa_off;	/* first XA block: byte offset into the XA arena */
+	uint64_t pcm_off;	/* PCM: byte offset into the PCM arena, multiple of 16 */
+	uint32_t blocks;	/* effective blocks (L+R = 1) to process */
+	uint32_t pcm_len;	/* decode: PCM bytes owed (truncates the last block
+				 * like fmt->data_len_pcm, libbjxa.c:622-624);
+				 * encode: PCM bytes available (rest is zero padding,
+				 * libbjxa.c:686-690).  Multiple of 2*channels. */
+	int16_t  prev[2][2];	/* decode: predictor state [channel][n-1, n-2];
+				 * in = on entry (header befL/befR, libbjxa.c:417-420),
+				 * out (bjxa_plan_fetch) = after the last block */
+	uint8_t  bits;		/* 4, 6 or 8 */
+	uint8_t  channels;	/* 1 or 2 */
+	uint16_t reserved;
+	uint32_t done;		/* out: effective blocks completed */
+	int32_t  result;	/* out: what bjxa_decode/encode returns: done, or -1 */
+	int32_t  error;		/* out: 0, or EPROTO (bad profile, libbjxa.c:550) */
+} bjxa_stream_desc_t;
+
+#define BJXA_PLAN_DECODE 0
+#define BJXA_PLAN_ENCODE 1
+
+typedef struct bjxa_plan bjxa_plan_t;
+
+/* Validates descs (EINVAL), builds and uploads the tile tables. */
+bjxa_plan_t *bjxa_plan_create(int kind, const bjxa_stream_desc_t *descs, size_t n);
+
+/* Re-targets an existing plan at a new table, reusing its device allocations. */
+int bjxa_plan_reset(bjxa_plan_t *plan, int kind, const bjxa_stream_desc_t *descs,
+    size_t n);
+
+/*
+ * Launches the batch on `cuda_stream` (a cudaStream_t, NULL = default stream)
+ * and returns without waiting.  dst/src are DEVICE pointers (16-byte aligned)
+ * to the arenas the descriptors index: decode reads the XA arena `src` and
+ * writes the PCM arena `dst`; encode the other way round.  ENOBUFS when an
+ * arena is smaller than the descriptors need.
+ * After a bad profile, PCM at and after the failing block is unspecified.
+ */
+int bjxa_plan_run(bjxa_plan_t *plan, void *dst, size_t dst_bytes, const void *src,
+    size_t src_bytes, void *cuda_stream);
+
+/* Waits for the last run and fills prev/done/result/error of descs[0..n). */
+int bjxa_plan_fetch(bjxa_plan_t *plan, bjxa_stream_desc_t *descs, size_t n);
+
+/* Kernel launches one bjxa_plan_run() issues (for launch accounting). */
+int bjxa_plan_launches(const bjxa_plan_t *plan);
+
+/* Arena bytes the plan reads / writes (so callers can size allocations). */
+int bjxa_plan_extent(const bjxa_plan_t *plan, uint64_t *src_bytes, uint64_t *dst_bytes);
+
+int bjxa_plan_free(bjxa_plan_t **planp);
+
+/* ---- level 3: codec objects <-> descriptors ---------------------------- */
+
+/*
+ * Fills bits/channels/prev and the remaining blocks / pcm_len of a parsed
+ * decoder (offsets are left to the caller).  EINVAL when the decoder is not
+ * ready.  bjxa_decoder_commit() applies a fetched descriptor back: advances
+ * fmt->blocks / fmt->data_len_pcm by `done` blocks and stores the state.
+ */
+int bjxa_decoder_describe(bjxa_decoder_t *dec, bjxa_stream_desc_t *desc);
+int bjxa_decoder_commit(bjxa_decoder_t *dec, const bjxa_stream_desc_t *desc);
+int bjxa_encoder_describe(bjxa_encoder_t *enc, bjxa_stream_desc_t *desc);
+int bjxa_encoder_commit(bjxa_encoder_t *enc, const bjxa_stream_desc_t *desc);
+
+/* ---- device helpers (so a C caller need not link the CUDA runtime) ----- */
+
+int    bjxa_gpu_count(void);			/* usable CUDA devices, 0 if none */
+int    bjxa_gpu_select(int device);		/* cudaSetDevice for this thread */
+void  *bjxa_gpu_alloc(size_t bytes);		/* device memory, 256-byte aligned */
+int    bjxa_gpu_free(void *dptr);
+void  *bjxa_host_alloc(size_t bytes);		/* pinned host memory */
+int    bjxa_host_free(void *hptr);
+int    bjxa_gpu_upload(void *dptr, const void *hptr, size_t bytes);
+int    bjxa_gpu_download(void *hptr, const void *dptr, size_t bytes);
+int    bjxa_gpu_sync(void *cuda_stream);
+
+/*
+ * Contiguous shard of n streams for `rank` of `world` (one process per GPU),
+ * balanced by bytes[] (per-stream work; NULL = by count).  No collective is
+ * involved: shards are independent.
+ */
+int bjxa_shard_range(const uint64_t *bytes, size_t n, int rank, int world,
+    size_t *first, size_t *count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BJXA_BATCH_H */

@@ -1,0 +1,201 @@
+/*
+ * xa_emul.cc -- CPU single-stepper of the tile code.  TEST HARNESS ONLY.
+ *
+ * Compiles bjxa_b200/csrc/xa_tile.h + xa_plan.h (the exact phase code the
+ * sm_100a kernels run) with a host compiler and executes a batch the way the
+ * GPU would: tiles in ticket order, every phase as a loop over the CTA's
+ * threads with the barriers where xa_kernels.cu has them.  It exists so that
+ * indexing / scheduling logic can be checked against the oracle on a machine
+ * without a GPU (tests/test_emul.py).  It is never linked into the product
+ * library and nothing in bjxa_b200/ refers to it.
+ */
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/bjxa_batch.h"
+#include "../../bjxa_b200/csrc/xa_plan.h"
+
+using namespace xa;
+
+/* thread visiting order inside a phase: 0 ascending, 1 descending, 2 strided */
+static uint32_t
+visit(uint32_t i, uint32_t nt, int order)
+{
+	if (order == 1)
+		return nt - 1 - i;
+	if (order == 2)
+		return (i * 37u + 11u) % nt;	/* 37 coprime with 128/256 */
+	return i;
+}
+
+template <int BITS, int CH>
+static void
+emul_decode_bucket(const DecodeParams &p, int order)
+{
+	typedef DecTile<BITS, CH, kDecTBQ> Tile;
+	typename Tile::Smem *sm = new typename Tile::Smem();
+	const uint32_t nt = kDecThreads;
+
+	for (uint32_t ticket = 0; ticket < p.n_tiles; ticket++) {
+		memset(sm, 0xa5, sizeof *sm);	/* smem is garbage at CTA start */
+		Tile t(p, *sm, ticket);
+		uint32_t nb = t.bulk_bytes();
+		memcpy(sm->in, p.src + t.a0, nb);
+		for (uint32_t i = 0; i < nt; i++)
+			t.load_tail(visit(i, nt, order), nt);
+		for (uint32_t i = 0; i < nt; i++)
+			t.phase_a(visit(i, nt, order), nt);
+		/* phase_a's thread 0 zeroes the counters: redo in case order != 0
+		 * ran other threads first (on the GPU nobody touches them in A) */
+		for (uint32_t i = 0; i < nt; i++)
+			t.phase_seed(visit(i, nt, order), nt);
+		for (int cur = 0;; cur ^= 1) {
+			int n = sm->n_live[cur];
+			if (n == 0)
+				break;
+			for (uint32_t i = 0; i < nt; i++)
+				t.phase_round(visit(i, nt, order), nt, cur, n);
+			sm->n_live[cur] = 0;
+		}
+		for (uint32_t i = 0; i < nt; i++)
+			t.phase_store(visit(i, nt, order), nt);
+	}
+	delete sm;
+}
+
+template <int BITS, int CH>
+static void
+emul_encode_bucket(const EncodeParams &p, int order)
+{
+	typedef EncTile<BITS, CH, kEncTBE> Tile;
+	typename Tile::Smem *sm = new typename Tile::Smem();
+	const uint32_t nt = kEncThreads;
+
+	for (uint32_t tile = 0; tile < p.n_tiles; tile++) {
+		memset(sm, 0xa5, sizeof *sm);
+		Tile t(p, *sm, tile);
+		memcpy(sm->in, p.src + t.in0, t.bulk_bytes());
+		for (uint32_t i = 0; i < nt; i++)
+			t.load_tail(visit(i, nt, order), nt);
+		for (uint32_t i = 0; i < nt; i++)
+			t.phase_pack(visit(i, nt, order), nt);
+		for (uint32_t i = 0; i < nt; i++)
+			t.phase_store(visit(i, nt, order), nt);
+	}
+	delete sm;
+}
+
+extern "C" {
+
+/*
+ * Runs a decode batch.  prev_out: n * 4 int16 (final states as the kernel
+ * publishes them), first_bad: n uint32 (0xffffffff = none).  Returns 0 or an
+ * errno value from plan validation.
+ */
+int
+xa_emul_decode(const bjxa_stream_desc_t *descs, size_t n, const uint8_t *src,
+    uint64_t src_bytes, uint8_t *dst, int16_t *prev_out, uint32_t *first_bad,
+    int order)
+{
+	HostPlan hp;
+	size_t bad = 0;
+	int rc = build_plan(hp, kKindDecode, descs, n, &bad);
+	if (rc)
+		return rc;
+	std::vector<StreamRes> res(n);
+	std::vector<unsigned long long> carry((size_t)hp.n_slots * 2 + 2, 0ULL);
+	unsigned long long ticket = 0;
+	for (size_t i = 0; i < n; i++) {
+		first_bad[i] = 0xffffffffu;
+		memset(&res[i], 0x5a, sizeof res[i]);
+	}
+	for (int b = 0; b < 6; b++) {
+		uint32_t t0 = hp.tile_begin[b], t1 = hp.tile_begin[b + 1];
+		if (t0 == t1)
+			continue;
+		DecodeParams p;
+		p.src = src;
+		p.src_bytes = src_bytes;
+		p.dst = dst;
+		p.streams = hp.streams.data();
+		p.results = res.data();
+		p.first_bad = first_bad;
+		p.tiles = hp.tiles.data() + t0;
+		p.n_tiles = t1 - t0;
+		p.carry = carry.data();
+		p.ticket = &ticket;
+		p.ticket_base = 0;
+		p.epoch = 7;
+		switch (b) {
+		case 0: emul_decode_bucket<4, 1>(p, order); break;
+		case 1: emul_decode_bucket<4, 2>(p, order); break;
+		case 2: emul_decode_bucket<6, 1>(p, order); break;
+		case 3: emul_decode_bucket<6, 2>(p, order); break;
+		case 4: emul_decode_bucket<8, 1>(p, order); break;
+		default: emul_decode_bucket<8, 2>(p, order); break;
+		}
+	}
+	memcpy(prev_out, res.data(), n * sizeof(StreamRes));
+	return 0;
+}
+
+int
+xa_emul_encode(const bjxa_stream_desc_t *descs, size_t n, const uint8_t *src,
+    uint64_t src_bytes, uint8_t *dst, uint64_t dst_bytes, int order)
+{
+	HostPlan hp;
+	size_t bad = 0;
+	int rc = build_plan(hp, kKindEncode, descs, n, &bad);
+	if (rc)
+		return rc;
+	for (int b = 0; b < 6; b++) {
+		uint32_t t0 = hp.tile_begin[b], t1 = hp.tile_begin[b + 1];
+		if (t0 == t1)
+			continue;
+		EncodeParams p;
+		p.src = src;
+		p.src_bytes = src_bytes;
+		p.dst = dst;
+		p.dst_bytes = dst_bytes;
+		p.streams = hp.streams.data();
+		p.tiles = hp.tiles.data() + t0;
+		p.n_tiles = t1 - t0;
+		switch (b) {
+		case 0: emul_encode_bucket<4, 1>(p, order); break;
+		case 1: emul_encode_bucket<4, 2>(p, order); break;
+		case 2: emul_encode_bucket<6, 1>(p, order); break;
+		case 3: emul_encode_bucket<6, 2>(p, order); break;
+		case 4: emul_encode_bucket<8, 1>(p, order); break;
+		default: emul_encode_bucket<8, 2>(p, order); break;
+		}
+	}
+	return 0;
+}
+
+/* plan introspection for the host-logic tests */
+int
+xa_emul_plan(int kind, const bjxa_stream_desc_t *descs, size_t n,
+    uint32_t *tile_stream, uint32_t *tile_first, uint32_t cap,
+    uint32_t *tile_begin /* 7 */, uint32_t *n_slots)
+{
+	HostPlan hp;
+	size_t bad = 0;
+	int rc = build_plan(hp, kind, descs, n, &bad);
+	if (rc)
+		return -rc;
+	uint32_t nt = (uint32_t)hp.tiles.size();
+	for (uint32_t i = 0; i < nt && i < cap; i++) {
+		tile_stream[i] = hp.tiles[i].stream;
+		tile_first[i] = hp.tiles[i].first_eb;
+	}
+	memcpy(tile_begin, hp.tile_begin, 7 * sizeof(uint32_t));
+	*n_slots = hp.n_slots;
+	return (int)nt;
+}
+
+int xa_emul_dec_tile_blocks(int ch) { return kDecTBQ / ch; }
+int xa_emul_enc_tile_blocks(void) { return kEncTBE; }
+
+}

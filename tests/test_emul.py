@@ -1,0 +1,170 @@
+"""The tile code (bjxa_b200/csrc/xa_tile.h, xa_plan.h) single-stepped on the
+CPU and compared with the oracle.  This exercises the exact phase code the
+sm_100a kernels run -- scheduling, carries across tiles, swizzled staging,
+truncation, misaligned sources -- without a GPU.  The harness
+(tests/emul/xa_emul.cc) is test-only; the product has no CPU path."""
+import numpy as np
+import pytest
+
+import batchgen
+from bjxa_b200 import synth
+from emul_binding import Emul
+
+
+@pytest.fixture(scope="module")
+def emul():
+    return Emul()
+
+
+def _run_decode(emul, oracle, specs, order=0, **kw):
+    descs, arena, pcm_bytes, pays = batchgen.decode_batch(specs, **kw)
+    rc, dst, prev, bad = emul.decode(descs, arena, pcm_bytes + 64, order)
+    assert rc == 0
+    return batchgen.check_decode(oracle, specs, descs, pays, dst, prev, bad)
+
+
+@pytest.mark.parametrize("bits", [4, 6, 8])
+@pytest.mark.parametrize("ch", [1, 2])
+@pytest.mark.parametrize("mix", ["P0", "P1", "P2", "P3"])
+def test_decode_one_stream_multi_tile(emul, oracle, bits, ch, mix):
+    tb = emul.dec_tile_blocks(ch)
+    samples = 32 * (2 * tb + 37) + 11          # 3 tiles, ragged last block
+    specs = [dict(bits=bits, channels=ch, samples=samples, mix=mix,
+                  prev=((1234, -4321), (-77, 31000)), key=bits * 10 + ch)]
+    _run_decode(emul, oracle, specs)
+
+
+@pytest.mark.parametrize("order", [0, 1, 2])
+def test_decode_mixed_batch(emul, oracle, order):
+    specs = []
+    k = 0
+    for bits in (4, 6, 8):
+        for ch in (1, 2):
+            for samples in (1, 31, 32, 33, 700, 32 * 600 + 5, 32 * 1500):
+                k += 1
+                specs.append(dict(bits=bits, channels=ch, samples=samples,
+                                  mix=synth.MIXES[k % 4], key=100 + k,
+                                  prev=((k, -k), (7 * k, 3))))
+    _run_decode(emul, oracle, specs, order=order, xa_gap=5)
+
+
+def test_decode_every_tail_length(emul, oracle):
+    specs = [dict(bits=(4, 6, 8)[r % 3], channels=1 + r % 2, samples=64 + r,
+                  mix="P2", key=300 + r) for r in range(32)]
+    _run_decode(emul, oracle, specs, xa_gap=3)
+
+
+def test_decode_exact_tile_multiples(emul, oracle):
+    specs = []
+    for ch in (1, 2):
+        tb = emul.dec_tile_blocks(ch)
+        for nt in (1, 2):
+            specs.append(dict(bits=8, channels=ch, samples=32 * tb * nt, mix="P3",
+                              key=400 + ch * 10 + nt))
+            specs.append(dict(bits=4, channels=ch, samples=32 * tb * nt + 1, mix="P2",
+                              key=450 + ch * 10 + nt))
+    _run_decode(emul, oracle, specs)
+
+
+def test_decode_bad_profile(emul, oracle):
+    """filter >= 5: the stream reports its first bad block; everything before
+    it is exact (src/libbjxa.c:550,634,642)."""
+    tb = emul.dec_tile_blocks(2)
+    specs = [
+        dict(bits=8, channels=1, samples=32 * 40, mix="P2", key=1, patch={17: 0xFF}),
+        dict(bits=6, channels=2, samples=32 * 40, mix="P2", key=2, patch={2 * 9 + 1: 0x50}),
+        dict(bits=4, channels=2, samples=32 * (tb + 40), mix="P3", key=3,
+             patch={2 * (tb + 3): 0x9A, 2 * (tb + 20) + 1: 0xF0}),
+        dict(bits=8, channels=2, samples=32 * 10, mix="P1", key=4, patch={0: 0x77}),
+        dict(bits=8, channels=1, samples=32 * 10, mix="P0", key=5),
+    ]
+    descs, arena, pcm_bytes, pays = batchgen.decode_batch(specs)
+    rc, dst, prev, bad = emul.decode(descs, arena, pcm_bytes + 64)
+    assert rc == 0
+    assert list(bad) == [17, 19, 2 * (tb + 3), 0, 0xFFFFFFFF]
+    batchgen.check_decode(oracle, specs, descs, pays, dst, prev, bad)
+
+
+def test_decode_saturation_vector(emul, oracle):
+    """/root/reference/test/test_decode.sh:80-122 through the tile code."""
+    pay = np.frombuffer(b"\x20" + b"\x7f" * 32 + b"\x20" + b"\x80" * 32, dtype=np.uint8)
+    descs = batchgen.make_descs(1)
+    descs[0]["blocks"] = 1
+    descs[0]["pcm_len"] = 128
+    descs[0]["bits"] = 8
+    descs[0]["channels"] = 2
+    rc, dst, prev, bad = emul.decode(descs, pay, 128)
+    pcm = dst[:128].view(np.int16).reshape(32, 2)
+    assert pcm[0, 0] == 32512 and (pcm[1:, 0] == 32767).all() and (pcm[:, 1] == -32768).all()
+
+
+def test_decode_chunked_equals_whole(emul, oracle):
+    """Feeding a stream in pieces with the state carried by the caller gives the
+    same bytes (the codec object is the checkpoint: libbjxa.c:570-571,654-655)."""
+    bits, ch, blocks = 6, 2, 900
+    pay = synth.xa_payload(9, 9, bits, ch, blocks, "P3")
+    bs = synth.block_size(bits) * ch
+    whole = oracle.decode_blocks(bits, ch, [[5, 6], [7, 8]], pay, blocks, blocks * 64 * ch)
+    state = np.array([[5, 6], [7, 8]], dtype=np.int16)
+    out = []
+    cuts = [0, 1, 2, 300, 301, 812, 900]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        d = batchgen.make_descs(1)
+        d[0]["blocks"] = b - a
+        d[0]["pcm_len"] = (b - a) * 64 * ch
+        d[0]["bits"], d[0]["channels"] = bits, ch
+        d[0]["prev"] = state
+        rc, dst, prev, bad = emul.decode(d, pay[a * bs:b * bs], (b - a) * 64 * ch)
+        out.append(dst[:(b - a) * 64 * ch])
+        state = prev[0]
+    assert np.array_equal(np.concatenate(out).view(np.int16), whole[2])
+    assert np.array_equal(state, whole[3])
+
+
+def test_decode_arena_tail_not_multiple_of_16(emul, oracle):
+    """The last stream ends flush with an arena whose size is not a multiple of
+    16: the bulk copy must stop short and the tail be fetched bytewise."""
+    for trim in range(0, 16):
+        specs = [dict(bits=8, channels=1, samples=32 * 3 + trim, mix="P2", key=trim)]
+        descs, arena, pcm_bytes, pays = batchgen.decode_batch(specs)
+        pre = np.zeros(trim, dtype=np.uint8)
+        descs[0]["xa_off"] = trim
+        rc, dst, prev, bad = emul.decode(descs, np.concatenate([pre, arena]), pcm_bytes + 64)
+        batchgen.check_decode(oracle, specs, descs, pays, dst, prev, bad)
+
+
+@pytest.mark.parametrize("order", [0, 2])
+def test_encode_mixed_batch(emul, oracle, order):
+    te = emul.enc_tile_blocks()
+    specs = []
+    k = 0
+    for bits in (4, 6, 8):
+        for ch in (1, 2):
+            for frames in (1, 2, 31, 32, 33, 1000, 32 * te, 32 * te + 1, 32 * (2 * te + 3) + 17):
+                k += 1
+                specs.append(dict(bits=bits, channels=ch, frames=frames, key=k))
+    descs, arena, xa_bytes, pcms = batchgen.encode_batch(specs, xa_gap=7)
+    rc, dst = emul.encode(descs, arena, xa_bytes, order)
+    assert rc == 0
+    batchgen.check_encode(oracle, specs, descs, pcms, dst)
+
+
+def test_plan_order_and_validation(emul):
+    """Host planning logic: every tile of a stream after its predecessor,
+    time-major issue, EINVAL on bad descriptors."""
+    tb1, tb2 = emul.dec_tile_blocks(1), emul.dec_tile_blocks(2)
+    d = batchgen.make_descs(5)
+    for i, (bits, ch, blocks) in enumerate([(8, 1, 3 * tb1 + 1), (8, 1, tb1), (4, 2, 2 * tb2),
+                                            (8, 1, 0), (8, 1, 2 * tb1 + 5)]):
+        d[i]["bits"], d[i]["channels"], d[i]["blocks"] = bits, ch, blocks
+        d[i]["pcm_len"] = blocks * 64 * ch
+    n, ts, tf, tb, slots = emul.plan(0, d)
+    assert n == 4 + 1 + 2 + 0 + 3 and slots == n
+    b81 = slice(tb[4], tb[5])
+    assert list(zip(ts[b81], tf[b81])) == [(0, 0), (4, 0), (1, 0), (0, tb1), (4, tb1),
+                                           (0, 2 * tb1), (4, 2 * tb1), (0, 3 * tb1)]
+    assert list(zip(ts[tb[1]:tb[2]], tf[tb[1]:tb[2]])) == [(2, 0), (2, tb2)]
+    for field, val in (("bits", 5), ("channels", 3), ("pcm_off", 8), ("pcm_len", 3)):
+        e = d.copy()
+        e[0][field] = val
+        assert emul.plan(0, e)[0] == -22

@@ -1,0 +1,487 @@
+#!/usr/bin/env python
+"""Benchmark of the libbjxa block transform on B200 (see BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d "Config 2"): a batch
+of 4096 synthetic mono 8-bit XA streams x 60 s @ 44.1 kHz per GPU, generated
+on the device.  A "step" is one pass of the decode hot path over the whole
+batch = one bjxa_plan_run() = one kernel launch.  With N > 1 (torchrun, one
+process per GPU) every rank decodes its own 4096-stream shard -- the streams
+are independent, so there is no data-path collective (weak scaling); only the
+timing is reduced (max over ranks).
+
+One JSON line is printed by rank 0; its keys are described in DESIGN.md.
+`--impl reference` times the UNMODIFIED reference library (compiled to
+oracle/_ref/libbjxa_ref.so) on the host cores for the same metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+# ---- workload constants ------------------------------------------------------
+N_STREAMS = int(os.environ.get("BJXA_BENCH_STREAMS", 4096))
+SECONDS = 60
+RATE = 44100
+SAMPLES = SECONDS * RATE                       # 2 646 000 per stream
+BLOCKS = (SAMPLES + 31) // 32                  # 82 688, last one holds 16 samples
+BITS, CH = 8, 1
+BS = 4 * BITS + 1
+XA_BYTES = BLOCKS * BS * CH                    # 2 728 704
+PCM_BYTES = SAMPLES * 2 * CH                   # 5 292 000
+PCM_PITCH = (BLOCKS * 64 * CH + 15) & ~15      # 5 292 032
+ALGO_BYTES_PER_STREAM = XA_BYTES + PCM_BYTES   # data_len + samples*ch*2
+HEADLINE_MIX = "P1"
+MIXES = ("P0", "P1", "P2", "P3")
+E2E_STREAMS = int(os.environ.get("BJXA_BENCH_E2E_STREAMS", 256))
+
+
+def mix_profiles(torch, mix, n, blocks, device, seed):
+    """(n, blocks) uint8 profile bytes on the device; same distributions as
+    bjxa_b200/synth.py:profile_bytes."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    u = torch.rand((n, blocks), device=device, generator=g)
+    v = torch.rand((n, blocks), device=device, generator=g)
+    if mix == "P0":
+        filt = torch.zeros_like(u, dtype=torch.int32)
+        rng = (v * 9).to(torch.int32)
+    elif mix == "P1":
+        filt = torch.where(u < 0.0066, 1, torch.where(u < 0.0511, 2,
+                           torch.where(u < 0.05115, 3, 0))).to(torch.int32)
+        for _ in range(4):                    # non-zero filters are isolated
+            clash = (filt[:, 1:] != 0) & (filt[:, :-1] != 0)
+            if not bool(clash.any()):
+                break
+            filt[:, 1:][clash] = 0
+        hist = torch.tensor([8790, 6891, 3447, 487, 137, 920], device=device,
+                            dtype=torch.float32)
+        vals = torch.tensor([0, 1, 2, 3, 4, 6], device=device, dtype=torch.int32)
+        cum = torch.cumsum(hist, 0) / hist.sum()
+        rng = vals[torch.bucketize(v, cum).clamp_(max=5)]
+    elif mix == "P2":
+        filt = (u * 5).to(torch.int32).clamp_(max=4)
+        rng = (v * 16).to(torch.int32).clamp_(max=15)
+    elif mix == "P3":
+        filt = 1 + (u * 4).to(torch.int32).clamp_(max=3)
+        rng = (v * 16).to(torch.int32).clamp_(max=15)
+    else:
+        raise ValueError(mix)
+    return ((filt << 4) | rng).to(torch.uint8)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region
+    (/opt/skills/guides/B200_PROFILING.md, 'clocks' recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        sm, smax, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            if t < t0 - 0.05 or t > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                smax = max(smax, float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """Per-launch DRAM bytes of the decode kernel from the committed ncu capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "decode_traffic.json")) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        return None
+
+
+# ---- CPU baseline (the unmodified reference, oracle/_ref) ---------------------
+
+def cpu_reference_rate(xa_streams, steps=1, warmup=0):
+    """Decodes `xa_streams` (list of payload arrays, all mono 8-bit 60 s) with
+    the reference library on every host core; returns (Msamples/s, info)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from bjxa_b200 import synth
+    from oracle import binding
+    if binding.have_ref():
+        lib, kind = binding.reference_lib(), "reference"
+    else:
+        lib, kind = None, "port"
+        orc = binding.Oracle()
+    cores = os.cpu_count() or 1
+    hdr = synth.xa_header(XA_BYTES, SAMPLES, RATE, BITS, CH)
+    outs = [np.empty(PCM_PITCH, dtype=np.uint8) for _ in range(cores)]
+
+    def job(arg):
+        slot, pay = arg
+        if lib is not None:
+            dec = lib.decoder()
+            lib.parse_header(dec, hdr)
+            got = lib.decode(dec, outs[slot], PCM_PITCH, pay, pay.size)   # GIL released
+            lib.free_decoder(dec)
+            assert got == BLOCKS
+        else:
+            orc.decode_blocks(BITS, CH, [[0, 0], [0, 0]], pay, BLOCKS, PCM_BYTES)
+
+    def one_pass():
+        # static partition: thread t owns streams t, t+cores, ...
+        def worker(t):
+            for i in range(t, len(xa_streams), cores):
+                job((t, xa_streams[i]))
+        with ThreadPoolExecutor(cores) as ex:
+            list(ex.map(worker, range(cores)))
+
+    for _ in range(warmup):
+        one_pass()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_pass()
+    dt = (time.perf_counter() - t0) / steps
+    rate = len(xa_streams) * SAMPLES * CH / dt / 1e6
+    return rate, dt, {"kind": kind, "cores": cores}
+
+
+def host_sample_streams(n, mix, seed=0xB7A):
+    from bjxa_b200 import synth
+    return [synth.xa_payload(seed, 100000 + i, BITS, CH, BLOCKS, mix) for i in range(n)]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    # bounded sample: ~0.02 s of CPU per stream and core -> a few seconds per step
+    n = max(cores * 32, 64)
+    base = host_sample_streams(min(n, 32), HEADLINE_MIX)
+    streams = [base[i % len(base)] for i in range(n)]
+    rate, dt, info = cpu_reference_rate(streams, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "decode throughput", "value": round(rate, 2),
+        "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": round(dt * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic",
+        "config": workload_config(N_STREAMS),
+        "cpu_baseline": {"value": round(rate, 2), "unit": "Msamples/s", "cores": info["cores"],
+                         "kind": info["kind"],
+                         "sample": f"{n} of the workload's streams per step "
+                                   f"({len(base)} distinct), one decoder per stream, "
+                                   f"static partition over {info['cores']} threads"},
+        "e2e": {"value": round(rate, 2), "unit": "Msamples/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_streams):
+    return {"workload": f"batched decode: {n_streams} synthetic mono 8-bit XA streams x "
+                        f"{SECONDS} s @ {RATE} Hz per GPU (BASELINE.json configs[1])",
+            "streams_per_gpu": n_streams, "samples_per_stream": SAMPLES,
+            "blocks_per_stream": BLOCKS, "bits": BITS, "channels": CH,
+            "profile_mix": f"{HEADLINE_MIX} (xa.exe-like: 94.9 % filter 0, isolated filters 1-3)",
+            "l2": "inputs (11.2 GB) and outputs (21.7 GB) exceed the 126 MB L2; no flush needed",
+            "parallelism": "streams sharded by index, one process per GPU, no collective"}
+
+
+# ---- GPU arm -------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the per-mix, encode, e2e and CPU-baseline legs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import bjxa_b200
+    from bjxa_b200.api import PLAN_DECODE, PLAN_ENCODE, make_descs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = bjxa_b200.load()
+    warm = max(args.warmup, 3)
+    S = N_STREAMS
+
+    # every rank owns S streams: global stream index = rank * S + i (weak scaling);
+    # bjxa_shard_range gives the same partition for a global table of world*S streams
+    first, count = lib.shard_range(world * S, rank, world)
+    assert (first, count) == (rank * S, S)
+
+    # ---- synthetic batch, generated on the device ------------------------------
+    xa = torch.empty((S, BLOCKS, BS), dtype=torch.uint8, device=dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(0xB7A + rank)
+    step_s = 128
+    for s0 in range(0, S, step_s):
+        xa[s0:s0 + step_s].random_(0, 256, generator=g)
+
+    def set_mix(mix):
+        for s0 in range(0, S, 512):
+            n = min(512, S - s0)
+            xa[s0:s0 + n, :, 0] = mix_profiles(torch, mix, n, BLOCKS, dev,
+                                               1000 * rank + s0 + MIXES.index(mix))
+        torch.cuda.synchronize()
+
+    pcm = torch.empty(S * PCM_PITCH, dtype=torch.uint8, device=dev)
+    descs = make_descs(S)
+    descs["xa_off"] = np.arange(S, dtype=np.uint64) * XA_BYTES
+    descs["pcm_off"] = np.arange(S, dtype=np.uint64) * PCM_PITCH
+    descs["blocks"] = BLOCKS
+    descs["pcm_len"] = PCM_BYTES
+    descs["bits"], descs["channels"] = BITS, CH
+    plan = lib.plan_create(PLAN_DECODE, descs)
+    launches_per_step = lib.plan_launches(plan)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        lib.plan_run(plan, pcm.data_ptr(), pcm.numel(), xa.data_ptr(), xa.numel(), stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(k):
+        """k steps bracketed by barrier + synchronize; device time, max over ranks."""
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(k + 1)]
+        barrier()
+        t0 = time.time()
+        ev[0].record()
+        for i in range(k):
+            step()
+            ev[i + 1].record()
+        barrier()
+        t1 = time.time()
+        total_ms = ev[0].elapsed_time(ev[k])
+        per = [ev[i].elapsed_time(ev[i + 1]) for i in range(k)]
+        if world > 1:
+            t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms, per, (t0, t1)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    set_mix(HEADLINE_MIX)
+    for _ in range(warm):
+        step()
+    total_ms, per_launch, window = timed(args.steps)
+    ms_per_step = total_ms / args.steps
+    samples_per_step = world * S * SAMPLES * CH
+    value = samples_per_step / (ms_per_step * 1e-3) / 1e6
+    clocks = sampler.window(*window) if sampler else None
+
+    # ---- parity of what was just timed (rank 0, a few streams, the oracle) -----
+    parity = None
+    if rank == 0:
+        from oracle import binding
+        orc = binding.Oracle()
+        res = lib.plan_fetch(plan, S)
+        assert (res["result"] == BLOCKS).all(), "decode reported failures"
+        for i in (0, S // 2 + 1, S - 1):
+            pay = xa[i].reshape(-1).cpu().numpy()
+            got = pcm[i * PCM_PITCH:i * PCM_PITCH + PCM_BYTES].cpu().numpy().view(np.int16)
+            done, bad, want, st = orc.decode_blocks(BITS, CH, [[0, 0], [0, 0]], pay, BLOCKS,
+                                                    PCM_BYTES)
+            if not np.array_equal(got, want) or not np.array_equal(res[i]["prev"][0], st[0]):
+                raise SystemExit(f"bench.py: stream {i} differs from the oracle")
+        parity = "3 streams (7.9 Msamples) bit-exact vs oracle after the timed region"
+
+    # ---- roofline of the decode kernel ------------------------------------------
+    peak, peak_src = measured_peak()
+    algo_bytes = S * ALGO_BYTES_PER_STREAM          # per launch, per GPU
+    avg_launch_ms = float(np.mean(per_launch))
+    achieved = algo_bytes / (avg_launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": ncu_traffic(),
+                "kernel": "xa_decode_kernel<8,1>", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_bytes,
+                "avg_launch_ms": round(avg_launch_ms, 4),
+                "frac_of_nominal_8000": round(achieved / 8000.0, 4)}
+
+    line = {
+        "metric": "decode throughput", "value": round(value, 1), "unit": "Msamples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": workload_config(S), "roofline": roofline,
+        "gpu_launches": args.steps * launches_per_step, "clocks": clocks, "parity": parity,
+    }
+
+    if not args.no_extras:
+        # ---- the other profile mixes (each reported separately) ----
+        by_mix = {HEADLINE_MIX: {"Msamples_per_s": round(value, 1),
+                                 "hbm_frac": roofline["frac"]}}
+        for mix in MIXES:
+            if mix == HEADLINE_MIX:
+                continue
+            set_mix(mix)
+            step()
+            k = 3
+            tms, _, _ = timed(k)
+            v = samples_per_step / (tms / k * 1e-3) / 1e6
+            by_mix[mix] = {"Msamples_per_s": round(v, 1),
+                           "hbm_frac": round(v * 1e6 / world * ALGO_BYTES_PER_STREAM / SAMPLES
+                                             / 1e9 / peak, 4)}
+        line["by_profile_mix"] = by_mix
+        set_mix(HEADLINE_MIX)
+        step()
+        torch.cuda.synchronize()
+
+        # ---- encode (reference-exact) over the PCM just produced ------------------
+        eplan = lib.plan_create(PLAN_ENCODE, descs)
+        xa_out = torch.empty(S * XA_BYTES + 16, dtype=torch.uint8, device=dev)
+
+        def estep():
+            lib.plan_run(eplan, xa_out.data_ptr(), xa_out.numel(), pcm.data_ptr(),
+                         pcm.numel(), stream)
+        for _ in range(3):
+            estep()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(5):
+            estep()
+        ev1.record()
+        barrier()
+        ems = ev0.elapsed_time(ev1) / 5
+        if world > 1:
+            t = torch.tensor([ems], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        line["encode"] = {"Msamples_per_s": round(samples_per_step / (ems * 1e-3) / 1e6, 1),
+                          "ms_per_step": round(ems, 4), "mode": "reference-exact (profile 0)",
+                          "hbm_frac": round(algo_bytes / (ems * 1e-3) / 1e9 / peak, 4)}
+        lib.plan_free(eplan)
+        del xa_out
+
+        # ---- end to end through the host-buffer C-ABI call ------------------------
+        ne = min(E2E_STREAMS, S)
+        h_src = torch.empty((ne, XA_BYTES), dtype=torch.uint8).pin_memory()
+        h_dst = torch.empty((ne, PCM_PITCH), dtype=torch.uint8).pin_memory()
+        h_src.copy_(xa[:ne].reshape(ne, -1))
+        from bjxa_b200 import synth
+        hdr = synth.xa_header(XA_BYTES, SAMPLES, RATE, BITS, CH)
+        srcs = [h_src[i].numpy() for i in range(ne)]
+        dsts = [h_dst[i].numpy() for i in range(ne)]
+
+        def e2e_step():
+            decs = []
+            for _ in range(ne):
+                d = lib.decoder()
+                lib.parse_header(d, hdr)
+                decs.append(d)
+            res, errs = lib.batch_decode(decs, dsts, srcs)
+            for d in decs:
+                lib.free_decoder(d)
+            assert all(r == BLOCKS for r in res)
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        k = 3
+        for _ in range(k):
+            e2e_step()
+        barrier()
+        edt = (time.perf_counter() - t0) / k
+        if world > 1:
+            t = torch.tensor([edt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            edt = float(t.item())
+        want = pcm[:PCM_BYTES].cpu().numpy()
+        assert np.array_equal(h_dst[0].numpy()[:PCM_BYTES], want), "e2e output differs"
+        line["e2e"] = {"value": round(world * ne * SAMPLES * CH / edt / 1e6, 1),
+                       "unit": "Msamples/s", "h2d_bytes_per_step": ne * XA_BYTES,
+                       "d2h_bytes_per_step": ne * PCM_BYTES,
+                       "call": f"bjxa_batch_decode on {ne} streams per GPU per step, pinned "
+                               f"host buffers, copies inside the timed region"}
+
+        # ---- CPU baseline: the reference on this box's host cores (rank 0, N=1) ---
+        if rank == 0 and world == 1:
+            cores = os.cpu_count() or 1
+            n = max(2 * cores, 16)
+            base = [xa[i].reshape(-1).cpu().numpy() for i in range(min(n, 16))]
+            streams = [base[i % len(base)] for i in range(n)]
+            rate, dt, info = cpu_reference_rate(streams, steps=1, warmup=0)
+            line["cpu_baseline"] = {
+                "value": round(rate, 2), "unit": "Msamples/s", "cores": info["cores"],
+                "kind": info["kind"],
+                "sample": f"{n} streams of this workload ({len(base)} distinct) decoded once, "
+                          f"one reference decoder per stream, static partition over "
+                          f"{info['cores']} threads, {dt:.2f} s"}
+
+    if sampler:
+        sampler.stop()
+    lib.plan_free(plan)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

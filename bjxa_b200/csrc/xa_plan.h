@@ -72,6 +72,13 @@ inline int build_plan(HostPlan &hp, int kind, const Desc *d, size_t n,
 	std::vector<uint32_t> order[6];
 	for (size_t i = 0; i < n; i++) {
 		const Desc &s = d[i];
+		if (s.blocks == 0) {
+			/* takes no part: no tiles, nothing validated */
+			std::memset(&hp.streams[i], 0, sizeof hp.streams[i]);
+			hp.streams[i].slot_base = hp.n_slots;
+			hp.bucket[i] = 0;
+			continue;
+		}
 		bool ok = (s.bits == 4 || s.bits == 6 || s.bits == 8) &&
 		    (s.channels == 1 || s.channels == 2) && (s.pcm_off % 16 == 0) &&
 		    (s.pcm_len % (2u * s.channels) == 0) &&

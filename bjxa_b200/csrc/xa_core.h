@@ -23,6 +23,12 @@
 #define XA_HD inline
 #endif
 
+#if !defined(__CUDACC__)
+/* host twins of the CUDA vector types the tile code moves data with */
+struct uint2 { uint32_t x, y; };
+struct alignas(16) uint4 { uint32_t x, y, z, w; };
+#endif
+
 namespace xa {
 
 constexpr int kBlockSamples = 32;

@@ -78,52 +78,94 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src,
 
 /* ---- kernels -------------------------------------------------------------- */
 
+/* consumer-only CTA barrier (the producer warp never takes part) */
+__device__ __forceinline__ void consumer_sync()
+{
+	asm volatile("bar.sync 1, %0;" :: "n"(kDecThreads) : "memory");
+}
+
+/*
+ * Persistent, warp-specialised decode kernel.  Grid = (CTAs that fit one SM) x
+ * (SM count).  Per CTA:
+ *   producer   one thread of the extra warp: draws tile tickets in order,
+ *              computes the tile context, and starts the bulk-async (TMA) copy
+ *              of the tile's contiguous XA bytes into the next free stage
+ *              buffer, kDecStages tiles ahead of the consumers;
+ *   consumers  kDecThreads threads: wait on the stage's "full" mbarrier, run
+ *              phase A / the chain rounds / the store of xa_tile.h, and hand
+ *              the buffer back through the stage's "empty" mbarrier.
+ */
 template <int BITS, int CH>
-__global__ void __launch_bounds__(kDecThreads)
+__global__ void __launch_bounds__(kDecThreads + 32)
 xa_decode_kernel(const DecodeParams p)
 {
-	typedef DecTile<BITS, CH, kDecTBQ> Tile;
+	typedef DecTile<BITS, CH, kDecTBQ, kDecStages> Tile;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	typename Tile::Smem &sm = *reinterpret_cast<typename Tile::Smem *>(smem_raw);
 	const uint32_t tid = threadIdx.x;
-	const uint32_t bar = smem_u32(&sm.mbar);
 
 	if (tid == 0) {
-		sm.ticket = (uint32_t)(atomicAdd(p.ticket, 1ULL) - p.ticket_base);
-		mbar_init(bar, 1);
+		for (int s = 0; s < kDecStages; s++) {
+			mbar_init(smem_u32(&sm.full[s]), 1);
+			mbar_init(smem_u32(&sm.empty[s]), 1);
+		}
+		sm.n_live[0] = sm.n_live[1] = sm.n_live[2] = 0;
 	}
 	__syncthreads();
 
-	Tile t(p, sm, sm.ticket);
-	if (tid == 0) {
-		const uint32_t nb = t.bulk_bytes();
-		if (nb) {
-			mbar_expect_tx(bar, nb);
-			bulk_g2s(smem_u32(sm.in), p.src + t.a0, nb, bar);
-		} else {
-			mbar_arrive(bar);
+	if (tid >= kDecThreads) {
+		if (tid != kDecThreads)
+			return;
+		for (uint32_t it = 0;; it++) {
+			const int s = (int)(it % kDecStages);
+			if (it >= (uint32_t)kDecStages)
+				mbar_wait(smem_u32(&sm.empty[s]), (it / kDecStages - 1) & 1);
+			/* the counter is preset to ~0 with first_bad[]: old + 1 = ticket */
+			const unsigned long long t = atomicAdd(p.ticket, 1ULL) + 1ULL;
+			const uint32_t full = smem_u32(&sm.full[s]);
+			if (t >= p.n_tiles) {
+				sm.ctx[s].flags = kCtxEnd;
+				mbar_arrive(full);
+				return;
+			}
+			DecCtx c;
+			make_dec_ctx<BITS, CH, kDecTBQ>(c, p, (uint32_t)t);
+			sm.ctx[s] = c;
+			if (c.bulk) {
+				mbar_expect_tx(full, c.bulk);
+				bulk_g2s(smem_u32(sm.in[s]), p.src + c.a0, c.bulk, full);
+			} else {
+				mbar_arrive(full);
+			}
 		}
 	}
-	t.load_tail(tid, kDecThreads);
-	mbar_wait(bar, 0);
-	__syncthreads();
 
-	t.phase_a(tid, kDecThreads);
-	__syncthreads();
-	t.phase_seed(tid, kDecThreads);
+	for (uint32_t it = 0;; it++) {
+		const int s = (int)(it % kDecStages);
+		mbar_wait(smem_u32(&sm.full[s]), (it / kDecStages) & 1);
+		if (sm.ctx[s].flags & kCtxEnd)
+			return;
+		Tile t(p, sm, s);
+		if (t.in_need > t.bulk) {	/* only at the very end of the arena */
+			t.load_tail(tid, kDecThreads, sm.in[s]);
+			consumer_sync();
+		}
 
-	for (int cur = 0;; cur ^= 1) {
-		__syncthreads();
-		const int n = sm.n_live[cur];
-		if (n == 0)
-			break;
-		t.phase_round(tid, kDecThreads, cur, n);
-		__syncthreads();
+		t.phase_a(tid, kDecThreads);
+		for (int r = 0;; r++) {
+			consumer_sync();
+			const int n = sm.n_live[r % 3];
+			if (n == 0)
+				break;
+			t.phase_round(tid, kDecThreads, r, n);
+		}
+		/* nobody reads this stage's source bytes or context any more */
 		if (tid == 0)
-			sm.n_live[cur] = 0;
+			mbar_arrive(smem_u32(&sm.empty[s]));
+		t.reset_counters(tid);
+		t.phase_store(tid, kDecThreads);
+		consumer_sync();	/* rows are free for the next tile's phase A */
 	}
-
-	t.phase_store(tid, kDecThreads);
 }
 
 template <int BITS, int CH>
@@ -321,8 +363,7 @@ struct bjxa_plan {
 	DevBuf<uint32_t> d_first_bad;
 	DevBuf<TileEnt> d_tiles;
 	DevBuf<unsigned long long> d_carry;
-	DevBuf<unsigned long long> d_ticket;	/* one counter per bucket */
-	unsigned long long ticket_base[6];
+	DevBuf<uint32_t> d_fault;		/* set when a carry never arrived */
 	uint32_t epoch;
 	/* last run */
 	bool ran;
@@ -341,7 +382,7 @@ set_attrs_one(void)
 {
 	cudaError_t e = cudaFuncSetAttribute(xa_decode_kernel<BITS, CH>,
 	    cudaFuncAttributeMaxDynamicSharedMemorySize,
-	    (int)sizeof(DecSmem<BITS, CH, kDecTBQ>));
+	    (int)sizeof(DecSmem<BITS, CH, kDecTBQ, kDecStages>));
 	if (e != cudaSuccess)
 		return e;
 	return cudaFuncSetAttribute(xa_encode_kernel<BITS, CH>,
@@ -380,16 +421,12 @@ plan_upload(bjxa_plan *pl)
 
 	if ((rc = pl->d_streams.reserve(n, false)) ||
 	    (rc = pl->d_results.reserve(n, false)) ||
-	    (rc = pl->d_first_bad.reserve(n, false)) ||
+	    (rc = pl->d_first_bad.reserve(n + 16, false)) ||	/* + 6 ticket counters */
+	    (rc = pl->d_fault.reserve(4, true)) ||
 	    (rc = pl->d_tiles.reserve(hp.tiles.size(), false)) ||
-	    (rc = pl->d_carry.reserve((size_t)hp.n_slots * 2, true)) ||
-	    (rc = pl->d_ticket.reserve(8, true))) {
+	    (rc = pl->d_carry.reserve((size_t)hp.n_slots * 2, true))) {
 		errno = rc;
 		return (-1);
-	}
-	if (pl->d_ticket.cap && pl->ticket_base[0] == ~0ULL) {
-		/* fresh counter allocation */
-		memset(pl->ticket_base, 0, sizeof pl->ticket_base);
 	}
 	if (n)
 		XA_CUDA(cudaMemcpy(pl->d_streams.p, hp.streams.data(),
@@ -442,7 +479,6 @@ bjxa_plan_create(int kind, const bjxa_stream_desc_t *descs, size_t n)
 	pl->magic = BJXA_PLAN_MAGIC;
 	pl->epoch = 0;
 	pl->ran = false;
-	pl->ticket_base[0] = ~0ULL;
 	if (plan_build(pl, kind, descs, n) < 0) {
 		int e = errno;
 		bjxa_plan_free(&pl);
@@ -484,7 +520,7 @@ bjxa_plan_free(bjxa_plan_t **planp)
 	pl->d_first_bad.release();
 	pl->d_tiles.release();
 	pl->d_carry.release();
-	pl->d_ticket.release();
+	pl->d_fault.release();
 	pl->magic = 0;
 	delete pl;
 	*planp = NULL;
@@ -513,8 +549,29 @@ template <int BITS, int CH>
 static cudaError_t
 launch_decode(const DecodeParams &p, cudaStream_t st)
 {
-	xa_decode_kernel<BITS, CH><<<p.n_tiles, kDecThreads,
-	    sizeof(DecSmem<BITS, CH, kDecTBQ>), st>>>(p);
+	/* persistent: as many CTAs as fit the device at once, never more than tiles */
+	static thread_local int grid_cache[2] = { -1, 0 };
+	const size_t smem = sizeof(DecSmem<BITS, CH, kDecTBQ, kDecStages>);
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess)
+		return e;
+	if (grid_cache[0] != dev) {
+		int per_sm = 0, sms = 0;
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm,
+		    xa_decode_kernel<BITS, CH>, kDecThreads + 32, smem);
+		if (e != cudaSuccess)
+			return e;
+		e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		if (e != cudaSuccess)
+			return e;
+		grid_cache[0] = dev;
+		grid_cache[1] = per_sm * sms > 0 ? per_sm * sms : sms;
+	}
+	uint32_t grid = (uint32_t)grid_cache[1];
+	if (grid > p.n_tiles)
+		grid = p.n_tiles;
+	xa_decode_kernel<BITS, CH><<<grid, kDecThreads + 32, smem, st>>>(p);
 	return cudaGetLastError();
 }
 
@@ -564,8 +621,13 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 		    pl->d_carry.cap * sizeof(unsigned long long), st));
 		pl->epoch = 1;
 	}
-	if (hp.kind == kKindDecode)
-		XA_CUDA(cudaMemsetAsync(pl->d_first_bad.p, 0xff, n * sizeof(uint32_t), st));
+	if (hp.kind == kKindDecode) {
+		/* one memset arms both the per-stream "first bad block" words and
+		 * the six tile-ticket counters that follow them (~0 = no ticket
+		 * drawn yet, see the producer in xa_decode_kernel) */
+		XA_CUDA(cudaMemsetAsync(pl->d_first_bad.p, 0xff,
+		    (n + 16) * sizeof(uint32_t), st));
+	}
 
 	for (int b = 0; b < 6; b++) {
 		uint32_t t0 = hp.tile_begin[b], t1 = hp.tile_begin[b + 1];
@@ -583,10 +645,10 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 			p.tiles = pl->d_tiles.p + t0;
 			p.n_tiles = t1 - t0;
 			p.carry = pl->d_carry.p;
-			p.ticket = pl->d_ticket.p + b;
-			p.ticket_base = pl->ticket_base[b];
+			p.ticket = reinterpret_cast<unsigned long long *>(
+			    pl->d_first_bad.p + ((n + 3) & ~(size_t)3)) + b;
+			p.fault = pl->d_fault.p;
 			p.epoch = pl->epoch;
-			pl->ticket_base[b] += p.n_tiles;
 			switch (b) {
 			case 0: e = launch_decode<4, 1>(p, st); break;
 			case 1: e = launch_decode<4, 2>(p, st); break;
@@ -709,6 +771,15 @@ bjxa_plan_fetch(bjxa_plan_t *pl, bjxa_stream_desc_t *out, size_t n)
 
 	std::vector<StreamRes> res(n);
 	std::vector<uint32_t> bad(n);
+	uint32_t fault = 0;
+	XA_CUDA(cudaMemcpy(&fault, pl->d_fault.p, sizeof fault, cudaMemcpyDeviceToHost));
+	if (fault != 0) {
+		/* a tile gave up waiting for its predecessor's state: internal
+		 * error, the output is not trustworthy */
+		(void)cudaMemset(pl->d_fault.p, 0, sizeof fault);
+		errno = EIO;
+		return (-1);
+	}
 	if (n) {
 		XA_CUDA(cudaMemcpy(res.data(), pl->d_results.p, n * sizeof(StreamRes),
 		    cudaMemcpyDeviceToHost));

@@ -27,10 +27,21 @@ struct bjxa_stream_desc;
 namespace xa {
 
 /* tile geometry: block-channels per decode tile, effective blocks per encode tile */
-constexpr int kDecTBQ = 512;
-constexpr int kDecThreads = 128;
+#ifndef XA_DEC_TBQ
+#define XA_DEC_TBQ 512
+#endif
+#ifndef XA_DEC_NT
+#define XA_DEC_NT 256
+#endif
+#ifndef XA_DEC_STAGES
+#define XA_DEC_STAGES 2
+#endif
+constexpr int kDecTBQ = XA_DEC_TBQ;		/* block-channels per tile */
+constexpr int kDecThreads = XA_DEC_NT;		/* consumer threads (+1 producer warp) */
+constexpr int kDecStages = XA_DEC_STAGES;	/* source buffers in flight per CTA */
 constexpr int kEncTBE = 256;
 constexpr int kEncThreads = 128;
+static_assert(kDecThreads % 32 == 0 && kDecTBQ % 2 == 0, "tile geometry");
 
 enum { kKindDecode = 0, kKindEncode = 1 };
 

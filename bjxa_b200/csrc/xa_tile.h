@@ -65,8 +65,8 @@ struct DecodeParams {
 	const TileEnt *tiles;
 	uint32_t n_tiles;
 	unsigned long long *carry;	/* [slot][2] mailboxes */
-	unsigned long long *ticket;
-	unsigned long long ticket_base;
+	unsigned long long *ticket;	/* preset to ~0 before every launch */
+	uint32_t *fault;		/* set if a carry never arrived */
 	uint32_t epoch;
 };
 
@@ -89,21 +89,28 @@ XA_HD void mailbox_put(unsigned long long *p, unsigned long long v)
 {
 	asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
-XA_HD unsigned long long mailbox_get(const unsigned long long *p, uint32_t epoch)
+XA_HD unsigned long long mailbox_get(const unsigned long long *p, uint32_t epoch,
+    uint32_t *fault)
 {
 	unsigned long long v;
-	for (;;) {
+	/* The predecessor tile holds a lower ticket, so it is running or done
+	 * and this wait is short.  It is still bounded (~10 s): a kernel must
+	 * never hang the device; on expiry the launch is flagged as failed. */
+	for (uint32_t spins = 0; spins < (1u << 24); spins++) {
 		asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
 		if ((uint32_t)(v >> 32) == epoch)
 			return v;
-		__nanosleep(64);
+		__nanosleep(spins < 64 ? 32 : 512);
 	}
+	atomicExch(fault, 1u);
+	return 0;
 }
 #else
 XA_HD int smem_inc(int *p) { return (*p)++; }
 XA_HD void global_min_u32(uint32_t *p, uint32_t v) { if (v < *p) *p = v; }
 XA_HD void mailbox_put(unsigned long long *p, unsigned long long v) { *p = v; }
-XA_HD unsigned long long mailbox_get(const unsigned long long *p, uint32_t epoch)
+XA_HD unsigned long long mailbox_get(const unsigned long long *p, uint32_t epoch,
+    uint32_t *)
 {
 	/* the emulator runs tiles in ticket order: the value must be there */
 	if ((uint32_t)(*p >> 32) != epoch)
@@ -114,80 +121,104 @@ XA_HD unsigned long long mailbox_get(const unsigned long long *p, uint32_t epoch
 
 /* ---- decode -------------------------------------------------------------- */
 
+/*
+ * Everything a CTA needs to know about one tile.  Computed once per tile by
+ * the producer thread (xa_kernels.cu) and handed to the consumer warps through
+ * shared memory together with the tile's source bytes.
+ */
+struct DecCtx {
+	uint64_t a0;		/* first source byte rounded down to 16 */
+	uint64_t out0;		/* first destination byte */
+	uint32_t stream, first_eb, neb, nq;
+	uint32_t in_off;	/* source misalignment, 0..15 */
+	uint32_t in_need;	/* bytes from a0 covering the tile's blocks */
+	uint32_t bulk;		/* bytes the bulk-async engine fetches (16-byte units) */
+	uint32_t out_valid;	/* PCM bytes this tile owes */
+	uint32_t slot;		/* carry mailbox index */
+	uint32_t flags;
+};
+enum { kCtxFirst = 1u, kCtxLast = 2u, kCtxEnd = 0x80000000u };
+
 template <int BITS, int CH, int TBQ>
+XA_HD void make_dec_ctx(DecCtx &c, const DecodeParams &p, uint32_t ticket)
+{
+	constexpr int BS = block_bytes(BITS);
+	constexpr uint32_t TBE = TBQ / CH;
+	const TileEnt te = p.tiles[ticket];
+	const StreamDev &s = p.streams[te.stream];
+	c.stream = te.stream;
+	c.first_eb = te.first_eb;
+	uint32_t blocks = s.blocks;
+	uint32_t rem = blocks - te.first_eb;
+	c.neb = rem < TBE ? rem : TBE;
+	c.nq = c.neb * CH;
+	uint64_t g0 = s.xa_off + (uint64_t)te.first_eb * (BS * CH);
+	c.a0 = g0 & ~(uint64_t)15;
+	c.in_off = (uint32_t)(g0 - c.a0);
+	c.in_need = c.in_off + c.nq * BS;
+	/* whole 16-byte units that lie inside the arena */
+	uint64_t end = c.a0 + ((c.in_need + 15u) & ~15u);
+	uint64_t lim = p.src_bytes & ~(uint64_t)15;
+	if (end > lim)
+		end = lim > c.a0 ? lim : c.a0;
+	c.bulk = (uint32_t)(end - c.a0);
+	uint64_t pcm_done = (uint64_t)te.first_eb * (64 * CH);
+	c.out0 = s.pcm_off + pcm_done;
+	uint64_t owed = s.pcm_len > pcm_done ? s.pcm_len - pcm_done : 0;
+	uint64_t full = (uint64_t)c.neb * (64 * CH);
+	c.out_valid = (uint32_t)(owed < full ? owed : full);
+	c.slot = s.slot_base + te.first_eb / TBE;
+	c.flags = (te.first_eb == 0 ? kCtxFirst : 0u) |
+	    (te.first_eb + c.neb == blocks ? kCtxLast : 0u);
+}
+
+template <int BITS, int CH, int TBQ, int STAGES>
 struct DecSmem {
 	static constexpr int BS = block_bytes(BITS);
 	/* payload + up to 15 bytes of misalignment, in 16-byte units, plus one
 	 * unit of slack for load_payload's one-word over-read */
 	static constexpr int IN_BYTES = ((TBQ * BS + 15 + 15) / 16) * 16 + 16;
 
-	alignas(16) uint8_t in[IN_BYTES];
+	alignas(16) uint8_t in[STAGES][IN_BYTES];
 	alignas(16) uint32_t out[TBQ * 16];	/* planar rows, 64 B each, swizzled */
-	uint8_t prof[TBQ];
 	uint16_t live[2][TBQ];
-	int n_live[2];
-	uint32_t ticket;
-	alignas(8) unsigned long long mbar;
+	int n_live[3];
+	DecCtx ctx[STAGES];
+	alignas(8) unsigned long long full[STAGES];
+	alignas(8) unsigned long long empty[STAGES];
 };
 
-template <int BITS, int CH, int TBQ>
+template <int BITS, int CH, int TBQ, int STAGES>
 struct DecTile {
-	typedef DecSmem<BITS, CH, TBQ> Smem;
+	typedef DecSmem<BITS, CH, TBQ, STAGES> Smem;
 	static constexpr int BS = block_bytes(BITS);
-	static constexpr int TBE = TBQ / CH;	/* effective blocks per tile */
 	static_assert(TBQ % CH == 0, "tile must hold whole effective blocks");
 
 	const DecodeParams &p;
 	Smem &sm;
-	uint32_t stream, first_eb, neb, nq;
-	uint64_t g0;		/* first source byte */
-	uint64_t a0;		/* g0 rounded down to 16 */
-	uint32_t in_off;	/* g0 - a0 */
-	uint32_t in_need;	/* bytes from a0 covering the tile's blocks */
-	uint64_t out0;		/* first destination byte */
-	uint32_t out_valid;	/* PCM bytes this tile owes */
-	uint32_t slot;
-	bool first_tile, last_tile;
+	const uint8_t *in;	/* this tile's stage buffer */
+	const uint64_t a0, out0;
+	const uint32_t stream, first_eb, neb, nq, in_off, in_need, bulk, out_valid, slot;
+	const bool first_tile, last_tile;
 
-	XA_HD DecTile(const DecodeParams &p_, Smem &sm_, uint32_t ticket)
-	    : p(p_), sm(sm_)
+	XA_HD DecTile(const DecodeParams &p_, Smem &sm_, int stage)
+	    : p(p_), sm(sm_), in(sm_.in[stage]),
+	      a0(sm_.ctx[stage].a0), out0(sm_.ctx[stage].out0),
+	      stream(sm_.ctx[stage].stream), first_eb(sm_.ctx[stage].first_eb),
+	      neb(sm_.ctx[stage].neb), nq(sm_.ctx[stage].nq),
+	      in_off(sm_.ctx[stage].in_off), in_need(sm_.ctx[stage].in_need),
+	      bulk(sm_.ctx[stage].bulk), out_valid(sm_.ctx[stage].out_valid),
+	      slot(sm_.ctx[stage].slot),
+	      first_tile((sm_.ctx[stage].flags & kCtxFirst) != 0),
+	      last_tile((sm_.ctx[stage].flags & kCtxLast) != 0)
 	{
-		const TileEnt te = p.tiles[ticket];
-		const StreamDev &s = p.streams[te.stream];
-		stream = te.stream;
-		first_eb = te.first_eb;
-		uint32_t rem = s.blocks - first_eb;
-		neb = rem < (uint32_t)TBE ? rem : (uint32_t)TBE;
-		nq = neb * CH;
-		g0 = s.xa_off + (uint64_t)first_eb * (BS * CH);
-		a0 = g0 & ~(uint64_t)15;
-		in_off = (uint32_t)(g0 - a0);
-		in_need = in_off + nq * BS;
-		uint64_t pcm_done = (uint64_t)first_eb * (64 * CH);
-		out0 = s.pcm_off + pcm_done;
-		uint64_t owed = s.pcm_len > pcm_done ? s.pcm_len - pcm_done : 0;
-		uint64_t full = (uint64_t)neb * (64 * CH);
-		out_valid = (uint32_t)(owed < full ? owed : full);
-		slot = s.slot_base + first_eb / TBE;
-		first_tile = first_eb == 0;
-		last_tile = first_eb + neb == s.blocks;
 	}
 
-	/* bytes the bulk-async engine can fetch: whole 16-byte units inside the arena */
-	XA_HD uint32_t bulk_bytes() const
+	/* bytes past `bulk` fetched one by one (only at the arena's very end) */
+	XA_HD void load_tail(uint32_t tid, uint32_t nt, uint8_t *in_w)
 	{
-		uint64_t end = a0 + ((in_need + 15u) & ~15u);
-		uint64_t lim = p.src_bytes & ~(uint64_t)15;
-		if (end > lim)
-			end = lim > a0 ? lim : a0;
-		return (uint32_t)(end - a0);
-	}
-
-	/* bytes past bulk_bytes() fetched one by one (only at the arena's end) */
-	XA_HD void load_tail(uint32_t tid, uint32_t nt)
-	{
-		for (uint32_t i = bulk_bytes() + tid; i < in_need; i += nt)
-			sm.in[i] = p.src[a0 + i];
+		for (uint32_t i = bulk + tid; i < in_need; i += nt)
+			in_w[i] = p.src[a0 + i];
 	}
 
 	XA_HD static int row_word(uint32_t q, int chunk, int w)
@@ -210,10 +241,12 @@ struct DecTile {
 		}
 	}
 
+	XA_HD uint32_t profile_of(uint32_t q) const { return in[in_off + q * BS]; }
+
 	XA_HD void fetch_block(uint32_t q, uint32_t (&pw)[BITS]) const
 	{
 		uint32_t pay = in_off + q * BS + 1;	/* first payload byte */
-		const uint32_t *w = reinterpret_cast<const uint32_t *>(sm.in) + (pay >> 2);
+		const uint32_t *w = reinterpret_cast<const uint32_t *>(in) + (pay >> 2);
 		load_payload<BITS>(pw, w, (pay & 3u) * 8u);
 	}
 
@@ -237,25 +270,28 @@ struct DecTile {
 			p1 = p.streams[stream].prev[c][1];
 		} else {
 			unsigned long long v = mailbox_get(
-			    &p.carry[(uint64_t)(slot - 1) * 2 + c], p.epoch);
+			    &p.carry[(uint64_t)(slot - 1) * 2 + c], p.epoch, p.fault);
 			p0 = (int16_t)(uint16_t)v;
 			p1 = (int16_t)(uint16_t)(v >> 16);
 		}
 	}
 
-	/* phase A: profiles, cut blocks */
+	/*
+	 * phase A: every cut block is decoded; every chain block whose
+	 * predecessor in its channel is not a chain block (or lies in the
+	 * previous tile) is queued as the head of a chain.  Needs n_live[0..2]
+	 * to be zero on entry.
+	 */
 	XA_HD void phase_a(uint32_t tid, uint32_t nt)
 	{
-		if (tid == 0) {
-			sm.n_live[0] = 0;
-			sm.n_live[1] = 0;
-		}
 		for (uint32_t q = tid; q < nq; q += nt) {
-			uint32_t prof = sm.in[in_off + q * BS];
-			sm.prof[q] = (uint8_t)prof;
+			uint32_t prof = profile_of(q);
 			int kind = block_kind(prof);
-			if (kind == kChain)
+			if (kind == kChain) {
+				if (q < (uint32_t)CH || block_kind(profile_of(q - CH)) != kChain)
+					sm.live[0][smem_inc(&sm.n_live[0])] = (uint16_t)q;
 				continue;
+			}
 			if (kind == kBad)
 				global_min_u32(&p.first_bad[stream], first_eb * CH + q);
 			/* a bad block is decoded as if it were a cut so that
@@ -271,24 +307,20 @@ struct DecTile {
 		}
 	}
 
-	/* heads of chains: a chain block whose predecessor is not a chain block */
-	XA_HD void phase_seed(uint32_t tid, uint32_t nt)
+	/*
+	 * round r: the r-th block of every live chain.  Reads list r&1 /
+	 * counter r%3, appends survivors to list (r+1)&1 / counter (r+1)%3 and
+	 * clears counter (r+2)%3 for the round after -- one barrier per round.
+	 */
+	XA_HD void phase_round(uint32_t tid, uint32_t nt, int r, int n)
 	{
-		for (uint32_t q = tid; q < nq; q += nt) {
-			if (block_kind(sm.prof[q]) != kChain)
-				continue;
-			if (q >= (uint32_t)CH && block_kind(sm.prof[q - CH]) == kChain)
-				continue;
-			sm.live[0][smem_inc(&sm.n_live[0])] = (uint16_t)q;
-		}
-	}
-
-	/* one round: the next block of every live chain */
-	XA_HD void phase_round(uint32_t tid, uint32_t nt, int cur, int n)
-	{
+		const int cur = r & 1, nxt = cur ^ 1;
+		int *cnt_next = &sm.n_live[(r + 1) % 3];
+		if (tid == 0)
+			sm.n_live[(r + 2) % 3] = 0;
 		for (uint32_t i = tid; i < (uint32_t)n; i += nt) {
 			uint32_t q = sm.live[cur][i];
-			uint32_t prof = sm.prof[q];
+			uint32_t prof = profile_of(q);
 			int p0, p1;
 			if (q < (uint32_t)CH) {
 				carried_in(q, p0, p1);
@@ -303,50 +335,89 @@ struct DecTile {
 			store_row(q, o);
 			if (q + CH >= nq)
 				publish(q % CH, p0, p1);
-			else if (block_kind(sm.prof[q + CH]) == kChain)
-				sm.live[cur ^ 1][smem_inc(&sm.n_live[cur ^ 1])] =
-				    (uint16_t)(q + CH);
+			else if (block_kind(profile_of(q + CH)) == kChain)
+				sm.live[nxt][smem_inc(cnt_next)] = (uint16_t)(q + CH);
 		}
 	}
 
-	/* staged rows -> interleaved PCM, 16 bytes per step */
+	/* after the last round: leave all three counters zero for the next tile */
+	XA_HD void reset_counters(uint32_t tid)
+	{
+		if (tid == 0)
+			sm.n_live[0] = sm.n_live[1] = sm.n_live[2] = 0;
+	}
+
+	/* one 16-byte unit of interleaved PCM from the staged rows */
+	XA_HD void gather_chunk(uint32_t i, uint32_t (&w)[4]) const
+	{
+		if (CH == 1) {
+			const uint32_t *s = &sm.out[row_word(i >> 2, (int)(i & 3u), 0)];
+			w[0] = s[0]; w[1] = s[1]; w[2] = s[2]; w[3] = s[3];
+		} else {
+			uint32_t eb = i >> 3, jj = i & 7u;
+			int j = (int)(jj >> 1), h = (int)(jj & 1u) * 2;
+			const uint32_t *l = &sm.out[row_word(2 * eb, j, h)];
+			const uint32_t *r = &sm.out[row_word(2 * eb + 1, j, h)];
+			w[0] = byte_perm(l[0], r[0], 0x5410);
+			w[1] = byte_perm(l[0], r[0], 0x7632);
+			w[2] = byte_perm(l[1], r[1], 0x5410);
+			w[3] = byte_perm(l[1], r[1], 0x7632);
+		}
+	}
+
+	/* staged rows -> interleaved PCM, 16 bytes per step.  nt % 32 == 0. */
 	XA_HD void phase_store(uint32_t tid, uint32_t nt)
 	{
 		uint8_t *dst = p.dst + out0;
 		const uint32_t nchunk = neb * (4 * CH);
-		for (uint32_t i = tid; i < nchunk; i += nt) {
-			uint32_t w0, w1, w2, w3;
+		if (out_valid == nchunk * 16u) {
+			/* every unit is whole.  With nt a multiple of 32 the
+			 * swizzle term of a thread's units is the same for all of
+			 * them, so both addresses advance by nt*16 bytes per step. */
+			uint4 *g = reinterpret_cast<uint4 *>(dst) + tid;
 			if (CH == 1) {
-				uint32_t q = i >> 2;
-				int j = (int)(i & 3u);
-				const uint32_t *s = &sm.out[row_word(q, j, 0)];
-				w0 = s[0]; w1 = s[1]; w2 = s[2]; w3 = s[3];
+				const uint4 *s = reinterpret_cast<const uint4 *>(
+				    &sm.out[row_word(tid >> 2, (int)(tid & 3u), 0)]);
+				for (uint32_t i = tid; i < nchunk; i += nt) {
+					*g = *s;
+					g += nt;
+					s += nt;
+				}
 			} else {
-				uint32_t eb = i >> 3, jj = i & 7u;
-				int j = (int)(jj >> 1), h = (int)(jj & 1u) * 2;
-				const uint32_t *l = &sm.out[row_word(2 * eb, j, h)];
-				const uint32_t *r = &sm.out[row_word(2 * eb + 1, j, h)];
-				w0 = byte_perm(l[0], r[0], 0x5410);
-				w1 = byte_perm(l[0], r[0], 0x7632);
-				w2 = byte_perm(l[1], r[1], 0x5410);
-				w3 = byte_perm(l[1], r[1], 0x7632);
+				const uint32_t jj = tid & 7u;
+				const int j = (int)(jj >> 1), h = (int)(jj & 1u) * 2;
+				const uint2 *l = reinterpret_cast<const uint2 *>(
+				    &sm.out[row_word(2 * (tid >> 3), j, h)]);
+				const uint2 *r = reinterpret_cast<const uint2 *>(
+				    &sm.out[row_word(2 * (tid >> 3) + 1, j, h)]);
+				for (uint32_t i = tid; i < nchunk; i += nt) {
+					uint2 a = *l, b = *r;
+					uint4 v;
+					v.x = byte_perm(a.x, b.x, 0x5410);
+					v.y = byte_perm(a.x, b.x, 0x7632);
+					v.z = byte_perm(a.y, b.y, 0x5410);
+					v.w = byte_perm(a.y, b.y, 0x7632);
+					*g = v;
+					g += nt;
+					l += nt * 2;	/* nt units = nt/8 pairs of rows = nt*16 B */
+					r += nt * 2;
+				}
 			}
+			return;
+		}
+		/* the truncated last block of a stream */
+		for (uint32_t i = tid; i < nchunk; i += nt) {
+			uint32_t w[4];
 			uint32_t boff = i * 16u;
-			if (boff + 16u <= out_valid) {
-#if defined(__CUDA_ARCH__)
-				*reinterpret_cast<uint4 *>(dst + boff) = make_uint4(w0, w1, w2, w3);
-#else
-				uint32_t *d = reinterpret_cast<uint32_t *>(dst + boff);
-				d[0] = w0; d[1] = w1; d[2] = w2; d[3] = w3;
-#endif
-			} else if (boff < out_valid) {
-				/* the truncated last block of a stream */
-				uint32_t w[4] = { w0, w1, w2, w3 };
-				uint16_t *d = reinterpret_cast<uint16_t *>(dst + boff);
-				uint32_t n16 = (out_valid - boff) / 2u;
-				for (uint32_t k = 0; k < n16; k++)
-					d[k] = (uint16_t)(w[k >> 1] >> (16u * (k & 1u)));
-			}
+			if (boff >= out_valid)
+				continue;
+			gather_chunk(i, w);
+			uint32_t n16 = (out_valid - boff) / 2u;
+			if (n16 > 8u)
+				n16 = 8u;
+			uint16_t *d = reinterpret_cast<uint16_t *>(dst + boff);
+			for (uint32_t k = 0; k < n16; k++)
+				d[k] = (uint16_t)(w[k >> 1] >> (16u * (k & 1u)));
 		}
 	}
 };

@@ -34,31 +34,33 @@ template <int BITS, int CH>
 static void
 emul_decode_bucket(const DecodeParams &p, int order)
 {
-	typedef DecTile<BITS, CH, kDecTBQ> Tile;
+	typedef DecTile<BITS, CH, kDecTBQ, kDecStages> Tile;
 	typename Tile::Smem *sm = new typename Tile::Smem();
 	const uint32_t nt = kDecThreads;
 
+	memset(sm, 0xa5, sizeof *sm);	/* smem is garbage at CTA start */
+	sm->n_live[0] = sm->n_live[1] = sm->n_live[2] = 0;
 	for (uint32_t ticket = 0; ticket < p.n_tiles; ticket++) {
-		memset(sm, 0xa5, sizeof *sm);	/* smem is garbage at CTA start */
-		Tile t(p, *sm, ticket);
-		uint32_t nb = t.bulk_bytes();
-		memcpy(sm->in, p.src + t.a0, nb);
-		for (uint32_t i = 0; i < nt; i++)
-			t.load_tail(visit(i, nt, order), nt);
+		/* one persistent CTA draws every ticket; stages rotate as on the GPU */
+		const int s = (int)(ticket % kDecStages);
+		memset(sm->in[s], 0xa5, sizeof sm->in[s]);
+		make_dec_ctx<BITS, CH, kDecTBQ>(sm->ctx[s], p, ticket);
+		memcpy(sm->in[s], p.src + sm->ctx[s].a0, sm->ctx[s].bulk);
+		Tile t(p, *sm, s);
+		if (t.in_need > t.bulk)
+			for (uint32_t i = 0; i < nt; i++)
+				t.load_tail(visit(i, nt, order), nt, sm->in[s]);
 		for (uint32_t i = 0; i < nt; i++)
 			t.phase_a(visit(i, nt, order), nt);
-		/* phase_a's thread 0 zeroes the counters: redo in case order != 0
-		 * ran other threads first (on the GPU nobody touches them in A) */
-		for (uint32_t i = 0; i < nt; i++)
-			t.phase_seed(visit(i, nt, order), nt);
-		for (int cur = 0;; cur ^= 1) {
-			int n = sm->n_live[cur];
+		for (int r = 0;; r++) {
+			int n = sm->n_live[r % 3];
 			if (n == 0)
 				break;
 			for (uint32_t i = 0; i < nt; i++)
-				t.phase_round(visit(i, nt, order), nt, cur, n);
-			sm->n_live[cur] = 0;
+				t.phase_round(visit(i, nt, order), nt, r, n);
 		}
+		for (uint32_t i = 0; i < nt; i++)
+			t.reset_counters(visit(i, nt, order));
 		for (uint32_t i = 0; i < nt; i++)
 			t.phase_store(visit(i, nt, order), nt);
 	}
@@ -107,6 +109,7 @@ xa_emul_decode(const bjxa_stream_desc_t *descs, size_t n, const uint8_t *src,
 	std::vector<StreamRes> res(n);
 	std::vector<unsigned long long> carry((size_t)hp.n_slots * 2 + 2, 0ULL);
 	unsigned long long ticket = 0;
+	uint32_t fault = 0;
 	for (size_t i = 0; i < n; i++) {
 		first_bad[i] = 0xffffffffu;
 		memset(&res[i], 0x5a, sizeof res[i]);
@@ -126,7 +129,7 @@ xa_emul_decode(const bjxa_stream_desc_t *descs, size_t n, const uint8_t *src,
 		p.n_tiles = t1 - t0;
 		p.carry = carry.data();
 		p.ticket = &ticket;
-		p.ticket_base = 0;
+		p.fault = &fault;
 		p.epoch = 7;
 		switch (b) {
 		case 0: emul_decode_bucket<4, 1>(p, order); break;

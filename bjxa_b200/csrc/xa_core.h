@@ -154,10 +154,30 @@ XA_HD int sample_cut(int x, int sh) { return x >> sh; }
  */
 XA_HD int sample_chain(int x, int sh, int k0, int k1, int &p0, int &p1)
 {
-	int g = p0 * k0 + p1 * k1;
-	/* truncating /256 as shift + sign fix-up: add 255 when g < 0 */
-	int q = (g + ((g >> 31) & 255)) >> 8;
-	int s = (x >> sh) + q;
+	/*
+	 * Arranged for a short dependent path from p0 to the next p0 (the chain
+	 * is latency bound): with r = x >> sh and g = p0*k0 + p1*k1,
+	 *   r + trunc(g / 256) = (g + 256 r) >> 8          when g >= 0
+	 *                      = (g + 256 r + 255) >> 8    when g <  0
+	 * so three independent multiply-adds leave p0 at once (the sum, the sum
+	 * plus 255, and g itself for its sign), then shift, select, clamp.
+	 * p1*k1 and r do not depend on p0.
+	 */
+	const int c = p1 * k1;
+	const int a = ((x >> sh) << 8) + c;
+	const int g = p0 * k0 + c;
+	int u = p0 * k0 + a;
+	int v = p0 * k0 + (a + 255);
+#if defined(__CUDA_ARCH__)
+	/* opaque shifts: keep both candidates alive so that the select comes
+	 * AFTER the shift instead of a predicated add in front of the multiply */
+	asm("shr.s32 %0, %0, 8;" : "+r"(u));
+	asm("shr.s32 %0, %0, 8;" : "+r"(v));
+#else
+	u >>= 8;
+	v >>= 8;
+#endif
+	int s = g < 0 ? v : u;
 	s = s < -32768 ? -32768 : s;
 	s = s > 32767 ? 32767 : s;
 	p1 = p0;

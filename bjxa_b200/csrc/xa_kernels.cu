@@ -87,19 +87,19 @@ __device__ __forceinline__ void consumer_sync()
 /*
  * Persistent, warp-specialised decode kernel.  Grid = (CTAs that fit one SM) x
  * (SM count).  Per CTA:
- *   producer   one thread of the extra warp: draws tile tickets in order,
- *              computes the tile context, and starts the bulk-async (TMA) copy
- *              of the tile's contiguous XA bytes into the next free stage
- *              buffer, kDecStages tiles ahead of the consumers;
+ *   producer   the extra warp: lane 0 draws tile tickets in order; lane i
+ *              builds the context of strip i and starts the bulk-async (TMA)
+ *              copy of that strip's contiguous XA bytes into the next free
+ *              stage buffer, kDecStages tiles ahead of the consumers;
  *   consumers  kDecThreads threads: wait on the stage's "full" mbarrier, run
- *              phase A / the chain rounds / the store of xa_tile.h, and hand
+ *              phase A / the chain walkers / the store of xa_tile.h, and hand
  *              the buffer back through the stage's "empty" mbarrier.
  */
-template <int BITS, int CH>
+template <int BITS, int CH, int NS>
 __global__ void __launch_bounds__(kDecThreads + 32)
 xa_decode_kernel(const DecodeParams p)
 {
-	typedef DecTile<BITS, CH, kDecTBQ, kDecStages> Tile;
+	typedef DecTile<BITS, CH, kDecTBQ, NS, kDecStages> Tile;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	typename Tile::Smem &sm = *reinterpret_cast<typename Tile::Smem *>(smem_raw);
 	const uint32_t tid = threadIdx.x;
@@ -109,62 +109,84 @@ xa_decode_kernel(const DecodeParams p)
 			mbar_init(smem_u32(&sm.full[s]), 1);
 			mbar_init(smem_u32(&sm.empty[s]), 1);
 		}
-		sm.n_live[0] = sm.n_live[1] = sm.n_live[2] = 0;
+		sm.n_heads = 0;
 	}
 	__syncthreads();
 
 	if (tid >= kDecThreads) {
-		if (tid != kDecThreads)
-			return;
+		const uint32_t lane = tid - kDecThreads;
 		for (uint32_t it = 0;; it++) {
 			const int s = (int)(it % kDecStages);
 			if (it >= (uint32_t)kDecStages)
 				mbar_wait(smem_u32(&sm.empty[s]), (it / kDecStages - 1) & 1);
 			/* the counter is preset to ~0 with first_bad[]: old + 1 = ticket */
-			const unsigned long long t = atomicAdd(p.ticket, 1ULL) + 1ULL;
+			unsigned long long t = 0;
+			if (lane == 0)
+				t = atomicAdd(p.ticket, 1ULL) + 1ULL;
+			t = __shfl_sync(0xffffffffu, t, 0);
 			const uint32_t full = smem_u32(&sm.full[s]);
 			if (t >= p.n_tiles) {
-				sm.ctx[s].flags = kCtxEnd;
-				mbar_arrive(full);
+				if (lane == 0) {
+					sm.tile_flags[s] = kCtxEnd;
+					mbar_arrive(full);
+				}
 				return;
 			}
-			DecCtx c;
-			make_dec_ctx<BITS, CH, kDecTBQ>(c, p, (uint32_t)t);
-			sm.ctx[s] = c;
-			if (c.bulk) {
-				mbar_expect_tx(full, c.bulk);
-				bulk_g2s(smem_u32(sm.in[s]), p.src + c.a0, c.bulk, full);
-			} else {
-				mbar_arrive(full);
+			const TileEnt te = p.tiles[t];
+			uint32_t bulk = 0, tail = 0;
+			StripCtx c;
+			if (lane < te.count) {
+				make_strip_ctx<BITS, CH, kDecTBQ, NS>(c, p, p.order[te.first + lane],
+				    te.j, lane);
+				sm.ctx[s][lane] = c;
+				bulk = c.bulk;
+				tail = c.flags & kCtxTail;
 			}
+			uint32_t total = bulk;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1)
+				total += __shfl_xor_sync(0xffffffffu, total, o);
+			const uint32_t any_tail = __ballot_sync(0xffffffffu, tail != 0);
+			if (lane == 0) {
+				sm.tile_flags[s] = any_tail ? kCtxTail : 0u;
+				sm.n_strips[s] = te.count;
+				if (total)
+					mbar_expect_tx(full, total);
+				else
+					mbar_arrive(full);
+			}
+			__syncwarp();
+			if (bulk)
+				bulk_g2s(smem_u32(sm.in[s]) + lane * Tile::G::SLOT, p.src + c.a0,
+				    bulk, full);
 		}
 	}
 
 	for (uint32_t it = 0;; it++) {
 		const int s = (int)(it % kDecStages);
 		mbar_wait(smem_u32(&sm.full[s]), (it / kDecStages) & 1);
-		if (sm.ctx[s].flags & kCtxEnd)
+		const uint32_t tf = sm.tile_flags[s];
+		if (tf & kCtxEnd)
 			return;
 		Tile t(p, sm, s);
-		if (t.in_need > t.bulk) {	/* only at the very end of the arena */
+		if (tf & kCtxTail) {	/* only at the very end of the arena */
 			t.load_tail(tid, kDecThreads, sm.in[s]);
 			consumer_sync();
 		}
 
 		t.phase_a(tid, kDecThreads);
-		for (int r = 0;; r++) {
+		consumer_sync();
+		const int heads = sm.n_heads;
+		if (heads != 0) {
+			t.phase_walk(tid, kDecThreads, heads);
 			consumer_sync();
-			const int n = sm.n_live[r % 3];
-			if (n == 0)
-				break;
-			t.phase_round(tid, kDecThreads, r, n);
 		}
-		/* nobody reads this stage's source bytes or context any more */
-		if (tid == 0)
-			mbar_arrive(smem_u32(&sm.empty[s]));
 		t.reset_counters(tid);
 		t.phase_store(tid, kDecThreads);
 		consumer_sync();	/* rows are free for the next tile's phase A */
+		/* nobody reads this stage's source bytes or context any more */
+		if (tid == 0)
+			mbar_arrive(smem_u32(&sm.empty[s]));
 	}
 }
 
@@ -362,6 +384,7 @@ struct bjxa_plan {
 	DevBuf<StreamRes> d_results;
 	DevBuf<uint32_t> d_first_bad;
 	DevBuf<TileEnt> d_tiles;
+	DevBuf<uint32_t> d_order;
 	DevBuf<unsigned long long> d_carry;
 	DevBuf<uint32_t> d_fault;		/* set when a carry never arrived */
 	uint32_t epoch;
@@ -380,9 +403,14 @@ template <int BITS, int CH>
 static cudaError_t
 set_attrs_one(void)
 {
-	cudaError_t e = cudaFuncSetAttribute(xa_decode_kernel<BITS, CH>,
+	cudaError_t e = cudaFuncSetAttribute(xa_decode_kernel<BITS, CH, 1>,
 	    cudaFuncAttributeMaxDynamicSharedMemorySize,
-	    (int)sizeof(DecSmem<BITS, CH, kDecTBQ, kDecStages>));
+	    (int)sizeof(DecSmem<BITS, CH, kDecTBQ, 1, kDecStages>));
+	if (e != cudaSuccess)
+		return e;
+	e = cudaFuncSetAttribute(xa_decode_kernel<BITS, CH, kDecWide>,
+	    cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    (int)sizeof(DecSmem<BITS, CH, kDecTBQ, kDecWide, kDecStages>));
 	if (e != cudaSuccess)
 		return e;
 	return cudaFuncSetAttribute(xa_encode_kernel<BITS, CH>,
@@ -424,6 +452,7 @@ plan_upload(bjxa_plan *pl)
 	    (rc = pl->d_first_bad.reserve(n + 16, false)) ||	/* + 6 ticket counters */
 	    (rc = pl->d_fault.reserve(4, true)) ||
 	    (rc = pl->d_tiles.reserve(hp.tiles.size(), false)) ||
+	    (rc = pl->d_order.reserve(hp.order.size(), false)) ||
 	    (rc = pl->d_carry.reserve((size_t)hp.n_slots * 2, true))) {
 		errno = rc;
 		return (-1);
@@ -434,6 +463,9 @@ plan_upload(bjxa_plan *pl)
 	if (!hp.tiles.empty())
 		XA_CUDA(cudaMemcpy(pl->d_tiles.p, hp.tiles.data(),
 		    hp.tiles.size() * sizeof(TileEnt), cudaMemcpyHostToDevice));
+	if (!hp.order.empty())
+		XA_CUDA(cudaMemcpy(pl->d_order.p, hp.order.data(),
+		    hp.order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
 	return (0);
 }
 
@@ -450,7 +482,9 @@ plan_build(bjxa_plan *pl, int kind, const bjxa_stream_desc_t *descs, size_t n)
 		errno = EFAULT;
 		return (-1);
 	}
-	int rc = build_plan(pl->hp, kind, descs, n, &bad);
+	/* BJXA_B200_STRIPS=1|32 forces the decode tile shape (tuning aid) */
+	const char *env = getenv("BJXA_B200_STRIPS");
+	int rc = build_plan(pl->hp, kind, descs, n, &bad, env ? atoi(env) : 0);
 	if (rc) {
 		errno = rc;
 		return (-1);
@@ -519,6 +553,7 @@ bjxa_plan_free(bjxa_plan_t **planp)
 	pl->d_results.release();
 	pl->d_first_bad.release();
 	pl->d_tiles.release();
+	pl->d_order.release();
 	pl->d_carry.release();
 	pl->d_fault.release();
 	pl->magic = 0;
@@ -545,13 +580,13 @@ bjxa_plan_extent(const bjxa_plan_t *pl, uint64_t *src_bytes, uint64_t *dst_bytes
 	return (0);
 }
 
-template <int BITS, int CH>
+template <int BITS, int CH, int NS>
 static cudaError_t
-launch_decode(const DecodeParams &p, cudaStream_t st)
+launch_decode_ns(const DecodeParams &p, cudaStream_t st)
 {
 	/* persistent: as many CTAs as fit the device at once, never more than tiles */
 	static thread_local int grid_cache[2] = { -1, 0 };
-	const size_t smem = sizeof(DecSmem<BITS, CH, kDecTBQ, kDecStages>);
+	const size_t smem = sizeof(DecSmem<BITS, CH, kDecTBQ, NS, kDecStages>);
 	int dev = 0;
 	cudaError_t e = cudaGetDevice(&dev);
 	if (e != cudaSuccess)
@@ -559,7 +594,7 @@ launch_decode(const DecodeParams &p, cudaStream_t st)
 	if (grid_cache[0] != dev) {
 		int per_sm = 0, sms = 0;
 		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm,
-		    xa_decode_kernel<BITS, CH>, kDecThreads + 32, smem);
+		    xa_decode_kernel<BITS, CH, NS>, kDecThreads + 32, smem);
 		if (e != cudaSuccess)
 			return e;
 		e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -571,8 +606,16 @@ launch_decode(const DecodeParams &p, cudaStream_t st)
 	uint32_t grid = (uint32_t)grid_cache[1];
 	if (grid > p.n_tiles)
 		grid = p.n_tiles;
-	xa_decode_kernel<BITS, CH><<<grid, kDecThreads + 32, smem, st>>>(p);
+	xa_decode_kernel<BITS, CH, NS><<<grid, kDecThreads + 32, smem, st>>>(p);
 	return cudaGetLastError();
+}
+
+template <int BITS, int CH>
+static cudaError_t
+launch_decode(const DecodeParams &p, int ns, cudaStream_t st)
+{
+	return ns == 1 ? launch_decode_ns<BITS, CH, 1>(p, st) :
+	    launch_decode_ns<BITS, CH, kDecWide>(p, st);
 }
 
 template <int BITS, int CH>
@@ -644,18 +687,19 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 			p.first_bad = pl->d_first_bad.p;
 			p.tiles = pl->d_tiles.p + t0;
 			p.n_tiles = t1 - t0;
+			p.order = pl->d_order.p;
 			p.carry = pl->d_carry.p;
 			p.ticket = reinterpret_cast<unsigned long long *>(
 			    pl->d_first_bad.p + ((n + 3) & ~(size_t)3)) + b;
 			p.fault = pl->d_fault.p;
 			p.epoch = pl->epoch;
 			switch (b) {
-			case 0: e = launch_decode<4, 1>(p, st); break;
-			case 1: e = launch_decode<4, 2>(p, st); break;
-			case 2: e = launch_decode<6, 1>(p, st); break;
-			case 3: e = launch_decode<6, 2>(p, st); break;
-			case 4: e = launch_decode<8, 1>(p, st); break;
-			default: e = launch_decode<8, 2>(p, st); break;
+			case 0: e = launch_decode<4, 1>(p, hp.ns[b], st); break;
+			case 1: e = launch_decode<4, 2>(p, hp.ns[b], st); break;
+			case 2: e = launch_decode<6, 1>(p, hp.ns[b], st); break;
+			case 3: e = launch_decode<6, 2>(p, hp.ns[b], st); break;
+			case 4: e = launch_decode<8, 1>(p, hp.ns[b], st); break;
+			default: e = launch_decode<8, 2>(p, hp.ns[b], st); break;
 			}
 		} else {
 			EncodeParams p;

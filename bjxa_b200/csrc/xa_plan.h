@@ -36,12 +36,17 @@ namespace xa {
 #ifndef XA_DEC_STAGES
 #define XA_DEC_STAGES 2
 #endif
+#ifndef XA_DEC_WIDE
+#define XA_DEC_WIDE 32
+#endif
 constexpr int kDecTBQ = XA_DEC_TBQ;		/* block-channels per tile */
 constexpr int kDecThreads = XA_DEC_NT;		/* consumer threads (+1 producer warp) */
 constexpr int kDecStages = XA_DEC_STAGES;	/* source buffers in flight per CTA */
+constexpr int kDecWide = XA_DEC_WIDE;		/* strips per tile in "wide" mode */
 constexpr int kEncTBE = 256;
 constexpr int kEncThreads = 128;
 static_assert(kDecThreads % 32 == 0 && kDecTBQ % 2 == 0, "tile geometry");
+static_assert(kDecWide <= 32, "one producer lane per strip");
 
 enum { kKindDecode = 0, kKindEncode = 1 };
 
@@ -53,16 +58,38 @@ struct HostPlan {
 	int kind;
 	std::vector<StreamDev> streams;
 	std::vector<uint8_t> bucket;		/* per stream */
+	std::vector<uint32_t> order;		/* streams in issue order, by bucket */
 	std::vector<TileEnt> tiles;		/* all buckets, concatenated */
 	uint32_t tile_begin[7];			/* bucket b owns [b], [b+1]) */
+	int ns[6];				/* decode: strips per tile of bucket b */
 	uint32_t n_slots;
 	uint64_t src_need, dst_need;		/* arena bytes the batch touches */
 };
 
-/* effective blocks per tile for a stream with `ch` channels */
-inline uint32_t tile_blocks(int kind, int ch)
+/*
+ * Strips per decode tile for a bucket of n streams.  kDecWide short strips of
+ * different streams give every tile kDecWide independent chains even when the
+ * streams have no cut block at all, but only pay off when the batch is large
+ * enough that a strip's predecessor (n/kDecWide tickets earlier) has left the
+ * device before the strip starts -- about 2 * resident CTAs * kDecWide
+ * streams; measured on B200 (profiles/): at 4096 streams the wide shape is
+ * 6x faster on all-chain data and 1.4-1.6x slower on cut-rich data, so the
+ * automatic choice keeps one long strip per tile below kDecWideMinStreams.
+ * `force` (0 = automatic) is a tuning/testing override.
+ */
+constexpr size_t kDecWideMinStreams = 16384;
+
+inline int choose_strips(size_t n_streams, int force)
 {
-	return kind == kKindDecode ? (uint32_t)(kDecTBQ / ch) : (uint32_t)kEncTBE;
+	if (force == 1 || force == kDecWide)
+		return force;
+	return n_streams >= kDecWideMinStreams ? kDecWide : 1;
+}
+
+/* effective blocks per strip */
+inline uint32_t strip_blocks(int ns, int ch)
+{
+	return (uint32_t)(kDecTBQ / ns / ch);
 }
 
 /*
@@ -71,22 +98,22 @@ inline uint32_t tile_blocks(int kind, int ch)
  */
 template <class Desc>
 inline int build_plan(HostPlan &hp, int kind, const Desc *d, size_t n,
-    size_t *bad_index)
+    size_t *bad_index, int force_strips = 0)
 {
 	hp.kind = kind;
 	hp.streams.resize(n);
 	hp.bucket.resize(n);
 	hp.tiles.clear();
+	hp.order.clear();
 	hp.n_slots = 0;
 	hp.src_need = hp.dst_need = 0;
 
-	std::vector<uint32_t> order[6];
+	std::vector<uint32_t> members[6];
 	for (size_t i = 0; i < n; i++) {
 		const Desc &s = d[i];
 		if (s.blocks == 0) {
 			/* takes no part: no tiles, nothing validated */
 			std::memset(&hp.streams[i], 0, sizeof hp.streams[i]);
-			hp.streams[i].slot_base = hp.n_slots;
 			hp.bucket[i] = 0;
 			continue;
 		}
@@ -108,41 +135,62 @@ inline int build_plan(HostPlan &hp, int kind, const Desc *d, size_t n,
 		std::memcpy(sd.prev, s.prev, sizeof sd.prev);
 		int b = bucket_of(s.bits, s.channels);
 		hp.bucket[i] = (uint8_t)b;
-		uint32_t tbe = tile_blocks(kind, s.channels);
-		uint32_t nt = (s.blocks + tbe - 1) / tbe;
-		sd.slot_base = hp.n_slots;
-		hp.n_slots += nt;
-		if (s.blocks) {
-			order[b].push_back((uint32_t)i);
-			uint64_t xa_end = s.xa_off + (uint64_t)s.blocks *
-			    (uint64_t)(block_bytes(s.bits) * s.channels);
-			uint64_t pcm_end = s.pcm_off + s.pcm_len;
-			uint64_t &src = kind == kKindDecode ? hp.src_need : hp.dst_need;
-			uint64_t &dst = kind == kKindDecode ? hp.dst_need : hp.src_need;
-			src = std::max(src, xa_end);
-			dst = std::max(dst, pcm_end);
-		}
+		members[b].push_back((uint32_t)i);
+		uint64_t xa_end = s.xa_off + (uint64_t)s.blocks *
+		    (uint64_t)(block_bytes(s.bits) * s.channels);
+		uint64_t pcm_end = s.pcm_off + s.pcm_len;
+		uint64_t &src = kind == kKindDecode ? hp.src_need : hp.dst_need;
+		uint64_t &dst = kind == kKindDecode ? hp.dst_need : hp.src_need;
+		src = std::max(src, xa_end);
+		dst = std::max(dst, pcm_end);
 	}
 
 	for (int b = 0; b < 6; b++) {
 		hp.tile_begin[b] = (uint32_t)hp.tiles.size();
-		std::vector<uint32_t> &o = order[b];
+		hp.ns[b] = 1;
+		std::vector<uint32_t> &o = members[b];
 		if (o.empty())
 			continue;
-		uint32_t tbe = tile_blocks(kind, bucket_ch(b));
-		/* longest first: the streams still active at tile j are a prefix */
+		/* longest first: the streams still active at step j are a prefix */
 		std::stable_sort(o.begin(), o.end(), [&](uint32_t x, uint32_t y) {
 			return hp.streams[x].blocks > hp.streams[y].blocks;
 		});
+		const uint32_t order0 = (uint32_t)hp.order.size();
+		hp.order.insert(hp.order.end(), o.begin(), o.end());
+
+		if (kind == kKindEncode) {
+			const uint32_t tbe = (uint32_t)kEncTBE;
+			size_t active = o.size();
+			for (uint32_t j = 0; active > 0; j++) {
+				while (active > 0 &&
+				    (uint64_t)j * tbe >= hp.streams[o[active - 1]].blocks)
+					active--;
+				for (size_t k = 0; k < active; k++) {
+					TileEnt te = { o[k], 1u, j * tbe, 0u };
+					hp.tiles.push_back(te);
+				}
+			}
+			continue;
+		}
+
+		const int ns = choose_strips(o.size(), force_strips);
+		const uint32_t sbe = strip_blocks(ns, bucket_ch(b));
+		hp.ns[b] = ns;
+		for (size_t k = 0; k < o.size(); k++) {
+			StreamDev &sd = hp.streams[o[k]];
+			sd.slot_base = hp.n_slots;
+			hp.n_slots += (sd.blocks + sbe - 1) / sbe;
+		}
+		/* time-major: strip j of every stream before strip j+1 of any, so a
+		 * strip's predecessor in its stream always holds a lower ticket */
 		size_t active = o.size();
 		for (uint32_t j = 0; active > 0; j++) {
 			while (active > 0 &&
-			    (uint64_t)j * tbe >= hp.streams[o[active - 1]].blocks)
+			    (uint64_t)j * sbe >= hp.streams[o[active - 1]].blocks)
 				active--;
-			for (size_t k = 0; k < active; k++) {
-				TileEnt te;
-				te.stream = o[k];
-				te.first_eb = j * tbe;
+			for (size_t base = 0; base < active; base += (size_t)ns) {
+				size_t cnt = std::min(active - base, (size_t)ns);
+				TileEnt te = { order0 + (uint32_t)base, (uint32_t)cnt, j, 0u };
 				hp.tiles.push_back(te);
 			}
 		}

@@ -50,9 +50,13 @@ struct StreamRes {		/* decode results, device resident */
 	int16_t  prev[2][2];	/* predictor state after the last block */
 };
 
-struct TileEnt {
-	uint32_t stream;
-	uint32_t first_eb;	/* first effective block of the tile */
+struct TileEnt {		/* decode: NS strips of consecutive streams in issue order */
+	uint32_t first;		/* index into order[] of the first strip's stream;
+				 * encode: the stream itself */
+	uint32_t count;		/* strips in this tile (<= NS); encode: unused */
+	uint32_t j;		/* strip index inside each stream;
+				 * encode: first effective block of the tile */
+	uint32_t pad;
 };
 
 struct DecodeParams {
@@ -64,6 +68,7 @@ struct DecodeParams {
 	uint32_t *first_bad;	/* per stream: lowest bad block-channel index */
 	const TileEnt *tiles;
 	uint32_t n_tiles;
+	const uint32_t *order;	/* streams in issue order (longest first) */
 	unsigned long long *carry;	/* [slot][2] mailboxes */
 	unsigned long long *ticket;	/* preset to ~0 before every launch */
 	uint32_t *fault;		/* set if a carry never arrived */
@@ -122,103 +127,124 @@ XA_HD unsigned long long mailbox_get(const unsigned long long *p, uint32_t epoch
 /* ---- decode -------------------------------------------------------------- */
 
 /*
- * Everything a CTA needs to know about one tile.  Computed once per tile by
- * the producer thread (xa_kernels.cu) and handed to the consumer warps through
- * shared memory together with the tile's source bytes.
+ * A decode tile is NS "strips" of SBQ block-channels each (NS * SBQ = TBQ):
+ *   NS == 1   one long run of one stream -- used when a batch has few streams,
+ *             so the parallelism must come from inside each stream;
+ *   NS == 32  32 short runs of 32 different streams at the same position --
+ *             used when a batch has many streams: even a stream without a
+ *             single cut block (filters 1..4 throughout) then still gives every
+ *             tile 32 independent chains, one per lane of a warp.
+ * A strip is contiguous in both arenas; what a strip needs from the stream's
+ * previous strip (the predictor state) travels through the carry mailbox.
  */
-struct DecCtx {
+struct StripCtx {
 	uint64_t a0;		/* first source byte rounded down to 16 */
-	uint64_t out0;		/* first destination byte */
-	uint32_t stream, first_eb, neb, nq;
-	uint32_t in_off;	/* source misalignment, 0..15 */
-	uint32_t in_need;	/* bytes from a0 covering the tile's blocks */
-	uint32_t bulk;		/* bytes the bulk-async engine fetches (16-byte units) */
-	uint32_t out_valid;	/* PCM bytes this tile owes */
+	uint64_t out0;		/* first destination byte (16-byte aligned) */
+	uint32_t stream;
+	uint32_t first_eb;	/* first effective block of the strip */
+	uint32_t nq;		/* block-channels in the strip */
+	uint32_t in_base;	/* stage-buffer offset of the strip's first block */
+	uint32_t in_need;	/* source bytes needed, counted from a0 */
+	uint32_t bulk;		/* of which fetched by the bulk-async engine */
+	uint32_t out_valid;	/* PCM bytes the strip owes */
 	uint32_t slot;		/* carry mailbox index */
 	uint32_t flags;
+	uint32_t pad;
 };
-enum { kCtxFirst = 1u, kCtxLast = 2u, kCtxEnd = 0x80000000u };
+enum { kCtxFirst = 1u, kCtxLast = 2u, kCtxTail = 4u, kCtxEnd = 0x80000000u };
 
-template <int BITS, int CH, int TBQ>
-XA_HD void make_dec_ctx(DecCtx &c, const DecodeParams &p, uint32_t ticket)
+template <int BITS, int CH, int TBQ, int NS>
+struct DecGeom {
+	static constexpr int BS = block_bytes(BITS);
+	static constexpr int SBQ = TBQ / NS;		/* block-channels per strip */
+	static constexpr int SBE = SBQ / CH;		/* effective blocks per strip */
+	/* one strip's slot in the stage buffer: payload + up to 15 bytes of
+	 * misalignment in 16-byte units, plus a unit of slack for
+	 * load_payload's one-word over-read */
+	static constexpr int SLOT = ((SBQ * BS + 15 + 15) / 16) * 16 + 16;
+	static constexpr int IN_BYTES = NS * SLOT;
+	static_assert(TBQ % NS == 0 && SBQ % CH == 0 && SBQ >= 2, "strip geometry");
+	static_assert((SBQ & (SBQ - 1)) == 0, "SBQ must be a power of two");
+};
+
+template <int BITS, int CH, int TBQ, int NS>
+XA_HD void make_strip_ctx(StripCtx &c, const DecodeParams &p, uint32_t stream,
+    uint32_t j, uint32_t strip)
 {
-	constexpr int BS = block_bytes(BITS);
-	constexpr uint32_t TBE = TBQ / CH;
-	const TileEnt te = p.tiles[ticket];
-	const StreamDev &s = p.streams[te.stream];
-	c.stream = te.stream;
-	c.first_eb = te.first_eb;
+	typedef DecGeom<BITS, CH, TBQ, NS> G;
+	const StreamDev &s = p.streams[stream];
+	c.stream = stream;
+	c.first_eb = j * G::SBE;
 	uint32_t blocks = s.blocks;
-	uint32_t rem = blocks - te.first_eb;
-	c.neb = rem < TBE ? rem : TBE;
-	c.nq = c.neb * CH;
-	uint64_t g0 = s.xa_off + (uint64_t)te.first_eb * (BS * CH);
+	uint32_t rem = blocks - c.first_eb;
+	uint32_t neb = rem < (uint32_t)G::SBE ? rem : (uint32_t)G::SBE;
+	c.nq = neb * CH;
+	uint64_t g0 = s.xa_off + (uint64_t)c.first_eb * (G::BS * CH);
 	c.a0 = g0 & ~(uint64_t)15;
-	c.in_off = (uint32_t)(g0 - c.a0);
-	c.in_need = c.in_off + c.nq * BS;
+	uint32_t in_off = (uint32_t)(g0 - c.a0);
+	c.in_base = strip * G::SLOT + in_off;
+	c.in_need = in_off + c.nq * G::BS;
 	/* whole 16-byte units that lie inside the arena */
 	uint64_t end = c.a0 + ((c.in_need + 15u) & ~15u);
 	uint64_t lim = p.src_bytes & ~(uint64_t)15;
 	if (end > lim)
 		end = lim > c.a0 ? lim : c.a0;
 	c.bulk = (uint32_t)(end - c.a0);
-	uint64_t pcm_done = (uint64_t)te.first_eb * (64 * CH);
+	uint64_t pcm_done = (uint64_t)c.first_eb * (64 * CH);
 	c.out0 = s.pcm_off + pcm_done;
 	uint64_t owed = s.pcm_len > pcm_done ? s.pcm_len - pcm_done : 0;
-	uint64_t full = (uint64_t)c.neb * (64 * CH);
+	uint64_t full = (uint64_t)neb * (64 * CH);
 	c.out_valid = (uint32_t)(owed < full ? owed : full);
-	c.slot = s.slot_base + te.first_eb / TBE;
-	c.flags = (te.first_eb == 0 ? kCtxFirst : 0u) |
-	    (te.first_eb + c.neb == blocks ? kCtxLast : 0u);
+	c.slot = s.slot_base + j;
+	c.flags = (c.first_eb == 0 ? kCtxFirst : 0u) |
+	    (c.first_eb + neb == blocks ? kCtxLast : 0u) |
+	    (c.in_need > c.bulk ? kCtxTail : 0u);
+	c.pad = 0;
 }
 
-template <int BITS, int CH, int TBQ, int STAGES>
+template <int BITS, int CH, int TBQ, int NS, int STAGES>
 struct DecSmem {
-	static constexpr int BS = block_bytes(BITS);
-	/* payload + up to 15 bytes of misalignment, in 16-byte units, plus one
-	 * unit of slack for load_payload's one-word over-read */
-	static constexpr int IN_BYTES = ((TBQ * BS + 15 + 15) / 16) * 16 + 16;
+	typedef DecGeom<BITS, CH, TBQ, NS> G;
 
-	alignas(16) uint8_t in[STAGES][IN_BYTES];
+	alignas(16) uint8_t in[STAGES][G::IN_BYTES];
 	alignas(16) uint32_t out[TBQ * 16];	/* planar rows, 64 B each, swizzled */
-	uint16_t live[2][TBQ];
-	int n_live[3];
-	DecCtx ctx[STAGES];
+	StripCtx ctx[STAGES][NS];
+	uint32_t tile_flags[STAGES];		/* kCtxEnd, kCtxTail (any strip) */
+	uint32_t n_strips[STAGES];
+	uint16_t heads[TBQ];			/* heads of chains found in phase A */
+	int n_heads;
 	alignas(8) unsigned long long full[STAGES];
 	alignas(8) unsigned long long empty[STAGES];
 };
 
-template <int BITS, int CH, int TBQ, int STAGES>
+template <int BITS, int CH, int TBQ, int NS, int STAGES>
 struct DecTile {
-	typedef DecSmem<BITS, CH, TBQ, STAGES> Smem;
-	static constexpr int BS = block_bytes(BITS);
-	static_assert(TBQ % CH == 0, "tile must hold whole effective blocks");
+	typedef DecGeom<BITS, CH, TBQ, NS> G;
+	typedef DecSmem<BITS, CH, TBQ, NS, STAGES> Smem;
+	static constexpr int BS = G::BS;
+	static constexpr uint32_t SBQ = G::SBQ;
 
 	const DecodeParams &p;
 	Smem &sm;
-	const uint8_t *in;	/* this tile's stage buffer */
-	const uint64_t a0, out0;
-	const uint32_t stream, first_eb, neb, nq, in_off, in_need, bulk, out_valid, slot;
-	const bool first_tile, last_tile;
+	const uint8_t *in;		/* this tile's stage buffer */
+	const StripCtx *ctx;		/* this tile's strips */
+	const uint32_t n_strips;
 
 	XA_HD DecTile(const DecodeParams &p_, Smem &sm_, int stage)
-	    : p(p_), sm(sm_), in(sm_.in[stage]),
-	      a0(sm_.ctx[stage].a0), out0(sm_.ctx[stage].out0),
-	      stream(sm_.ctx[stage].stream), first_eb(sm_.ctx[stage].first_eb),
-	      neb(sm_.ctx[stage].neb), nq(sm_.ctx[stage].nq),
-	      in_off(sm_.ctx[stage].in_off), in_need(sm_.ctx[stage].in_need),
-	      bulk(sm_.ctx[stage].bulk), out_valid(sm_.ctx[stage].out_valid),
-	      slot(sm_.ctx[stage].slot),
-	      first_tile((sm_.ctx[stage].flags & kCtxFirst) != 0),
-	      last_tile((sm_.ctx[stage].flags & kCtxLast) != 0)
+	    : p(p_), sm(sm_), in(sm_.in[stage]), ctx(sm_.ctx[stage]),
+	      n_strips(sm_.n_strips[stage])
 	{
 	}
 
-	/* bytes past `bulk` fetched one by one (only at the arena's very end) */
+	/* bytes past a strip's `bulk` fetched one by one (only at the arena's end) */
 	XA_HD void load_tail(uint32_t tid, uint32_t nt, uint8_t *in_w)
 	{
-		for (uint32_t i = bulk + tid; i < in_need; i += nt)
-			in_w[i] = p.src[a0 + i];
+		for (uint32_t st = 0; st < n_strips; st++) {
+			const StripCtx &c = ctx[st];
+			uint32_t slot0 = st * G::SLOT;
+			for (uint32_t i = c.bulk + tid; i < c.in_need; i += nt)
+				in_w[slot0 + i] = p.src[c.a0 + i];
+		}
 	}
 
 	XA_HD static int row_word(uint32_t q, int chunk, int w)
@@ -230,47 +256,47 @@ struct DecTile {
 	{
 #pragma unroll
 		for (int j = 0; j < 4; j++) {
-			uint32_t *d = &sm.out[row_word(q, j, 0)];
-#if defined(__CUDA_ARCH__)
-			*reinterpret_cast<uint4 *>(d) = make_uint4(o[4 * j], o[4 * j + 1],
-			    o[4 * j + 2], o[4 * j + 3]);
-#else
-			d[0] = o[4 * j]; d[1] = o[4 * j + 1];
-			d[2] = o[4 * j + 2]; d[3] = o[4 * j + 3];
-#endif
+			uint4 *d = reinterpret_cast<uint4 *>(&sm.out[row_word(q, j, 0)]);
+			uint4 v;
+			v.x = o[4 * j]; v.y = o[4 * j + 1]; v.z = o[4 * j + 2]; v.w = o[4 * j + 3];
+			*d = v;
 		}
 	}
 
-	XA_HD uint32_t profile_of(uint32_t q) const { return in[in_off + q * BS]; }
-
-	XA_HD void fetch_block(uint32_t q, uint32_t (&pw)[BITS]) const
+	/* byte address (in the stage buffer) of block lq of strip st */
+	XA_HD uint32_t block_at(const StripCtx &c, uint32_t lq) const
 	{
-		uint32_t pay = in_off + q * BS + 1;	/* first payload byte */
+		return c.in_base + lq * BS;
+	}
+
+	XA_HD void fetch_block(uint32_t at, uint32_t (&pw)[BITS]) const
+	{
+		uint32_t pay = at + 1;		/* first payload byte */
 		const uint32_t *w = reinterpret_cast<const uint32_t *>(in) + (pay >> 2);
 		load_payload<BITS>(pw, w, (pay & 3u) * 8u);
 	}
 
 	/* hand the channel's state to whoever continues it */
-	XA_HD void publish(uint32_t c, int p0, int p1)
+	XA_HD void publish(const StripCtx &c, uint32_t ch, int p0, int p1)
 	{
-		if (last_tile) {
-			p.results[stream].prev[c][0] = (int16_t)p0;
-			p.results[stream].prev[c][1] = (int16_t)p1;
+		if (c.flags & kCtxLast) {
+			p.results[c.stream].prev[ch][0] = (int16_t)p0;
+			p.results[c.stream].prev[ch][1] = (int16_t)p1;
 		} else {
 			unsigned long long v = ((unsigned long long)p.epoch << 32) |
 			    ((unsigned long long)(uint16_t)p1 << 16) | (uint16_t)p0;
-			mailbox_put(&p.carry[(uint64_t)slot * 2 + c], v);
+			mailbox_put(&p.carry[(uint64_t)c.slot * 2 + ch], v);
 		}
 	}
 
-	XA_HD void carried_in(uint32_t c, int &p0, int &p1) const
+	XA_HD void carried_in(const StripCtx &c, uint32_t ch, int &p0, int &p1) const
 	{
-		if (first_tile) {
-			p0 = p.streams[stream].prev[c][0];
-			p1 = p.streams[stream].prev[c][1];
+		if (c.flags & kCtxFirst) {
+			p0 = p.streams[c.stream].prev[ch][0];
+			p1 = p.streams[c.stream].prev[ch][1];
 		} else {
 			unsigned long long v = mailbox_get(
-			    &p.carry[(uint64_t)(slot - 1) * 2 + c], p.epoch, p.fault);
+			    &p.carry[(uint64_t)(c.slot - 1) * 2 + ch], p.epoch, p.fault);
 			p0 = (int16_t)(uint16_t)v;
 			p1 = (int16_t)(uint16_t)(v >> 16);
 		}
@@ -279,85 +305,96 @@ struct DecTile {
 	/*
 	 * phase A: every cut block is decoded; every chain block whose
 	 * predecessor in its channel is not a chain block (or lies in the
-	 * previous tile) is queued as the head of a chain.  Needs n_live[0..2]
-	 * to be zero on entry.
+	 * stream's previous strip) is queued as the head of a chain.  Needs
+	 * n_heads == 0 on entry.
 	 */
 	XA_HD void phase_a(uint32_t tid, uint32_t nt)
 	{
-		for (uint32_t q = tid; q < nq; q += nt) {
-			uint32_t prof = profile_of(q);
-			int kind = block_kind(prof);
+		const uint32_t nq_all = n_strips * SBQ;
+		for (uint32_t q = tid; q < nq_all; q += nt) {
+			const StripCtx &c = ctx[q / SBQ];
+			const uint32_t lq = q % SBQ;
+			if (lq >= c.nq)
+				continue;
+			const uint32_t at = block_at(c, lq);
+			const uint32_t prof = in[at];
+			const int kind = block_kind(prof);
 			if (kind == kChain) {
-				if (q < (uint32_t)CH || block_kind(profile_of(q - CH)) != kChain)
-					sm.live[0][smem_inc(&sm.n_live[0])] = (uint16_t)q;
+				if (lq < (uint32_t)CH || block_kind(in[at - CH * BS]) != kChain)
+					sm.heads[smem_inc(&sm.n_heads)] = (uint16_t)q;
 				continue;
 			}
 			if (kind == kBad)
-				global_min_u32(&p.first_bad[stream], first_eb * CH + q);
+				global_min_u32(&p.first_bad[c.stream], c.first_eb * CH + lq);
 			/* a bad block is decoded as if it were a cut so that
 			 * nothing downstream waits for it; what lies at and after
 			 * it is not part of the result */
 			uint32_t pw[BITS], o[16];
-			fetch_block(q, pw);
+			fetch_block(at, pw);
 			decode_block_cut<BITS>(o, pw, prof);
 			store_row(q, o);
-			if (q + CH >= nq)
-				publish(q % CH, (int)(int16_t)(o[15] >> 16),
+			if (lq + CH >= c.nq)
+				publish(c, lq % CH, (int)(int16_t)(o[15] >> 16),
 				    (int)(int16_t)(o[15] & 0xffffu));
 		}
 	}
 
 	/*
-	 * round r: the r-th block of every live chain.  Reads list r&1 /
-	 * counter r%3, appends survivors to list (r+1)&1 / counter (r+1)%3 and
-	 * clears counter (r+2)%3 for the round after -- one barrier per round.
+	 * phase B: one walker per chain.  Thread i takes head i and decodes the
+	 * chain's blocks one after the other with the predictor state in
+	 * registers; no barrier until every chain of the tile is done.
 	 */
-	XA_HD void phase_round(uint32_t tid, uint32_t nt, int r, int n)
+	XA_HD void phase_walk(uint32_t tid, uint32_t nt, int n)
 	{
-		const int cur = r & 1, nxt = cur ^ 1;
-		int *cnt_next = &sm.n_live[(r + 1) % 3];
-		if (tid == 0)
-			sm.n_live[(r + 2) % 3] = 0;
 		for (uint32_t i = tid; i < (uint32_t)n; i += nt) {
-			uint32_t q = sm.live[cur][i];
-			uint32_t prof = profile_of(q);
+			uint32_t q = sm.heads[i];
+			const StripCtx &c = ctx[q / SBQ];
+			uint32_t lq = q % SBQ;
+			uint32_t at = block_at(c, lq);
 			int p0, p1;
-			if (q < (uint32_t)CH) {
-				carried_in(q, p0, p1);
+			if (lq < (uint32_t)CH) {
+				carried_in(c, lq, p0, p1);
 			} else {
 				uint32_t last = sm.out[row_word(q - CH, 3, 3)];
 				p0 = (int)(int16_t)(last >> 16);
 				p1 = (int)(int16_t)(last & 0xffffu);
 			}
-			uint32_t pw[BITS], o[16];
-			fetch_block(q, pw);
-			decode_block_chain<BITS>(o, pw, prof, p0, p1);
-			store_row(q, o);
-			if (q + CH >= nq)
-				publish(q % CH, p0, p1);
-			else if (block_kind(profile_of(q + CH)) == kChain)
-				sm.live[nxt][smem_inc(cnt_next)] = (uint16_t)(q + CH);
+			for (;;) {
+				uint32_t pw[BITS], o[16];
+				fetch_block(at, pw);
+				decode_block_chain<BITS>(o, pw, in[at], p0, p1);
+				store_row(q, o);
+				if (lq + CH >= c.nq) {
+					publish(c, lq % CH, p0, p1);
+					break;
+				}
+				q += CH;
+				lq += CH;
+				at += CH * BS;
+				if (block_kind(in[at]) != kChain)
+					break;
+			}
 		}
 	}
 
-	/* after the last round: leave all three counters zero for the next tile */
+	/* after phase B: leave the head counter zero for the next tile */
 	XA_HD void reset_counters(uint32_t tid)
 	{
 		if (tid == 0)
-			sm.n_live[0] = sm.n_live[1] = sm.n_live[2] = 0;
+			sm.n_heads = 0;
 	}
 
-	/* one 16-byte unit of interleaved PCM from the staged rows */
-	XA_HD void gather_chunk(uint32_t i, uint32_t (&w)[4]) const
+	/* one 16-byte unit (index li within its strip) of interleaved PCM */
+	XA_HD void gather_chunk(uint32_t row0, uint32_t li, uint32_t (&w)[4]) const
 	{
 		if (CH == 1) {
-			const uint32_t *s = &sm.out[row_word(i >> 2, (int)(i & 3u), 0)];
+			const uint32_t *s = &sm.out[row_word(row0 + (li >> 2), (int)(li & 3u), 0)];
 			w[0] = s[0]; w[1] = s[1]; w[2] = s[2]; w[3] = s[3];
 		} else {
-			uint32_t eb = i >> 3, jj = i & 7u;
+			uint32_t eb = li >> 3, jj = li & 7u;
 			int j = (int)(jj >> 1), h = (int)(jj & 1u) * 2;
-			const uint32_t *l = &sm.out[row_word(2 * eb, j, h)];
-			const uint32_t *r = &sm.out[row_word(2 * eb + 1, j, h)];
+			const uint32_t *l = &sm.out[row_word(row0 + 2 * eb, j, h)];
+			const uint32_t *r = &sm.out[row_word(row0 + 2 * eb + 1, j, h)];
 			w[0] = byte_perm(l[0], r[0], 0x5410);
 			w[1] = byte_perm(l[0], r[0], 0x7632);
 			w[2] = byte_perm(l[1], r[1], 0x5410);
@@ -368,56 +405,68 @@ struct DecTile {
 	/* staged rows -> interleaved PCM, 16 bytes per step.  nt % 32 == 0. */
 	XA_HD void phase_store(uint32_t tid, uint32_t nt)
 	{
-		uint8_t *dst = p.dst + out0;
-		const uint32_t nchunk = neb * (4 * CH);
-		if (out_valid == nchunk * 16u) {
-			/* every unit is whole.  With nt a multiple of 32 the
-			 * swizzle term of a thread's units is the same for all of
-			 * them, so both addresses advance by nt*16 bytes per step. */
-			uint4 *g = reinterpret_cast<uint4 *>(dst) + tid;
-			if (CH == 1) {
-				const uint4 *s = reinterpret_cast<const uint4 *>(
-				    &sm.out[row_word(tid >> 2, (int)(tid & 3u), 0)]);
-				for (uint32_t i = tid; i < nchunk; i += nt) {
-					*g = *s;
-					g += nt;
-					s += nt;
+		constexpr uint32_t CPS = SBQ * 4;	/* 16-byte units per full strip */
+		if (NS == 1) {
+			const StripCtx &c = ctx[0];
+			const uint32_t nchunk = c.nq * 4;
+			if (c.out_valid == nchunk * 16u) {
+				/* every unit is whole.  With nt a multiple of 32 the
+				 * swizzle term of a thread's units is the same for
+				 * all of them, so both addresses advance by nt*16
+				 * bytes per step. */
+				uint4 *g = reinterpret_cast<uint4 *>(p.dst + c.out0) + tid;
+				if (CH == 1) {
+					const uint4 *s = reinterpret_cast<const uint4 *>(
+					    &sm.out[row_word(tid >> 2, (int)(tid & 3u), 0)]);
+					for (uint32_t i = tid; i < nchunk; i += nt) {
+						*g = *s;
+						g += nt;
+						s += nt;
+					}
+				} else {
+					const uint32_t jj = tid & 7u;
+					const int j = (int)(jj >> 1), h = (int)(jj & 1u) * 2;
+					const uint2 *l = reinterpret_cast<const uint2 *>(
+					    &sm.out[row_word(2 * (tid >> 3), j, h)]);
+					const uint2 *r = reinterpret_cast<const uint2 *>(
+					    &sm.out[row_word(2 * (tid >> 3) + 1, j, h)]);
+					for (uint32_t i = tid; i < nchunk; i += nt) {
+						uint2 a = *l, b = *r;
+						uint4 v;
+						v.x = byte_perm(a.x, b.x, 0x5410);
+						v.y = byte_perm(a.x, b.x, 0x7632);
+						v.z = byte_perm(a.y, b.y, 0x5410);
+						v.w = byte_perm(a.y, b.y, 0x7632);
+						*g = v;
+						g += nt;
+						l += nt * 2;	/* nt units = nt*16 B of rows */
+						r += nt * 2;
+					}
 				}
-			} else {
-				const uint32_t jj = tid & 7u;
-				const int j = (int)(jj >> 1), h = (int)(jj & 1u) * 2;
-				const uint2 *l = reinterpret_cast<const uint2 *>(
-				    &sm.out[row_word(2 * (tid >> 3), j, h)]);
-				const uint2 *r = reinterpret_cast<const uint2 *>(
-				    &sm.out[row_word(2 * (tid >> 3) + 1, j, h)]);
-				for (uint32_t i = tid; i < nchunk; i += nt) {
-					uint2 a = *l, b = *r;
-					uint4 v;
-					v.x = byte_perm(a.x, b.x, 0x5410);
-					v.y = byte_perm(a.x, b.x, 0x7632);
-					v.z = byte_perm(a.y, b.y, 0x5410);
-					v.w = byte_perm(a.y, b.y, 0x7632);
-					*g = v;
-					g += nt;
-					l += nt * 2;	/* nt units = nt/8 pairs of rows = nt*16 B */
-					r += nt * 2;
-				}
+				return;
 			}
-			return;
 		}
-		/* the truncated last block of a stream */
-		for (uint32_t i = tid; i < nchunk; i += nt) {
-			uint32_t w[4];
-			uint32_t boff = i * 16u;
-			if (boff >= out_valid)
+		/* general form: many strips, or the truncated last block of a stream */
+		const uint32_t total = n_strips * CPS;
+		for (uint32_t i = tid; i < total; i += nt) {
+			const uint32_t st = i / CPS, li = i % CPS;
+			const StripCtx &c = ctx[st];
+			const uint32_t boff = li * 16u;
+			if (boff >= c.out_valid)
 				continue;
-			gather_chunk(i, w);
-			uint32_t n16 = (out_valid - boff) / 2u;
-			if (n16 > 8u)
-				n16 = 8u;
-			uint16_t *d = reinterpret_cast<uint16_t *>(dst + boff);
-			for (uint32_t k = 0; k < n16; k++)
-				d[k] = (uint16_t)(w[k >> 1] >> (16u * (k & 1u)));
+			uint32_t w[4];
+			gather_chunk(st * SBQ, li, w);
+			uint8_t *d8 = p.dst + c.out0 + boff;
+			if (boff + 16u <= c.out_valid) {
+				uint4 v;
+				v.x = w[0]; v.y = w[1]; v.z = w[2]; v.w = w[3];
+				*reinterpret_cast<uint4 *>(d8) = v;
+			} else {
+				uint16_t *d = reinterpret_cast<uint16_t *>(d8);
+				uint32_t n16 = (c.out_valid - boff) / 2u;
+				for (uint32_t k = 0; k < n16; k++)
+					d[k] = (uint16_t)(w[k >> 1] >> (16u * (k & 1u)));
+			}
 		}
 	}
 };
@@ -458,9 +507,9 @@ struct EncTile {
 	    : p(p_), sm(sm_)
 	{
 		const TileEnt te = p.tiles[tile];
-		const StreamDev &s = p.streams[te.stream];
-		stream = te.stream;
-		first_eb = te.first_eb;
+		const StreamDev &s = p.streams[te.first];
+		stream = te.first;
+		first_eb = te.j;
 		uint32_t rem = s.blocks - first_eb;
 		neb = rem < (uint32_t)TBE ? rem : (uint32_t)TBE;
 		uint64_t done = (uint64_t)first_eb * (64 * CH);

@@ -30,41 +30,57 @@ visit(uint32_t i, uint32_t nt, int order)
 	return i;
 }
 
-template <int BITS, int CH>
+template <int BITS, int CH, int NS>
 static void
-emul_decode_bucket(const DecodeParams &p, int order)
+emul_decode_ns(const DecodeParams &p, int order)
 {
-	typedef DecTile<BITS, CH, kDecTBQ, kDecStages> Tile;
+	typedef DecTile<BITS, CH, kDecTBQ, NS, kDecStages> Tile;
 	typename Tile::Smem *sm = new typename Tile::Smem();
 	const uint32_t nt = kDecThreads;
 
 	memset(sm, 0xa5, sizeof *sm);	/* smem is garbage at CTA start */
-	sm->n_live[0] = sm->n_live[1] = sm->n_live[2] = 0;
+	sm->n_heads = 0;
 	for (uint32_t ticket = 0; ticket < p.n_tiles; ticket++) {
 		/* one persistent CTA draws every ticket; stages rotate as on the GPU */
 		const int s = (int)(ticket % kDecStages);
 		memset(sm->in[s], 0xa5, sizeof sm->in[s]);
-		make_dec_ctx<BITS, CH, kDecTBQ>(sm->ctx[s], p, ticket);
-		memcpy(sm->in[s], p.src + sm->ctx[s].a0, sm->ctx[s].bulk);
+		const TileEnt te = p.tiles[ticket];
+		bool tail = false;
+		for (uint32_t lane = 0; lane < te.count; lane++) {
+			StripCtx &c = sm->ctx[s][lane];
+			make_strip_ctx<BITS, CH, kDecTBQ, NS>(c, p, p.order[te.first + lane],
+			    te.j, lane);
+			memcpy(sm->in[s] + lane * Tile::G::SLOT, p.src + c.a0, c.bulk);
+			tail |= (c.flags & kCtxTail) != 0;
+		}
+		sm->n_strips[s] = te.count;
+		sm->tile_flags[s] = tail ? kCtxTail : 0u;
 		Tile t(p, *sm, s);
-		if (t.in_need > t.bulk)
+		if (tail)
 			for (uint32_t i = 0; i < nt; i++)
 				t.load_tail(visit(i, nt, order), nt, sm->in[s]);
 		for (uint32_t i = 0; i < nt; i++)
 			t.phase_a(visit(i, nt, order), nt);
-		for (int r = 0;; r++) {
-			int n = sm->n_live[r % 3];
-			if (n == 0)
-				break;
+		int heads = sm->n_heads;
+		if (heads != 0)
 			for (uint32_t i = 0; i < nt; i++)
-				t.phase_round(visit(i, nt, order), nt, r, n);
-		}
+				t.phase_walk(visit(i, nt, order), nt, heads);
 		for (uint32_t i = 0; i < nt; i++)
 			t.reset_counters(visit(i, nt, order));
 		for (uint32_t i = 0; i < nt; i++)
 			t.phase_store(visit(i, nt, order), nt);
 	}
 	delete sm;
+}
+
+template <int BITS, int CH>
+static void
+emul_decode_bucket(const DecodeParams &p, int ns, int order)
+{
+	if (ns == 1)
+		emul_decode_ns<BITS, CH, 1>(p, order);
+	else
+		emul_decode_ns<BITS, CH, kDecWide>(p, order);
 }
 
 template <int BITS, int CH>
@@ -99,11 +115,11 @@ extern "C" {
 int
 xa_emul_decode(const bjxa_stream_desc_t *descs, size_t n, const uint8_t *src,
     uint64_t src_bytes, uint8_t *dst, int16_t *prev_out, uint32_t *first_bad,
-    int order)
+    int order, int force_strips)
 {
 	HostPlan hp;
 	size_t bad = 0;
-	int rc = build_plan(hp, kKindDecode, descs, n, &bad);
+	int rc = build_plan(hp, kKindDecode, descs, n, &bad, force_strips);
 	if (rc)
 		return rc;
 	std::vector<StreamRes> res(n);
@@ -127,17 +143,18 @@ xa_emul_decode(const bjxa_stream_desc_t *descs, size_t n, const uint8_t *src,
 		p.first_bad = first_bad;
 		p.tiles = hp.tiles.data() + t0;
 		p.n_tiles = t1 - t0;
+		p.order = hp.order.data();
 		p.carry = carry.data();
 		p.ticket = &ticket;
 		p.fault = &fault;
 		p.epoch = 7;
 		switch (b) {
-		case 0: emul_decode_bucket<4, 1>(p, order); break;
-		case 1: emul_decode_bucket<4, 2>(p, order); break;
-		case 2: emul_decode_bucket<6, 1>(p, order); break;
-		case 3: emul_decode_bucket<6, 2>(p, order); break;
-		case 4: emul_decode_bucket<8, 1>(p, order); break;
-		default: emul_decode_bucket<8, 2>(p, order); break;
+		case 0: emul_decode_bucket<4, 1>(p, hp.ns[b], order); break;
+		case 1: emul_decode_bucket<4, 2>(p, hp.ns[b], order); break;
+		case 2: emul_decode_bucket<6, 1>(p, hp.ns[b], order); break;
+		case 3: emul_decode_bucket<6, 2>(p, hp.ns[b], order); break;
+		case 4: emul_decode_bucket<8, 1>(p, hp.ns[b], order); break;
+		default: emul_decode_bucket<8, 2>(p, hp.ns[b], order); break;
 		}
 	}
 	memcpy(prev_out, res.data(), n * sizeof(StreamRes));
@@ -177,28 +194,33 @@ xa_emul_encode(const bjxa_stream_desc_t *descs, size_t n, const uint8_t *src,
 	return 0;
 }
 
-/* plan introspection for the host-logic tests */
+/* plan introspection for the host-logic tests: tiles as (first stream of the
+ * tile, strip count, j) */
 int
-xa_emul_plan(int kind, const bjxa_stream_desc_t *descs, size_t n,
-    uint32_t *tile_stream, uint32_t *tile_first, uint32_t cap,
-    uint32_t *tile_begin /* 7 */, uint32_t *n_slots)
+xa_emul_plan(int kind, const bjxa_stream_desc_t *descs, size_t n, int force_strips,
+    uint32_t *tile_stream, uint32_t *tile_count, uint32_t *tile_j, uint32_t cap,
+    uint32_t *tile_begin /* 7 */, uint32_t *n_slots, int *ns /* 6 */)
 {
 	HostPlan hp;
 	size_t bad = 0;
-	int rc = build_plan(hp, kind, descs, n, &bad);
+	int rc = build_plan(hp, kind, descs, n, &bad, force_strips);
 	if (rc)
 		return -rc;
 	uint32_t nt = (uint32_t)hp.tiles.size();
 	for (uint32_t i = 0; i < nt && i < cap; i++) {
-		tile_stream[i] = hp.tiles[i].stream;
-		tile_first[i] = hp.tiles[i].first_eb;
+		tile_stream[i] = kind == kKindDecode ? hp.order[hp.tiles[i].first] :
+		    hp.tiles[i].first;
+		tile_count[i] = hp.tiles[i].count;
+		tile_j[i] = hp.tiles[i].j;
 	}
 	memcpy(tile_begin, hp.tile_begin, 7 * sizeof(uint32_t));
+	memcpy(ns, hp.ns, 6 * sizeof(int));
 	*n_slots = hp.n_slots;
 	return (int)nt;
 }
 
-int xa_emul_dec_tile_blocks(int ch) { return kDecTBQ / ch; }
+int xa_emul_strip_blocks(int ns, int ch) { return (int)strip_blocks(ns, ch); }
+int xa_emul_wide(void) { return kDecWide; }
 int xa_emul_enc_tile_blocks(void) { return kEncTBE; }
 
 }

@@ -18,17 +18,23 @@ class Emul:
         self.dll = d = C.CDLL(SO)
         d.xa_emul_decode.restype = C.c_int
         d.xa_emul_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64,
-                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         d.xa_emul_encode.restype = C.c_int
         d.xa_emul_encode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64,
                                      C.c_void_p, C.c_uint64, C.c_int]
         d.xa_emul_plan.restype = C.c_int
-        d.xa_emul_plan.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
-                                   C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
-        self.dec_tile_blocks = d.xa_emul_dec_tile_blocks
+        d.xa_emul_plan.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]
+        self.strip_blocks = d.xa_emul_strip_blocks      # (ns, ch) -> effective blocks
+        self.wide = d.xa_emul_wide()
         self.enc_tile_blocks = d.xa_emul_enc_tile_blocks
 
-    def decode(self, descs, src, dst_bytes, order=0):
+    def dec_tile_blocks(self, ch):
+        """effective blocks of one long (NS = 1) strip"""
+        return self.strip_blocks(1, ch)
+
+    def decode(self, descs, src, dst_bytes, order=0, strips=0):
         assert descs.dtype == DESC_DTYPE
         src = np.ascontiguousarray(src, dtype=np.uint8)
         dst = np.full(dst_bytes, 0xCD, dtype=np.uint8)
@@ -36,7 +42,7 @@ class Emul:
         bad = np.zeros(descs.size, dtype=np.uint32)
         rc = self.dll.xa_emul_decode(descs.ctypes.data, descs.size, src.ctypes.data,
                                      src.size, dst.ctypes.data, prev.ctypes.data,
-                                     bad.ctypes.data, order)
+                                     bad.ctypes.data, order, strips)
         return rc, dst, prev, bad
 
     def encode(self, descs, src, dst_bytes, order=0):
@@ -46,13 +52,18 @@ class Emul:
                                      src.size, dst.ctypes.data, dst.size, order)
         return rc, dst
 
-    def plan(self, kind, descs, cap=1 << 20):
+    def plan(self, kind, descs, strips=0, cap=1 << 20):
+        """-> (n_tiles, first stream of each tile, strip counts, j, tile_begin,
+        n_slots, strips per tile of each bucket)"""
         ts = np.zeros(cap, dtype=np.uint32)
-        tf = np.zeros(cap, dtype=np.uint32)
+        tc = np.zeros(cap, dtype=np.uint32)
+        tj = np.zeros(cap, dtype=np.uint32)
         tb = np.zeros(7, dtype=np.uint32)
+        nsb = np.zeros(6, dtype=np.int32)
         ns = C.c_uint32(0)
-        n = self.dll.xa_emul_plan(kind, descs.ctypes.data, descs.size, ts.ctypes.data,
-                                  tf.ctypes.data, cap, tb.ctypes.data, C.byref(ns))
+        n = self.dll.xa_emul_plan(kind, descs.ctypes.data, descs.size, strips,
+                                  ts.ctypes.data, tc.ctypes.data, tj.ctypes.data, cap,
+                                  tb.ctypes.data, C.byref(ns), nsb.ctypes.data)
         if n < 0:
-            return n, None, None, None, None
-        return n, ts[:n], tf[:n], tb, ns.value
+            return n, None, None, None, None, None, None
+        return n, ts[:n], tc[:n], tj[:n], tb, ns.value, nsb

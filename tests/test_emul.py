@@ -16,9 +16,12 @@ def emul():
     return Emul()
 
 
-def _run_decode(emul, oracle, specs, order=0, **kw):
+STRIP_MODES = [1, 32]      # one long strip per tile / 32 short ones
+
+
+def _run_decode(emul, oracle, specs, order=0, strips=0, **kw):
     descs, arena, pcm_bytes, pays = batchgen.decode_batch(specs, **kw)
-    rc, dst, prev, bad = emul.decode(descs, arena, pcm_bytes + 64, order)
+    rc, dst, prev, bad = emul.decode(descs, arena, pcm_bytes + 64, order, strips)
     assert rc == 0
     return batchgen.check_decode(oracle, specs, descs, pays, dst, prev, bad)
 
@@ -26,16 +29,28 @@ def _run_decode(emul, oracle, specs, order=0, **kw):
 @pytest.mark.parametrize("bits", [4, 6, 8])
 @pytest.mark.parametrize("ch", [1, 2])
 @pytest.mark.parametrize("mix", ["P0", "P1", "P2", "P3"])
-def test_decode_one_stream_multi_tile(emul, oracle, bits, ch, mix):
+@pytest.mark.parametrize("strips", STRIP_MODES)
+def test_decode_one_stream_multi_tile(emul, oracle, bits, ch, mix, strips):
     tb = emul.dec_tile_blocks(ch)
-    samples = 32 * (2 * tb + 37) + 11          # 3 tiles, ragged last block
+    samples = 32 * (2 * tb + 37) + 11          # 3 long tiles, ragged last block
     specs = [dict(bits=bits, channels=ch, samples=samples, mix=mix,
                   prev=((1234, -4321), (-77, 31000)), key=bits * 10 + ch)]
-    _run_decode(emul, oracle, specs)
+    _run_decode(emul, oracle, specs, strips=strips)
+
+
+@pytest.mark.parametrize("mix", ["P1", "P3"])
+def test_decode_many_streams_wide(emul, oracle, mix):
+    """Wide tiles over many streams of different lengths, so the last tiles of
+    every step are only partly filled."""
+    specs = [dict(bits=(8, 4, 6)[i % 3], channels=1 + (i // 3) % 2,
+                  samples=32 * (20 + (i * 7) % 50) + i % 32, mix=mix, key=700 + i,
+                  prev=((i, -i), (3 * i, 1))) for i in range(240)]
+    _run_decode(emul, oracle, specs, strips=32, xa_gap=4)
 
 
 @pytest.mark.parametrize("order", [0, 1, 2])
-def test_decode_mixed_batch(emul, oracle, order):
+@pytest.mark.parametrize("strips", STRIP_MODES)
+def test_decode_mixed_batch(emul, oracle, order, strips):
     specs = []
     k = 0
     for bits in (4, 6, 8):
@@ -45,28 +60,31 @@ def test_decode_mixed_batch(emul, oracle, order):
                 specs.append(dict(bits=bits, channels=ch, samples=samples,
                                   mix=synth.MIXES[k % 4], key=100 + k,
                                   prev=((k, -k), (7 * k, 3))))
-    _run_decode(emul, oracle, specs, order=order, xa_gap=5)
+    _run_decode(emul, oracle, specs, order=order, strips=strips, xa_gap=5)
 
 
-def test_decode_every_tail_length(emul, oracle):
+@pytest.mark.parametrize("strips", STRIP_MODES)
+def test_decode_every_tail_length(emul, oracle, strips):
     specs = [dict(bits=(4, 6, 8)[r % 3], channels=1 + r % 2, samples=64 + r,
                   mix="P2", key=300 + r) for r in range(32)]
-    _run_decode(emul, oracle, specs, xa_gap=3)
+    _run_decode(emul, oracle, specs, strips=strips, xa_gap=3)
 
 
-def test_decode_exact_tile_multiples(emul, oracle):
+@pytest.mark.parametrize("strips", STRIP_MODES)
+def test_decode_exact_tile_multiples(emul, oracle, strips):
     specs = []
     for ch in (1, 2):
-        tb = emul.dec_tile_blocks(ch)
+        tb = emul.strip_blocks(strips, ch)
         for nt in (1, 2):
             specs.append(dict(bits=8, channels=ch, samples=32 * tb * nt, mix="P3",
                               key=400 + ch * 10 + nt))
             specs.append(dict(bits=4, channels=ch, samples=32 * tb * nt + 1, mix="P2",
                               key=450 + ch * 10 + nt))
-    _run_decode(emul, oracle, specs)
+    _run_decode(emul, oracle, specs, strips=strips)
 
 
-def test_decode_bad_profile(emul, oracle):
+@pytest.mark.parametrize("strips", STRIP_MODES)
+def test_decode_bad_profile(emul, oracle, strips):
     """filter >= 5: the stream reports its first bad block; everything before
     it is exact (src/libbjxa.c:550,634,642)."""
     tb = emul.dec_tile_blocks(2)
@@ -79,7 +97,7 @@ def test_decode_bad_profile(emul, oracle):
         dict(bits=8, channels=1, samples=32 * 10, mix="P0", key=5),
     ]
     descs, arena, pcm_bytes, pays = batchgen.decode_batch(specs)
-    rc, dst, prev, bad = emul.decode(descs, arena, pcm_bytes + 64)
+    rc, dst, prev, bad = emul.decode(descs, arena, pcm_bytes + 64, 0, strips)
     assert rc == 0
     assert list(bad) == [17, 19, 2 * (tb + 3), 0, 0xFFFFFFFF]
     batchgen.check_decode(oracle, specs, descs, pays, dst, prev, bad)
@@ -98,7 +116,8 @@ def test_decode_saturation_vector(emul, oracle):
     assert pcm[0, 0] == 32512 and (pcm[1:, 0] == 32767).all() and (pcm[:, 1] == -32768).all()
 
 
-def test_decode_chunked_equals_whole(emul, oracle):
+@pytest.mark.parametrize("strips", STRIP_MODES)
+def test_decode_chunked_equals_whole(emul, oracle, strips):
     """Feeding a stream in pieces with the state carried by the caller gives the
     same bytes (the codec object is the checkpoint: libbjxa.c:570-571,654-655)."""
     bits, ch, blocks = 6, 2, 900
@@ -114,14 +133,15 @@ def test_decode_chunked_equals_whole(emul, oracle):
         d[0]["pcm_len"] = (b - a) * 64 * ch
         d[0]["bits"], d[0]["channels"] = bits, ch
         d[0]["prev"] = state
-        rc, dst, prev, bad = emul.decode(d, pay[a * bs:b * bs], (b - a) * 64 * ch)
+        rc, dst, prev, bad = emul.decode(d, pay[a * bs:b * bs], (b - a) * 64 * ch, 0, strips)
         out.append(dst[:(b - a) * 64 * ch])
         state = prev[0]
     assert np.array_equal(np.concatenate(out).view(np.int16), whole[2])
     assert np.array_equal(state, whole[3])
 
 
-def test_decode_arena_tail_not_multiple_of_16(emul, oracle):
+@pytest.mark.parametrize("strips", STRIP_MODES)
+def test_decode_arena_tail_not_multiple_of_16(emul, oracle, strips):
     """The last stream ends flush with an arena whose size is not a multiple of
     16: the bulk copy must stop short and the tail be fetched bytewise."""
     for trim in range(0, 16):
@@ -129,7 +149,8 @@ def test_decode_arena_tail_not_multiple_of_16(emul, oracle):
         descs, arena, pcm_bytes, pays = batchgen.decode_batch(specs)
         pre = np.zeros(trim, dtype=np.uint8)
         descs[0]["xa_off"] = trim
-        rc, dst, prev, bad = emul.decode(descs, np.concatenate([pre, arena]), pcm_bytes + 64)
+        rc, dst, prev, bad = emul.decode(descs, np.concatenate([pre, arena]), pcm_bytes + 64,
+                                         0, strips)
         batchgen.check_decode(oracle, specs, descs, pays, dst, prev, bad)
 
 
@@ -150,21 +171,41 @@ def test_encode_mixed_batch(emul, oracle, order):
 
 
 def test_plan_order_and_validation(emul):
-    """Host planning logic: every tile of a stream after its predecessor,
-    time-major issue, EINVAL on bad descriptors."""
-    tb1, tb2 = emul.dec_tile_blocks(1), emul.dec_tile_blocks(2)
+    """Host planning logic: every strip of a stream after its predecessor,
+    time-major issue, the tile shape follows the stream count, EINVAL on bad
+    descriptors."""
+    tb1, tb2 = emul.strip_blocks(1, 1), emul.strip_blocks(1, 2)
     d = batchgen.make_descs(5)
     for i, (bits, ch, blocks) in enumerate([(8, 1, 3 * tb1 + 1), (8, 1, tb1), (4, 2, 2 * tb2),
                                             (8, 1, 0), (8, 1, 2 * tb1 + 5)]):
         d[i]["bits"], d[i]["channels"], d[i]["blocks"] = bits, ch, blocks
         d[i]["pcm_len"] = blocks * 64 * ch
-    n, ts, tf, tb, slots = emul.plan(0, d)
-    assert n == 4 + 1 + 2 + 0 + 3 and slots == n
+    n, ts, tc, tj, tb, slots, nsb = emul.plan(0, d)
+    assert n == 4 + 1 + 2 + 0 + 3 and slots == n and (tc == 1).all()
+    assert list(nsb) == [1] * 6             # few streams: one long strip per tile
     b81 = slice(tb[4], tb[5])
-    assert list(zip(ts[b81], tf[b81])) == [(0, 0), (4, 0), (1, 0), (0, tb1), (4, tb1),
-                                           (0, 2 * tb1), (4, 2 * tb1), (0, 3 * tb1)]
-    assert list(zip(ts[tb[1]:tb[2]], tf[tb[1]:tb[2]])) == [(2, 0), (2, tb2)]
+    assert list(zip(ts[b81], tj[b81])) == [(0, 0), (4, 0), (1, 0), (0, 1), (4, 1),
+                                           (0, 2), (4, 2), (0, 3)]
+    assert list(zip(ts[tb[1]:tb[2]], tj[tb[1]:tb[2]])) == [(2, 0), (2, 1)]
     for field, val in (("bits", 5), ("channels", 3), ("pcm_off", 8), ("pcm_len", 3)):
         e = d.copy()
         e[0][field] = val
         assert emul.plan(0, e)[0] == -22
+
+    # wide tiles of `wide` strips, partly filled at the end of a step
+    w = emul.wide
+    sb = emul.strip_blocks(w, 1)
+    m = 2 * w + 5
+    d = batchgen.make_descs(m)
+    d["bits"], d["channels"] = 8, 1
+    d["blocks"] = [3 * sb if i < w + 2 else sb + 1 for i in range(m)]
+    d["pcm_len"] = d["blocks"] * 64
+    assert emul.plan(0, d)[6][4] == 1       # too few streams for the automatic choice
+    n, ts, tc, tj, tb, slots, nsb = emul.plan(0, d, strips=w)
+    assert nsb[4] == w
+    assert list(tc) == [w, w, 5, w, w, 5, w, 2]
+    assert list(tj) == [0, 0, 0, 1, 1, 1, 2, 2]
+    assert slots == (w + 2) * 3 + (w + 3) * 2
+    big = batchgen.make_descs(20000)
+    big["bits"], big["channels"], big["blocks"], big["pcm_len"] = 4, 2, 3, 3 * 128
+    assert emul.plan(0, big)[6][1] == w     # a corpus-sized batch goes wide by itself

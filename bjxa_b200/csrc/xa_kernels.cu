@@ -174,6 +174,12 @@ xa_decode_kernel(const DecodeParams p)
 			consumer_sync();
 		}
 
+		/* NS == 1: the store needs three words of the context; every thread
+		 * takes them to registers BEFORE the next barrier so that the stage
+		 * (context included) can go back to the producer ahead of the store */
+		const uint64_t c0_out0 = sm.ctx[s][0].out0;
+		const uint32_t c0_nq = sm.ctx[s][0].nq, c0_valid = sm.ctx[s][0].out_valid;
+
 		t.phase_a(tid, kDecThreads);
 		consumer_sync();
 		const int heads = sm.n_heads;
@@ -182,11 +188,17 @@ xa_decode_kernel(const DecodeParams p)
 			consumer_sync();
 		}
 		t.reset_counters(tid);
-		t.phase_store(tid, kDecThreads);
-		consumer_sync();	/* rows are free for the next tile's phase A */
-		/* nobody reads this stage's source bytes or context any more */
-		if (tid == 0)
-			mbar_arrive(smem_u32(&sm.empty[s]));
+		if (NS == 1) {
+			if (tid == 0)
+				mbar_arrive(smem_u32(&sm.empty[s]));
+			t.phase_store_one(tid, kDecThreads, c0_out0, c0_nq, c0_valid);
+			consumer_sync();	/* rows are free for the next tile's phase A */
+		} else {
+			t.phase_store(tid, kDecThreads);
+			consumer_sync();
+			if (tid == 0)
+				mbar_arrive(smem_u32(&sm.empty[s]));
+		}
 	}
 }
 

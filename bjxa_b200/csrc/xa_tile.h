@@ -92,7 +92,10 @@ XA_HD int smem_inc(int *p) { return atomicAdd(p, 1); }
 XA_HD void global_min_u32(uint32_t *p, uint32_t v) { atomicMin(p, v); }
 XA_HD void mailbox_put(unsigned long long *p, unsigned long long v)
 {
-	asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+	/* the 64-bit word carries its own tag and payload: no ordering with any
+	 * other store is needed, so no fence (a release store costs a MEMBAR that
+	 * stalls the publishing warp -- and the CTA barrier behind it) */
+	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 XA_HD unsigned long long mailbox_get(const unsigned long long *p, uint32_t epoch,
     uint32_t *fault)
@@ -102,7 +105,7 @@ XA_HD unsigned long long mailbox_get(const unsigned long long *p, uint32_t epoch
 	 * and this wait is short.  It is still bounded (~10 s): a kernel must
 	 * never hang the device; on expiry the launch is flagged as failed. */
 	for (uint32_t spins = 0; spins < (1u << 24); spins++) {
-		asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+		asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
 		if ((uint32_t)(v >> 32) == epoch)
 			return v;
 		__nanosleep(spins < 64 ? 32 : 512);
@@ -402,51 +405,75 @@ struct DecTile {
 		}
 	}
 
-	/* staged rows -> interleaved PCM, 16 bytes per step.  nt % 32 == 0. */
+	/*
+	 * staged rows -> interleaved PCM, 16 bytes per step, for a tile that is
+	 * one strip (NS == 1); takes what it needs of the context by value so
+	 * that the stage can be handed back before the store.  nt % 32 == 0.
+	 */
+	XA_HD void phase_store_one(uint32_t tid, uint32_t nt, uint64_t out0, uint32_t nq,
+	    uint32_t out_valid)
+	{
+		const uint32_t nchunk = nq * 4;
+		uint8_t *dst = p.dst + out0;
+		if (out_valid == nchunk * 16u) {
+			/* every unit is whole.  With nt a multiple of 32 the swizzle
+			 * term of a thread's units is the same for all of them, so
+			 * both addresses advance by nt*16 bytes per step. */
+			uint4 *g = reinterpret_cast<uint4 *>(dst) + tid;
+			if (CH == 1) {
+				const uint4 *s = reinterpret_cast<const uint4 *>(
+				    &sm.out[row_word(tid >> 2, (int)(tid & 3u), 0)]);
+				for (uint32_t i = tid; i < nchunk; i += nt) {
+					*g = *s;
+					g += nt;
+					s += nt;
+				}
+			} else {
+				const uint32_t jj = tid & 7u;
+				const int j = (int)(jj >> 1), h = (int)(jj & 1u) * 2;
+				const uint2 *l = reinterpret_cast<const uint2 *>(
+				    &sm.out[row_word(2 * (tid >> 3), j, h)]);
+				const uint2 *r = reinterpret_cast<const uint2 *>(
+				    &sm.out[row_word(2 * (tid >> 3) + 1, j, h)]);
+				for (uint32_t i = tid; i < nchunk; i += nt) {
+					uint2 a = *l, b = *r;
+					uint4 v;
+					v.x = byte_perm(a.x, b.x, 0x5410);
+					v.y = byte_perm(a.x, b.x, 0x7632);
+					v.z = byte_perm(a.y, b.y, 0x5410);
+					v.w = byte_perm(a.y, b.y, 0x7632);
+					*g = v;
+					g += nt;
+					l += nt * 2;	/* nt units = nt*16 B of rows */
+					r += nt * 2;
+				}
+			}
+			return;
+		}
+		/* the truncated last block of a stream */
+		for (uint32_t i = tid; i < nchunk; i += nt) {
+			const uint32_t boff = i * 16u;
+			if (boff >= out_valid)
+				continue;
+			uint32_t w[4];
+			gather_chunk(0, i, w);
+			uint32_t n16 = (out_valid - boff) / 2u;
+			if (n16 > 8u)
+				n16 = 8u;
+			uint16_t *d = reinterpret_cast<uint16_t *>(dst + boff);
+			for (uint32_t k = 0; k < n16; k++)
+				d[k] = (uint16_t)(w[k >> 1] >> (16u * (k & 1u)));
+		}
+	}
+
+	/* the same for any number of strips, reading the contexts in place */
 	XA_HD void phase_store(uint32_t tid, uint32_t nt)
 	{
 		constexpr uint32_t CPS = SBQ * 4;	/* 16-byte units per full strip */
 		if (NS == 1) {
-			const StripCtx &c = ctx[0];
-			const uint32_t nchunk = c.nq * 4;
-			if (c.out_valid == nchunk * 16u) {
-				/* every unit is whole.  With nt a multiple of 32 the
-				 * swizzle term of a thread's units is the same for
-				 * all of them, so both addresses advance by nt*16
-				 * bytes per step. */
-				uint4 *g = reinterpret_cast<uint4 *>(p.dst + c.out0) + tid;
-				if (CH == 1) {
-					const uint4 *s = reinterpret_cast<const uint4 *>(
-					    &sm.out[row_word(tid >> 2, (int)(tid & 3u), 0)]);
-					for (uint32_t i = tid; i < nchunk; i += nt) {
-						*g = *s;
-						g += nt;
-						s += nt;
-					}
-				} else {
-					const uint32_t jj = tid & 7u;
-					const int j = (int)(jj >> 1), h = (int)(jj & 1u) * 2;
-					const uint2 *l = reinterpret_cast<const uint2 *>(
-					    &sm.out[row_word(2 * (tid >> 3), j, h)]);
-					const uint2 *r = reinterpret_cast<const uint2 *>(
-					    &sm.out[row_word(2 * (tid >> 3) + 1, j, h)]);
-					for (uint32_t i = tid; i < nchunk; i += nt) {
-						uint2 a = *l, b = *r;
-						uint4 v;
-						v.x = byte_perm(a.x, b.x, 0x5410);
-						v.y = byte_perm(a.x, b.x, 0x7632);
-						v.z = byte_perm(a.y, b.y, 0x5410);
-						v.w = byte_perm(a.y, b.y, 0x7632);
-						*g = v;
-						g += nt;
-						l += nt * 2;	/* nt units = nt*16 B of rows */
-						r += nt * 2;
-					}
-				}
-				return;
-			}
+			phase_store_one(tid, nt, ctx[0].out0, ctx[0].nq, ctx[0].out_valid);
+			return;
 		}
-		/* general form: many strips, or the truncated last block of a stream */
 		const uint32_t total = n_strips * CPS;
 		for (uint32_t i = tid; i < total; i += nt) {
 			const uint32_t st = i / CPS, li = i % CPS;

@@ -44,7 +44,7 @@ PCM_PITCH = (BLOCKS * 64 * CH + 15) & ~15      # 5 292 032
 ALGO_BYTES_PER_STREAM = XA_BYTES + PCM_BYTES   # data_len + samples*ch*2
 HEADLINE_MIX = "P1"
 MIXES = ("P0", "P1", "P2", "P3")
-E2E_STREAMS = int(os.environ.get("BJXA_BENCH_E2E_STREAMS", 256))
+E2E_STREAMS = int(os.environ.get("BJXA_BENCH_E2E_STREAMS", 512))
 
 
 def mix_profiles(torch, mix, n, blocks, device, seed):

@@ -69,6 +69,10 @@ BATCH_SYMBOLS = {
     "bjxa_gpu_upload": (C.c_int, [_VP, _VP, _SZ]),
     "bjxa_gpu_download": (C.c_int, [_VP, _VP, _SZ]),
     "bjxa_gpu_sync": (C.c_int, [_VP]),
+    "bjxa_gpu_stream_create": (_VP, []),
+    "bjxa_gpu_stream_destroy": (C.c_int, [_VP]),
+    "bjxa_gpu_upload_async": (C.c_int, [_VP, _VP, _SZ, _VP]),
+    "bjxa_gpu_download_async": (C.c_int, [_VP, _VP, _SZ, _VP]),
     "bjxa_shard_range": (C.c_int, [_VP, _SZ, C.c_int, C.c_int,
                                    C.POINTER(_SZ), C.POINTER(_SZ)]),
 }

@@ -588,8 +588,22 @@ bjxa_encoder_commit(bjxa_encoder_t *enc, const bjxa_stream_desc_t *d)
 
 /* ---- per-thread staging for the host-buffer calls -------------------------- */
 
+/*
+ * Host batches are cut into chunks of streams and pushed through a software
+ * pipeline PIPE_DEPTH deep, one CUDA stream per slot:
+ *     upload(c) -> kernels(c) -> [results(c)] -> download(c)
+ * so that, with pinned caller buffers, the upload of one chunk overlaps the
+ * download of another (PCIe is full duplex) and both overlap the kernels.
+ * The results of a chunk are fetched BEFORE its download is queued because a
+ * stream that met a bad profile must only deliver the blocks in front of it
+ * (libbjxa.c:634-648 leaves the rest of dst untouched).
+ */
+#define PIPE_DEPTH	3
+#define CHUNK_BYTES	((uint64_t)96 << 20)	/* PCM bytes per chunk, about */
+
 struct stage {
-	bjxa_plan_t	*plan;
+	bjxa_plan_t	*plan[PIPE_DEPTH];
+	void		*stream[PIPE_DEPTH];
 	void		*d_xa, *d_pcm;
 	size_t		 cap_xa, cap_pcm;
 };
@@ -614,29 +628,106 @@ stage_reserve(void **p, size_t *cap, size_t need)
 }
 
 static int
-stage_plan(struct stage *sg, int kind, const bjxa_stream_desc_t *d, size_t n)
+stage_plan(struct stage *sg, int slot, int kind, const bjxa_stream_desc_t *d,
+    size_t n)
 {
-	if (sg->plan == NULL) {
-		sg->plan = bjxa_plan_create(kind, d, n);
-		return (sg->plan == NULL ? -1 : 0);
+	if (sg->stream[slot] == NULL) {
+		sg->stream[slot] = bjxa_gpu_stream_create();
+		if (sg->stream[slot] == NULL)
+			return (-1);
 	}
-	return (bjxa_plan_reset(sg->plan, kind, d, n));
+	if (sg->plan[slot] == NULL) {
+		sg->plan[slot] = bjxa_plan_create(kind, d, n);
+		return (sg->plan[slot] == NULL ? -1 : 0);
+	}
+	return (bjxa_plan_reset(sg->plan[slot], kind, d, n));
 }
 
 #define ALIGN16(x)	(((x) + 15u) & ~(uint64_t)15u)
 
+struct chunk {
+	size_t		first, count;
+	int		slot;
+};
+
+/* queue the upload and the kernels of one chunk on its slot's stream */
+static int
+chunk_start(struct stage *sg, int kind, const struct chunk *ck,
+    bjxa_stream_desc_t *work, const void *const *srcs, const uint32_t *xa_bytes)
+{
+	void *st;
+	size_t i;
+
+	if (stage_plan(sg, ck->slot, kind, work + ck->first, ck->count) < 0)
+		return (-1);
+	st = sg->stream[ck->slot];
+	for (i = ck->first; i < ck->first + ck->count; i++) {
+		if (work[i].blocks == 0)
+			continue;
+		if (kind == BJXA_PLAN_DECODE) {
+			if (bjxa_gpu_upload_async((uint8_t *)sg->d_xa + work[i].xa_off,
+			    srcs[i], xa_bytes[i], st) < 0)
+				return (-1);
+		} else {
+			if (bjxa_gpu_upload_async((uint8_t *)sg->d_pcm + work[i].pcm_off,
+			    srcs[i], work[i].pcm_len, st) < 0)
+				return (-1);
+		}
+	}
+	if (kind == BJXA_PLAN_DECODE)
+		return (bjxa_plan_run(sg->plan[ck->slot], sg->d_pcm, sg->cap_pcm,
+		    sg->d_xa, sg->cap_xa, st));
+	return (bjxa_plan_run(sg->plan[ck->slot], sg->d_xa, sg->cap_xa, sg->d_pcm,
+	    sg->cap_pcm, st));
+}
+
+/* wait for the chunk's kernels, take its results, queue its download */
+static int
+chunk_finish(struct stage *sg, int kind, const struct chunk *ck,
+    bjxa_stream_desc_t *work, void *const *dsts)
+{
+	void *st = sg->stream[ck->slot];
+	size_t i;
+
+	if (bjxa_plan_fetch(sg->plan[ck->slot], work + ck->first, ck->count) < 0)
+		return (-1);
+	for (i = ck->first; i < ck->first + ck->count; i++) {
+		size_t bytes;
+
+		if (work[i].blocks == 0)
+			continue;
+		if (kind == BJXA_PLAN_DECODE) {
+			bytes = work[i].done == work[i].blocks ? work[i].pcm_len :
+			    (size_t)work[i].done * 64u * work[i].channels;
+			if (bytes != 0 && bjxa_gpu_download_async(dsts[i],
+			    (uint8_t *)sg->d_pcm + work[i].pcm_off, bytes, st) < 0)
+				return (-1);
+		} else {
+			bytes = (size_t)work[i].done * (4u * work[i].bits + 1u) *
+			    work[i].channels;
+			if (bytes != 0 && bjxa_gpu_download_async(dsts[i],
+			    (uint8_t *)sg->d_xa + work[i].xa_off, bytes, st) < 0)
+				return (-1);
+		}
+	}
+	return (0);
+}
+
 /*
  * The common engine behind bjxa_decode, bjxa_encode and their batch forms.
  * work[i].blocks == 0 marks a stream that takes no part (already failed its
- * argument checks).  On return work[] holds the fetched results.
+ * argument checks).  On return work[] holds the fetched results and every
+ * delivered byte has landed in the caller's buffers.
  */
 static int
 run_host_batch(int kind, bjxa_stream_desc_t *work, void *const *dsts,
     const void *const *srcs, const uint32_t *xa_bytes, size_t n)
 {
 	struct stage *sg = &tls_stage;
-	uint64_t xa_total = 0, pcm_total = 0;
-	size_t i;
+	struct chunk ring[PIPE_DEPTH];
+	uint64_t xa_total = 0, pcm_total = 0, in_chunk = 0;
+	size_t i, first = 0, queued = 0, finished = 0;
+	int k, rc = 0;
 
 	if (bjxa_gpu_count() <= 0)
 		FAIL(ENODEV);
@@ -655,57 +746,47 @@ run_host_batch(int kind, bjxa_stream_desc_t *work, void *const *dsts,
 	if (stage_reserve(&sg->d_xa, &sg->cap_xa, xa_total) < 0 ||
 	    stage_reserve(&sg->d_pcm, &sg->cap_pcm, pcm_total) < 0)
 		return (-1);
-	if (stage_plan(sg, kind, work, n) < 0)
-		return (-1);
 
-	for (i = 0; i < n; i++) {
-		if (work[i].blocks == 0)
-			continue;
-		if (kind == BJXA_PLAN_DECODE) {
-			if (bjxa_gpu_upload((uint8_t *)sg->d_xa + work[i].xa_off,
-			    srcs[i], xa_bytes[i]) < 0)
-				return (-1);
-		} else {
-			if (bjxa_gpu_upload((uint8_t *)sg->d_pcm + work[i].pcm_off,
-			    srcs[i], work[i].pcm_len) < 0)
-				return (-1);
+	for (i = 0; i <= n && rc == 0; i++) {
+		if (i < n) {
+			in_chunk += (uint64_t)work[i].blocks * 64u * work[i].channels;
+			if (in_chunk < CHUNK_BYTES && i + 1 < n)
+				continue;
+		} else if (first >= n) {
+			break;
 		}
-	}
-
-	if (kind == BJXA_PLAN_DECODE) {
-		if (bjxa_plan_run(sg->plan, sg->d_pcm, sg->cap_pcm, sg->d_xa,
-		    sg->cap_xa, NULL) < 0)
-			return (-1);
-	} else {
-		if (bjxa_plan_run(sg->plan, sg->d_xa, sg->cap_xa, sg->d_pcm,
-		    sg->cap_pcm, NULL) < 0)
-			return (-1);
-	}
-	if (bjxa_plan_fetch(sg->plan, work, n) < 0)
-		return (-1);
-
-	for (i = 0; i < n; i++) {
-		size_t bytes;
-
-		if (work[i].blocks == 0)
-			continue;
-		if (kind == BJXA_PLAN_DECODE) {
-			/* after a bad profile only the blocks before it were
-			 * copied out by the reference (libbjxa.c:634-648) */
-			bytes = work[i].done == work[i].blocks ? work[i].pcm_len :
-			    (size_t)work[i].done * 64u * work[i].channels;
-			if (bytes != 0 && bjxa_gpu_download(dsts[i],
-			    (uint8_t *)sg->d_pcm + work[i].pcm_off, bytes) < 0)
-				return (-1);
-		} else {
-			bytes = (size_t)work[i].done * (4u * work[i].bits + 1u) *
-			    work[i].channels;
-			if (bytes != 0 && bjxa_gpu_download(dsts[i],
-			    (uint8_t *)sg->d_xa + work[i].xa_off, bytes) < 0)
-				return (-1);
+		/* streams [first, i] form the next chunk */
+		if (queued - finished == PIPE_DEPTH) {
+			rc = chunk_finish(sg, kind, &ring[finished % PIPE_DEPTH], work, dsts);
+			finished++;
+			if (rc < 0)
+				break;
 		}
+		ring[queued % PIPE_DEPTH].first = first;
+		ring[queued % PIPE_DEPTH].count = (i < n ? i + 1 : n) - first;
+		ring[queued % PIPE_DEPTH].slot = (int)(queued % PIPE_DEPTH);
+		rc = chunk_start(sg, kind, &ring[queued % PIPE_DEPTH], work, srcs, xa_bytes);
+		queued++;
+		first = i + 1;
+		in_chunk = 0;
 	}
-	return (0);
+	while (rc == 0 && finished < queued) {
+		rc = chunk_finish(sg, kind, &ring[finished % PIPE_DEPTH], work, dsts);
+		finished++;
+	}
+	/* drain every slot, also on the error path: the caller's buffers must not
+	 * be written to after we return */
+	{
+		int e = errno;
+
+		for (k = 0; k < PIPE_DEPTH; k++)
+			if (sg->stream[k] != NULL && bjxa_gpu_sync(sg->stream[k]) < 0 && rc == 0) {
+				rc = -1;
+				e = errno;
+			}
+		errno = e;
+	}
+	return (rc);
 }
 
 /* argument checks of bjxa_decode, in the reference's order (libbjxa.c:612-620) */

@@ -342,6 +342,37 @@ bjxa_gpu_download(void *hptr, const void *dptr, size_t bytes)
 	return (0);
 }
 
+extern "C" void *
+bjxa_gpu_stream_create(void)
+{
+	cudaStream_t st = NULL;
+	XA_CUDA_NULL(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+	return ((void *)st);
+}
+
+extern "C" int
+bjxa_gpu_stream_destroy(void *cuda_stream)
+{
+	XA_CUDA(cudaStreamDestroy((cudaStream_t)cuda_stream));
+	return (0);
+}
+
+extern "C" int
+bjxa_gpu_upload_async(void *dptr, const void *hptr, size_t bytes, void *cuda_stream)
+{
+	XA_CUDA(cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice,
+	    (cudaStream_t)cuda_stream));
+	return (0);
+}
+
+extern "C" int
+bjxa_gpu_download_async(void *hptr, const void *dptr, size_t bytes, void *cuda_stream)
+{
+	XA_CUDA(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost,
+	    (cudaStream_t)cuda_stream));
+	return (0);
+}
+
 extern "C" int
 bjxa_gpu_sync(void *cuda_stream)
 {

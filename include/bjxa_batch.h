@@ -129,6 +129,13 @@ int    bjxa_host_free(void *hptr);
 int    bjxa_gpu_upload(void *dptr, const void *hptr, size_t bytes);
 int    bjxa_gpu_download(void *hptr, const void *dptr, size_t bytes);
 int    bjxa_gpu_sync(void *cuda_stream);
+/* asynchronous forms on a stream of the caller's (overlap needs pinned memory) */
+void  *bjxa_gpu_stream_create(void);		/* a non-blocking cudaStream_t */
+int    bjxa_gpu_stream_destroy(void *cuda_stream);
+int    bjxa_gpu_upload_async(void *dptr, const void *hptr, size_t bytes,
+	    void *cuda_stream);
+int    bjxa_gpu_download_async(void *hptr, const void *dptr, size_t bytes,
+	    void *cuda_stream);
 
 /*
  * Contiguous shard of n streams for `rank` of `world` (one process per GPU),

@@ -262,5 +262,27 @@ XA_HD void deflate_block(uint32_t (&pw)[BITS], const uint32_t (&in)[16])
 	}
 }
 
+/*
+ * The same truncation for FOUR samples at a time: returns the BITS/2 payload
+ * bytes they occupy (4-bit: 2, 6-bit: 3, 8-bit: 4), first byte in bits 0..7.
+ * s0..s3 hold the samples in their low 16 bits (upper bits ignored).
+ */
+template <int BITS>
+XA_HD uint32_t pack4(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3)
+{
+	if (BITS == 8) {
+		return ((s0 >> 8) & 0xffu) | (s1 & 0xff00u) | ((s2 & 0xff00u) << 8) |
+		    ((s3 & 0xff00u) << 16);
+	} else if (BITS == 4) {
+		uint32_t b0 = ((s0 >> 8) & 0xf0u) | ((s1 >> 12) & 0x0fu);
+		uint32_t b1 = ((s2 >> 8) & 0xf0u) | ((s3 >> 12) & 0x0fu);
+		return b0 | (b1 << 8);
+	} else {
+		uint32_t v = ((s0 >> 10) & 0x3fu) << 18 | ((s1 >> 10) & 0x3fu) << 12 |
+		    ((s2 >> 10) & 0x3fu) << 6 | ((s3 >> 10) & 0x3fu);
+		return byte_perm(v, 0u, 0x4012);	/* big-endian 24 bits -> byte order */
+	}
+}
+
 } /* namespace xa */
 #endif

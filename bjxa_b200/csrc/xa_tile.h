@@ -565,77 +565,57 @@ struct EncTile {
 			sm.in[i] = p.src[in0 + i];
 	}
 
-	/* write BS bytes (profile 0 + payload) at an arbitrary smem byte address */
-	XA_HD void put_block(uint32_t at, const uint32_t (&pw)[BITS])
+	/* n <= 4 bytes of v to an arbitrary byte address of the output image */
+	XA_HD void put_bytes(uint32_t at, uint32_t v, int n)
 	{
-		/* the block as BITS+1 little-endian words: byte 0 = profile */
-		uint32_t sw[BITS + 2];
-		sw[0] = pw[0] << 8;
 #pragma unroll
-		for (int k = 1; k < BITS; k++)
-			sw[k] = funnel_r(pw[k - 1], pw[k], 24);
-		sw[BITS] = pw[BITS - 1] >> 24;
-		sw[BITS + 1] = 0;
-
-		const uint32_t d = at & 3u;
-		uint32_t *base = reinterpret_cast<uint32_t *>(sm.out) + (at >> 2);
-		uint8_t *bbase = sm.out + (at & ~3u);
-		const uint32_t sh = (4u - d) * 8u;	/* 32 when d == 0 */
-		uint32_t prev = 0;
-#pragma unroll
-		for (int j = 0; j < BITS + 2; j++) {
-			/* destination word j holds block bytes [4j-d, 4j-d+4) */
-			uint32_t cur = sw[j];
-			uint32_t v = d ? funnel_r(prev, cur, sh & 31u) : cur;
-			prev = cur;
-			int lo = 4 * j - (int)d;
-			if (lo >= BS)
-				break;
-			if (lo >= 0 && lo + 4 <= BS) {
-				base[j] = v;
-			} else {
-#pragma unroll
-				for (int b = 0; b < 4; b++)
-					if (lo + b >= 0 && lo + b < BS)
-						bbase[4 * j + b] = (uint8_t)(v >> (8 * b));
-			}
-		}
+		for (int b = 0; b < 4; b++)
+			if (b < n)
+				sm.out[at + b] = (uint8_t)(v >> (8 * b));
 	}
 
+	/*
+	 * One thread per 16-byte unit of PCM (8 mono samples, or 4 stereo
+	 * frames): neighbouring threads read neighbouring units, so the shared
+	 * memory reads are conflict free and nothing diverges.  Every unit maps
+	 * to BITS/2 payload bytes per channel-quad at a fixed place of its
+	 * block; the profile bytes (0, libbjxa.c:679) are written separately.
+	 */
 	XA_HD void phase_pack(uint32_t tid, uint32_t nt)
 	{
-		const uint32_t *in32 = reinterpret_cast<const uint32_t *>(sm.in);
-		for (uint32_t eb = tid; eb < neb; eb += nt) {
-			/* frames of this block that exist (the rest are zero) */
-			uint32_t fr_have = in_valid / (2u * CH);
-			uint32_t fr0 = eb * 32u;
-			uint32_t fv = fr_have > fr0 ? fr_have - fr0 : 0u;
-			if (fv > 32u)
-				fv = 32u;
-#pragma unroll
-			for (int c = 0; c < CH; c++) {
-				uint32_t s16[16];
-#pragma unroll
-				for (int i = 0; i < 16; i++) {
-					uint32_t w;
-					if (CH == 1) {
-						w = in32[eb * 16u + i];
-					} else {
-						uint32_t f0 = in32[eb * 32u + 2 * i];
-						uint32_t f1 = in32[eb * 32u + 2 * i + 1];
-						w = byte_perm(f0, f1, c ? 0x7632 : 0x5410);
-					}
-					if (fv < 32u) {		/* zero-pad (libbjxa.c:686-690) */
-						if (2u * i >= fv)
-							w = 0;
-						else if (2u * i + 1 >= fv)
-							w &= 0xffffu;
-					}
-					s16[i] = w;
-				}
-				uint32_t pw[BITS];
-				deflate_block<BITS>(pw, s16);
-				put_block(out_off + (eb * CH + c) * BS, pw);
+		constexpr uint32_t UPE = 4 * CH;	/* units per effective block */
+		constexpr int QB = BITS / 2;		/* payload bytes per 4 samples */
+		const uint32_t nunits = neb * UPE;
+		const uint32_t whole = in_valid / 16u;	/* units with nothing missing */
+		for (uint32_t q = tid; q < neb * CH; q += nt)
+			sm.out[out_off + q * BS] = 0;
+		for (uint32_t u = tid; u < nunits; u += nt) {
+			uint4 w;
+			if (u < whole) {
+				w = *reinterpret_cast<const uint4 *>(sm.in + u * 16u);
+			} else {
+				/* the stream ends inside or before this unit: take the
+				 * bytes that exist, zero the rest (libbjxa.c:686-690) */
+				uint32_t t[4] = { 0, 0, 0, 0 };
+				for (uint32_t k = 0; k < 16u && u * 16u + k < in_valid; k++)
+					t[k >> 2] |= (uint32_t)sm.in[u * 16u + k] << (8 * (k & 3u));
+				w.x = t[0]; w.y = t[1]; w.z = t[2]; w.w = t[3];
+			}
+			const uint32_t eb = u / UPE, k = u % UPE;
+			if (CH == 1) {
+				/* 8 samples of one block: two quads */
+				uint32_t a = pack4<BITS>(w.x, w.x >> 16, w.y, w.y >> 16);
+				uint32_t b = pack4<BITS>(w.z, w.z >> 16, w.w, w.w >> 16);
+				uint32_t at = out_off + eb * BS + 1 + k * (2 * QB);
+				put_bytes(at, a, QB);
+				put_bytes(at + QB, b, QB);
+			} else {
+				/* 4 frames: one quad of the left, one of the right block */
+				uint32_t l = pack4<BITS>(w.x, w.y, w.z, w.w);
+				uint32_t r = pack4<BITS>(w.x >> 16, w.y >> 16, w.z >> 16, w.w >> 16);
+				uint32_t at = out_off + (eb * 2) * BS + 1 + k * QB;
+				put_bytes(at, l, QB);
+				put_bytes(at + BS, r, QB);
 			}
 		}
 	}

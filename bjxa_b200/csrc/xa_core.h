@@ -154,35 +154,42 @@ XA_HD int sample_cut(int x, int sh) { return x >> sh; }
  */
 XA_HD int sample_chain(int x, int sh, int k0, int k1, int &p0, int &p1)
 {
-	/*
-	 * Arranged for a short dependent path from p0 to the next p0 (the chain
-	 * is latency bound): with r = x >> sh and g = p0*k0 + p1*k1,
-	 *   r + trunc(g / 256) = (g + 256 r) >> 8          when g >= 0
-	 *                      = (g + 256 r + 255) >> 8    when g <  0
-	 * so three independent multiply-adds leave p0 at once (the sum, the sum
-	 * plus 255, and g itself for its sign), then shift, select, clamp.
-	 * p1*k1 and r do not depend on p0.
-	 */
-	const int c = p1 * k1;
-	const int a = ((x >> sh) << 8) + c;
-	const int g = p0 * k0 + c;
-	int u = p0 * k0 + a;
-	int v = p0 * k0 + (a + 255);
-#if defined(__CUDA_ARCH__)
-	/* opaque shifts: keep both candidates alive so that the select comes
-	 * AFTER the shift instead of a predicated add in front of the multiply */
-	asm("shr.s32 %0, %0, 8;" : "+r"(u));
-	asm("shr.s32 %0, %0, 8;" : "+r"(v));
-#else
-	u >>= 8;
-	v >>= 8;
-#endif
-	int s = g < 0 ? v : u;
+	/* tools/lat_bench.cu: written like this the dependent path costs 34
+	 * cycles/sample on B200 (26 of them without the clamp); rearrangements
+	 * with two shifted candidates and a select measured 34-37 */
+	int g = p0 * k0 + p1 * k1;
+	int q = (g + ((g >> 31) & 255)) >> 8;	/* truncating /256 */
+	int s = (x >> sh) + q;
 	s = s < -32768 ? -32768 : s;
 	s = s > 32767 ? 32767 : s;
 	p1 = p0;
 	p0 = s;
 	return s;
+}
+
+/*
+ * The four codes of one "quad" (4 consecutive samples = BITS/2 payload bytes,
+ * given in the low bytes of w), each top-aligned in 32 bits with zeros below.
+ */
+template <int BITS>
+XA_HD void quad_codes(uint32_t w, int (&x)[4])
+{
+	if (BITS == 8) {
+#pragma unroll
+		for (int i = 0; i < 4; i++)
+			x[i] = (int)byte_perm(w, 0u, (uint32_t)((i << 12) | 0x0444));
+	} else if (BITS == 4) {
+		x[0] = (int)((w << 24) & 0xf0000000u);	/* high nibble of byte 0 */
+		x[1] = (int)((w << 28) & 0xf0000000u);	/* low nibble of byte 0 */
+		x[2] = (int)((w << 16) & 0xf0000000u);
+		x[3] = (int)((w << 20) & 0xf0000000u);
+	} else {
+		/* three bytes, big endian: b0<<24 | b1<<16 | b2<<8 */
+		uint32_t t = byte_perm(w, 0u, 0x0124);
+#pragma unroll
+		for (int i = 0; i < 4; i++)
+			x[i] = (int)((t << (6 * i)) & 0xfc000000u);
+	}
 }
 
 /* ---- whole blocks, results as 16 packed words (sample 2i | 2i+1 << 16) -- */

@@ -92,11 +92,18 @@ __device__ __forceinline__ void consumer_sync()
  *              copy of that strip's contiguous XA bytes into the next free
  *              stage buffer, kDecStages tiles ahead of the consumers;
  *   consumers  kDecThreads threads: wait on the stage's "full" mbarrier, run
- *              phase A / the chain walkers / the store of xa_tile.h, and hand
- *              the buffer back through the stage's "empty" mbarrier.
+ *              phase A (direct blocks, stored straight from registers) and
+ *              phase B (walkers) of xa_tile.h, and hand the buffer back
+ *              through the stage's "empty" mbarrier, one arrival per warp.
+ * There is ONE CTA barrier per tile (between the phases); a warp that has no
+ * walker to run goes on to the next tile's phase A while others still walk.
+ * (A variant with a dedicated walker warp fed through mbarriers was measured
+ * and was slower: profiles/history_r1.md.)
  */
+constexpr int kDecBlock = kDecThreads + 32;
+
 template <int BITS, int CH, int NS>
-__global__ void __launch_bounds__(kDecThreads + 32)
+__global__ void __launch_bounds__(kDecBlock)
 xa_decode_kernel(const DecodeParams p)
 {
 	typedef DecTile<BITS, CH, kDecTBQ, NS, kDecStages> Tile;
@@ -107,9 +114,9 @@ xa_decode_kernel(const DecodeParams p)
 	if (tid == 0) {
 		for (int s = 0; s < kDecStages; s++) {
 			mbar_init(smem_u32(&sm.full[s]), 1);
-			mbar_init(smem_u32(&sm.empty[s]), 1);
+			mbar_init(smem_u32(&sm.empty[s]), kDecThreads / 32);
 		}
-		sm.n_heads = 0;
+		sm.n_heads[0] = sm.n_heads[1] = sm.n_heads[2] = 0;
 	}
 	__syncthreads();
 
@@ -168,37 +175,27 @@ xa_decode_kernel(const DecodeParams p)
 		const uint32_t tf = sm.tile_flags[s];
 		if (tf & kCtxEnd)
 			return;
-		Tile t(p, sm, s);
+		Tile t(p, sm, s, it);
 		if (tf & kCtxTail) {	/* only at the very end of the arena */
 			t.load_tail(tid, kDecThreads, sm.in[s]);
 			consumer_sync();
 		}
 
-		/* NS == 1: the store needs three words of the context; every thread
-		 * takes them to registers BEFORE the next barrier so that the stage
-		 * (context included) can go back to the producer ahead of the store */
-		const uint64_t c0_out0 = sm.ctx[s][0].out0;
-		const uint32_t c0_nq = sm.ctx[s][0].nq, c0_valid = sm.ctx[s][0].out_valid;
-
 		t.phase_a(tid, kDecThreads);
 		consumer_sync();
-		const int heads = sm.n_heads;
-		if (heads != 0) {
+		/* tail[], heads[] and the counter of this tile are complete.  The
+		 * counter two tiles ahead can be cleared now: nobody can be in that
+		 * tile's phase A before passing the NEXT tile's barrier, and every
+		 * reader of its previous use is behind us. */
+		if (tid == 0)
+			sm.n_heads[(it + 2) % 3] = 0;
+		const int heads = *t.n_heads;
+		if (heads != 0)
 			t.phase_walk(tid, kDecThreads, heads);
-			consumer_sync();
-		}
-		t.reset_counters(tid);
-		if (NS == 1) {
-			if (tid == 0)
-				mbar_arrive(smem_u32(&sm.empty[s]));
-			t.phase_store_one(tid, kDecThreads, c0_out0, c0_nq, c0_valid);
-			consumer_sync();	/* rows are free for the next tile's phase A */
-		} else {
-			t.phase_store(tid, kDecThreads);
-			consumer_sync();
-			if (tid == 0)
-				mbar_arrive(smem_u32(&sm.empty[s]));
-		}
+		/* this warp is done with the stage's bytes and contexts */
+		__syncwarp();
+		if ((tid & 31u) == 0)
+			mbar_arrive(smem_u32(&sm.empty[s]));
 	}
 }
 
@@ -637,7 +634,7 @@ launch_decode_ns(const DecodeParams &p, cudaStream_t st)
 	if (grid_cache[0] != dev) {
 		int per_sm = 0, sms = 0;
 		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm,
-		    xa_decode_kernel<BITS, CH, NS>, kDecThreads + 32, smem);
+		    xa_decode_kernel<BITS, CH, NS>, kDecBlock, smem);
 		if (e != cudaSuccess)
 			return e;
 		e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -649,7 +646,7 @@ launch_decode_ns(const DecodeParams &p, cudaStream_t st)
 	uint32_t grid = (uint32_t)grid_cache[1];
 	if (grid > p.n_tiles)
 		grid = p.n_tiles;
-	xa_decode_kernel<BITS, CH, NS><<<grid, kDecThreads + 32, smem, st>>>(p);
+	xa_decode_kernel<BITS, CH, NS><<<grid, kDecBlock, smem, st>>>(p);
 	return cudaGetLastError();
 }
 

@@ -34,7 +34,7 @@ namespace xa {
 #define XA_DEC_NT 256
 #endif
 #ifndef XA_DEC_STAGES
-#define XA_DEC_STAGES 2
+#define XA_DEC_STAGES 3
 #endif
 #ifndef XA_DEC_WIDE
 #define XA_DEC_WIDE 32

@@ -210,32 +210,59 @@ struct DecSmem {
 	typedef DecGeom<BITS, CH, TBQ, NS> G;
 
 	alignas(16) uint8_t in[STAGES][G::IN_BYTES];
-	alignas(16) uint32_t out[TBQ * 16];	/* planar rows, 64 B each, swizzled */
 	StripCtx ctx[STAGES][NS];
 	uint32_t tile_flags[STAGES];		/* kCtxEnd, kCtxTail (any strip) */
 	uint32_t n_strips[STAGES];
-	uint16_t heads[TBQ];			/* heads of chains found in phase A */
-	int n_heads;
+	/* per tile parity: last two samples of every directly decoded block, and
+	 * the effective blocks at which a walker has to start */
+	uint32_t tail[2][TBQ];
+	uint16_t heads[2][TBQ];
+	int n_heads[3];
 	alignas(8) unsigned long long full[STAGES];
 	alignas(8) unsigned long long empty[STAGES];
 };
 
+/*
+ * Work decomposition of a decode tile.
+ *
+ * Phase A gives every 16-byte unit of output (8 mono samples / 4 stereo frames)
+ * to one thread.  For each channel whose block is a CUT block (filter 0, or an
+ * invalid filter, which is decoded as filter 0 and reported) the thread unpacks
+ * the BITS/2 payload bytes per 4 samples it needs and stores the samples
+ * straight to global memory: whole 16-byte units when every channel of the
+ * effective block is cut (neighbouring threads then write neighbouring 16
+ * bytes), single int16 around the other channel otherwise.  Nothing is staged
+ * in shared memory.  The thread of an effective block's last unit leaves each
+ * cut block's last two samples in tail[].
+ *
+ * Every chain (a run of filter-1..4 blocks of one channel) is walked by one
+ * thread in phase B with the predictor state in registers, starting from
+ * tail[] of the cut block in front of it, or from the carry mailbox at the
+ * start of a strip; the walker stores its samples itself.
+ */
 template <int BITS, int CH, int TBQ, int NS, int STAGES>
 struct DecTile {
 	typedef DecGeom<BITS, CH, TBQ, NS> G;
 	typedef DecSmem<BITS, CH, TBQ, NS, STAGES> Smem;
 	static constexpr int BS = G::BS;
-	static constexpr uint32_t SBQ = G::SBQ;
+	static constexpr int QB = BITS / 2;		/* payload bytes of 4 samples */
+	static constexpr uint32_t SBE = G::SBE;		/* effective blocks per strip */
+	static constexpr uint32_t UPE = 4 * CH;		/* 16-byte units per effective block */
+	static constexpr uint32_t UPS = SBE * UPE;	/* ... per strip */
 
 	const DecodeParams &p;
 	Smem &sm;
 	const uint8_t *in;		/* this tile's stage buffer */
 	const StripCtx *ctx;		/* this tile's strips */
 	const uint32_t n_strips;
+	uint32_t *tail;			/* this tile's tail[] */
+	uint16_t *heads;
+	int *n_heads;
 
-	XA_HD DecTile(const DecodeParams &p_, Smem &sm_, int stage)
+	XA_HD DecTile(const DecodeParams &p_, Smem &sm_, int stage, uint32_t tile_no)
 	    : p(p_), sm(sm_), in(sm_.in[stage]), ctx(sm_.ctx[stage]),
-	      n_strips(sm_.n_strips[stage])
+	      n_strips(sm_.n_strips[stage]), tail(sm_.tail[tile_no & 1u]),
+	      heads(sm_.heads[tile_no & 1u]), n_heads(&sm_.n_heads[tile_no % 3u])
 	{
 	}
 
@@ -250,26 +277,17 @@ struct DecTile {
 		}
 	}
 
-	XA_HD static int row_word(uint32_t q, int chunk, int w)
-	{
-		return (int)(q * 16 + (uint32_t)((chunk ^ (int)((q >> 1) & 3u)) * 4 + w));
-	}
-
-	XA_HD void store_row(uint32_t q, const uint32_t (&o)[16])
-	{
-#pragma unroll
-		for (int j = 0; j < 4; j++) {
-			uint4 *d = reinterpret_cast<uint4 *>(&sm.out[row_word(q, j, 0)]);
-			uint4 v;
-			v.x = o[4 * j]; v.y = o[4 * j + 1]; v.z = o[4 * j + 2]; v.w = o[4 * j + 3];
-			*d = v;
-		}
-	}
-
-	/* byte address (in the stage buffer) of block lq of strip st */
+	/* stage-buffer address of block-channel lq of a strip */
 	XA_HD uint32_t block_at(const StripCtx &c, uint32_t lq) const
 	{
 		return c.in_base + lq * BS;
+	}
+
+	/* 4 bytes starting at an arbitrary stage-buffer address */
+	XA_HD uint32_t bytes_at(uint32_t at) const
+	{
+		const uint32_t *w = reinterpret_cast<const uint32_t *>(in) + (at >> 2);
+		return funnel_r(w[0], w[1], (at & 3u) * 8u);
 	}
 
 	XA_HD void fetch_block(uint32_t at, uint32_t (&pw)[BITS]) const
@@ -305,194 +323,226 @@ struct DecTile {
 		}
 	}
 
-	/*
-	 * phase A: every cut block is decoded; every chain block whose
-	 * predecessor in its channel is not a chain block (or lies in the
-	 * stream's previous strip) is queued as the head of a chain.  Needs
-	 * n_heads == 0 on entry.
-	 */
-	XA_HD void phase_a(uint32_t tid, uint32_t nt)
+	/* up to 16 bytes to global memory, honouring the strip's PCM length */
+	XA_HD void put_unit(const StripCtx &c, uint32_t boff, const uint4 &v)
 	{
-		const uint32_t nq_all = n_strips * SBQ;
-		for (uint32_t q = tid; q < nq_all; q += nt) {
-			const StripCtx &c = ctx[q / SBQ];
-			const uint32_t lq = q % SBQ;
-			if (lq >= c.nq)
-				continue;
-			const uint32_t at = block_at(c, lq);
-			const uint32_t prof = in[at];
-			const int kind = block_kind(prof);
-			if (kind == kChain) {
-				if (lq < (uint32_t)CH || block_kind(in[at - CH * BS]) != kChain)
-					sm.heads[smem_inc(&sm.n_heads)] = (uint16_t)q;
-				continue;
-			}
-			if (kind == kBad)
-				global_min_u32(&p.first_bad[c.stream], c.first_eb * CH + lq);
-			/* a bad block is decoded as if it were a cut so that
-			 * nothing downstream waits for it; what lies at and after
-			 * it is not part of the result */
-			uint32_t pw[BITS], o[16];
-			fetch_block(at, pw);
-			decode_block_cut<BITS>(o, pw, prof);
-			store_row(q, o);
-			if (lq + CH >= c.nq)
-				publish(c, lq % CH, (int)(int16_t)(o[15] >> 16),
-				    (int)(int16_t)(o[15] & 0xffffu));
-		}
-	}
-
-	/*
-	 * phase B: one walker per chain.  Thread i takes head i and decodes the
-	 * chain's blocks one after the other with the predictor state in
-	 * registers; no barrier until every chain of the tile is done.
-	 */
-	XA_HD void phase_walk(uint32_t tid, uint32_t nt, int n)
-	{
-		for (uint32_t i = tid; i < (uint32_t)n; i += nt) {
-			uint32_t q = sm.heads[i];
-			const StripCtx &c = ctx[q / SBQ];
-			uint32_t lq = q % SBQ;
-			uint32_t at = block_at(c, lq);
-			int p0, p1;
-			if (lq < (uint32_t)CH) {
-				carried_in(c, lq, p0, p1);
-			} else {
-				uint32_t last = sm.out[row_word(q - CH, 3, 3)];
-				p0 = (int)(int16_t)(last >> 16);
-				p1 = (int)(int16_t)(last & 0xffffu);
-			}
-			for (;;) {
-				uint32_t pw[BITS], o[16];
-				fetch_block(at, pw);
-				decode_block_chain<BITS>(o, pw, in[at], p0, p1);
-				store_row(q, o);
-				if (lq + CH >= c.nq) {
-					publish(c, lq % CH, p0, p1);
-					break;
-				}
-				q += CH;
-				lq += CH;
-				at += CH * BS;
-				if (block_kind(in[at]) != kChain)
-					break;
-			}
-		}
-	}
-
-	/* after phase B: leave the head counter zero for the next tile */
-	XA_HD void reset_counters(uint32_t tid)
-	{
-		if (tid == 0)
-			sm.n_heads = 0;
-	}
-
-	/* one 16-byte unit (index li within its strip) of interleaved PCM */
-	XA_HD void gather_chunk(uint32_t row0, uint32_t li, uint32_t (&w)[4]) const
-	{
-		if (CH == 1) {
-			const uint32_t *s = &sm.out[row_word(row0 + (li >> 2), (int)(li & 3u), 0)];
-			w[0] = s[0]; w[1] = s[1]; w[2] = s[2]; w[3] = s[3];
-		} else {
-			uint32_t eb = li >> 3, jj = li & 7u;
-			int j = (int)(jj >> 1), h = (int)(jj & 1u) * 2;
-			const uint32_t *l = &sm.out[row_word(row0 + 2 * eb, j, h)];
-			const uint32_t *r = &sm.out[row_word(row0 + 2 * eb + 1, j, h)];
-			w[0] = byte_perm(l[0], r[0], 0x5410);
-			w[1] = byte_perm(l[0], r[0], 0x7632);
-			w[2] = byte_perm(l[1], r[1], 0x5410);
-			w[3] = byte_perm(l[1], r[1], 0x7632);
-		}
-	}
-
-	/*
-	 * staged rows -> interleaved PCM, 16 bytes per step, for a tile that is
-	 * one strip (NS == 1); takes what it needs of the context by value so
-	 * that the stage can be handed back before the store.  nt % 32 == 0.
-	 */
-	XA_HD void phase_store_one(uint32_t tid, uint32_t nt, uint64_t out0, uint32_t nq,
-	    uint32_t out_valid)
-	{
-		const uint32_t nchunk = nq * 4;
-		uint8_t *dst = p.dst + out0;
-		if (out_valid == nchunk * 16u) {
-			/* every unit is whole.  With nt a multiple of 32 the swizzle
-			 * term of a thread's units is the same for all of them, so
-			 * both addresses advance by nt*16 bytes per step. */
-			uint4 *g = reinterpret_cast<uint4 *>(dst) + tid;
-			if (CH == 1) {
-				const uint4 *s = reinterpret_cast<const uint4 *>(
-				    &sm.out[row_word(tid >> 2, (int)(tid & 3u), 0)]);
-				for (uint32_t i = tid; i < nchunk; i += nt) {
-					*g = *s;
-					g += nt;
-					s += nt;
-				}
-			} else {
-				const uint32_t jj = tid & 7u;
-				const int j = (int)(jj >> 1), h = (int)(jj & 1u) * 2;
-				const uint2 *l = reinterpret_cast<const uint2 *>(
-				    &sm.out[row_word(2 * (tid >> 3), j, h)]);
-				const uint2 *r = reinterpret_cast<const uint2 *>(
-				    &sm.out[row_word(2 * (tid >> 3) + 1, j, h)]);
-				for (uint32_t i = tid; i < nchunk; i += nt) {
-					uint2 a = *l, b = *r;
-					uint4 v;
-					v.x = byte_perm(a.x, b.x, 0x5410);
-					v.y = byte_perm(a.x, b.x, 0x7632);
-					v.z = byte_perm(a.y, b.y, 0x5410);
-					v.w = byte_perm(a.y, b.y, 0x7632);
-					*g = v;
-					g += nt;
-					l += nt * 2;	/* nt units = nt*16 B of rows */
-					r += nt * 2;
-				}
-			}
-			return;
-		}
-		/* the truncated last block of a stream */
-		for (uint32_t i = tid; i < nchunk; i += nt) {
-			const uint32_t boff = i * 16u;
-			if (boff >= out_valid)
-				continue;
-			uint32_t w[4];
-			gather_chunk(0, i, w);
-			uint32_t n16 = (out_valid - boff) / 2u;
-			if (n16 > 8u)
-				n16 = 8u;
-			uint16_t *d = reinterpret_cast<uint16_t *>(dst + boff);
+		uint8_t *d8 = p.dst + c.out0 + boff;
+		if (boff + 16u <= c.out_valid) {
+			*reinterpret_cast<uint4 *>(d8) = v;
+		} else if (boff < c.out_valid) {
+			/* the truncated last block of a stream (libbjxa.c:622-624) */
+			const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+			uint16_t *d = reinterpret_cast<uint16_t *>(d8);
+			uint32_t n16 = (c.out_valid - boff) / 2u;
 			for (uint32_t k = 0; k < n16; k++)
 				d[k] = (uint16_t)(w[k >> 1] >> (16u * (k & 1u)));
 		}
 	}
 
-	/* the same for any number of strips, reading the contexts in place */
-	XA_HD void phase_store(uint32_t tid, uint32_t nt)
+	/* one int16 of channel ch, sample n of effective block eb (stereo walkers
+	 * and half-direct blocks write their channel around the other one) */
+	XA_HD void put_sample(const StripCtx &c, uint32_t eb, uint32_t n, uint32_t ch,
+	    uint32_t v16)
 	{
-		constexpr uint32_t CPS = SBQ * 4;	/* 16-byte units per full strip */
-		if (NS == 1) {
-			phase_store_one(tid, nt, ctx[0].out0, ctx[0].nq, ctx[0].out_valid);
-			return;
-		}
-		const uint32_t total = n_strips * CPS;
-		for (uint32_t i = tid; i < total; i += nt) {
-			const uint32_t st = i / CPS, li = i % CPS;
+		const uint32_t boff = ((eb * 32u + n) * CH + ch) * 2u;
+		if (boff < c.out_valid)
+			*reinterpret_cast<uint16_t *>(p.dst + c.out0 + boff) = (uint16_t)v16;
+	}
+
+	XA_HD void keep_tail(const StripCtx &c, uint32_t st, uint32_t eb, uint32_t ch,
+	    uint32_t t)
+	{
+		tail[st * G::SBQ + eb * CH + ch] = t;
+		if ((eb + 1) * CH >= c.nq)
+			publish(c, ch, (int)(int16_t)(t >> 16), (int)(int16_t)(t & 0xffffu));
+	}
+
+	/*
+	 * phase A: one thread per 16-byte unit of output (8 mono samples / 4
+	 * stereo frames).  Cut blocks are decoded here; a chain block whose
+	 * predecessor in its channel is not a chain block is queued for a walker
+	 * by the thread of its first unit.
+	 */
+	XA_HD void phase_a(uint32_t tid, uint32_t nt)
+	{
+		if (CH == 1)
+			phase_a_mono(tid, nt);
+		else
+			phase_a_stereo(tid, nt);
+	}
+
+	XA_HD void phase_a_mono(uint32_t tid, uint32_t nt)
+	{
+		const uint32_t total = n_strips * UPS;
+		for (uint32_t u = tid; u < total; u += nt) {
+			const uint32_t st = u / UPS, lu = u % UPS;
 			const StripCtx &c = ctx[st];
-			const uint32_t boff = li * 16u;
-			if (boff >= c.out_valid)
+			const uint32_t eb = lu / UPE, k = lu % UPE;
+			if (eb >= c.nq)
 				continue;
-			uint32_t w[4];
-			gather_chunk(st * SBQ, li, w);
-			uint8_t *d8 = p.dst + c.out0 + boff;
-			if (boff + 16u <= c.out_valid) {
+			const uint32_t at0 = block_at(c, eb);
+			const uint32_t prof0 = in[at0];
+			const int kind0 = block_kind(prof0);
+			if (kind0 == kChain) {
+				/* the first unit of a chain's first block queues a walker */
+				if (k == 0 && (eb == 0 || block_kind(in[at0 - BS]) != kChain))
+					heads[smem_inc(n_heads)] = (uint16_t)(st * G::SBQ + eb);
+				continue;
+			}
+			if (k == 0 && kind0 == kBad)
+				global_min_u32(&p.first_bad[c.stream], c.first_eb + eb);
+			/* 8 consecutive samples: quads 2k and 2k+1 of the block */
+			uint4 v;
+			int x[4], y[4];
+			const int sh = 16 + (int)(prof0 & 15u);
+			const uint32_t a = at0 + 1 + k * (2 * QB);
+			quad_codes<BITS>(bytes_at(a), x);
+			quad_codes<BITS>(bytes_at(a + QB), y);
+			v.x = pack2(x[0] >> sh, x[1] >> sh);
+			v.y = pack2(x[2] >> sh, x[3] >> sh);
+			v.z = pack2(y[0] >> sh, y[1] >> sh);
+			v.w = pack2(y[2] >> sh, y[3] >> sh);
+			put_unit(c, lu * 16u, v);
+			if (k == UPE - 1) {
+				/* this unit ends the block: keep (and, at the end of the
+				 * strip, publish) the last two samples */
+				const uint32_t t0 = v.w;
+				tail[st * G::SBQ + eb] = t0;
+				if (eb + 1 >= c.nq)
+					publish(c, 0, (int)(int16_t)(t0 >> 16),
+					    (int)(int16_t)(t0 & 0xffffu));
+			}
+		}
+	}
+
+	XA_HD void phase_a_stereo(uint32_t tid, uint32_t nt)
+	{
+		const uint32_t total = n_strips * UPS;
+		for (uint32_t u = tid; u < total; u += nt) {
+			const uint32_t st = u / UPS, lu = u % UPS;
+			const StripCtx &c = ctx[st];
+			const uint32_t eb = lu / UPE, k = lu % UPE;
+			if (eb * 2 >= c.nq)
+				continue;
+			const uint32_t at0 = block_at(c, eb * 2);
+			const uint32_t prof0 = in[at0];
+			const uint32_t prof1 = in[at0 + BS];
+			const int kind0 = block_kind(prof0);
+			const int kind1 = block_kind(prof1);
+			/* 4 frames: quad k of the left and of the right block */
+			const uint32_t a = at0 + 1 + k * QB;
+			int x[4], y[4];
+			if (kind0 != kChain && kind1 != kChain) {
+				/* the common case: the whole unit, 16 bytes at once */
+				if (k == 0) {
+					if (kind0 == kBad)
+						global_min_u32(&p.first_bad[c.stream],
+						    (c.first_eb + eb) * 2);
+					if (kind1 == kBad)
+						global_min_u32(&p.first_bad[c.stream],
+						    (c.first_eb + eb) * 2 + 1);
+				}
+				const int shl = 16 + (int)(prof0 & 15u);
+				const int shr = 16 + (int)(prof1 & 15u);
+				quad_codes<BITS>(bytes_at(a), x);
+				quad_codes<BITS>(bytes_at(a + BS), y);
 				uint4 v;
-				v.x = w[0]; v.y = w[1]; v.z = w[2]; v.w = w[3];
-				*reinterpret_cast<uint4 *>(d8) = v;
+				v.x = pack2(x[0] >> shl, y[0] >> shr);
+				v.y = pack2(x[1] >> shl, y[1] >> shr);
+				v.z = pack2(x[2] >> shl, y[2] >> shr);
+				v.w = pack2(x[3] >> shl, y[3] >> shr);
+				put_unit(c, lu * 16u, v);
+				if (k == UPE - 1) {
+					keep_tail(c, st, eb, 0, byte_perm(v.z, v.w, 0x5410));
+					keep_tail(c, st, eb, 1, byte_perm(v.z, v.w, 0x7632));
+				}
+				continue;
+			}
+			/* at least one channel is a chain block: queue its walker, and
+			 * write the other channel (if it is cut) around it */
+			if (k == 0) {
+				if (kind0 == kBad)
+					global_min_u32(&p.first_bad[c.stream], (c.first_eb + eb) * 2);
+				if (kind1 == kBad)
+					global_min_u32(&p.first_bad[c.stream],
+					    (c.first_eb + eb) * 2 + 1);
+				if (kind0 == kChain && (eb == 0 ||
+				    block_kind(in[at0 - 2 * BS]) != kChain))
+					heads[smem_inc(n_heads)] = (uint16_t)(st * G::SBQ + eb * 2);
+				if (kind1 == kChain && (eb == 0 ||
+				    block_kind(in[at0 - BS]) != kChain))
+					heads[smem_inc(n_heads)] = (uint16_t)(st * G::SBQ + eb * 2 + 1);
+			}
+			if (kind0 != kChain) {
+				const int sh = 16 + (int)(prof0 & 15u);
+				quad_codes<BITS>(bytes_at(a), x);
+#pragma unroll
+				for (int i = 0; i < 4; i++)
+					put_sample(c, eb, k * 4 + i, 0, (uint32_t)(x[i] >> sh));
+				if (k == UPE - 1)
+					keep_tail(c, st, eb, 0, pack2(x[2] >> sh, x[3] >> sh));
+			}
+			if (kind1 != kChain) {
+				const int sh = 16 + (int)(prof1 & 15u);
+				quad_codes<BITS>(bytes_at(a + BS), y);
+#pragma unroll
+				for (int i = 0; i < 4; i++)
+					put_sample(c, eb, k * 4 + i, 1, (uint32_t)(y[i] >> sh));
+				if (k == UPE - 1)
+					keep_tail(c, st, eb, 1, pack2(y[2] >> sh, y[3] >> sh));
+			}
+		}
+	}
+
+	/*
+	 * phase B: one walker per chain (a run of filter-1..4 blocks of one
+	 * channel), predictor state in registers, output stored by the walker.
+	 */
+	XA_HD void phase_walk(uint32_t tid, uint32_t nt, int n)
+	{
+		for (uint32_t i = tid; i < (uint32_t)n; i += nt) {
+			const uint32_t h = heads[i];
+			const uint32_t st = h / G::SBQ;
+			uint32_t lq = h % G::SBQ;
+			const uint32_t ch = lq % CH;
+			const StripCtx &c = ctx[st];
+			int p0, p1;
+			if (lq < (uint32_t)CH) {
+				carried_in(c, ch, p0, p1);
 			} else {
-				uint16_t *d = reinterpret_cast<uint16_t *>(d8);
-				uint32_t n16 = (c.out_valid - boff) / 2u;
-				for (uint32_t k = 0; k < n16; k++)
-					d[k] = (uint16_t)(w[k >> 1] >> (16u * (k & 1u)));
+				uint32_t t = tail[st * G::SBQ + lq - CH];
+				p0 = (int)(int16_t)(t >> 16);
+				p1 = (int)(int16_t)(t & 0xffffu);
+			}
+			uint32_t at = block_at(c, lq);
+			for (;;) {
+				uint32_t pw[BITS], o[16];
+				fetch_block(at, pw);
+				decode_block_chain<BITS>(o, pw, in[at], p0, p1);
+				const uint32_t eb = lq / CH;
+				if (CH == 1) {
+#pragma unroll
+					for (int j = 0; j < 4; j++) {
+						uint4 v;
+						v.x = o[4 * j]; v.y = o[4 * j + 1];
+						v.z = o[4 * j + 2]; v.w = o[4 * j + 3];
+						put_unit(c, (eb * 4u + (uint32_t)j) * 16u, v);
+					}
+				} else {
+#pragma unroll
+					for (int j = 0; j < 16; j++) {
+						put_sample(c, eb, 2 * j, ch, o[j]);
+						put_sample(c, eb, 2 * j + 1, ch, o[j] >> 16);
+					}
+				}
+				if (lq + CH >= c.nq) {
+					publish(c, ch, p0, p1);
+					break;
+				}
+				lq += CH;
+				at += CH * BS;
+				if (block_kind(in[at]) != kChain)
+					break;
 			}
 		}
 	}

@@ -39,7 +39,7 @@ emul_decode_ns(const DecodeParams &p, int order)
 	const uint32_t nt = kDecThreads;
 
 	memset(sm, 0xa5, sizeof *sm);	/* smem is garbage at CTA start */
-	sm->n_heads = 0;
+	sm->n_heads[0] = sm->n_heads[1] = sm->n_heads[2] = 0;
 	for (uint32_t ticket = 0; ticket < p.n_tiles; ticket++) {
 		/* one persistent CTA draws every ticket; stages rotate as on the GPU */
 		const int s = (int)(ticket % kDecStages);
@@ -55,20 +55,19 @@ emul_decode_ns(const DecodeParams &p, int order)
 		}
 		sm->n_strips[s] = te.count;
 		sm->tile_flags[s] = tail ? kCtxTail : 0u;
-		Tile t(p, *sm, s);
+		Tile t(p, *sm, s, ticket);
 		if (tail)
 			for (uint32_t i = 0; i < nt; i++)
 				t.load_tail(visit(i, nt, order), nt, sm->in[s]);
 		for (uint32_t i = 0; i < nt; i++)
 			t.phase_a(visit(i, nt, order), nt);
-		int heads = sm->n_heads;
+		sm->n_heads[(ticket + 2) % 3] = 0;
+		int heads = *t.n_heads;
 		if (heads != 0)
 			for (uint32_t i = 0; i < nt; i++)
 				t.phase_walk(visit(i, nt, order), nt, heads);
-		for (uint32_t i = 0; i < nt; i++)
-			t.reset_counters(visit(i, nt, order));
-		for (uint32_t i = 0; i < nt; i++)
-			t.phase_store(visit(i, nt, order), nt);
+		/* poison what the next tile must not rely on */
+		memset(sm->tail[ticket & 1u], 0x5c, sizeof sm->tail[0]);
 	}
 	delete sm;
 }

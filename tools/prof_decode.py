@@ -63,7 +63,10 @@ def main():
     for mix in a.mix.split(","):
         for s0 in range(0, S, 256):
             n = min(256, S - s0)
-            xa[s0:s0 + n, :, 0] = bench.mix_profiles(torch, mix, n, blocks * ch, dev, s0 + 7)
+            # one profile sequence per stream-CHANNEL (filters of the two channels
+            # of a stereo stream are independent), interleaved L,R,L,R like the blocks
+            pr = bench.mix_profiles(torch, mix, n * ch, blocks, dev, s0 + 7)
+            xa[s0:s0 + n, :, 0] = pr.view(n, ch, blocks).transpose(1, 2).reshape(n, blocks * ch)
         plan = lib.plan_create(PLAN_DECODE, descs)
 
         def step():

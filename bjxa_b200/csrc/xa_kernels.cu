@@ -199,6 +199,117 @@ xa_decode_kernel(const DecodeParams p)
 	}
 }
 
+/* The staged variant of the decode kernel (stereo), same producer / consumer
+ * layout; see DecTileStaged in xa_tile.h. */
+constexpr int kDecStagedStages = 2;
+
+template <int BITS, int CH, int NS>
+__global__ void __launch_bounds__(kDecThreads + 32)
+xa_decode_staged_kernel(const DecodeParams p)
+{
+	typedef DecTileStaged<BITS, CH, kDecTBQ, NS, kDecStagedStages> Tile;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	typename Tile::Smem &sm = *reinterpret_cast<typename Tile::Smem *>(smem_raw);
+	const uint32_t tid = threadIdx.x;
+
+	if (tid == 0) {
+		for (int s = 0; s < kDecStagedStages; s++) {
+			mbar_init(smem_u32(&sm.full[s]), 1);
+			mbar_init(smem_u32(&sm.empty[s]), 1);
+		}
+		sm.n_heads = 0;
+	}
+	__syncthreads();
+
+	if (tid >= kDecThreads) {
+		const uint32_t lane = tid - kDecThreads;
+		for (uint32_t it = 0;; it++) {
+			const int s = (int)(it % kDecStagedStages);
+			if (it >= (uint32_t)kDecStagedStages)
+				mbar_wait(smem_u32(&sm.empty[s]), (it / kDecStagedStages - 1) & 1);
+			/* the counter is preset to ~0 with first_bad[]: old + 1 = ticket */
+			unsigned long long t = 0;
+			if (lane == 0)
+				t = atomicAdd(p.ticket, 1ULL) + 1ULL;
+			t = __shfl_sync(0xffffffffu, t, 0);
+			const uint32_t full = smem_u32(&sm.full[s]);
+			if (t >= p.n_tiles) {
+				if (lane == 0) {
+					sm.tile_flags[s] = kCtxEnd;
+					mbar_arrive(full);
+				}
+				return;
+			}
+			const TileEnt te = p.tiles[t];
+			uint32_t bulk = 0, tail = 0;
+			StripCtx c;
+			if (lane < te.count) {
+				make_strip_ctx<BITS, CH, kDecTBQ, NS>(c, p, p.order[te.first + lane],
+				    te.j, lane);
+				sm.ctx[s][lane] = c;
+				bulk = c.bulk;
+				tail = c.flags & kCtxTail;
+			}
+			uint32_t total = bulk;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1)
+				total += __shfl_xor_sync(0xffffffffu, total, o);
+			const uint32_t any_tail = __ballot_sync(0xffffffffu, tail != 0);
+			if (lane == 0) {
+				sm.tile_flags[s] = any_tail ? kCtxTail : 0u;
+				sm.n_strips[s] = te.count;
+				if (total)
+					mbar_expect_tx(full, total);
+				else
+					mbar_arrive(full);
+			}
+			__syncwarp();
+			if (bulk)
+				bulk_g2s(smem_u32(sm.in[s]) + lane * Tile::G::SLOT, p.src + c.a0,
+				    bulk, full);
+		}
+	}
+
+	for (uint32_t it = 0;; it++) {
+		const int s = (int)(it % kDecStagedStages);
+		mbar_wait(smem_u32(&sm.full[s]), (it / kDecStagedStages) & 1);
+		const uint32_t tf = sm.tile_flags[s];
+		if (tf & kCtxEnd)
+			return;
+		Tile t(p, sm, s);
+		if (tf & kCtxTail) {	/* only at the very end of the arena */
+			t.load_tail(tid, kDecThreads, sm.in[s]);
+			consumer_sync();
+		}
+
+		/* NS == 1: the store needs three words of the context; every thread
+		 * takes them to registers BEFORE the next barrier so that the stage
+		 * (context included) can go back to the producer ahead of the store */
+		const uint64_t c0_out0 = sm.ctx[s][0].out0;
+		const uint32_t c0_nq = sm.ctx[s][0].nq, c0_valid = sm.ctx[s][0].out_valid;
+
+		t.phase_a(tid, kDecThreads);
+		consumer_sync();
+		const int heads = sm.n_heads;
+		if (heads != 0) {
+			t.phase_walk(tid, kDecThreads, heads);
+			consumer_sync();
+		}
+		t.reset_counters(tid);
+		if (NS == 1) {
+			if (tid == 0)
+				mbar_arrive(smem_u32(&sm.empty[s]));
+			t.phase_store_one(tid, kDecThreads, c0_out0, c0_nq, c0_valid);
+			consumer_sync();	/* rows are free for the next tile's phase A */
+		} else {
+			t.phase_store(tid, kDecThreads);
+			consumer_sync();
+			if (tid == 0)
+				mbar_arrive(smem_u32(&sm.empty[s]));
+		}
+	}
+}
+
 template <int BITS, int CH>
 __global__ void __launch_bounds__(kEncThreads)
 xa_encode_kernel(const EncodeParams p)
@@ -453,6 +564,16 @@ set_attrs_one(void)
 	    (int)sizeof(DecSmem<BITS, CH, kDecTBQ, kDecWide, kDecStages>));
 	if (e != cudaSuccess)
 		return e;
+	e = cudaFuncSetAttribute(xa_decode_staged_kernel<BITS, CH, 1>,
+	    cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    (int)sizeof(DecSmemStaged<BITS, CH, kDecTBQ, 1, kDecStagedStages>));
+	if (e != cudaSuccess)
+		return e;
+	e = cudaFuncSetAttribute(xa_decode_staged_kernel<BITS, CH, kDecWide>,
+	    cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    (int)sizeof(DecSmemStaged<BITS, CH, kDecTBQ, kDecWide, kDecStagedStages>));
+	if (e != cudaSuccess)
+		return e;
 	return cudaFuncSetAttribute(xa_encode_kernel<BITS, CH>,
 	    cudaFuncAttributeMaxDynamicSharedMemorySize,
 	    (int)sizeof(EncSmem<BITS, CH, kEncTBE>));
@@ -624,17 +745,24 @@ template <int BITS, int CH, int NS>
 static cudaError_t
 launch_decode_ns(const DecodeParams &p, cudaStream_t st)
 {
-	/* persistent: as many CTAs as fit the device at once, never more than tiles */
+	/* persistent: as many CTAs as fit the device at once, never more than
+	 * tiles.  Mono streams use the direct form of the tile algorithm, stereo
+	 * streams the staged one (xa_tile.h). */
 	static thread_local int grid_cache[2] = { -1, 0 };
-	const size_t smem = sizeof(DecSmem<BITS, CH, kDecTBQ, NS, kDecStages>);
+	constexpr bool staged = CH == 2;
+	const size_t smem = staged ?
+	    sizeof(DecSmemStaged<BITS, CH, kDecTBQ, NS, kDecStagedStages>) :
+	    sizeof(DecSmem<BITS, CH, kDecTBQ, NS, kDecStages>);
+	void (*kern)(const DecodeParams) = staged ?
+	    xa_decode_staged_kernel<BITS, CH, NS> : xa_decode_kernel<BITS, CH, NS>;
+	const int block = staged ? kDecThreads + 32 : kDecBlock;
 	int dev = 0;
 	cudaError_t e = cudaGetDevice(&dev);
 	if (e != cudaSuccess)
 		return e;
 	if (grid_cache[0] != dev) {
 		int per_sm = 0, sms = 0;
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm,
-		    xa_decode_kernel<BITS, CH, NS>, kDecBlock, smem);
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem);
 		if (e != cudaSuccess)
 			return e;
 		e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -646,7 +774,7 @@ launch_decode_ns(const DecodeParams &p, cudaStream_t st)
 	uint32_t grid = (uint32_t)grid_cache[1];
 	if (grid > p.n_tiles)
 		grid = p.n_tiles;
-	xa_decode_kernel<BITS, CH, NS><<<grid, kDecBlock, smem, st>>>(p);
+	kern<<<grid, block, smem, st>>>(p);
 	return cudaGetLastError();
 }
 

@@ -548,6 +548,310 @@ struct DecTile {
 	}
 };
 
+/* ---- decode, staged variant (used for stereo) ------------------------------ */
+/*
+ * The first complete form of the tile algorithm, kept for STEREO streams: every
+ * block-channel is decoded into a 64-byte row of a shared-memory image of the
+ * tile (cut blocks in phase A, chains by one walker lane each), and a store
+ * phase interleaves left and right rows into 16-byte units.  For stereo this is
+ * faster than the direct form below whenever chains are present, because a
+ * walker that owns only one channel of an effective block would otherwise have
+ * to write its int16 samples around the other channel's (measured:
+ * profiles/history_r1.md).
+ */
+template <int BITS, int CH, int TBQ, int NS, int STAGES>
+struct DecSmemStaged {
+	typedef DecGeom<BITS, CH, TBQ, NS> G;
+
+	alignas(16) uint8_t in[STAGES][G::IN_BYTES];
+	alignas(16) uint32_t out[TBQ * 16];	/* planar rows, 64 B each, swizzled */
+	StripCtx ctx[STAGES][NS];
+	uint32_t tile_flags[STAGES];		/* kCtxEnd, kCtxTail (any strip) */
+	uint32_t n_strips[STAGES];
+	uint16_t heads[TBQ];			/* heads of chains found in phase A */
+	int n_heads;
+	alignas(8) unsigned long long full[STAGES];
+	alignas(8) unsigned long long empty[STAGES];
+};
+
+template <int BITS, int CH, int TBQ, int NS, int STAGES>
+struct DecTileStaged {
+	typedef DecGeom<BITS, CH, TBQ, NS> G;
+	typedef DecSmemStaged<BITS, CH, TBQ, NS, STAGES> Smem;
+	static constexpr int BS = G::BS;
+	static constexpr uint32_t SBQ = G::SBQ;
+
+	const DecodeParams &p;
+	Smem &sm;
+	const uint8_t *in;		/* this tile's stage buffer */
+	const StripCtx *ctx;		/* this tile's strips */
+	const uint32_t n_strips;
+
+	XA_HD DecTileStaged(const DecodeParams &p_, Smem &sm_, int stage)
+	    : p(p_), sm(sm_), in(sm_.in[stage]), ctx(sm_.ctx[stage]),
+	      n_strips(sm_.n_strips[stage])
+	{
+	}
+
+	/* bytes past a strip's `bulk` fetched one by one (only at the arena's end) */
+	XA_HD void load_tail(uint32_t tid, uint32_t nt, uint8_t *in_w)
+	{
+		for (uint32_t st = 0; st < n_strips; st++) {
+			const StripCtx &c = ctx[st];
+			uint32_t slot0 = st * G::SLOT;
+			for (uint32_t i = c.bulk + tid; i < c.in_need; i += nt)
+				in_w[slot0 + i] = p.src[c.a0 + i];
+		}
+	}
+
+	XA_HD static int row_word(uint32_t q, int chunk, int w)
+	{
+		return (int)(q * 16 + (uint32_t)((chunk ^ (int)((q >> 1) & 3u)) * 4 + w));
+	}
+
+	XA_HD void store_row(uint32_t q, const uint32_t (&o)[16])
+	{
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			uint4 *d = reinterpret_cast<uint4 *>(&sm.out[row_word(q, j, 0)]);
+			uint4 v;
+			v.x = o[4 * j]; v.y = o[4 * j + 1]; v.z = o[4 * j + 2]; v.w = o[4 * j + 3];
+			*d = v;
+		}
+	}
+
+	/* byte address (in the stage buffer) of block lq of strip st */
+	XA_HD uint32_t block_at(const StripCtx &c, uint32_t lq) const
+	{
+		return c.in_base + lq * BS;
+	}
+
+	XA_HD void fetch_block(uint32_t at, uint32_t (&pw)[BITS]) const
+	{
+		uint32_t pay = at + 1;		/* first payload byte */
+		const uint32_t *w = reinterpret_cast<const uint32_t *>(in) + (pay >> 2);
+		load_payload<BITS>(pw, w, (pay & 3u) * 8u);
+	}
+
+	/* hand the channel's state to whoever continues it */
+	XA_HD void publish(const StripCtx &c, uint32_t ch, int p0, int p1)
+	{
+		if (c.flags & kCtxLast) {
+			p.results[c.stream].prev[ch][0] = (int16_t)p0;
+			p.results[c.stream].prev[ch][1] = (int16_t)p1;
+		} else {
+			unsigned long long v = ((unsigned long long)p.epoch << 32) |
+			    ((unsigned long long)(uint16_t)p1 << 16) | (uint16_t)p0;
+			mailbox_put(&p.carry[(uint64_t)c.slot * 2 + ch], v);
+		}
+	}
+
+	XA_HD void carried_in(const StripCtx &c, uint32_t ch, int &p0, int &p1) const
+	{
+		if (c.flags & kCtxFirst) {
+			p0 = p.streams[c.stream].prev[ch][0];
+			p1 = p.streams[c.stream].prev[ch][1];
+		} else {
+			unsigned long long v = mailbox_get(
+			    &p.carry[(uint64_t)(c.slot - 1) * 2 + ch], p.epoch, p.fault);
+			p0 = (int16_t)(uint16_t)v;
+			p1 = (int16_t)(uint16_t)(v >> 16);
+		}
+	}
+
+	/*
+	 * phase A: every cut block is decoded; every chain block whose
+	 * predecessor in its channel is not a chain block (or lies in the
+	 * stream's previous strip) is queued as the head of a chain.  Needs
+	 * n_heads == 0 on entry.
+	 */
+	XA_HD void phase_a(uint32_t tid, uint32_t nt)
+	{
+		const uint32_t nq_all = n_strips * SBQ;
+		for (uint32_t q = tid; q < nq_all; q += nt) {
+			const StripCtx &c = ctx[q / SBQ];
+			const uint32_t lq = q % SBQ;
+			if (lq >= c.nq)
+				continue;
+			const uint32_t at = block_at(c, lq);
+			const uint32_t prof = in[at];
+			const int kind = block_kind(prof);
+			if (kind == kChain) {
+				if (lq < (uint32_t)CH || block_kind(in[at - CH * BS]) != kChain)
+					sm.heads[smem_inc(&sm.n_heads)] = (uint16_t)q;
+				continue;
+			}
+			if (kind == kBad)
+				global_min_u32(&p.first_bad[c.stream], c.first_eb * CH + lq);
+			/* a bad block is decoded as if it were a cut so that
+			 * nothing downstream waits for it; what lies at and after
+			 * it is not part of the result */
+			uint32_t pw[BITS], o[16];
+			fetch_block(at, pw);
+			decode_block_cut<BITS>(o, pw, prof);
+			store_row(q, o);
+			if (lq + CH >= c.nq)
+				publish(c, lq % CH, (int)(int16_t)(o[15] >> 16),
+				    (int)(int16_t)(o[15] & 0xffffu));
+		}
+	}
+
+	/*
+	 * phase B: one walker per chain.  Thread i takes head i and decodes the
+	 * chain's blocks one after the other with the predictor state in
+	 * registers; no barrier until every chain of the tile is done.
+	 */
+	XA_HD void phase_walk(uint32_t tid, uint32_t nt, int n)
+	{
+		for (uint32_t i = tid; i < (uint32_t)n; i += nt) {
+			uint32_t q = sm.heads[i];
+			const StripCtx &c = ctx[q / SBQ];
+			uint32_t lq = q % SBQ;
+			uint32_t at = block_at(c, lq);
+			int p0, p1;
+			if (lq < (uint32_t)CH) {
+				carried_in(c, lq, p0, p1);
+			} else {
+				uint32_t last = sm.out[row_word(q - CH, 3, 3)];
+				p0 = (int)(int16_t)(last >> 16);
+				p1 = (int)(int16_t)(last & 0xffffu);
+			}
+			for (;;) {
+				uint32_t pw[BITS], o[16];
+				fetch_block(at, pw);
+				decode_block_chain<BITS>(o, pw, in[at], p0, p1);
+				store_row(q, o);
+				if (lq + CH >= c.nq) {
+					publish(c, lq % CH, p0, p1);
+					break;
+				}
+				q += CH;
+				lq += CH;
+				at += CH * BS;
+				if (block_kind(in[at]) != kChain)
+					break;
+			}
+		}
+	}
+
+	/* after phase B: leave the head counter zero for the next tile */
+	XA_HD void reset_counters(uint32_t tid)
+	{
+		if (tid == 0)
+			sm.n_heads = 0;
+	}
+
+	/* one 16-byte unit (index li within its strip) of interleaved PCM */
+	XA_HD void gather_chunk(uint32_t row0, uint32_t li, uint32_t (&w)[4]) const
+	{
+		if (CH == 1) {
+			const uint32_t *s = &sm.out[row_word(row0 + (li >> 2), (int)(li & 3u), 0)];
+			w[0] = s[0]; w[1] = s[1]; w[2] = s[2]; w[3] = s[3];
+		} else {
+			uint32_t eb = li >> 3, jj = li & 7u;
+			int j = (int)(jj >> 1), h = (int)(jj & 1u) * 2;
+			const uint32_t *l = &sm.out[row_word(row0 + 2 * eb, j, h)];
+			const uint32_t *r = &sm.out[row_word(row0 + 2 * eb + 1, j, h)];
+			w[0] = byte_perm(l[0], r[0], 0x5410);
+			w[1] = byte_perm(l[0], r[0], 0x7632);
+			w[2] = byte_perm(l[1], r[1], 0x5410);
+			w[3] = byte_perm(l[1], r[1], 0x7632);
+		}
+	}
+
+	/*
+	 * staged rows -> interleaved PCM, 16 bytes per step, for a tile that is
+	 * one strip (NS == 1); takes what it needs of the context by value so
+	 * that the stage can be handed back before the store.  nt % 32 == 0.
+	 */
+	XA_HD void phase_store_one(uint32_t tid, uint32_t nt, uint64_t out0, uint32_t nq,
+	    uint32_t out_valid)
+	{
+		const uint32_t nchunk = nq * 4;
+		uint8_t *dst = p.dst + out0;
+		if (out_valid == nchunk * 16u) {
+			/* every unit is whole.  With nt a multiple of 32 the swizzle
+			 * term of a thread's units is the same for all of them, so
+			 * both addresses advance by nt*16 bytes per step. */
+			uint4 *g = reinterpret_cast<uint4 *>(dst) + tid;
+			if (CH == 1) {
+				const uint4 *s = reinterpret_cast<const uint4 *>(
+				    &sm.out[row_word(tid >> 2, (int)(tid & 3u), 0)]);
+				for (uint32_t i = tid; i < nchunk; i += nt) {
+					*g = *s;
+					g += nt;
+					s += nt;
+				}
+			} else {
+				const uint32_t jj = tid & 7u;
+				const int j = (int)(jj >> 1), h = (int)(jj & 1u) * 2;
+				const uint2 *l = reinterpret_cast<const uint2 *>(
+				    &sm.out[row_word(2 * (tid >> 3), j, h)]);
+				const uint2 *r = reinterpret_cast<const uint2 *>(
+				    &sm.out[row_word(2 * (tid >> 3) + 1, j, h)]);
+				for (uint32_t i = tid; i < nchunk; i += nt) {
+					uint2 a = *l, b = *r;
+					uint4 v;
+					v.x = byte_perm(a.x, b.x, 0x5410);
+					v.y = byte_perm(a.x, b.x, 0x7632);
+					v.z = byte_perm(a.y, b.y, 0x5410);
+					v.w = byte_perm(a.y, b.y, 0x7632);
+					*g = v;
+					g += nt;
+					l += nt * 2;	/* nt units = nt*16 B of rows */
+					r += nt * 2;
+				}
+			}
+			return;
+		}
+		/* the truncated last block of a stream */
+		for (uint32_t i = tid; i < nchunk; i += nt) {
+			const uint32_t boff = i * 16u;
+			if (boff >= out_valid)
+				continue;
+			uint32_t w[4];
+			gather_chunk(0, i, w);
+			uint32_t n16 = (out_valid - boff) / 2u;
+			if (n16 > 8u)
+				n16 = 8u;
+			uint16_t *d = reinterpret_cast<uint16_t *>(dst + boff);
+			for (uint32_t k = 0; k < n16; k++)
+				d[k] = (uint16_t)(w[k >> 1] >> (16u * (k & 1u)));
+		}
+	}
+
+	/* the same for any number of strips, reading the contexts in place */
+	XA_HD void phase_store(uint32_t tid, uint32_t nt)
+	{
+		constexpr uint32_t CPS = SBQ * 4;	/* 16-byte units per full strip */
+		if (NS == 1) {
+			phase_store_one(tid, nt, ctx[0].out0, ctx[0].nq, ctx[0].out_valid);
+			return;
+		}
+		const uint32_t total = n_strips * CPS;
+		for (uint32_t i = tid; i < total; i += nt) {
+			const uint32_t st = i / CPS, li = i % CPS;
+			const StripCtx &c = ctx[st];
+			const uint32_t boff = li * 16u;
+			if (boff >= c.out_valid)
+				continue;
+			uint32_t w[4];
+			gather_chunk(st * SBQ, li, w);
+			uint8_t *d8 = p.dst + c.out0 + boff;
+			if (boff + 16u <= c.out_valid) {
+				uint4 v;
+				v.x = w[0]; v.y = w[1]; v.z = w[2]; v.w = w[3];
+				*reinterpret_cast<uint4 *>(d8) = v;
+			} else {
+				uint16_t *d = reinterpret_cast<uint16_t *>(d8);
+				uint32_t n16 = (c.out_valid - boff) / 2u;
+				for (uint32_t k = 0; k < n16; k++)
+					d[k] = (uint16_t)(w[k >> 1] >> (16u * (k & 1u)));
+			}
+		}
+	}
+};
+
 /* ---- encode -------------------------------------------------------------- */
 /*
  * Reference-exact encoder (/root/reference/src/libbjxa.c:665-691,759-819):

@@ -72,14 +72,64 @@ emul_decode_ns(const DecodeParams &p, int order)
 	delete sm;
 }
 
+template <int BITS, int CH, int NS>
+static void
+emul_decode_staged_ns(const DecodeParams &p, int order)
+{
+	typedef DecTileStaged<BITS, CH, kDecTBQ, NS, 2> Tile;
+	typename Tile::Smem *sm = new typename Tile::Smem();
+	const uint32_t nt = kDecThreads;
+
+	memset(sm, 0xa5, sizeof *sm);	/* smem is garbage at CTA start */
+	sm->n_heads = 0;
+	for (uint32_t ticket = 0; ticket < p.n_tiles; ticket++) {
+		/* one persistent CTA draws every ticket; stages rotate as on the GPU */
+		const int s = (int)(ticket % 2);
+		memset(sm->in[s], 0xa5, sizeof sm->in[s]);
+		const TileEnt te = p.tiles[ticket];
+		bool tail = false;
+		for (uint32_t lane = 0; lane < te.count; lane++) {
+			StripCtx &c = sm->ctx[s][lane];
+			make_strip_ctx<BITS, CH, kDecTBQ, NS>(c, p, p.order[te.first + lane],
+			    te.j, lane);
+			memcpy(sm->in[s] + lane * Tile::G::SLOT, p.src + c.a0, c.bulk);
+			tail |= (c.flags & kCtxTail) != 0;
+		}
+		sm->n_strips[s] = te.count;
+		sm->tile_flags[s] = tail ? kCtxTail : 0u;
+		Tile t(p, *sm, s);
+		if (tail)
+			for (uint32_t i = 0; i < nt; i++)
+				t.load_tail(visit(i, nt, order), nt, sm->in[s]);
+		for (uint32_t i = 0; i < nt; i++)
+			t.phase_a(visit(i, nt, order), nt);
+		int heads = sm->n_heads;
+		if (heads != 0)
+			for (uint32_t i = 0; i < nt; i++)
+				t.phase_walk(visit(i, nt, order), nt, heads);
+		for (uint32_t i = 0; i < nt; i++)
+			t.reset_counters(visit(i, nt, order));
+		for (uint32_t i = 0; i < nt; i++)
+			t.phase_store(visit(i, nt, order), nt);
+	}
+	delete sm;
+}
+
 template <int BITS, int CH>
 static void
 emul_decode_bucket(const DecodeParams &p, int ns, int order)
 {
-	if (ns == 1)
+	/* same choice as launch_decode_ns: mono direct, stereo staged */
+	if (CH == 2) {
+		if (ns == 1)
+			emul_decode_staged_ns<BITS, CH, 1>(p, order);
+		else
+			emul_decode_staged_ns<BITS, CH, kDecWide>(p, order);
+	} else if (ns == 1) {
 		emul_decode_ns<BITS, CH, 1>(p, order);
-	else
+	} else {
 		emul_decode_ns<BITS, CH, kDecWide>(p, order);
+	}
 }
 
 template <int BITS, int CH>

@@ -85,28 +85,30 @@ __device__ __forceinline__ void consumer_sync()
 }
 
 /*
- * Persistent, warp-specialised decode kernel.  Grid = (CTAs that fit one SM) x
- * (SM count).  Per CTA:
- *   producer   the extra warp: lane 0 draws tile tickets in order; lane i
- *              builds the context of strip i and starts the bulk-async (TMA)
- *              copy of that strip's contiguous XA bytes into the next free
- *              stage buffer, kDecStages tiles ahead of the consumers;
- *   consumers  kDecThreads threads: wait on the stage's "full" mbarrier, run
- *              phase A (direct blocks, stored straight from registers) and
- *              phase B (walkers) of xa_tile.h, and hand the buffer back
- *              through the stage's "empty" mbarrier, one arrival per warp.
- * There is ONE CTA barrier per tile (between the phases); a warp that has no
- * walker to run goes on to the next tile's phase A while others still walk.
- * (A variant with a dedicated walker warp fed through mbarriers was measured
- * and was slower: profiles/history_r1.md.)
+ * Persistent, warp-specialised decode kernel, direct form (mono streams).
+ * Grid = (CTAs that fit one SM) x (SM count).  Per CTA:
+ *   loader     (1 warp) lane 0 draws tile tickets in order; lane i builds the
+ *              context of strip i and starts the bulk-async (TMA) copy of that
+ *              strip's contiguous XA bytes into the next free stage buffer,
+ *              kDecStages tiles ahead;
+ *   scanner    (1 warp) when a tile's bytes have landed, scans its profile
+ *              bytes for the heads of chains and publishes the tile on its
+ *              "ready" mbarrier;
+ *   consumers  (kDecThreads threads) wait for "ready", walk their share of
+ *              the chains and decode their share of the 16-byte units of the
+ *              cut blocks (xa_tile.h), storing everything straight from
+ *              registers, then arrive -- one arrival per warp -- on the
+ *              stage's "empty" mbarrier.
+ * There is no CTA barrier: the three kinds of warps only meet at mbarriers.
  */
-constexpr int kDecBlock = kDecThreads + 32;
+constexpr int kDecBlock = kDecThreads + 64;	/* consumers + loader warp + scanner warp */
 
-template <int BITS, int CH, int NS>
+template <int BITS, int NS>
 __global__ void __launch_bounds__(kDecBlock)
 xa_decode_kernel(const DecodeParams p)
 {
-	typedef DecTile<BITS, CH, kDecTBQ, NS, kDecStages> Tile;
+	typedef DecTile<BITS, kDecTBQ, NS, kDecStages> Tile;
+	typedef typename Tile::G G;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	typename Tile::Smem &sm = *reinterpret_cast<typename Tile::Smem *>(smem_raw);
 	const uint32_t tid = threadIdx.x;
@@ -114,23 +116,38 @@ xa_decode_kernel(const DecodeParams p)
 	if (tid == 0) {
 		for (int s = 0; s < kDecStages; s++) {
 			mbar_init(smem_u32(&sm.full[s]), 1);
+			mbar_init(smem_u32(&sm.ready[s]), 1);
 			mbar_init(smem_u32(&sm.empty[s]), kDecThreads / 32);
 		}
-		sm.n_heads[0] = sm.n_heads[1] = sm.n_heads[2] = 0;
 	}
 	__syncthreads();
 
-	if (tid >= kDecThreads) {
-		const uint32_t lane = tid - kDecThreads;
+	if (tid >= kDecThreads + 32) {
+		/* ---- loader warp: tickets, strip contexts, bulk-async copies ----
+		 * The ticket and the records of the NEXT tile (ticket -> tile table ->
+		 * issue order -> stream record: four dependent global round trips)
+		 * are fetched while the warp waits for a free stage. */
+		const uint32_t lane = tid - (kDecThreads + 32);
+		unsigned long long t = 0;
+		TileEnt te = { 0u, 0u, 0u, 0u };
+		StripCtx c;
+		auto prefetch = [&]() {
+			/* the counter is preset to ~0 with first_bad[]: old + 1 = ticket */
+			if (lane == 0)
+				t = atomicAdd(p.ticket, 1ULL) + 1ULL;
+			t = __shfl_sync(0xffffffffu, t, 0);
+			if (t < p.n_tiles) {
+				te = p.tiles[t];
+				if (lane < te.count)
+					make_strip_ctx<BITS, 1, kDecTBQ, NS>(c, p,
+					    p.order[te.first + lane], te.j, lane);
+			}
+		};
+		prefetch();
 		for (uint32_t it = 0;; it++) {
 			const int s = (int)(it % kDecStages);
 			if (it >= (uint32_t)kDecStages)
 				mbar_wait(smem_u32(&sm.empty[s]), (it / kDecStages - 1) & 1);
-			/* the counter is preset to ~0 with first_bad[]: old + 1 = ticket */
-			unsigned long long t = 0;
-			if (lane == 0)
-				t = atomicAdd(p.ticket, 1ULL) + 1ULL;
-			t = __shfl_sync(0xffffffffu, t, 0);
 			const uint32_t full = smem_u32(&sm.full[s]);
 			if (t >= p.n_tiles) {
 				if (lane == 0) {
@@ -139,15 +156,13 @@ xa_decode_kernel(const DecodeParams p)
 				}
 				return;
 			}
-			const TileEnt te = p.tiles[t];
 			uint32_t bulk = 0, tail = 0;
-			StripCtx c;
+			const unsigned char *src = p.src;
 			if (lane < te.count) {
-				make_strip_ctx<BITS, CH, kDecTBQ, NS>(c, p, p.order[te.first + lane],
-				    te.j, lane);
 				sm.ctx[s][lane] = c;
 				bulk = c.bulk;
 				tail = c.flags & kCtxTail;
+				src += c.a0;
 			}
 			uint32_t total = bulk;
 #pragma unroll
@@ -164,35 +179,80 @@ xa_decode_kernel(const DecodeParams p)
 			}
 			__syncwarp();
 			if (bulk)
-				bulk_g2s(smem_u32(sm.in[s]) + lane * Tile::G::SLOT, p.src + c.a0,
-				    bulk, full);
+				bulk_g2s(smem_u32(sm.in[s]) + lane * G::SLOT, src, bulk, full);
+			prefetch();
 		}
 	}
 
+	if (tid >= kDecThreads) {
+		/* ---- scanner warp: heads of chains of every landed tile ---- */
+		const uint32_t lane = tid - kDecThreads;
+		for (uint32_t it = 0;; it++) {
+			const int s = (int)(it % kDecStages);
+			mbar_wait(smem_u32(&sm.full[s]), (it / kDecStages) & 1);
+			const uint32_t tf = sm.tile_flags[s];
+			if (tf & kCtxEnd) {
+				if (lane == 0)
+					mbar_arrive(smem_u32(&sm.ready[s]));
+				return;
+			}
+			Tile t(p, sm, s);
+			if (tf & kCtxTail) {	/* only at the very end of the arena */
+				t.load_tail(lane, 32, sm.in[s]);
+				__syncwarp();
+			}
+			uint32_t count = 0;
+			if (NS == 1) {
+				/* one strip: one profile byte per lane and step; "the
+				 * block in front is a chain block" comes out of the ballot */
+				const StripCtx &c0 = sm.ctx[s][0];
+				const uint32_t nq = c0.nq;
+				uint32_t at = c0.in_base + lane * G::BS;
+				uint32_t prev_last = 0;		/* block -1: not a chain */
+				for (uint32_t base = 0; base < nq; base += 32, at += 32 * G::BS) {
+					const uint32_t q = base + lane;
+					const bool ch = q < nq && block_kind(sm.in[s][at]) == kChain;
+					const uint32_t m = __ballot_sync(0xffffffffu, ch);
+					const uint32_t before = lane ? (m >> (lane - 1)) & 1u : prev_last;
+					const bool h = ch && !before;
+					const uint32_t mh = __ballot_sync(0xffffffffu, h);
+					if (h)
+						sm.heads[s][count + __popc(mh & ((1u << lane) - 1u))] =
+						    (uint16_t)q;
+					count += __popc(mh);
+					prev_last = m >> 31;
+				}
+			} else {
+				const uint32_t nq = t.n_strips * G::SBQ;
+				for (uint32_t base = 0; base < nq; base += 32) {
+					const uint32_t q = base + lane;
+					const bool h = q < nq && t.is_head(q);
+					const uint32_t m = __ballot_sync(0xffffffffu, h);
+					if (h)
+						sm.heads[s][count + __popc(m & ((1u << lane) - 1u))] =
+						    (uint16_t)q;
+					count += __popc(m);
+				}
+			}
+			__syncwarp();
+			if (lane == 0) {
+				sm.n_heads[s] = count;
+				mbar_arrive(smem_u32(&sm.ready[s]));
+			}
+		}
+	}
+
+	/* ---- consumer warps ---- */
 	for (uint32_t it = 0;; it++) {
 		const int s = (int)(it % kDecStages);
-		mbar_wait(smem_u32(&sm.full[s]), (it / kDecStages) & 1);
-		const uint32_t tf = sm.tile_flags[s];
-		if (tf & kCtxEnd)
+		mbar_wait(smem_u32(&sm.ready[s]), (it / kDecStages) & 1);
+		if (sm.tile_flags[s] & kCtxEnd)
 			return;
-		Tile t(p, sm, s, it);
-		if (tf & kCtxTail) {	/* only at the very end of the arena */
-			t.load_tail(tid, kDecThreads, sm.in[s]);
-			consumer_sync();
-		}
-
-		t.phase_a(tid, kDecThreads);
-		consumer_sync();
-		/* tail[], heads[] and the counter of this tile are complete.  The
-		 * counter two tiles ahead can be cleared now: nobody can be in that
-		 * tile's phase A before passing the NEXT tile's barrier, and every
-		 * reader of its previous use is behind us. */
-		if (tid == 0)
-			sm.n_heads[(it + 2) % 3] = 0;
-		const int heads = *t.n_heads;
-		if (heads != 0)
-			t.phase_walk(tid, kDecThreads, heads);
-		/* this warp is done with the stage's bytes and contexts */
+		/* already complete; waiting on it orders the bulk copy's bytes for us */
+		mbar_wait(smem_u32(&sm.full[s]), (it / kDecStages) & 1);
+		Tile t(p, sm, s);
+		t.phase_walk(tid, kDecThreads, sm.heads[s], sm.n_heads[s], it * 96u);
+		t.phase_units(tid, kDecThreads);
 		__syncwarp();
 		if ((tid & 31u) == 0)
 			mbar_arrive(smem_u32(&sm.empty[s]));
@@ -554,16 +614,19 @@ template <int BITS, int CH>
 static cudaError_t
 set_attrs_one(void)
 {
-	cudaError_t e = cudaFuncSetAttribute(xa_decode_kernel<BITS, CH, 1>,
-	    cudaFuncAttributeMaxDynamicSharedMemorySize,
-	    (int)sizeof(DecSmem<BITS, CH, kDecTBQ, 1, kDecStages>));
-	if (e != cudaSuccess)
-		return e;
-	e = cudaFuncSetAttribute(xa_decode_kernel<BITS, CH, kDecWide>,
-	    cudaFuncAttributeMaxDynamicSharedMemorySize,
-	    (int)sizeof(DecSmem<BITS, CH, kDecTBQ, kDecWide, kDecStages>));
-	if (e != cudaSuccess)
-		return e;
+	cudaError_t e = cudaSuccess;
+	if (CH == 1) {
+		e = cudaFuncSetAttribute(xa_decode_kernel<BITS, 1>,
+		    cudaFuncAttributeMaxDynamicSharedMemorySize,
+		    (int)sizeof(DecSmem<BITS, kDecTBQ, 1, kDecStages>));
+		if (e != cudaSuccess)
+			return e;
+		e = cudaFuncSetAttribute(xa_decode_kernel<BITS, kDecWide>,
+		    cudaFuncAttributeMaxDynamicSharedMemorySize,
+		    (int)sizeof(DecSmem<BITS, kDecTBQ, kDecWide, kDecStages>));
+		if (e != cudaSuccess)
+			return e;
+	}
 	e = cudaFuncSetAttribute(xa_decode_staged_kernel<BITS, CH, 1>,
 	    cudaFuncAttributeMaxDynamicSharedMemorySize,
 	    (int)sizeof(DecSmemStaged<BITS, CH, kDecTBQ, 1, kDecStagedStages>));
@@ -752,9 +815,9 @@ launch_decode_ns(const DecodeParams &p, cudaStream_t st)
 	constexpr bool staged = CH == 2;
 	const size_t smem = staged ?
 	    sizeof(DecSmemStaged<BITS, CH, kDecTBQ, NS, kDecStagedStages>) :
-	    sizeof(DecSmem<BITS, CH, kDecTBQ, NS, kDecStages>);
+	    sizeof(DecSmem<BITS, kDecTBQ, NS, kDecStages>);
 	void (*kern)(const DecodeParams) = staged ?
-	    xa_decode_staged_kernel<BITS, CH, NS> : xa_decode_kernel<BITS, CH, NS>;
+	    xa_decode_staged_kernel<BITS, CH, NS> : xa_decode_kernel<BITS, NS>;
 	const int block = staged ? kDecThreads + 32 : kDecBlock;
 	int dev = 0;
 	cudaError_t e = cudaGetDevice(&dev);

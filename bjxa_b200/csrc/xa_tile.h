@@ -205,69 +205,66 @@ XA_HD void make_strip_ctx(StripCtx &c, const DecodeParams &p, uint32_t stream,
 	c.pad = 0;
 }
 
-template <int BITS, int CH, int TBQ, int NS, int STAGES>
+/* ---- decode, direct form (mono) -------------------------------------------- */
+
+template <int BITS, int TBQ, int NS, int STAGES>
 struct DecSmem {
-	typedef DecGeom<BITS, CH, TBQ, NS> G;
+	typedef DecGeom<BITS, 1, TBQ, NS> G;
 
 	alignas(16) uint8_t in[STAGES][G::IN_BYTES];
 	StripCtx ctx[STAGES][NS];
 	uint32_t tile_flags[STAGES];		/* kCtxEnd, kCtxTail (any strip) */
 	uint32_t n_strips[STAGES];
-	/* per tile parity: last two samples of every directly decoded block, and
-	 * the effective blocks at which a walker has to start */
-	uint32_t tail[2][TBQ];
-	uint16_t heads[2][TBQ];
-	int n_heads[3];
-	alignas(8) unsigned long long full[STAGES];
-	alignas(8) unsigned long long empty[STAGES];
+	uint16_t heads[STAGES][TBQ];		/* first block of every chain of the tile */
+	uint32_t n_heads[STAGES];
+	alignas(8) unsigned long long full[STAGES];	/* source bytes have landed */
+	alignas(8) unsigned long long ready[STAGES];	/* ... and have been scanned */
+	alignas(8) unsigned long long empty[STAGES];	/* every consumer warp is done */
 };
 
 /*
- * Work decomposition of a decode tile.
+ * Work decomposition of a mono decode tile.  Nothing is staged and no thread
+ * ever waits for another thread of its CTA:
  *
- * Phase A gives every 16-byte unit of output (8 mono samples / 4 stereo frames)
- * to one thread.  For each channel whose block is a CUT block (filter 0, or an
- * invalid filter, which is decoded as filter 0 and reported) the thread unpacks
- * the BITS/2 payload bytes per 4 samples it needs and stores the samples
- * straight to global memory: whole 16-byte units when every channel of the
- * effective block is cut (neighbouring threads then write neighbouring 16
- * bytes), single int16 around the other channel otherwise.  Nothing is staged
- * in shared memory.  The thread of an effective block's last unit leaves each
- * cut block's last two samples in tail[].
+ *   scan     (producer warp, after the tile's bytes have landed) finds the
+ *            head of every chain: a filter-1..4 block whose predecessor is not
+ *            one (or lies in the stream's previous strip);
+ *   units    one consumer thread per 16-byte unit of output (8 samples) of
+ *            every CUT block (filter 0, or an invalid filter, which is decoded
+ *            as filter 0 and reported): it unpacks the 2 * BITS/2 payload bytes
+ *            it needs and stores the unit straight from registers --
+ *            neighbouring threads write neighbouring 16 bytes;
+ *   walkers  one consumer thread per chain: predictor state in registers,
+ *            starting from the last two samples of the cut block in front of
+ *            the chain -- which the walker recomputes itself from that block's
+ *            bytes -- or from the carry mailbox at the start of a strip; it
+ *            stores its own 64-byte rows.
  *
- * Every chain (a run of filter-1..4 blocks of one channel) is walked by one
- * thread in phase B with the predictor state in registers, starting from
- * tail[] of the cut block in front of it, or from the carry mailbox at the
- * start of a strip; the walker stores its samples itself.
+ * A consumer warp that is done with its share of a tile arrives on the stage's
+ * "empty" mbarrier and moves on; warps may drift up to STAGES tiles apart, so
+ * one long chain delays nobody until the ring of source buffers wraps.
  */
-template <int BITS, int CH, int TBQ, int NS, int STAGES>
+template <int BITS, int TBQ, int NS, int STAGES>
 struct DecTile {
-	typedef DecGeom<BITS, CH, TBQ, NS> G;
-	typedef DecSmem<BITS, CH, TBQ, NS, STAGES> Smem;
+	typedef DecGeom<BITS, 1, TBQ, NS> G;
+	typedef DecSmem<BITS, TBQ, NS, STAGES> Smem;
 	static constexpr int BS = G::BS;
 	static constexpr int QB = BITS / 2;		/* payload bytes of 4 samples */
-	static constexpr uint32_t SBE = G::SBE;		/* effective blocks per strip */
-	static constexpr uint32_t UPE = 4 * CH;		/* 16-byte units per effective block */
-	static constexpr uint32_t UPS = SBE * UPE;	/* ... per strip */
+	static constexpr uint32_t SBQ = G::SBQ;		/* blocks per strip */
+	static constexpr uint32_t UPS = SBQ * 4;	/* 16-byte units per strip */
 
 	const DecodeParams &p;
-	Smem &sm;
 	const uint8_t *in;		/* this tile's stage buffer */
 	const StripCtx *ctx;		/* this tile's strips */
 	const uint32_t n_strips;
-	uint32_t *tail;			/* this tile's tail[] */
-	uint16_t *heads;
-	int *n_heads;
 
-	XA_HD DecTile(const DecodeParams &p_, Smem &sm_, int stage, uint32_t tile_no)
-	    : p(p_), sm(sm_), in(sm_.in[stage]), ctx(sm_.ctx[stage]),
-	      n_strips(sm_.n_strips[stage]), tail(sm_.tail[tile_no & 1u]),
-	      heads(sm_.heads[tile_no & 1u]), n_heads(&sm_.n_heads[tile_no % 3u])
+	XA_HD DecTile(const DecodeParams &p_, const Smem &sm_, int stage)
+	    : p(p_), in(sm_.in[stage]), ctx(sm_.ctx[stage]), n_strips(sm_.n_strips[stage])
 	{
 	}
 
 	/* bytes past a strip's `bulk` fetched one by one (only at the arena's end) */
-	XA_HD void load_tail(uint32_t tid, uint32_t nt, uint8_t *in_w)
+	XA_HD void load_tail(uint32_t tid, uint32_t nt, uint8_t *in_w) const
 	{
 		for (uint32_t st = 0; st < n_strips; st++) {
 			const StripCtx &c = ctx[st];
@@ -277,7 +274,7 @@ struct DecTile {
 		}
 	}
 
-	/* stage-buffer address of block-channel lq of a strip */
+	/* stage-buffer address of block lq of a strip */
 	XA_HD uint32_t block_at(const StripCtx &c, uint32_t lq) const
 	{
 		return c.in_base + lq * BS;
@@ -297,34 +294,46 @@ struct DecTile {
 		load_payload<BITS>(pw, w, (pay & 3u) * 8u);
 	}
 
-	/* hand the channel's state to whoever continues it */
-	XA_HD void publish(const StripCtx &c, uint32_t ch, int p0, int p1)
+	/* is block q of the tile (strip-major numbering) the head of a chain? */
+	XA_HD bool is_head(uint32_t q) const
+	{
+		const StripCtx &c = ctx[q / SBQ];
+		const uint32_t lq = q % SBQ;
+		if (lq >= c.nq)
+			return false;
+		const uint32_t at = block_at(c, lq);
+		return block_kind(in[at]) == kChain &&
+		    (lq == 0 || block_kind(in[at - BS]) != kChain);
+	}
+
+	/* hand the stream's state to whoever continues it */
+	XA_HD void publish(const StripCtx &c, int p0, int p1) const
 	{
 		if (c.flags & kCtxLast) {
-			p.results[c.stream].prev[ch][0] = (int16_t)p0;
-			p.results[c.stream].prev[ch][1] = (int16_t)p1;
+			p.results[c.stream].prev[0][0] = (int16_t)p0;
+			p.results[c.stream].prev[0][1] = (int16_t)p1;
 		} else {
 			unsigned long long v = ((unsigned long long)p.epoch << 32) |
 			    ((unsigned long long)(uint16_t)p1 << 16) | (uint16_t)p0;
-			mailbox_put(&p.carry[(uint64_t)c.slot * 2 + ch], v);
+			mailbox_put(&p.carry[(uint64_t)c.slot * 2], v);
 		}
 	}
 
-	XA_HD void carried_in(const StripCtx &c, uint32_t ch, int &p0, int &p1) const
+	XA_HD void carried_in(const StripCtx &c, int &p0, int &p1) const
 	{
 		if (c.flags & kCtxFirst) {
-			p0 = p.streams[c.stream].prev[ch][0];
-			p1 = p.streams[c.stream].prev[ch][1];
+			p0 = p.streams[c.stream].prev[0][0];
+			p1 = p.streams[c.stream].prev[0][1];
 		} else {
 			unsigned long long v = mailbox_get(
-			    &p.carry[(uint64_t)(c.slot - 1) * 2 + ch], p.epoch, p.fault);
+			    &p.carry[(uint64_t)(c.slot - 1) * 2], p.epoch, p.fault);
 			p0 = (int16_t)(uint16_t)v;
 			p1 = (int16_t)(uint16_t)(v >> 16);
 		}
 	}
 
 	/* up to 16 bytes to global memory, honouring the strip's PCM length */
-	XA_HD void put_unit(const StripCtx &c, uint32_t boff, const uint4 &v)
+	XA_HD void put_unit(const StripCtx &c, uint32_t boff, const uint4 &v) const
 	{
 		uint8_t *d8 = p.dst + c.out0 + boff;
 		if (boff + 16u <= c.out_valid) {
@@ -339,212 +348,147 @@ struct DecTile {
 		}
 	}
 
-	/* one int16 of channel ch, sample n of effective block eb (stereo walkers
-	 * and half-direct blocks write their channel around the other one) */
-	XA_HD void put_sample(const StripCtx &c, uint32_t eb, uint32_t n, uint32_t ch,
-	    uint32_t v16)
+	/* the two quads (8 samples) that start at stage-buffer address a: their
+	 * 2 * BITS/2 payload bytes, each quad in the low bytes of its word */
+	XA_HD void load_quads(uint32_t a, uint32_t &qa, uint32_t &qb) const
 	{
-		const uint32_t boff = ((eb * 32u + n) * CH + ch) * 2u;
-		if (boff < c.out_valid)
-			*reinterpret_cast<uint16_t *>(p.dst + c.out0 + boff) = (uint16_t)v16;
+		const uint32_t *w = reinterpret_cast<const uint32_t *>(in) + (a >> 2);
+		const uint32_t sh = (a & 3u) * 8u;
+		if (BITS == 4) {
+			qa = funnel_r(w[0], w[1], sh);		/* 4 bytes: 2 + 2 */
+			qb = qa >> 16;
+		} else if (BITS == 6) {
+			const uint32_t t0 = funnel_r(w[0], w[1], sh);	/* bytes 0..3 */
+			const uint32_t t1 = funnel_r(w[1], w[2], sh);	/* bytes 4..7 */
+			qa = t0;				/* 3 bytes */
+			qb = funnel_r(t0, t1, 24);		/* bytes 3..5 */
+		} else {
+			qa = funnel_r(w[0], w[1], sh);
+			qb = funnel_r(w[1], w[2], sh);
+		}
 	}
 
-	XA_HD void keep_tail(const StripCtx &c, uint32_t st, uint32_t eb, uint32_t ch,
-	    uint32_t t)
+	XA_HD uint4 decode_unit(uint32_t a, uint32_t prof) const
 	{
-		tail[st * G::SBQ + eb * CH + ch] = t;
-		if ((eb + 1) * CH >= c.nq)
-			publish(c, ch, (int)(int16_t)(t >> 16), (int)(int16_t)(t & 0xffffu));
+		uint32_t qa, qb;
+		int x[4], y[4];
+		load_quads(a, qa, qb);
+		quad_codes<BITS>(qa, x);
+		quad_codes<BITS>(qb, y);
+		const int sh = 16 + (int)(prof & 15u);
+		uint4 v;
+		v.x = pack2(x[0] >> sh, x[1] >> sh);
+		v.y = pack2(x[2] >> sh, x[3] >> sh);
+		v.z = pack2(y[0] >> sh, y[1] >> sh);
+		v.w = pack2(y[2] >> sh, y[3] >> sh);
+		return v;
 	}
 
-	/*
-	 * phase A: one thread per 16-byte unit of output (8 mono samples / 4
-	 * stereo frames).  Cut blocks are decoded here; a chain block whose
-	 * predecessor in its channel is not a chain block is queued for a walker
-	 * by the thread of its first unit.
-	 */
-	XA_HD void phase_a(uint32_t tid, uint32_t nt)
+	/* units: one thread per 16-byte unit of output of every cut block */
+	XA_HD void phase_units(uint32_t tid, uint32_t nt) const
 	{
-		if (CH == 1)
-			phase_a_mono(tid, nt);
-		else
-			phase_a_stereo(tid, nt);
-	}
-
-	XA_HD void phase_a_mono(uint32_t tid, uint32_t nt)
-	{
+		if (NS == 1 && nt % 4u == 0) {
+			/*
+			 * One strip: a thread's units are 4 * (nt/4) apart, so its
+			 * position inside the block never changes and every address
+			 * advances by a constant -- (nt/4) * BS bytes of source (a
+			 * multiple of 4 when nt is a multiple of 16, which keeps the
+			 * realignment shift constant as well) and nt * 16 of output.
+			 */
+			const StripCtx &c = ctx[0];
+			const uint32_t nq = c.nq, k = tid & 3u, step_q = nt >> 2;
+			const uint32_t nfull = c.out_valid / 16u;
+			uint32_t at = c.in_base + (tid >> 2) * BS;
+			uint8_t *out = p.dst + c.out0 + (uint64_t)tid * 16u;
+			uint32_t u = tid;
+			for (uint32_t lq = tid >> 2; lq < nq;
+			    lq += step_q, u += nt, at += step_q * BS, out += (uint64_t)nt * 16u) {
+				const uint32_t prof = in[at];
+				const uint32_t f = prof >> 4;
+				if (f - 1u < 4u)
+					continue;		/* a chain block: its walker's */
+				if (k == 0 && f >= 5u)
+					global_min_u32(&p.first_bad[c.stream], c.first_eb + lq);
+				const uint4 v = decode_unit(at + 1 + k * (2 * QB), prof);
+				if (u < nfull)
+					*reinterpret_cast<uint4 *>(out) = v;
+				else
+					put_unit(c, u * 16u, v);
+				/* the last block of the strip hands its last two samples on */
+				if (k == 3 && lq + 1 >= nq)
+					publish(c, (int)(int16_t)(v.w >> 16), (int)(int16_t)(v.w & 0xffffu));
+			}
+			return;
+		}
 		const uint32_t total = n_strips * UPS;
 		for (uint32_t u = tid; u < total; u += nt) {
 			const uint32_t st = u / UPS, lu = u % UPS;
 			const StripCtx &c = ctx[st];
-			const uint32_t eb = lu / UPE, k = lu % UPE;
-			if (eb >= c.nq)
+			const uint32_t lq = lu / 4u, k = lu % 4u;
+			if (lq >= c.nq)
 				continue;
-			const uint32_t at0 = block_at(c, eb);
-			const uint32_t prof0 = in[at0];
-			const int kind0 = block_kind(prof0);
-			if (kind0 == kChain) {
-				/* the first unit of a chain's first block queues a walker */
-				if (k == 0 && (eb == 0 || block_kind(in[at0 - BS]) != kChain))
-					heads[smem_inc(n_heads)] = (uint16_t)(st * G::SBQ + eb);
+			const uint32_t at0 = block_at(c, lq);
+			const uint32_t prof = in[at0];
+			const int kind = block_kind(prof);
+			if (kind == kChain)
 				continue;
-			}
-			if (k == 0 && kind0 == kBad)
-				global_min_u32(&p.first_bad[c.stream], c.first_eb + eb);
-			/* 8 consecutive samples: quads 2k and 2k+1 of the block */
-			uint4 v;
-			int x[4], y[4];
-			const int sh = 16 + (int)(prof0 & 15u);
-			const uint32_t a = at0 + 1 + k * (2 * QB);
-			quad_codes<BITS>(bytes_at(a), x);
-			quad_codes<BITS>(bytes_at(a + QB), y);
-			v.x = pack2(x[0] >> sh, x[1] >> sh);
-			v.y = pack2(x[2] >> sh, x[3] >> sh);
-			v.z = pack2(y[0] >> sh, y[1] >> sh);
-			v.w = pack2(y[2] >> sh, y[3] >> sh);
+			if (k == 0 && kind == kBad)
+				global_min_u32(&p.first_bad[c.stream], c.first_eb + lq);
+			const uint4 v = decode_unit(at0 + 1 + k * (2 * QB), prof);
 			put_unit(c, lu * 16u, v);
-			if (k == UPE - 1) {
-				/* this unit ends the block: keep (and, at the end of the
-				 * strip, publish) the last two samples */
-				const uint32_t t0 = v.w;
-				tail[st * G::SBQ + eb] = t0;
-				if (eb + 1 >= c.nq)
-					publish(c, 0, (int)(int16_t)(t0 >> 16),
-					    (int)(int16_t)(t0 & 0xffffu));
-			}
+			if (k == 3 && lq + 1 >= c.nq)
+				publish(c, (int)(int16_t)(v.w >> 16), (int)(int16_t)(v.w & 0xffffu));
 		}
 	}
 
-	XA_HD void phase_a_stereo(uint32_t tid, uint32_t nt)
+	/* walk the chain that starts at block q (strip-major numbering) */
+	XA_HD void walk(uint32_t q) const
 	{
-		const uint32_t total = n_strips * UPS;
-		for (uint32_t u = tid; u < total; u += nt) {
-			const uint32_t st = u / UPS, lu = u % UPS;
-			const StripCtx &c = ctx[st];
-			const uint32_t eb = lu / UPE, k = lu % UPE;
-			if (eb * 2 >= c.nq)
-				continue;
-			const uint32_t at0 = block_at(c, eb * 2);
-			const uint32_t prof0 = in[at0];
-			const uint32_t prof1 = in[at0 + BS];
-			const int kind0 = block_kind(prof0);
-			const int kind1 = block_kind(prof1);
-			/* 4 frames: quad k of the left and of the right block */
-			const uint32_t a = at0 + 1 + k * QB;
-			int x[4], y[4];
-			if (kind0 != kChain && kind1 != kChain) {
-				/* the common case: the whole unit, 16 bytes at once */
-				if (k == 0) {
-					if (kind0 == kBad)
-						global_min_u32(&p.first_bad[c.stream],
-						    (c.first_eb + eb) * 2);
-					if (kind1 == kBad)
-						global_min_u32(&p.first_bad[c.stream],
-						    (c.first_eb + eb) * 2 + 1);
-				}
-				const int shl = 16 + (int)(prof0 & 15u);
-				const int shr = 16 + (int)(prof1 & 15u);
-				quad_codes<BITS>(bytes_at(a), x);
-				quad_codes<BITS>(bytes_at(a + BS), y);
+		const StripCtx &c = ctx[q / SBQ];
+		uint32_t lq = q % SBQ;
+		uint32_t at = block_at(c, lq);
+		int p0, p1;
+		if (lq == 0) {
+			carried_in(c, p0, p1);
+		} else {
+			/* the block in front is a cut block: its last two samples are
+			 * codes 2 and 3 of its last quad, shifted by its range */
+			const uint32_t pa = at - BS;
+			const int sh = 16 + (int)(in[pa] & 15u);
+			int x[4];
+			quad_codes<BITS>(bytes_at(pa + 1 + 7 * QB), x);
+			p1 = x[2] >> sh;
+			p0 = x[3] >> sh;
+		}
+		for (;;) {
+			uint32_t pw[BITS], o[16];
+			fetch_block(at, pw);
+			decode_block_chain<BITS>(o, pw, in[at], p0, p1);
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
 				uint4 v;
-				v.x = pack2(x[0] >> shl, y[0] >> shr);
-				v.y = pack2(x[1] >> shl, y[1] >> shr);
-				v.z = pack2(x[2] >> shl, y[2] >> shr);
-				v.w = pack2(x[3] >> shl, y[3] >> shr);
-				put_unit(c, lu * 16u, v);
-				if (k == UPE - 1) {
-					keep_tail(c, st, eb, 0, byte_perm(v.z, v.w, 0x5410));
-					keep_tail(c, st, eb, 1, byte_perm(v.z, v.w, 0x7632));
-				}
-				continue;
+				v.x = o[4 * j]; v.y = o[4 * j + 1];
+				v.z = o[4 * j + 2]; v.w = o[4 * j + 3];
+				put_unit(c, (lq * 4u + (uint32_t)j) * 16u, v);
 			}
-			/* at least one channel is a chain block: queue its walker, and
-			 * write the other channel (if it is cut) around it */
-			if (k == 0) {
-				if (kind0 == kBad)
-					global_min_u32(&p.first_bad[c.stream], (c.first_eb + eb) * 2);
-				if (kind1 == kBad)
-					global_min_u32(&p.first_bad[c.stream],
-					    (c.first_eb + eb) * 2 + 1);
-				if (kind0 == kChain && (eb == 0 ||
-				    block_kind(in[at0 - 2 * BS]) != kChain))
-					heads[smem_inc(n_heads)] = (uint16_t)(st * G::SBQ + eb * 2);
-				if (kind1 == kChain && (eb == 0 ||
-				    block_kind(in[at0 - BS]) != kChain))
-					heads[smem_inc(n_heads)] = (uint16_t)(st * G::SBQ + eb * 2 + 1);
+			if (lq + 1 >= c.nq) {
+				publish(c, p0, p1);
+				break;
 			}
-			if (kind0 != kChain) {
-				const int sh = 16 + (int)(prof0 & 15u);
-				quad_codes<BITS>(bytes_at(a), x);
-#pragma unroll
-				for (int i = 0; i < 4; i++)
-					put_sample(c, eb, k * 4 + i, 0, (uint32_t)(x[i] >> sh));
-				if (k == UPE - 1)
-					keep_tail(c, st, eb, 0, pack2(x[2] >> sh, x[3] >> sh));
-			}
-			if (kind1 != kChain) {
-				const int sh = 16 + (int)(prof1 & 15u);
-				quad_codes<BITS>(bytes_at(a + BS), y);
-#pragma unroll
-				for (int i = 0; i < 4; i++)
-					put_sample(c, eb, k * 4 + i, 1, (uint32_t)(y[i] >> sh));
-				if (k == UPE - 1)
-					keep_tail(c, st, eb, 1, pack2(y[2] >> sh, y[3] >> sh));
-			}
+			lq++;
+			at += BS;
+			if (block_kind(in[at]) != kChain)
+				break;
 		}
 	}
 
-	/*
-	 * phase B: one walker per chain (a run of filter-1..4 blocks of one
-	 * channel), predictor state in registers, output stored by the walker.
-	 */
-	XA_HD void phase_walk(uint32_t tid, uint32_t nt, int n)
+	/* walkers: chain i of the tile goes to thread (i + rot) mod nt, so that
+	 * over the tiles every warp takes its turn at the (slow) chains */
+	XA_HD void phase_walk(uint32_t tid, uint32_t nt, const uint16_t *heads, uint32_t n,
+	    uint32_t rot) const
 	{
-		for (uint32_t i = tid; i < (uint32_t)n; i += nt) {
-			const uint32_t h = heads[i];
-			const uint32_t st = h / G::SBQ;
-			uint32_t lq = h % G::SBQ;
-			const uint32_t ch = lq % CH;
-			const StripCtx &c = ctx[st];
-			int p0, p1;
-			if (lq < (uint32_t)CH) {
-				carried_in(c, ch, p0, p1);
-			} else {
-				uint32_t t = tail[st * G::SBQ + lq - CH];
-				p0 = (int)(int16_t)(t >> 16);
-				p1 = (int)(int16_t)(t & 0xffffu);
-			}
-			uint32_t at = block_at(c, lq);
-			for (;;) {
-				uint32_t pw[BITS], o[16];
-				fetch_block(at, pw);
-				decode_block_chain<BITS>(o, pw, in[at], p0, p1);
-				const uint32_t eb = lq / CH;
-				if (CH == 1) {
-#pragma unroll
-					for (int j = 0; j < 4; j++) {
-						uint4 v;
-						v.x = o[4 * j]; v.y = o[4 * j + 1];
-						v.z = o[4 * j + 2]; v.w = o[4 * j + 3];
-						put_unit(c, (eb * 4u + (uint32_t)j) * 16u, v);
-					}
-				} else {
-#pragma unroll
-					for (int j = 0; j < 16; j++) {
-						put_sample(c, eb, 2 * j, ch, o[j]);
-						put_sample(c, eb, 2 * j + 1, ch, o[j] >> 16);
-					}
-				}
-				if (lq + CH >= c.nq) {
-					publish(c, ch, p0, p1);
-					break;
-				}
-				lq += CH;
-				at += CH * BS;
-				if (block_kind(in[at]) != kChain)
-					break;
-			}
-		}
+		for (uint32_t i = (tid + nt - rot % nt) % nt; i < n; i += nt)
+			walk(heads[i]);
 	}
 };
 

@@ -30,16 +30,15 @@ visit(uint32_t i, uint32_t nt, int order)
 	return i;
 }
 
-template <int BITS, int CH, int NS>
+template <int BITS, int NS>
 static void
 emul_decode_ns(const DecodeParams &p, int order)
 {
-	typedef DecTile<BITS, CH, kDecTBQ, NS, kDecStages> Tile;
+	typedef DecTile<BITS, kDecTBQ, NS, kDecStages> Tile;
 	typename Tile::Smem *sm = new typename Tile::Smem();
 	const uint32_t nt = kDecThreads;
 
 	memset(sm, 0xa5, sizeof *sm);	/* smem is garbage at CTA start */
-	sm->n_heads[0] = sm->n_heads[1] = sm->n_heads[2] = 0;
 	for (uint32_t ticket = 0; ticket < p.n_tiles; ticket++) {
 		/* one persistent CTA draws every ticket; stages rotate as on the GPU */
 		const int s = (int)(ticket % kDecStages);
@@ -48,26 +47,28 @@ emul_decode_ns(const DecodeParams &p, int order)
 		bool tail = false;
 		for (uint32_t lane = 0; lane < te.count; lane++) {
 			StripCtx &c = sm->ctx[s][lane];
-			make_strip_ctx<BITS, CH, kDecTBQ, NS>(c, p, p.order[te.first + lane],
+			make_strip_ctx<BITS, 1, kDecTBQ, NS>(c, p, p.order[te.first + lane],
 			    te.j, lane);
 			memcpy(sm->in[s] + lane * Tile::G::SLOT, p.src + c.a0, c.bulk);
 			tail |= (c.flags & kCtxTail) != 0;
 		}
 		sm->n_strips[s] = te.count;
 		sm->tile_flags[s] = tail ? kCtxTail : 0u;
-		Tile t(p, *sm, s, ticket);
+		Tile t(p, *sm, s);
+		/* producer: tail bytes, then the scan for heads of chains */
 		if (tail)
-			for (uint32_t i = 0; i < nt; i++)
-				t.load_tail(visit(i, nt, order), nt, sm->in[s]);
+			for (uint32_t i = 0; i < 32; i++)
+				t.load_tail(i, 32, sm->in[s]);
+		uint32_t count = 0;
+		for (uint32_t q = 0; q < te.count * Tile::G::SBQ; q++)
+			if (t.is_head(q))
+				sm->heads[s][count++] = (uint16_t)q;
+		sm->n_heads[s] = count;
+		/* consumers */
 		for (uint32_t i = 0; i < nt; i++)
-			t.phase_a(visit(i, nt, order), nt);
-		sm->n_heads[(ticket + 2) % 3] = 0;
-		int heads = *t.n_heads;
-		if (heads != 0)
-			for (uint32_t i = 0; i < nt; i++)
-				t.phase_walk(visit(i, nt, order), nt, heads);
-		/* poison what the next tile must not rely on */
-		memset(sm->tail[ticket & 1u], 0x5c, sizeof sm->tail[0]);
+			t.phase_walk(visit(i, nt, order), nt, sm->heads[s], count, ticket * 96u);
+		for (uint32_t i = 0; i < nt; i++)
+			t.phase_units(visit(i, nt, order), nt);
 	}
 	delete sm;
 }
@@ -126,9 +127,9 @@ emul_decode_bucket(const DecodeParams &p, int ns, int order)
 		else
 			emul_decode_staged_ns<BITS, CH, kDecWide>(p, order);
 	} else if (ns == 1) {
-		emul_decode_ns<BITS, CH, 1>(p, order);
+		emul_decode_ns<BITS, 1>(p, order);
 	} else {
-		emul_decode_ns<BITS, CH, kDecWide>(p, order);
+		emul_decode_ns<BITS, kDecWide>(p, order);
 	}
 }
 

@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/bjxa_batch.h"
@@ -85,7 +86,7 @@ __device__ __forceinline__ void consumer_sync()
 }
 
 /*
- * Persistent, warp-specialised decode kernel, direct form (mono streams).
+ * Persistent, warp-specialised decode kernel, generic over the tile form.
  * Grid = (CTAs that fit one SM) x (SM count).  Per CTA:
  *   loader     (1 warp) lane 0 draws tile tickets in order; lane i builds the
  *              context of strip i and starts the bulk-async (TMA) copy of that
@@ -94,30 +95,77 @@ __device__ __forceinline__ void consumer_sync()
  *   scanner    (1 warp) when a tile's bytes have landed, scans its profile
  *              bytes for the heads of chains and publishes the tile on its
  *              "ready" mbarrier;
- *   consumers  (kDecThreads threads) wait for "ready", walk their share of
- *              the chains and decode their share of the 16-byte units of the
- *              cut blocks (xa_tile.h), storing everything straight from
- *              registers, then arrive -- one arrival per warp -- on the
- *              stage's "empty" mbarrier.
- * There is no CTA barrier: the three kinds of warps only meet at mbarriers.
+ *   consumers  (kDecThreads threads) wait for "ready" and run the tile's
+ *              phases (xa_tile.h).  Direct forms: walk their share of the
+ *              chains and decode their share of the 16-byte units of the cut
+ *              blocks, storing everything straight from registers, then arrive
+ *              -- one arrival per warp -- on the stage's "empty" mbarrier; no
+ *              CTA barrier at all.  Staged form (stereo): rows, barrier,
+ *              interleaving store, barrier.
  */
+#ifndef XA_DEC_STAGED_STAGES
+#define XA_DEC_STAGED_STAGES 2
+#endif
+constexpr int kDecStagedStages = XA_DEC_STAGED_STAGES;
 constexpr int kDecBlock = kDecThreads + 64;	/* consumers + loader warp + scanner warp */
 
-template <int BITS, int NS>
+/* one tile, direct forms: walkers and units, no CTA barrier */
+template <class Tile>
+__device__ __forceinline__ typename std::enable_if<!Tile::kStaged>::type
+consume_tile(Tile &t, typename Tile::Smem &sm, int s, uint32_t it, uint32_t tid)
+{
+	t.phase_walk(tid, kDecThreads, sm.heads[s], sm.n_heads[s], it * 96u);
+	t.phase_units(tid, kDecThreads);
+	__syncwarp();
+	if ((tid & 31u) == 0)
+		mbar_arrive(smem_u32(&sm.empty[s]));
+}
+
+/* one tile, staged form: rows (walkers and cut blocks in the same phase),
+ * barrier, interleaving store, barrier */
+template <class Tile>
+__device__ __forceinline__ typename std::enable_if<Tile::kStaged>::type
+consume_tile(Tile &t, typename Tile::Smem &sm, int s, uint32_t it, uint32_t tid)
+{
+	/* one strip per tile: the store needs three words of the context; every
+	 * thread takes them BEFORE the barrier so that the stage can go back to the
+	 * loader ahead of the store */
+	const uint64_t c0_out0 = sm.ctx[s][0].out0;
+	const uint32_t c0_nq = sm.ctx[s][0].nq, c0_valid = sm.ctx[s][0].out_valid;
+	t.phase_walk(tid, kDecThreads, sm.heads[s], sm.n_heads[s], it * 96u);
+	t.phase_a(tid, kDecThreads);
+	consumer_sync();
+	if (Tile::G::kNS == 1) {
+		if (tid == 0)
+			mbar_arrive(smem_u32(&sm.empty[s]));
+		t.phase_store_one(tid, kDecThreads, c0_out0, c0_nq, c0_valid);
+		consumer_sync();	/* rows are free for the next tile */
+	} else {
+		t.phase_store(tid, kDecThreads);
+		consumer_sync();
+		if (tid == 0)
+			mbar_arrive(smem_u32(&sm.empty[s]));
+	}
+}
+
+template <class Tile>
 __global__ void __launch_bounds__(kDecBlock)
 xa_decode_kernel(const DecodeParams p)
 {
-	typedef DecTile<BITS, kDecTBQ, NS, kDecStages> Tile;
 	typedef typename Tile::G G;
+	constexpr int NS = G::kNS;
+	constexpr int kStages = Tile::kStages;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	typename Tile::Smem &sm = *reinterpret_cast<typename Tile::Smem *>(smem_raw);
 	const uint32_t tid = threadIdx.x;
 
 	if (tid == 0) {
-		for (int s = 0; s < kDecStages; s++) {
+		for (int s = 0; s < kStages; s++) {
 			mbar_init(smem_u32(&sm.full[s]), 1);
 			mbar_init(smem_u32(&sm.ready[s]), 1);
-			mbar_init(smem_u32(&sm.empty[s]), kDecThreads / 32);
+			/* direct forms: one arrival per consumer warp; staged form: one
+			 * arrival after the CTA barrier that ends the row phase */
+			mbar_init(smem_u32(&sm.empty[s]), Tile::kStaged ? 1 : kDecThreads / 32);
 		}
 	}
 	__syncthreads();
@@ -139,15 +187,15 @@ xa_decode_kernel(const DecodeParams p)
 			if (t < p.n_tiles) {
 				te = p.tiles[t];
 				if (lane < te.count)
-					make_strip_ctx<BITS, 1, kDecTBQ, NS>(c, p,
+					make_strip_ctx<G::kBits, G::kCh, G::kTBQ, NS>(c, p,
 					    p.order[te.first + lane], te.j, lane);
 			}
 		};
 		prefetch();
 		for (uint32_t it = 0;; it++) {
-			const int s = (int)(it % kDecStages);
-			if (it >= (uint32_t)kDecStages)
-				mbar_wait(smem_u32(&sm.empty[s]), (it / kDecStages - 1) & 1);
+			const int s = (int)(it % kStages);
+			if (it >= (uint32_t)kStages)
+				mbar_wait(smem_u32(&sm.empty[s]), (it / kStages - 1) & 1);
 			const uint32_t full = smem_u32(&sm.full[s]);
 			if (t >= p.n_tiles) {
 				if (lane == 0) {
@@ -188,8 +236,8 @@ xa_decode_kernel(const DecodeParams p)
 		/* ---- scanner warp: heads of chains of every landed tile ---- */
 		const uint32_t lane = tid - kDecThreads;
 		for (uint32_t it = 0;; it++) {
-			const int s = (int)(it % kDecStages);
-			mbar_wait(smem_u32(&sm.full[s]), (it / kDecStages) & 1);
+			const int s = (int)(it % kStages);
+			mbar_wait(smem_u32(&sm.full[s]), (it / kStages) & 1);
 			const uint32_t tf = sm.tile_flags[s];
 			if (tf & kCtxEnd) {
 				if (lane == 0)
@@ -203,27 +251,29 @@ xa_decode_kernel(const DecodeParams p)
 			}
 			uint32_t count = 0;
 			if (NS == 1) {
-				/* one strip: one profile byte per lane and step; "the
-				 * block in front is a chain block" comes out of the ballot */
-				const StripCtx &c0 = sm.ctx[s][0];
-				const uint32_t nq = c0.nq;
-				uint32_t at = c0.in_base + lane * G::BS;
-				uint32_t prev_last = 0;		/* block -1: not a chain */
-				for (uint32_t base = 0; base < nq; base += 32, at += 32 * G::BS) {
+				/* one strip: one item (block, or pair of blocks) per lane
+				 * and step; "the item in front is a walker's too" comes out
+				 * of the ballots */
+				constexpr int LAG = Tile::kLag;	/* item q follows item q - LAG */
+				const uint32_t nq = Tile::kStaged ? sm.ctx[s][0].nq :
+				    sm.ctx[s][0].nq / G::kCh;
+				uint32_t prev_m = 0;		/* items -LAG..-1: not a walker's */
+				for (uint32_t base = 0; base < nq; base += 32) {
 					const uint32_t q = base + lane;
-					const bool ch = q < nq && block_kind(sm.in[s][at]) == kChain;
+					const bool ch = t.needs_walker(q);
 					const uint32_t m = __ballot_sync(0xffffffffu, ch);
-					const uint32_t before = lane ? (m >> (lane - 1)) & 1u : prev_last;
+					const uint32_t before = lane >= (uint32_t)LAG ?
+					    (m >> (lane - LAG)) & 1u : (prev_m >> (32 - LAG + lane)) & 1u;
 					const bool h = ch && !before;
 					const uint32_t mh = __ballot_sync(0xffffffffu, h);
 					if (h)
 						sm.heads[s][count + __popc(mh & ((1u << lane) - 1u))] =
 						    (uint16_t)q;
 					count += __popc(mh);
-					prev_last = m >> 31;
+					prev_m = m;
 				}
 			} else {
-				const uint32_t nq = t.n_strips * G::SBQ;
+				const uint32_t nq = t.n_strips * Tile::SCAN;
 				for (uint32_t base = 0; base < nq; base += 32) {
 					const uint32_t q = base + lane;
 					const bool h = q < nq && t.is_head(q);
@@ -244,129 +294,14 @@ xa_decode_kernel(const DecodeParams p)
 
 	/* ---- consumer warps ---- */
 	for (uint32_t it = 0;; it++) {
-		const int s = (int)(it % kDecStages);
-		mbar_wait(smem_u32(&sm.ready[s]), (it / kDecStages) & 1);
+		const int s = (int)(it % kStages);
+		mbar_wait(smem_u32(&sm.ready[s]), (it / kStages) & 1);
 		if (sm.tile_flags[s] & kCtxEnd)
 			return;
 		/* already complete; waiting on it orders the bulk copy's bytes for us */
-		mbar_wait(smem_u32(&sm.full[s]), (it / kDecStages) & 1);
+		mbar_wait(smem_u32(&sm.full[s]), (it / kStages) & 1);
 		Tile t(p, sm, s);
-		t.phase_walk(tid, kDecThreads, sm.heads[s], sm.n_heads[s], it * 96u);
-		t.phase_units(tid, kDecThreads);
-		__syncwarp();
-		if ((tid & 31u) == 0)
-			mbar_arrive(smem_u32(&sm.empty[s]));
-	}
-}
-
-/* The staged variant of the decode kernel (stereo), same producer / consumer
- * layout; see DecTileStaged in xa_tile.h. */
-constexpr int kDecStagedStages = 2;
-
-template <int BITS, int CH, int NS>
-__global__ void __launch_bounds__(kDecThreads + 32)
-xa_decode_staged_kernel(const DecodeParams p)
-{
-	typedef DecTileStaged<BITS, CH, kDecTBQ, NS, kDecStagedStages> Tile;
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	typename Tile::Smem &sm = *reinterpret_cast<typename Tile::Smem *>(smem_raw);
-	const uint32_t tid = threadIdx.x;
-
-	if (tid == 0) {
-		for (int s = 0; s < kDecStagedStages; s++) {
-			mbar_init(smem_u32(&sm.full[s]), 1);
-			mbar_init(smem_u32(&sm.empty[s]), 1);
-		}
-		sm.n_heads = 0;
-	}
-	__syncthreads();
-
-	if (tid >= kDecThreads) {
-		const uint32_t lane = tid - kDecThreads;
-		for (uint32_t it = 0;; it++) {
-			const int s = (int)(it % kDecStagedStages);
-			if (it >= (uint32_t)kDecStagedStages)
-				mbar_wait(smem_u32(&sm.empty[s]), (it / kDecStagedStages - 1) & 1);
-			/* the counter is preset to ~0 with first_bad[]: old + 1 = ticket */
-			unsigned long long t = 0;
-			if (lane == 0)
-				t = atomicAdd(p.ticket, 1ULL) + 1ULL;
-			t = __shfl_sync(0xffffffffu, t, 0);
-			const uint32_t full = smem_u32(&sm.full[s]);
-			if (t >= p.n_tiles) {
-				if (lane == 0) {
-					sm.tile_flags[s] = kCtxEnd;
-					mbar_arrive(full);
-				}
-				return;
-			}
-			const TileEnt te = p.tiles[t];
-			uint32_t bulk = 0, tail = 0;
-			StripCtx c;
-			if (lane < te.count) {
-				make_strip_ctx<BITS, CH, kDecTBQ, NS>(c, p, p.order[te.first + lane],
-				    te.j, lane);
-				sm.ctx[s][lane] = c;
-				bulk = c.bulk;
-				tail = c.flags & kCtxTail;
-			}
-			uint32_t total = bulk;
-#pragma unroll
-			for (int o = 16; o > 0; o >>= 1)
-				total += __shfl_xor_sync(0xffffffffu, total, o);
-			const uint32_t any_tail = __ballot_sync(0xffffffffu, tail != 0);
-			if (lane == 0) {
-				sm.tile_flags[s] = any_tail ? kCtxTail : 0u;
-				sm.n_strips[s] = te.count;
-				if (total)
-					mbar_expect_tx(full, total);
-				else
-					mbar_arrive(full);
-			}
-			__syncwarp();
-			if (bulk)
-				bulk_g2s(smem_u32(sm.in[s]) + lane * Tile::G::SLOT, p.src + c.a0,
-				    bulk, full);
-		}
-	}
-
-	for (uint32_t it = 0;; it++) {
-		const int s = (int)(it % kDecStagedStages);
-		mbar_wait(smem_u32(&sm.full[s]), (it / kDecStagedStages) & 1);
-		const uint32_t tf = sm.tile_flags[s];
-		if (tf & kCtxEnd)
-			return;
-		Tile t(p, sm, s);
-		if (tf & kCtxTail) {	/* only at the very end of the arena */
-			t.load_tail(tid, kDecThreads, sm.in[s]);
-			consumer_sync();
-		}
-
-		/* NS == 1: the store needs three words of the context; every thread
-		 * takes them to registers BEFORE the next barrier so that the stage
-		 * (context included) can go back to the producer ahead of the store */
-		const uint64_t c0_out0 = sm.ctx[s][0].out0;
-		const uint32_t c0_nq = sm.ctx[s][0].nq, c0_valid = sm.ctx[s][0].out_valid;
-
-		t.phase_a(tid, kDecThreads);
-		consumer_sync();
-		const int heads = sm.n_heads;
-		if (heads != 0) {
-			t.phase_walk(tid, kDecThreads, heads);
-			consumer_sync();
-		}
-		t.reset_counters(tid);
-		if (NS == 1) {
-			if (tid == 0)
-				mbar_arrive(smem_u32(&sm.empty[s]));
-			t.phase_store_one(tid, kDecThreads, c0_out0, c0_nq, c0_valid);
-			consumer_sync();	/* rows are free for the next tile's phase A */
-		} else {
-			t.phase_store(tid, kDecThreads);
-			consumer_sync();
-			if (tid == 0)
-				mbar_arrive(smem_u32(&sm.empty[s]));
-		}
+		consume_tile(t, sm, s, it, tid);
 	}
 }
 
@@ -610,33 +545,30 @@ struct bjxa_plan {
 
 static bool g_attr_done = false;
 
+template <class Tile>
+static cudaError_t
+set_dec_attr(void)
+{
+	return cudaFuncSetAttribute(xa_decode_kernel<Tile>,
+	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(typename Tile::Smem));
+}
+
 template <int BITS, int CH>
 static cudaError_t
 set_attrs_one(void)
 {
-	cudaError_t e = cudaSuccess;
+	cudaError_t e;
 	if (CH == 1) {
-		e = cudaFuncSetAttribute(xa_decode_kernel<BITS, 1>,
-		    cudaFuncAttributeMaxDynamicSharedMemorySize,
-		    (int)sizeof(DecSmem<BITS, kDecTBQ, 1, kDecStages>));
-		if (e != cudaSuccess)
+		if ((e = set_dec_attr<DecTile<BITS, kDecTBQ, 1, kDecStages> >()) != cudaSuccess ||
+		    (e = set_dec_attr<DecTile<BITS, kDecTBQ, kDecWide, kDecStages> >()) != cudaSuccess)
 			return e;
-		e = cudaFuncSetAttribute(xa_decode_kernel<BITS, kDecWide>,
-		    cudaFuncAttributeMaxDynamicSharedMemorySize,
-		    (int)sizeof(DecSmem<BITS, kDecTBQ, kDecWide, kDecStages>));
-		if (e != cudaSuccess)
+	} else {
+		if ((e = set_dec_attr<DecTileStereo<BITS, kDecTBQ, 1, kDecStages> >()) != cudaSuccess ||
+		    (e = set_dec_attr<DecTileStereo<BITS, kDecTBQ, kDecWide, kDecStages> >()) != cudaSuccess ||
+		    (e = set_dec_attr<DecTileStaged<BITS, 2, kDecTBQ, 1, kDecStagedStages> >()) != cudaSuccess ||
+		    (e = set_dec_attr<DecTileStaged<BITS, 2, kDecTBQ, kDecWide, kDecStagedStages> >()) != cudaSuccess)
 			return e;
 	}
-	e = cudaFuncSetAttribute(xa_decode_staged_kernel<BITS, CH, 1>,
-	    cudaFuncAttributeMaxDynamicSharedMemorySize,
-	    (int)sizeof(DecSmemStaged<BITS, CH, kDecTBQ, 1, kDecStagedStages>));
-	if (e != cudaSuccess)
-		return e;
-	e = cudaFuncSetAttribute(xa_decode_staged_kernel<BITS, CH, kDecWide>,
-	    cudaFuncAttributeMaxDynamicSharedMemorySize,
-	    (int)sizeof(DecSmemStaged<BITS, CH, kDecTBQ, kDecWide, kDecStagedStages>));
-	if (e != cudaSuccess)
-		return e;
 	return cudaFuncSetAttribute(xa_encode_kernel<BITS, CH>,
 	    cudaFuncAttributeMaxDynamicSharedMemorySize,
 	    (int)sizeof(EncSmem<BITS, CH, kEncTBE>));
@@ -804,28 +736,33 @@ bjxa_plan_extent(const bjxa_plan_t *pl, uint64_t *src_bytes, uint64_t *dst_bytes
 	return (0);
 }
 
-template <int BITS, int CH, int NS>
-static cudaError_t
-launch_decode_ns(const DecodeParams &p, cudaStream_t st)
+/* which stereo form: 1 = staged rows, 0 = direct (BJXA_B200_STEREO=staged|direct) */
+static int
+stereo_staged(void)
 {
-	/* persistent: as many CTAs as fit the device at once, never more than
-	 * tiles.  Mono streams use the direct form of the tile algorithm, stereo
-	 * streams the staged one (xa_tile.h). */
+	static int mode = -1;
+	if (mode < 0) {
+		const char *e = getenv("BJXA_B200_STEREO");
+		mode = (e != NULL && strcmp(e, "direct") == 0) ? 0 : 1;
+	}
+	return mode;
+}
+
+template <class Tile>
+static cudaError_t
+launch_persistent(const DecodeParams &p, cudaStream_t st)
+{
+	/* persistent: as many CTAs as fit the device at once, never more than tiles */
 	static thread_local int grid_cache[2] = { -1, 0 };
-	constexpr bool staged = CH == 2;
-	const size_t smem = staged ?
-	    sizeof(DecSmemStaged<BITS, CH, kDecTBQ, NS, kDecStagedStages>) :
-	    sizeof(DecSmem<BITS, kDecTBQ, NS, kDecStages>);
-	void (*kern)(const DecodeParams) = staged ?
-	    xa_decode_staged_kernel<BITS, CH, NS> : xa_decode_kernel<BITS, NS>;
-	const int block = staged ? kDecThreads + 32 : kDecBlock;
+	const size_t smem = sizeof(typename Tile::Smem);
 	int dev = 0;
 	cudaError_t e = cudaGetDevice(&dev);
 	if (e != cudaSuccess)
 		return e;
 	if (grid_cache[0] != dev) {
 		int per_sm = 0, sms = 0;
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem);
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm,
+		    xa_decode_kernel<Tile>, kDecBlock, smem);
 		if (e != cudaSuccess)
 			return e;
 		e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -837,8 +774,22 @@ launch_decode_ns(const DecodeParams &p, cudaStream_t st)
 	uint32_t grid = (uint32_t)grid_cache[1];
 	if (grid > p.n_tiles)
 		grid = p.n_tiles;
-	kern<<<grid, block, smem, st>>>(p);
+	xa_decode_kernel<Tile><<<grid, kDecBlock, smem, st>>>(p);
 	return cudaGetLastError();
+}
+
+template <int BITS, int CH, int NS>
+static cudaError_t
+launch_decode_ns(const DecodeParams &p, cudaStream_t st)
+{
+	/* mono: the direct form.  Stereo: the staged form unless the direct one
+	 * is asked for (xa_tile.h explains the forms, profiles/history_r1.md the
+	 * measurements behind the default). */
+	if (CH == 1)
+		return launch_persistent<DecTile<BITS, kDecTBQ, NS, kDecStages> >(p, st);
+	if (!stereo_staged())
+		return launch_persistent<DecTileStereo<BITS, kDecTBQ, NS, kDecStages> >(p, st);
+	return launch_persistent<DecTileStaged<BITS, 2, kDecTBQ, NS, kDecStagedStages> >(p, st);
 }
 
 template <int BITS, int CH>

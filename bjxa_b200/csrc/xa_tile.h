@@ -158,6 +158,7 @@ enum { kCtxFirst = 1u, kCtxLast = 2u, kCtxTail = 4u, kCtxEnd = 0x80000000u };
 
 template <int BITS, int CH, int TBQ, int NS>
 struct DecGeom {
+	static constexpr int kBits = BITS, kCh = CH, kTBQ = TBQ, kNS = NS;
 	static constexpr int BS = block_bytes(BITS);
 	static constexpr int SBQ = TBQ / NS;		/* block-channels per strip */
 	static constexpr int SBE = SBQ / CH;		/* effective blocks per strip */
@@ -207,9 +208,9 @@ XA_HD void make_strip_ctx(StripCtx &c, const DecodeParams &p, uint32_t stream,
 
 /* ---- decode, direct form (mono) -------------------------------------------- */
 
-template <int BITS, int TBQ, int NS, int STAGES>
+template <int BITS, int CH, int TBQ, int NS, int STAGES>
 struct DecSmem {
-	typedef DecGeom<BITS, 1, TBQ, NS> G;
+	typedef DecGeom<BITS, CH, TBQ, NS> G;
 
 	alignas(16) uint8_t in[STAGES][G::IN_BYTES];
 	StripCtx ctx[STAGES][NS];
@@ -247,10 +248,14 @@ struct DecSmem {
 template <int BITS, int TBQ, int NS, int STAGES>
 struct DecTile {
 	typedef DecGeom<BITS, 1, TBQ, NS> G;
-	typedef DecSmem<BITS, TBQ, NS, STAGES> Smem;
+	typedef DecSmem<BITS, 1, TBQ, NS, STAGES> Smem;
 	static constexpr int BS = G::BS;
 	static constexpr int QB = BITS / 2;		/* payload bytes of 4 samples */
 	static constexpr uint32_t SBQ = G::SBQ;		/* blocks per strip */
+	static constexpr uint32_t SCAN = G::SBQ;	/* items the scanner looks at per strip */
+	static constexpr int kLag = 1;
+	static constexpr bool kStaged = false;
+	static constexpr int kStages = STAGES;
 	static constexpr uint32_t UPS = SBQ * 4;	/* 16-byte units per strip */
 
 	const DecodeParams &p;
@@ -292,6 +297,12 @@ struct DecTile {
 		uint32_t pay = at + 1;		/* first payload byte */
 		const uint32_t *w = reinterpret_cast<const uint32_t *>(in) + (pay >> 2);
 		load_payload<BITS>(pw, w, (pay & 3u) * 8u);
+	}
+
+	/* scanner, one strip: does item q (a block) belong to a walker? */
+	XA_HD bool needs_walker(uint32_t q) const
+	{
+		return q < ctx[0].nq && block_kind(in[ctx[0].in_base + q * BS]) == kChain;
 	}
 
 	/* is block q of the tile (strip-major numbering) the head of a chain? */
@@ -492,6 +503,273 @@ struct DecTile {
 	}
 };
 
+/* ---- decode, direct form (stereo) ------------------------------------------ */
+/*
+ * The same barrier-free decomposition for two channels.  The unit of work is
+ * the EFFECTIVE block (left block + right block = 32 frames = 128 bytes of
+ * PCM):
+ *   units    one thread per 16-byte unit (4 frames) of every effective block
+ *            whose two blocks are both cut blocks: quad k of the left and of
+ *            the right block, interleaved in registers, one 128-bit store;
+ *   walkers  one thread per maximal run of effective blocks in which at least
+ *            one channel is a chain block.  The walker carries the predictor
+ *            state of BOTH channels and decodes them sample by sample side by
+ *            side (two independent dependency chains: tools/lat_bench.cu
+ *            measures 19 instead of 34 cycles per sample for two interleaved
+ *            chains); a cut block inside a run simply has k0 = k1 = 0.  It
+ *            writes whole interleaved 16-byte units, so nothing ever has to
+ *            be written around the other channel.
+ */
+template <int BITS, int TBQ, int NS, int STAGES>
+struct DecTileStereo {
+	typedef DecGeom<BITS, 2, TBQ, NS> G;
+	typedef DecSmem<BITS, 2, TBQ, NS, STAGES> Smem;
+	static constexpr int BS = G::BS;
+	static constexpr int QB = BITS / 2;
+	static constexpr uint32_t SBE = G::SBE;		/* effective blocks per strip */
+	static constexpr uint32_t SCAN = G::SBE;
+	static constexpr int kLag = 1;
+	static constexpr bool kStaged = false;
+	static constexpr int kStages = STAGES;
+	static constexpr uint32_t UPS = SBE * 8;	/* 16-byte units per strip */
+
+	const DecodeParams &p;
+	const uint8_t *in;
+	const StripCtx *ctx;
+	const uint32_t n_strips;
+
+	XA_HD DecTileStereo(const DecodeParams &p_, const Smem &sm_, int stage)
+	    : p(p_), in(sm_.in[stage]), ctx(sm_.ctx[stage]), n_strips(sm_.n_strips[stage])
+	{
+	}
+
+	XA_HD void load_tail(uint32_t tid, uint32_t nt, uint8_t *in_w) const
+	{
+		for (uint32_t st = 0; st < n_strips; st++) {
+			const StripCtx &c = ctx[st];
+			uint32_t slot0 = st * G::SLOT;
+			for (uint32_t i = c.bulk + tid; i < c.in_need; i += nt)
+				in_w[slot0 + i] = p.src[c.a0 + i];
+		}
+	}
+
+	/* stage-buffer address of the LEFT block of effective block eb */
+	XA_HD uint32_t eb_at(const StripCtx &c, uint32_t eb) const
+	{
+		return c.in_base + eb * (2 * BS);
+	}
+
+	XA_HD uint32_t bytes_at(uint32_t at) const
+	{
+		const uint32_t *w = reinterpret_cast<const uint32_t *>(in) + (at >> 2);
+		return funnel_r(w[0], w[1], (at & 3u) * 8u);
+	}
+
+	XA_HD void fetch_block(uint32_t at, uint32_t (&pw)[BITS]) const
+	{
+		uint32_t pay = at + 1;
+		const uint32_t *w = reinterpret_cast<const uint32_t *>(in) + (pay >> 2);
+		load_payload<BITS>(pw, w, (pay & 3u) * 8u);
+	}
+
+	/* does effective block eb (inside the strip) contain a chain block? */
+	XA_HD bool walked(const StripCtx &c, uint32_t eb) const
+	{
+		const uint32_t at = eb_at(c, eb);
+		return block_kind(in[at]) == kChain || block_kind(in[at + BS]) == kChain;
+	}
+
+	XA_HD bool needs_walker(uint32_t q) const	/* scanner, one strip */
+	{
+		return q * 2 < ctx[0].nq && walked(ctx[0], q);
+	}
+
+	/* q = strip * SBE + eb */
+	XA_HD bool is_head(uint32_t q) const
+	{
+		const StripCtx &c = ctx[q / SBE];
+		const uint32_t eb = q % SBE;
+		return eb * 2 < c.nq && walked(c, eb) && (eb == 0 || !walked(c, eb - 1));
+	}
+
+	XA_HD void publish(const StripCtx &c, uint32_t ch, int p0, int p1) const
+	{
+		if (c.flags & kCtxLast) {
+			p.results[c.stream].prev[ch][0] = (int16_t)p0;
+			p.results[c.stream].prev[ch][1] = (int16_t)p1;
+		} else {
+			unsigned long long v = ((unsigned long long)p.epoch << 32) |
+			    ((unsigned long long)(uint16_t)p1 << 16) | (uint16_t)p0;
+			mailbox_put(&p.carry[(uint64_t)c.slot * 2 + ch], v);
+		}
+	}
+
+	XA_HD void carried_in(const StripCtx &c, uint32_t ch, int &p0, int &p1) const
+	{
+		if (c.flags & kCtxFirst) {
+			p0 = p.streams[c.stream].prev[ch][0];
+			p1 = p.streams[c.stream].prev[ch][1];
+		} else {
+			unsigned long long v = mailbox_get(
+			    &p.carry[(uint64_t)(c.slot - 1) * 2 + ch], p.epoch, p.fault);
+			p0 = (int16_t)(uint16_t)v;
+			p1 = (int16_t)(uint16_t)(v >> 16);
+		}
+	}
+
+	XA_HD void put_unit(const StripCtx &c, uint32_t boff, const uint4 &v) const
+	{
+		uint8_t *d8 = p.dst + c.out0 + boff;
+		if (boff + 16u <= c.out_valid) {
+			*reinterpret_cast<uint4 *>(d8) = v;
+		} else if (boff < c.out_valid) {
+			const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+			uint16_t *d = reinterpret_cast<uint16_t *>(d8);
+			uint32_t n16 = (c.out_valid - boff) / 2u;
+			for (uint32_t k = 0; k < n16; k++)
+				d[k] = (uint16_t)(w[k >> 1] >> (16u * (k & 1u)));
+		}
+	}
+
+	/* quad k of both blocks of the effective block at `at`, as 4 frames */
+	XA_HD uint4 decode_unit(uint32_t at, uint32_t k, uint32_t profl, uint32_t profr) const
+	{
+		int x[4], y[4];
+		const uint32_t a = at + 1 + k * QB;
+		quad_codes<BITS>(bytes_at(a), x);
+		quad_codes<BITS>(bytes_at(a + BS), y);
+		const int shl = 16 + (int)(profl & 15u), shr = 16 + (int)(profr & 15u);
+		uint4 v;
+		v.x = pack2(x[0] >> shl, y[0] >> shr);
+		v.y = pack2(x[1] >> shl, y[1] >> shr);
+		v.z = pack2(x[2] >> shl, y[2] >> shr);
+		v.w = pack2(x[3] >> shl, y[3] >> shr);
+		return v;
+	}
+
+	XA_HD void unit_body(const StripCtx &c, uint32_t eb, uint32_t k, uint32_t at,
+	    uint32_t u_in_strip, uint8_t *out, bool whole) const
+	{
+		const uint32_t profl = in[at], profr = in[at + BS];
+		const uint32_t fl = profl >> 4, fr = profr >> 4;
+		if (fl - 1u < 4u || fr - 1u < 4u)
+			return;			/* a walker's */
+		if (k == 0) {
+			if (fl >= 5u)
+				global_min_u32(&p.first_bad[c.stream], (c.first_eb + eb) * 2);
+			if (fr >= 5u)
+				global_min_u32(&p.first_bad[c.stream], (c.first_eb + eb) * 2 + 1);
+		}
+		const uint4 v = decode_unit(at, k, profl, profr);
+		if (whole)
+			*reinterpret_cast<uint4 *>(out) = v;
+		else
+			put_unit(c, u_in_strip * 16u, v);
+		if (k == 7 && (eb + 1) * 2 >= c.nq) {
+			/* frames 30 and 31: v.z = L30 | R30 << 16, v.w = L31 | R31 << 16 */
+			publish(c, 0, (int)(int16_t)(v.w & 0xffffu), (int)(int16_t)(v.z & 0xffffu));
+			publish(c, 1, (int)(int16_t)(v.w >> 16), (int)(int16_t)(v.z >> 16));
+		}
+	}
+
+	XA_HD void phase_units(uint32_t tid, uint32_t nt) const
+	{
+		if (NS == 1 && nt % 8u == 0) {
+			const StripCtx &c = ctx[0];
+			const uint32_t neb = c.nq / 2u, k = tid & 7u, step = nt >> 3;
+			const uint32_t nfull = c.out_valid / 16u;
+			uint32_t at = c.in_base + (tid >> 3) * (2 * BS);
+			uint8_t *out = p.dst + c.out0 + (uint64_t)tid * 16u;
+			uint32_t u = tid;
+			for (uint32_t eb = tid >> 3; eb < neb;
+			    eb += step, u += nt, at += step * (2 * BS), out += (uint64_t)nt * 16u)
+				unit_body(c, eb, k, at, u, out, u < nfull);
+			return;
+		}
+		const uint32_t total = n_strips * UPS;
+		for (uint32_t u = tid; u < total; u += nt) {
+			const uint32_t st = u / UPS, lu = u % UPS;
+			const StripCtx &c = ctx[st];
+			const uint32_t eb = lu / 8u, k = lu % 8u;
+			if (eb * 2 >= c.nq)
+				continue;
+			unit_body(c, eb, k, eb_at(c, eb), lu, NULL, false);
+		}
+	}
+
+	/* walk the run of effective blocks that starts at q = strip * SBE + eb */
+	XA_HD void walk(uint32_t q) const
+	{
+		const StripCtx &c = ctx[q / SBE];
+		uint32_t eb = q % SBE;
+		uint32_t at = eb_at(c, eb);
+		int p0[2], p1[2];
+		if (eb == 0) {
+			carried_in(c, 0, p0[0], p1[0]);
+			carried_in(c, 1, p0[1], p1[1]);
+		} else {
+			/* the effective block in front is all cut: last two samples of
+			 * each of its blocks = codes 2, 3 of the block's last quad */
+#pragma unroll
+			for (int ch = 0; ch < 2; ch++) {
+				const uint32_t pa = at - 2 * BS + ch * BS;
+				const int sh = 16 + (int)(in[pa] & 15u);
+				int x[4];
+				quad_codes<BITS>(bytes_at(pa + 1 + 7 * QB), x);
+				p1[ch] = x[2] >> sh;
+				p0[ch] = x[3] >> sh;
+			}
+		}
+		for (;;) {
+			const uint32_t profl = in[at], profr = in[at + BS];
+			if (profl >> 4 >= 5u)
+				global_min_u32(&p.first_bad[c.stream], (c.first_eb + eb) * 2);
+			if (profr >> 4 >= 5u)
+				global_min_u32(&p.first_bad[c.stream], (c.first_eb + eb) * 2 + 1);
+			uint32_t pl[BITS], pr[BITS];
+			fetch_block(at, pl);
+			fetch_block(at + BS, pr);
+			const int shl = 16 + (int)(profl & 15u), shr = 16 + (int)(profr & 15u);
+			const int k0l = gain_k0(profl >> 4), k1l = gain_k1(profl >> 4);
+			const int k0r = gain_k0(profr >> 4), k1r = gain_k1(profr >> 4);
+			/* both channels side by side: two independent dependency chains */
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				int l[4], r[4];
+#pragma unroll
+				for (int i = 0; i < 4; i++) {
+					l[i] = sample_chain(top_code<BITS>(pl, 4 * j + i), shl, k0l, k1l,
+					    p0[0], p1[0]);
+					r[i] = sample_chain(top_code<BITS>(pr, 4 * j + i), shr, k0r, k1r,
+					    p0[1], p1[1]);
+				}
+				uint4 v;
+				v.x = pack2(l[0], r[0]);
+				v.y = pack2(l[1], r[1]);
+				v.z = pack2(l[2], r[2]);
+				v.w = pack2(l[3], r[3]);
+				put_unit(c, (eb * 8u + (uint32_t)j) * 16u, v);
+			}
+			if ((eb + 1) * 2 >= c.nq) {
+				publish(c, 0, p0[0], p1[0]);
+				publish(c, 1, p0[1], p1[1]);
+				break;
+			}
+			eb++;
+			at += 2 * BS;
+			if (!walked(c, eb))
+				break;
+		}
+	}
+
+	XA_HD void phase_walk(uint32_t tid, uint32_t nt, const uint16_t *heads, uint32_t n,
+	    uint32_t rot) const
+	{
+		for (uint32_t i = (tid + nt - rot % nt) % nt; i < n; i += nt)
+			walk(heads[i]);
+	}
+};
+
 /* ---- decode, staged variant (used for stereo) ------------------------------ */
 /*
  * The first complete form of the tile algorithm, kept for STEREO streams: every
@@ -512,9 +790,10 @@ struct DecSmemStaged {
 	StripCtx ctx[STAGES][NS];
 	uint32_t tile_flags[STAGES];		/* kCtxEnd, kCtxTail (any strip) */
 	uint32_t n_strips[STAGES];
-	uint16_t heads[TBQ];			/* heads of chains found in phase A */
-	int n_heads;
+	uint16_t heads[STAGES][TBQ];		/* first block of every chain of the tile */
+	uint32_t n_heads[STAGES];
 	alignas(8) unsigned long long full[STAGES];
+	alignas(8) unsigned long long ready[STAGES];
 	alignas(8) unsigned long long empty[STAGES];
 };
 
@@ -523,7 +802,12 @@ struct DecTileStaged {
 	typedef DecGeom<BITS, CH, TBQ, NS> G;
 	typedef DecSmemStaged<BITS, CH, TBQ, NS, STAGES> Smem;
 	static constexpr int BS = G::BS;
+	static constexpr int QB = BITS / 2;
 	static constexpr uint32_t SBQ = G::SBQ;
+	static constexpr uint32_t SCAN = G::SBQ;	/* scanner items: block-channels */
+	static constexpr int kLag = CH;			/* predecessor of item q is q - CH */
+	static constexpr bool kStaged = true;
+	static constexpr int kStages = STAGES;
 
 	const DecodeParams &p;
 	Smem &sm;
@@ -609,6 +893,25 @@ struct DecTileStaged {
 	 * stream's previous strip) is queued as the head of a chain.  Needs
 	 * n_heads == 0 on entry.
 	 */
+	/* scanner, one strip: is item q (a block-channel) a chain block? */
+	XA_HD bool needs_walker(uint32_t q) const
+	{
+		return q < ctx[0].nq && block_kind(in[ctx[0].in_base + q * BS]) == kChain;
+	}
+
+	/* is block-channel q of the tile (strip-major) the head of a chain? */
+	XA_HD bool is_head(uint32_t q) const
+	{
+		const StripCtx &c = ctx[q / SBQ];
+		const uint32_t lq = q % SBQ;
+		if (lq >= c.nq)
+			return false;
+		const uint32_t at = block_at(c, lq);
+		return block_kind(in[at]) == kChain &&
+		    (lq < (uint32_t)CH || block_kind(in[at - CH * BS]) != kChain);
+	}
+
+	/* phase A: every cut block-channel is decoded into its row */
 	XA_HD void phase_a(uint32_t tid, uint32_t nt)
 	{
 		const uint32_t nq_all = n_strips * SBQ;
@@ -620,11 +923,8 @@ struct DecTileStaged {
 			const uint32_t at = block_at(c, lq);
 			const uint32_t prof = in[at];
 			const int kind = block_kind(prof);
-			if (kind == kChain) {
-				if (lq < (uint32_t)CH || block_kind(in[at - CH * BS]) != kChain)
-					sm.heads[smem_inc(&sm.n_heads)] = (uint16_t)q;
-				continue;
-			}
+			if (kind == kChain)
+				continue;		/* a walker's */
 			if (kind == kBad)
 				global_min_u32(&p.first_bad[c.stream], c.first_eb * CH + lq);
 			/* a bad block is decoded as if it were a cut so that
@@ -641,14 +941,16 @@ struct DecTileStaged {
 	}
 
 	/*
-	 * phase B: one walker per chain.  Thread i takes head i and decodes the
-	 * chain's blocks one after the other with the predictor state in
-	 * registers; no barrier until every chain of the tile is done.
+	 * walkers: chain i of the tile goes to thread (i + rot) mod nt.  The
+	 * state at the head is recomputed from the bytes of the cut block in
+	 * front (codes 2 and 3 of its last quad), so walkers depend on nothing
+	 * phase A produces and both run in the same phase.
 	 */
-	XA_HD void phase_walk(uint32_t tid, uint32_t nt, int n)
+	XA_HD void phase_walk(uint32_t tid, uint32_t nt, const uint16_t *heads, uint32_t n,
+	    uint32_t rot)
 	{
-		for (uint32_t i = tid; i < (uint32_t)n; i += nt) {
-			uint32_t q = sm.heads[i];
+		for (uint32_t i = (tid + nt - rot % nt) % nt; i < n; i += nt) {
+			uint32_t q = heads[i];
 			const StripCtx &c = ctx[q / SBQ];
 			uint32_t lq = q % SBQ;
 			uint32_t at = block_at(c, lq);
@@ -656,9 +958,14 @@ struct DecTileStaged {
 			if (lq < (uint32_t)CH) {
 				carried_in(c, lq, p0, p1);
 			} else {
-				uint32_t last = sm.out[row_word(q - CH, 3, 3)];
-				p0 = (int)(int16_t)(last >> 16);
-				p1 = (int)(int16_t)(last & 0xffffu);
+				const uint32_t pa = at - CH * BS;
+				const int sh = 16 + (int)(in[pa] & 15u);
+				const uint32_t a = pa + 1 + 7 * QB;
+				const uint32_t *w = reinterpret_cast<const uint32_t *>(in) + (a >> 2);
+				int x[4];
+				quad_codes<BITS>(funnel_r(w[0], w[1], (a & 3u) * 8u), x);
+				p1 = x[2] >> sh;
+				p0 = x[3] >> sh;
 			}
 			for (;;) {
 				uint32_t pw[BITS], o[16];
@@ -676,13 +983,6 @@ struct DecTileStaged {
 					break;
 			}
 		}
-	}
-
-	/* after phase B: leave the head counter zero for the next tile */
-	XA_HD void reset_counters(uint32_t tid)
-	{
-		if (tid == 0)
-			sm.n_heads = 0;
 	}
 
 	/* one 16-byte unit (index li within its strip) of interleaved PCM */

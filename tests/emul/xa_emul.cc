@@ -19,6 +19,8 @@
 
 using namespace xa;
 
+static int g_stereo_direct = 0;
+
 /* thread visiting order inside a phase: 0 ascending, 1 descending, 2 strided */
 static uint32_t
 visit(uint32_t i, uint32_t nt, int order)
@@ -30,11 +32,11 @@ visit(uint32_t i, uint32_t nt, int order)
 	return i;
 }
 
-template <int BITS, int NS>
+template <class Tile>
 static void
 emul_decode_ns(const DecodeParams &p, int order)
 {
-	typedef DecTile<BITS, kDecTBQ, NS, kDecStages> Tile;
+	typedef typename Tile::G G;
 	typename Tile::Smem *sm = new typename Tile::Smem();
 	const uint32_t nt = kDecThreads;
 
@@ -47,8 +49,8 @@ emul_decode_ns(const DecodeParams &p, int order)
 		bool tail = false;
 		for (uint32_t lane = 0; lane < te.count; lane++) {
 			StripCtx &c = sm->ctx[s][lane];
-			make_strip_ctx<BITS, 1, kDecTBQ, NS>(c, p, p.order[te.first + lane],
-			    te.j, lane);
+			make_strip_ctx<G::kBits, G::kCh, G::kTBQ, G::kNS>(c, p,
+			    p.order[te.first + lane], te.j, lane);
 			memcpy(sm->in[s] + lane * Tile::G::SLOT, p.src + c.a0, c.bulk);
 			tail |= (c.flags & kCtxTail) != 0;
 		}
@@ -60,7 +62,7 @@ emul_decode_ns(const DecodeParams &p, int order)
 			for (uint32_t i = 0; i < 32; i++)
 				t.load_tail(i, 32, sm->in[s]);
 		uint32_t count = 0;
-		for (uint32_t q = 0; q < te.count * Tile::G::SBQ; q++)
+		for (uint32_t q = 0; q < te.count * Tile::SCAN; q++)
 			if (t.is_head(q))
 				sm->heads[s][count++] = (uint16_t)q;
 		sm->n_heads[s] = count;
@@ -82,9 +84,7 @@ emul_decode_staged_ns(const DecodeParams &p, int order)
 	const uint32_t nt = kDecThreads;
 
 	memset(sm, 0xa5, sizeof *sm);	/* smem is garbage at CTA start */
-	sm->n_heads = 0;
 	for (uint32_t ticket = 0; ticket < p.n_tiles; ticket++) {
-		/* one persistent CTA draws every ticket; stages rotate as on the GPU */
 		const int s = (int)(ticket % 2);
 		memset(sm->in[s], 0xa5, sizeof sm->in[s]);
 		const TileEnt te = p.tiles[ticket];
@@ -100,16 +100,17 @@ emul_decode_staged_ns(const DecodeParams &p, int order)
 		sm->tile_flags[s] = tail ? kCtxTail : 0u;
 		Tile t(p, *sm, s);
 		if (tail)
-			for (uint32_t i = 0; i < nt; i++)
-				t.load_tail(visit(i, nt, order), nt, sm->in[s]);
+			for (uint32_t i = 0; i < 32; i++)
+				t.load_tail(i, 32, sm->in[s]);
+		uint32_t count = 0;
+		for (uint32_t q = 0; q < te.count * Tile::SCAN; q++)
+			if (t.is_head(q))
+				sm->heads[s][count++] = (uint16_t)q;
+		sm->n_heads[s] = count;
+		for (uint32_t i = 0; i < nt; i++)
+			t.phase_walk(visit(i, nt, order), nt, sm->heads[s], count, ticket * 96u);
 		for (uint32_t i = 0; i < nt; i++)
 			t.phase_a(visit(i, nt, order), nt);
-		int heads = sm->n_heads;
-		if (heads != 0)
-			for (uint32_t i = 0; i < nt; i++)
-				t.phase_walk(visit(i, nt, order), nt, heads);
-		for (uint32_t i = 0; i < nt; i++)
-			t.reset_counters(visit(i, nt, order));
 		for (uint32_t i = 0; i < nt; i++)
 			t.phase_store(visit(i, nt, order), nt);
 	}
@@ -120,16 +121,22 @@ template <int BITS, int CH>
 static void
 emul_decode_bucket(const DecodeParams &p, int ns, int order)
 {
-	/* same choice as launch_decode_ns: mono direct, stereo staged */
-	if (CH == 2) {
+	/* same choice as launch_decode_ns: mono direct; stereo staged, or direct
+	 * when g_stereo_direct is set (the tests run both) */
+	if (CH == 2 && !g_stereo_direct) {
 		if (ns == 1)
 			emul_decode_staged_ns<BITS, CH, 1>(p, order);
 		else
 			emul_decode_staged_ns<BITS, CH, kDecWide>(p, order);
+	} else if (CH == 2) {
+		if (ns == 1)
+			emul_decode_ns<DecTileStereo<BITS, kDecTBQ, 1, kDecStages> >(p, order);
+		else
+			emul_decode_ns<DecTileStereo<BITS, kDecTBQ, kDecWide, kDecStages> >(p, order);
 	} else if (ns == 1) {
-		emul_decode_ns<BITS, 1>(p, order);
+		emul_decode_ns<DecTile<BITS, kDecTBQ, 1, kDecStages> >(p, order);
 	} else {
-		emul_decode_ns<BITS, kDecWide>(p, order);
+		emul_decode_ns<DecTile<BITS, kDecTBQ, kDecWide, kDecStages> >(p, order);
 	}
 }
 
@@ -269,6 +276,7 @@ xa_emul_plan(int kind, const bjxa_stream_desc_t *descs, size_t n, int force_stri
 	return (int)nt;
 }
 
+void xa_emul_stereo_direct(int on) { g_stereo_direct = on; }
 int xa_emul_strip_blocks(int ns, int ch) { return (int)strip_blocks(ns, ch); }
 int xa_emul_wide(void) { return kDecWide; }
 int xa_emul_enc_tile_blocks(void) { return kEncTBE; }

@@ -29,6 +29,7 @@ class Emul:
         self.strip_blocks = d.xa_emul_strip_blocks      # (ns, ch) -> effective blocks
         self.wide = d.xa_emul_wide()
         self.enc_tile_blocks = d.xa_emul_enc_tile_blocks
+        self.stereo_direct = d.xa_emul_stereo_direct    # (0|1): which stereo form to step
 
     def dec_tile_blocks(self, ch):
         """effective blocks of one long (NS = 1) strip"""

@@ -11,9 +11,14 @@ from bjxa_b200 import synth
 from emul_binding import Emul
 
 
-@pytest.fixture(scope="module")
-def emul():
-    return Emul()
+@pytest.fixture(scope="module", params=["stereo-staged", "stereo-direct"])
+def emul(request):
+    """Every decode case runs twice: stereo streams through the staged form and
+    through the direct form of the tile code (mono always uses the direct one)."""
+    e = Emul()
+    e.stereo_direct(1 if request.param == "stereo-direct" else 0)
+    yield e
+    e.stereo_direct(0)
 
 
 STRIP_MODES = [1, 32]      # one long strip per tile / 32 short ones

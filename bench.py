@@ -76,6 +76,14 @@ def mix_profiles(torch, mix, n, blocks, device, seed):
     elif mix == "P3":
         filt = 1 + (u * 4).to(torch.int32).clamp_(max=3)
         rng = (v * 16).to(torch.int32).clamp_(max=15)
+    elif mix.startswith("C"):
+        # "Cnn": every block independently a chain block (filter 1..4) with
+        # probability nn %, ranges uniform 0..15 -- used to find where one tile
+        # form overtakes another
+        frac = float(mix[1:]) / 100.0
+        w = torch.rand((n, blocks), device=device, generator=g)
+        filt = torch.where(u < frac, 1 + (w * 4).to(torch.int32).clamp_(max=3), 0).to(torch.int32)
+        rng = (v * 16).to(torch.int32).clamp_(max=15)
     else:
         raise ValueError(mix)
     return ((filt << 4) | rng).to(torch.uint8)

@@ -109,6 +109,48 @@ __device__ __forceinline__ void consumer_sync()
 constexpr int kDecStagedStages = XA_DEC_STAGED_STAGES;
 constexpr int kDecBlock = kDecThreads + 64;	/* consumers + loader warp + scanner warp */
 
+/*
+ * Census for a stereo class of a batch: looks at 16384 pseudo-randomly chosen
+ * blocks and writes which tile form to use -- the direct form (0) when fewer
+ * than kCensusPermille of the blocks are chain blocks (filters 1..4), the
+ * staged form (1) otherwise.  One CTA, no atomics, nothing to clear; about
+ * 32 KB of HBM traffic.  Measured crossover: profiles/history_r1.md.
+ */
+constexpr uint32_t kCensusThreads = 1024, kCensusPerThread = 16, kCensusPermille = 100;
+
+__global__ void __launch_bounds__(kCensusThreads)
+xa_census_kernel(const uint8_t *src, const StreamDev *streams, const uint32_t *order,
+    uint32_t n_streams, uint32_t block_bytes_all, uint32_t *choice)
+{
+	__shared__ uint32_t warp_sum[kCensusThreads / 32];
+	const uint32_t tid = threadIdx.x;
+	uint32_t chains = 0;
+#pragma unroll 4
+	for (uint32_t k = 0; k < kCensusPerThread; k++) {
+		uint32_t h = (tid * kCensusPerThread + k) * 2654435761u;
+		h ^= h >> 15;
+		h *= 2246822519u;
+		h ^= h >> 13;
+		const StreamDev &s = streams[order[h % n_streams]];
+		/* any block-channel of the stream: blocks * 2 of them, block_bytes each */
+		const uint32_t q = (h >> 7) % (s.blocks * 2u);
+		const uint32_t prof = src[s.xa_off + (uint64_t)q * block_bytes_all];
+		chains += block_kind(prof) == kChain;
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		chains += __shfl_xor_sync(0xffffffffu, chains, o);
+	if ((tid & 31u) == 0)
+		warp_sum[tid >> 5] = chains;
+	__syncthreads();
+	if (tid == 0) {
+		uint32_t total = 0;
+		for (uint32_t w = 0; w < kCensusThreads / 32; w++)
+			total += warp_sum[w];
+		*choice = total * 1000u < kCensusPermille * kCensusThreads * kCensusPerThread ? 0u : 1u;
+	}
+}
+
 /* one tile, direct forms: walkers and units, no CTA barrier */
 template <class Tile>
 __device__ __forceinline__ typename std::enable_if<!Tile::kStaged>::type
@@ -158,6 +200,9 @@ xa_decode_kernel(const DecodeParams p)
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	typename Tile::Smem &sm = *reinterpret_cast<typename Tile::Smem *>(smem_raw);
 	const uint32_t tid = threadIdx.x;
+
+	if (p.choice != NULL && *p.choice != p.want)
+		return;		/* the census picked the other tile form */
 
 	if (tid == 0) {
 		for (int s = 0; s < kStages; s++) {
@@ -257,20 +302,23 @@ xa_decode_kernel(const DecodeParams p)
 				constexpr int LAG = Tile::kLag;	/* item q follows item q - LAG */
 				const uint32_t nq = Tile::kStaged ? sm.ctx[s][0].nq :
 				    sm.ctx[s][0].nq / G::kCh;
-				uint32_t prev_m = 0;		/* items -LAG..-1: not a walker's */
+				uint32_t prev = 0;	/* items -LAG..-1: no chain channels */
 				for (uint32_t base = 0; base < nq; base += 32) {
 					const uint32_t q = base + lane;
-					const bool ch = t.needs_walker(q);
-					const uint32_t m = __ballot_sync(0xffffffffu, ch);
-					const uint32_t before = lane >= (uint32_t)LAG ?
-					    (m >> (lane - LAG)) & 1u : (prev_m >> (32 - LAG + lane)) & 1u;
-					const bool h = ch && !before;
+					/* chain channels of item q and of the item in front;
+					 * a head continues none of that one's chains */
+					const uint32_t cm = t.chain_mask(q);
+					const uint32_t up = __shfl_up_sync(0xffffffffu, cm, LAG);
+					const uint32_t old = __shfl_sync(0xffffffffu, prev,
+					    (32 - LAG + lane) & 31u);
+					const uint32_t before = lane >= (uint32_t)LAG ? up : old;
+					const bool h = cm != 0 && (cm & before) == 0;
 					const uint32_t mh = __ballot_sync(0xffffffffu, h);
 					if (h)
 						sm.heads[s][count + __popc(mh & ((1u << lane) - 1u))] =
 						    (uint16_t)q;
 					count += __popc(mh);
-					prev_m = m;
+					prev = cm;
 				}
 			} else {
 				const uint32_t nq = t.n_strips * Tile::SCAN;
@@ -521,6 +569,15 @@ struct DevBuf {
 	}
 };
 
+/* stereo tile form: 0 = direct, 1 = staged, 2 = let the census decide per launch
+ * (BJXA_B200_STEREO=direct|staged|auto, default auto) */
+static int
+stereo_mode(void)
+{
+	const char *e = getenv("BJXA_B200_STEREO");
+	return e == NULL ? 2 : strcmp(e, "direct") == 0 ? 0 : strcmp(e, "staged") == 0 ? 1 : 2;
+}
+
 struct bjxa_plan {
 	uint32_t magic;
 #define BJXA_PLAN_MAGIC 0x706c414eu
@@ -541,6 +598,7 @@ struct bjxa_plan {
 	uint64_t last_src_bytes;
 	cudaStream_t last_stream;
 	int launches;
+	int stereo;			/* stereo_mode() when the plan was built */
 };
 
 static bool g_attr_done = false;
@@ -605,7 +663,7 @@ plan_upload(bjxa_plan *pl)
 
 	if ((rc = pl->d_streams.reserve(n, false)) ||
 	    (rc = pl->d_results.reserve(n, false)) ||
-	    (rc = pl->d_first_bad.reserve(n + 16, false)) ||	/* + 6 ticket counters */
+	    (rc = pl->d_first_bad.reserve(n + 24, false)) ||	/* + 6 ticket counters, 6 census words */
 	    (rc = pl->d_fault.reserve(4, true)) ||
 	    (rc = pl->d_tiles.reserve(hp.tiles.size(), false)) ||
 	    (rc = pl->d_order.reserve(hp.order.size(), false)) ||
@@ -648,9 +706,15 @@ plan_build(bjxa_plan *pl, int kind, const bjxa_stream_desc_t *descs, size_t n)
 	pl->descs.assign(descs, descs + n);
 	pl->ran = false;
 	pl->launches = 0;
+	pl->stereo = stereo_mode();
 	for (int b = 0; b < 6; b++)
-		if (pl->hp.tile_begin[b + 1] > pl->hp.tile_begin[b])
-			pl->launches++;
+		if (pl->hp.tile_begin[b + 1] > pl->hp.tile_begin[b]) {
+			/* stereo decode, automatic form: census + both tile forms,
+			 * one of which returns at once */
+			const bool both = kind == kKindDecode && bucket_ch(b) == 2 &&
+			    pl->stereo == 2;
+			pl->launches += both ? 3 : 1;
+		}
 	return (plan_upload(pl));
 }
 
@@ -736,18 +800,6 @@ bjxa_plan_extent(const bjxa_plan_t *pl, uint64_t *src_bytes, uint64_t *dst_bytes
 	return (0);
 }
 
-/* which stereo form: 1 = staged rows, 0 = direct (BJXA_B200_STEREO=staged|direct) */
-static int
-stereo_staged(void)
-{
-	static int mode = -1;
-	if (mode < 0) {
-		const char *e = getenv("BJXA_B200_STEREO");
-		mode = (e != NULL && strcmp(e, "direct") == 0) ? 0 : 1;
-	}
-	return mode;
-}
-
 template <class Tile>
 static cudaError_t
 launch_persistent(const DecodeParams &p, cudaStream_t st)
@@ -780,24 +832,43 @@ launch_persistent(const DecodeParams &p, cudaStream_t st)
 
 template <int BITS, int CH, int NS>
 static cudaError_t
-launch_decode_ns(const DecodeParams &p, cudaStream_t st)
+launch_decode_ns(const DecodeParams &p0, int mode, uint32_t *d_choice, const uint32_t *d_order,
+    uint32_t n_streams, cudaStream_t st)
 {
-	/* mono: the direct form.  Stereo: the staged form unless the direct one
-	 * is asked for (xa_tile.h explains the forms, profiles/history_r1.md the
-	 * measurements behind the default). */
+	/* mono: the direct form.  Stereo: direct or staged form, chosen per launch
+	 * by a census of the batch's profile bytes unless one is forced
+	 * (xa_tile.h explains the forms, profiles/history_r1.md the numbers). */
 	if (CH == 1)
-		return launch_persistent<DecTile<BITS, kDecTBQ, NS, kDecStages> >(p, st);
-	if (!stereo_staged())
-		return launch_persistent<DecTileStereo<BITS, kDecTBQ, NS, kDecStages> >(p, st);
-	return launch_persistent<DecTileStaged<BITS, 2, kDecTBQ, NS, kDecStagedStages> >(p, st);
+		return launch_persistent<DecTile<BITS, kDecTBQ, NS, kDecStages> >(p0, st);
+	DecodeParams p = p0;
+	if (mode == 2) {
+		xa_census_kernel<<<1, kCensusThreads, 0, st>>>(p.src, p.streams, d_order, n_streams,
+		    (uint32_t)block_bytes(BITS), d_choice);
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess)
+			return e;
+		p.choice = d_choice;
+	}
+	if (mode != 1) {
+		p.want = 0;
+		cudaError_t e = launch_persistent<DecTileStereo<BITS, kDecTBQ, NS, kDecStages> >(p, st);
+		if (e != cudaSuccess)
+			return e;
+	}
+	if (mode != 0) {
+		p.want = 1;
+		return launch_persistent<DecTileStaged<BITS, 2, kDecTBQ, NS, kDecStagedStages> >(p, st);
+	}
+	return cudaSuccess;
 }
 
 template <int BITS, int CH>
 static cudaError_t
-launch_decode(const DecodeParams &p, int ns, cudaStream_t st)
+launch_decode(const DecodeParams &p, int ns, int mode, uint32_t *d_choice, const uint32_t *d_order,
+    uint32_t n_streams, cudaStream_t st)
 {
-	return ns == 1 ? launch_decode_ns<BITS, CH, 1>(p, st) :
-	    launch_decode_ns<BITS, CH, kDecWide>(p, st);
+	return ns == 1 ? launch_decode_ns<BITS, CH, 1>(p, mode, d_choice, d_order, n_streams, st) :
+	    launch_decode_ns<BITS, CH, kDecWide>(p, mode, d_choice, d_order, n_streams, st);
 }
 
 template <int BITS, int CH>
@@ -851,7 +922,7 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 		 * the six tile-ticket counters that follow them (~0 = no ticket
 		 * drawn yet, see the producer in xa_decode_kernel) */
 		XA_CUDA(cudaMemsetAsync(pl->d_first_bad.p, 0xff,
-		    (n + 16) * sizeof(uint32_t), st));
+		    (n + 24) * sizeof(uint32_t), st));
 	}
 
 	for (int b = 0; b < 6; b++) {
@@ -875,13 +946,18 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 			    pl->d_first_bad.p + ((n + 3) & ~(size_t)3)) + b;
 			p.fault = pl->d_fault.p;
 			p.epoch = pl->epoch;
+			p.choice = NULL;
+			p.want = 0;
+			uint32_t *choice = pl->d_first_bad.p + ((n + 3) & ~(size_t)3) + 12 + b;
+			const uint32_t *ord = pl->d_order.p + hp.order_begin[b];
+			const uint32_t cnt = hp.order_begin[b + 1] - hp.order_begin[b];
 			switch (b) {
-			case 0: e = launch_decode<4, 1>(p, hp.ns[b], st); break;
-			case 1: e = launch_decode<4, 2>(p, hp.ns[b], st); break;
-			case 2: e = launch_decode<6, 1>(p, hp.ns[b], st); break;
-			case 3: e = launch_decode<6, 2>(p, hp.ns[b], st); break;
-			case 4: e = launch_decode<8, 1>(p, hp.ns[b], st); break;
-			default: e = launch_decode<8, 2>(p, hp.ns[b], st); break;
+			case 0: e = launch_decode<4, 1>(p, hp.ns[b], pl->stereo, choice, ord, cnt, st); break;
+			case 1: e = launch_decode<4, 2>(p, hp.ns[b], pl->stereo, choice, ord, cnt, st); break;
+			case 2: e = launch_decode<6, 1>(p, hp.ns[b], pl->stereo, choice, ord, cnt, st); break;
+			case 3: e = launch_decode<6, 2>(p, hp.ns[b], pl->stereo, choice, ord, cnt, st); break;
+			case 4: e = launch_decode<8, 1>(p, hp.ns[b], pl->stereo, choice, ord, cnt, st); break;
+			default: e = launch_decode<8, 2>(p, hp.ns[b], pl->stereo, choice, ord, cnt, st); break;
 			}
 		} else {
 			EncodeParams p;

@@ -61,6 +61,7 @@ struct HostPlan {
 	std::vector<uint32_t> order;		/* streams in issue order, by bucket */
 	std::vector<TileEnt> tiles;		/* all buckets, concatenated */
 	uint32_t tile_begin[7];			/* bucket b owns [b], [b+1]) */
+	uint32_t order_begin[7];		/* likewise, into order */
 	int ns[6];				/* decode: strips per tile of bucket b */
 	uint32_t n_slots;
 	uint64_t src_need, dst_need;		/* arena bytes the batch touches */
@@ -148,6 +149,7 @@ inline int build_plan(HostPlan &hp, int kind, const Desc *d, size_t n,
 	for (int b = 0; b < 6; b++) {
 		hp.tile_begin[b] = (uint32_t)hp.tiles.size();
 		hp.ns[b] = 1;
+		hp.order_begin[b] = (uint32_t)hp.order.size();
 		std::vector<uint32_t> &o = members[b];
 		if (o.empty())
 			continue;
@@ -196,6 +198,7 @@ inline int build_plan(HostPlan &hp, int kind, const Desc *d, size_t n,
 		}
 	}
 	hp.tile_begin[6] = (uint32_t)hp.tiles.size();
+	hp.order_begin[6] = (uint32_t)hp.order.size();
 	return 0;
 }
 

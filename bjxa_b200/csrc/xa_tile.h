@@ -73,6 +73,10 @@ struct DecodeParams {
 	unsigned long long *ticket;	/* preset to ~0 before every launch */
 	uint32_t *fault;		/* set if a carry never arrived */
 	uint32_t epoch;
+	/* stereo: two tile forms are launched and the census decides which one
+	 * runs; a kernel whose `want` differs from *choice returns at once */
+	const uint32_t *choice;		/* NULL = run unconditionally */
+	uint32_t want;
 };
 
 struct EncodeParams {
@@ -299,8 +303,8 @@ struct DecTile {
 		load_payload<BITS>(pw, w, (pay & 3u) * 8u);
 	}
 
-	/* scanner, one strip: does item q (a block) belong to a walker? */
-	XA_HD bool needs_walker(uint32_t q) const
+	/* scanner, one strip: the chain channels of item q (a block: bit 0) */
+	XA_HD uint32_t chain_mask(uint32_t q) const
 	{
 		return q < ctx[0].nq && block_kind(in[ctx[0].in_base + q * BS]) == kChain;
 	}
@@ -361,10 +365,8 @@ struct DecTile {
 
 	/* the two quads (8 samples) that start at stage-buffer address a: their
 	 * 2 * BITS/2 payload bytes, each quad in the low bytes of its word */
-	XA_HD void load_quads(uint32_t a, uint32_t &qa, uint32_t &qb) const
+	XA_HD static void load_quads(const uint32_t *w, uint32_t sh, uint32_t &qa, uint32_t &qb)
 	{
-		const uint32_t *w = reinterpret_cast<const uint32_t *>(in) + (a >> 2);
-		const uint32_t sh = (a & 3u) * 8u;
 		if (BITS == 4) {
 			qa = funnel_r(w[0], w[1], sh);		/* 4 bytes: 2 + 2 */
 			qb = qa >> 16;
@@ -379,11 +381,12 @@ struct DecTile {
 		}
 	}
 
-	XA_HD uint4 decode_unit(uint32_t a, uint32_t prof) const
+	/* 8 samples from the payload window (aligned words w, bit offset sh) */
+	XA_HD static uint4 unit_from(const uint32_t *w, uint32_t bit, uint32_t prof)
 	{
 		uint32_t qa, qb;
 		int x[4], y[4];
-		load_quads(a, qa, qb);
+		load_quads(w, bit, qa, qb);
 		quad_codes<BITS>(qa, x);
 		quad_codes<BITS>(qb, y);
 		const int sh = 16 + (int)(prof & 15u);
@@ -395,39 +398,65 @@ struct DecTile {
 		return v;
 	}
 
+	XA_HD uint4 decode_unit(uint32_t a, uint32_t prof) const
+	{
+		return unit_from(reinterpret_cast<const uint32_t *>(in) + (a >> 2), (a & 3u) * 8u, prof);
+	}
+
+	/* a block with a filter nibble set: false = a walker's, true = an invalid
+	 * filter, which is recorded (by the k == 0 thread) and decoded as cut */
+	XA_HD bool unit_uncut(const StripCtx &c, uint32_t lq, uint32_t k, uint32_t prof) const
+	{
+		const uint32_t f = prof >> 4;
+		if (f - 1u < 4u)
+			return false;
+		if (k == 0)
+			global_min_u32(&p.first_bad[c.stream], c.first_eb + lq);
+		return true;
+	}
+
 	/* units: one thread per 16-byte unit of output of every cut block */
 	XA_HD void phase_units(uint32_t tid, uint32_t nt) const
 	{
-		if (NS == 1 && nt % 4u == 0) {
+		if (NS == 1 && nt % 16u == 0) {
 			/*
-			 * One strip: a thread's units are 4 * (nt/4) apart, so its
-			 * position inside the block never changes and every address
-			 * advances by a constant -- (nt/4) * BS bytes of source (a
-			 * multiple of 4 when nt is a multiple of 16, which keeps the
-			 * realignment shift constant as well) and nt * 16 of output.
+			 * One strip: thread t owns units t, t + nt, ...: always the same
+			 * quad pair of blocks nt / 4 apart.  That is (nt / 4) * BS bytes
+			 * of stage buffer, a multiple of 4, so the word alignment of the
+			 * thread's payload window never changes and the loop advances two
+			 * pointers and a counter.  Whole units first; the (at most one)
+			 * ragged unit and the carry out of the strip come after the loop.
 			 */
 			const StripCtx &c = ctx[0];
-			const uint32_t nq = c.nq, k = tid & 3u, step_q = nt >> 2;
-			const uint32_t nfull = c.out_valid / 16u;
-			uint32_t at = c.in_base + (tid >> 2) * BS;
-			uint8_t *out = p.dst + c.out0 + (uint64_t)tid * 16u;
+			const uint32_t total = c.nq * 4u;
+			const uint32_t nfull = c.out_valid / 16u < total ? c.out_valid / 16u : total;
+			const uint32_t k = tid & 3u, stepb = (nt >> 2) * BS;
+			const uint32_t at = c.in_base + (tid >> 2) * BS;
+			const uint32_t a = at + 1 + k * (2 * QB);
+			const uint8_t *pin = in + at;
+			const uint32_t *w = reinterpret_cast<const uint32_t *>(in + (a & ~3u));
+			const uint32_t bit = (a & 3u) * 8u;
+			uint8_t *const out = p.dst + c.out0;
 			uint32_t u = tid;
-			for (uint32_t lq = tid >> 2; lq < nq;
-			    lq += step_q, u += nt, at += step_q * BS, out += (uint64_t)nt * 16u) {
-				const uint32_t prof = in[at];
-				const uint32_t f = prof >> 4;
-				if (f - 1u < 4u)
-					continue;		/* a chain block: its walker's */
-				if (k == 0 && f >= 5u)
-					global_min_u32(&p.first_bad[c.stream], c.first_eb + lq);
-				const uint4 v = decode_unit(at + 1 + k * (2 * QB), prof);
-				if (u < nfull)
-					*reinterpret_cast<uint4 *>(out) = v;
-				else
-					put_unit(c, u * 16u, v);
+			for (; u < nfull; u += nt, pin += stepb, w += stepb / 4) {
+				const uint32_t prof = pin[0];
+				if ((prof & 0xf0u) != 0 && !unit_uncut(c, u >> 2, k, prof))
+					continue;
+				*reinterpret_cast<uint4 *>(out + (uint64_t)u * 16u) = unit_from(w, bit, prof);
+			}
+			if (u < total) {
+				const uint32_t prof = pin[0];
+				if ((prof & 0xf0u) == 0 || unit_uncut(c, u >> 2, k, prof))
+					put_unit(c, u * 16u, unit_from(w, bit, prof));
+			}
+			if (total != 0 && (total - 1u) % nt == tid) {
 				/* the last block of the strip hands its last two samples on */
-				if (k == 3 && lq + 1 >= nq)
+				const uint32_t lat = block_at(c, c.nq - 1u);
+				const uint32_t prof = in[lat];
+				if (block_kind(prof) != kChain) {
+					const uint4 v = decode_unit(lat + 1 + 3 * (2 * QB), prof);
 					publish(c, (int)(int16_t)(v.w >> 16), (int)(int16_t)(v.w & 0xffffu));
+				}
 			}
 			return;
 		}
@@ -572,24 +601,37 @@ struct DecTileStereo {
 		load_payload<BITS>(pw, w, (pay & 3u) * 8u);
 	}
 
-	/* does effective block eb (inside the strip) contain a chain block? */
-	XA_HD bool walked(const StripCtx &c, uint32_t eb) const
+	/* which channels of effective block eb (inside the strip) are chain blocks:
+	 * bit 0 left, bit 1 right */
+	XA_HD uint32_t chains(const StripCtx &c, uint32_t eb) const
 	{
 		const uint32_t at = eb_at(c, eb);
-		return block_kind(in[at]) == kChain || block_kind(in[at + BS]) == kChain;
+		return (uint32_t)(block_kind(in[at]) == kChain) |
+		    (uint32_t)(block_kind(in[at + BS]) == kChain) << 1;
 	}
 
-	XA_HD bool needs_walker(uint32_t q) const	/* scanner, one strip */
+	XA_HD uint32_t chain_mask(uint32_t q) const	/* scanner, one strip */
 	{
-		return q * 2 < ctx[0].nq && walked(ctx[0], q);
+		return q * 2 < ctx[0].nq ? chains(ctx[0], q) : 0u;
 	}
 
-	/* q = strip * SBE + eb */
+	/*
+	 * A walker starts at an effective block with a chain block whose chain
+	 * channels all follow a block that is not a chain block (its last two
+	 * samples can be read off its bytes), and goes on for as long as the next
+	 * effective block continues a chain in either channel.  Splitting runs
+	 * wherever the state can be recomputed keeps them short: with isolated
+	 * chain blocks (the usual case) every run is one effective block and the
+	 * walker lanes of a warp stay converged.   q = strip * SBE + eb
+	 */
 	XA_HD bool is_head(uint32_t q) const
 	{
 		const StripCtx &c = ctx[q / SBE];
 		const uint32_t eb = q % SBE;
-		return eb * 2 < c.nq && walked(c, eb) && (eb == 0 || !walked(c, eb - 1));
+		if (eb * 2 >= c.nq)
+			return false;
+		const uint32_t m = chains(c, eb);
+		return m != 0 && (eb == 0 || (m & chains(c, eb - 1)) == 0);
 	}
 
 	XA_HD void publish(const StripCtx &c, uint32_t ch, int p0, int p1) const
@@ -672,18 +714,84 @@ struct DecTileStereo {
 		}
 	}
 
+	/* the four frames of quad k from the two payload windows of an effective block */
+	XA_HD static uint4 frames(uint32_t lw, uint32_t rw, uint32_t profl, uint32_t profr)
+	{
+		int x[4], y[4];
+		quad_codes<BITS>(lw, x);
+		quad_codes<BITS>(rw, y);
+		const int shl = 16 + (int)(profl & 15u), shr = 16 + (int)(profr & 15u);
+		uint4 v;
+		v.x = pack2(x[0] >> shl, y[0] >> shr);
+		v.y = pack2(x[1] >> shl, y[1] >> shr);
+		v.z = pack2(x[2] >> shl, y[2] >> shr);
+		v.w = pack2(x[3] >> shl, y[3] >> shr);
+		return v;
+	}
+
+	/* an effective block with a filter nibble set: false = a walker's, true = an
+	 * invalid filter, which is recorded (by the k == 0 thread) and decoded as cut */
+	XA_HD bool unit_uncut(const StripCtx &c, uint32_t eb, uint32_t k, uint32_t profl,
+	    uint32_t profr) const
+	{
+		const uint32_t fl = profl >> 4, fr = profr >> 4;
+		if (fl - 1u < 4u || fr - 1u < 4u)
+			return false;
+		if (k == 0) {
+			if (fl >= 5u)
+				global_min_u32(&p.first_bad[c.stream], (c.first_eb + eb) * 2);
+			if (fr >= 5u)
+				global_min_u32(&p.first_bad[c.stream], (c.first_eb + eb) * 2 + 1);
+		}
+		return true;
+	}
+
 	XA_HD void phase_units(uint32_t tid, uint32_t nt) const
 	{
-		if (NS == 1 && nt % 8u == 0) {
+		if (NS == 1 && nt % 16u == 0) {
+			/*
+			 * One strip: thread t owns units t, t + nt, ...  The byte distance
+			 * between two of them in the stage buffer, (nt / 8) * 2 * BS, is a
+			 * multiple of 4, so the word alignment of a thread's payload
+			 * windows never changes and the loop only advances three
+			 * pointers; whole units first, the (at most one) ragged unit and
+			 * the carry out of the strip after the loop.
+			 */
 			const StripCtx &c = ctx[0];
-			const uint32_t neb = c.nq / 2u, k = tid & 7u, step = nt >> 3;
-			const uint32_t nfull = c.out_valid / 16u;
-			uint32_t at = c.in_base + (tid >> 3) * (2 * BS);
-			uint8_t *out = p.dst + c.out0 + (uint64_t)tid * 16u;
+			const uint32_t total = (c.nq / 2u) * 8u;
+			const uint32_t nfull = c.out_valid / 16u < total ? c.out_valid / 16u : total;
+			const uint32_t k = tid & 7u, stepb = (nt >> 3) * (2 * BS);
+			const uint32_t at = c.in_base + (tid >> 3) * (2 * BS);
+			const uint32_t al = at + 1 + k * QB, ar = al + BS;
+			const uint8_t *pin = in + at;
+			const uint32_t *wl = reinterpret_cast<const uint32_t *>(in + (al & ~3u));
+			const uint32_t *wr = reinterpret_cast<const uint32_t *>(in + (ar & ~3u));
+			const uint32_t bl = (al & 3u) * 8u, br = (ar & 3u) * 8u;
+			uint8_t *const out = p.dst + c.out0;
 			uint32_t u = tid;
-			for (uint32_t eb = tid >> 3; eb < neb;
-			    eb += step, u += nt, at += step * (2 * BS), out += (uint64_t)nt * 16u)
-				unit_body(c, eb, k, at, u, out, u < nfull);
+			for (; u < nfull; u += nt, pin += stepb, wl += stepb / 4, wr += stepb / 4) {
+				const uint32_t profl = pin[0], profr = pin[BS];
+				if (((profl | profr) & 0xf0u) != 0 && !unit_uncut(c, u >> 3, k, profl, profr))
+					continue;
+				*reinterpret_cast<uint4 *>(out + (uint64_t)u * 16u) =
+				    frames(funnel_r(wl[0], wl[1], bl), funnel_r(wr[0], wr[1], br), profl, profr);
+			}
+			if (u < total) {
+				const uint32_t profl = pin[0], profr = pin[BS];
+				if (((profl | profr) & 0xf0u) == 0 || unit_uncut(c, u >> 3, k, profl, profr))
+					put_unit(c, u * 16u, frames(funnel_r(wl[0], wl[1], bl),
+					    funnel_r(wr[0], wr[1], br), profl, profr));
+			}
+			if (total != 0 && (total - 1u) % nt == tid) {
+				/* last unit of the strip (k == 7): frames 30, 31 go on as the carry */
+				const uint32_t lat = eb_at(c, total / 8u - 1u);
+				const uint32_t profl = in[lat], profr = in[lat + BS];
+				if (block_kind(profl) != kChain && block_kind(profr) != kChain) {
+					const uint4 v = decode_unit(lat, 7, profl, profr);
+					publish(c, 0, (int)(int16_t)(v.w & 0xffffu), (int)(int16_t)(v.z & 0xffffu));
+					publish(c, 1, (int)(int16_t)(v.w >> 16), (int)(int16_t)(v.z >> 16));
+				}
+			}
 			return;
 		}
 		const uint32_t total = n_strips * UPS;
@@ -703,13 +811,18 @@ struct DecTileStereo {
 		const StripCtx &c = ctx[q / SBE];
 		uint32_t eb = q % SBE;
 		uint32_t at = eb_at(c, eb);
-		int p0[2], p1[2];
+		int p0[2] = { 0, 0 }, p1[2] = { 0, 0 };
+		uint32_t m = chains(c, eb);
 		if (eb == 0) {
-			carried_in(c, 0, p0[0], p1[0]);
-			carried_in(c, 1, p0[1], p1[1]);
+			/* a channel that starts with a cut block needs no history */
+			if (m & 1u)
+				carried_in(c, 0, p0[0], p1[0]);
+			if (m & 2u)
+				carried_in(c, 1, p0[1], p1[1]);
 		} else {
-			/* the effective block in front is all cut: last two samples of
-			 * each of its blocks = codes 2, 3 of the block's last quad */
+			/* the blocks in front of this run's chain blocks are not chain
+			 * blocks: their last two samples = codes 2, 3 of the last quad
+			 * (read for both channels; only a chain channel's matter) */
 #pragma unroll
 			for (int ch = 0; ch < 2; ch++) {
 				const uint32_t pa = at - 2 * BS + ch * BS;
@@ -757,8 +870,10 @@ struct DecTileStereo {
 			}
 			eb++;
 			at += 2 * BS;
-			if (!walked(c, eb))
-				break;
+			const uint32_t next = chains(c, eb);
+			if ((next & m) == 0)
+				break;		/* all cut, or the head of another run */
+			m = next;
 		}
 	}
 
@@ -893,8 +1008,8 @@ struct DecTileStaged {
 	 * stream's previous strip) is queued as the head of a chain.  Needs
 	 * n_heads == 0 on entry.
 	 */
-	/* scanner, one strip: is item q (a block-channel) a chain block? */
-	XA_HD bool needs_walker(uint32_t q) const
+	/* scanner, one strip: is item q (a block-channel) a chain block?  (bit 0) */
+	XA_HD uint32_t chain_mask(uint32_t q) const
 	{
 		return q < ctx[0].nq && block_kind(in[ctx[0].in_base + q * BS]) == kChain;
 	}

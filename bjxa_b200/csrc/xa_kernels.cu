@@ -110,33 +110,50 @@ constexpr int kDecStagedStages = XA_DEC_STAGED_STAGES;
 constexpr int kDecBlock = kDecThreads + 64;	/* consumers + loader warp + scanner warp */
 
 /*
- * Census for a stereo class of a batch: looks at 16384 pseudo-randomly chosen
- * blocks and writes which tile form to use -- the direct form (0) when fewer
- * than kCensusPermille of the blocks are chain blocks (filters 1..4), the
- * staged form (1) otherwise.  One CTA, no atomics, nothing to clear; about
- * 32 KB of HBM traffic.  Measured crossover: profiles/history_r1.md.
+ * Census of one class of a batch: looks at 8192 pseudo-randomly chosen blocks
+ * and writes which of the launched tile forms is to run, from the share of
+ * chain blocks (filters 1..4) among them:
+ *   bit 0  the staged stereo form instead of the direct one (share >= staged)
+ *   bit 1  the wide tile list instead of the long-strip one  (share >= wide)
+ * A threshold above 1000 permille switches that choice off.  One CTA, no
+ * atomics, nothing to clear; all of a thread's loads in flight together.  Measured crossovers:
+ * profiles/history_r1.md.
  */
-constexpr uint32_t kCensusThreads = 1024, kCensusPerThread = 16, kCensusPermille = 100;
+constexpr uint32_t kCensusThreads = 1024, kCensusPerThread = 8;
+constexpr uint32_t kStagedPermille = 100;		/* stereo: direct below, staged above */
+/* wide tiles: the more streams, the more chains they keep in flight, so the
+ * share of chain blocks from which they win drops with the size of the class */
+constexpr uint32_t kWideManyStreams = 8192;
+constexpr uint32_t kWidePermilleMono[2] = { 985, 930 }, kWidePermilleStereo[2] = { 920, 700 };
+constexpr uint32_t kNever = 1001;
+enum { kFormStaged = 1, kFormWide = 2 };
 
 __global__ void __launch_bounds__(kCensusThreads)
 xa_census_kernel(const uint8_t *src, const StreamDev *streams, const uint32_t *order,
-    uint32_t n_streams, uint32_t block_bytes_all, uint32_t *choice)
+    uint32_t n_streams, uint32_t block_bytes_one, uint32_t ch, uint32_t staged_permille,
+    uint32_t wide_permille, uint32_t *choice)
 {
 	__shared__ uint32_t warp_sum[kCensusThreads / 32];
 	const uint32_t tid = threadIdx.x;
-	uint32_t chains = 0;
-#pragma unroll 4
+	uint32_t chains = 0, h[kCensusPerThread], who[kCensusPerThread], prof[kCensusPerThread];
+#pragma unroll
 	for (uint32_t k = 0; k < kCensusPerThread; k++) {
-		uint32_t h = (tid * kCensusPerThread + k) * 2654435761u;
-		h ^= h >> 15;
-		h *= 2246822519u;
-		h ^= h >> 13;
-		const StreamDev &s = streams[order[h % n_streams]];
-		/* any block-channel of the stream: blocks * 2 of them, block_bytes each */
-		const uint32_t q = (h >> 7) % (s.blocks * 2u);
-		const uint32_t prof = src[s.xa_off + (uint64_t)q * block_bytes_all];
-		chains += block_kind(prof) == kChain;
+		uint32_t x = (tid * kCensusPerThread + k) * 2654435761u;
+		x ^= x >> 15;
+		x *= 2246822519u;
+		h[k] = x ^ x >> 13;
+		who[k] = order[h[k] % n_streams];
 	}
+#pragma unroll
+	for (uint32_t k = 0; k < kCensusPerThread; k++) {
+		const StreamDev &s = streams[who[k]];
+		/* any block-channel of the stream */
+		const uint32_t q = (h[k] >> 7) % (s.blocks * ch);
+		prof[k] = src[s.xa_off + (uint64_t)q * block_bytes_one];
+	}
+#pragma unroll
+	for (uint32_t k = 0; k < kCensusPerThread; k++)
+		chains += block_kind(prof[k]) == kChain;
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1)
 		chains += __shfl_xor_sync(0xffffffffu, chains, o);
@@ -147,7 +164,9 @@ xa_census_kernel(const uint8_t *src, const StreamDev *streams, const uint32_t *o
 		uint32_t total = 0;
 		for (uint32_t w = 0; w < kCensusThreads / 32; w++)
 			total += warp_sum[w];
-		*choice = total * 1000u < kCensusPermille * kCensusThreads * kCensusPerThread ? 0u : 1u;
+		const uint32_t permille = total * 1000u / (kCensusThreads * kCensusPerThread);
+		*choice = (permille >= staged_permille ? kFormStaged : 0u) |
+		    (permille >= wide_permille ? kFormWide : 0u);
 	}
 }
 
@@ -578,6 +597,8 @@ stereo_mode(void)
 	return e == NULL ? 2 : strcmp(e, "direct") == 0 ? 0 : strcmp(e, "staged") == 0 ? 1 : 2;
 }
 
+static int decode_class_launches(int ch, int stereo, bool alt);
+
 struct bjxa_plan {
 	uint32_t magic;
 #define BJXA_PLAN_MAGIC 0x706c414eu
@@ -708,13 +729,9 @@ plan_build(bjxa_plan *pl, int kind, const bjxa_stream_desc_t *descs, size_t n)
 	pl->launches = 0;
 	pl->stereo = stereo_mode();
 	for (int b = 0; b < 6; b++)
-		if (pl->hp.tile_begin[b + 1] > pl->hp.tile_begin[b]) {
-			/* stereo decode, automatic form: census + both tile forms,
-			 * one of which returns at once */
-			const bool both = kind == kKindDecode && bucket_ch(b) == 2 &&
-			    pl->stereo == 2;
-			pl->launches += both ? 3 : 1;
-		}
+		if (pl->hp.tile_begin[b + 1] > pl->hp.tile_begin[b])
+			pl->launches += kind == kKindDecode ? decode_class_launches(bucket_ch(b),
+			    pl->stereo, pl->hp.alt_ns[b] != 0) : 1;
 	return (plan_upload(pl));
 }
 
@@ -830,45 +847,86 @@ launch_persistent(const DecodeParams &p, cudaStream_t st)
 	return cudaGetLastError();
 }
 
+/*
+ * One class of a decode plan.  Up to four tile forms can serve it -- long-strip
+ * or wide tiles, and for stereo the direct or the staged form (xa_tile.h
+ * explains them, profiles/history_r1.md has the numbers).  When more than one
+ * is possible the census kernel decides on the device and every candidate is
+ * launched; the ones not chosen return at once.
+ */
+struct DecodeClass {
+	DecodeParams p;			/* tiles / n_tiles: the primary list */
+	const TileEnt *alt_tiles;	/* the list in the wide shape, or NULL */
+	uint32_t alt_n;
+	int ns;				/* strips per tile of the primary list */
+	int stereo;			/* 0 direct, 1 staged, 2 census (stereo classes) */
+	uint32_t *d_choice;
+	const uint32_t *d_order;	/* the class's streams */
+	uint32_t n_streams;
+};
+
 template <int BITS, int CH, int NS>
 static cudaError_t
-launch_decode_ns(const DecodeParams &p0, int mode, uint32_t *d_choice, const uint32_t *d_order,
-    uint32_t n_streams, cudaStream_t st)
+launch_form(const DecodeParams &p, bool staged, cudaStream_t st)
 {
-	/* mono: the direct form.  Stereo: direct or staged form, chosen per launch
-	 * by a census of the batch's profile bytes unless one is forced
-	 * (xa_tile.h explains the forms, profiles/history_r1.md the numbers). */
 	if (CH == 1)
-		return launch_persistent<DecTile<BITS, kDecTBQ, NS, kDecStages> >(p0, st);
-	DecodeParams p = p0;
-	if (mode == 2) {
-		xa_census_kernel<<<1, kCensusThreads, 0, st>>>(p.src, p.streams, d_order, n_streams,
-		    (uint32_t)block_bytes(BITS), d_choice);
-		cudaError_t e = cudaGetLastError();
-		if (e != cudaSuccess)
-			return e;
-		p.choice = d_choice;
-	}
-	if (mode != 1) {
-		p.want = 0;
-		cudaError_t e = launch_persistent<DecTileStereo<BITS, kDecTBQ, NS, kDecStages> >(p, st);
-		if (e != cudaSuccess)
-			return e;
-	}
-	if (mode != 0) {
-		p.want = 1;
+		return launch_persistent<DecTile<BITS, kDecTBQ, NS, kDecStages> >(p, st);
+	if (staged)
 		return launch_persistent<DecTileStaged<BITS, 2, kDecTBQ, NS, kDecStagedStages> >(p, st);
-	}
-	return cudaSuccess;
+	return launch_persistent<DecTileStereo<BITS, kDecTBQ, NS, kDecStages> >(p, st);
+}
+
+/* how many kernels decode_class() launches */
+static int
+decode_class_launches(int ch, int stereo, bool alt)
+{
+	const int forms = (ch == 2 && stereo == 2 ? 2 : 1) + (alt ? 1 : 0);
+	return forms == 1 ? 1 : forms + 1;
 }
 
 template <int BITS, int CH>
 static cudaError_t
-launch_decode(const DecodeParams &p, int ns, int mode, uint32_t *d_choice, const uint32_t *d_order,
-    uint32_t n_streams, cudaStream_t st)
+decode_class(const DecodeClass &c, cudaStream_t st)
 {
-	return ns == 1 ? launch_decode_ns<BITS, CH, 1>(p, mode, d_choice, d_order, n_streams, st) :
-	    launch_decode_ns<BITS, CH, kDecWide>(p, mode, d_choice, d_order, n_streams, st);
+	const bool alt = c.alt_tiles != NULL;
+	const bool pick_form = CH == 2 && c.stereo == 2;
+	DecodeParams p = c.p;
+	cudaError_t e;
+	if (!alt && !pick_form) {
+		const bool staged = CH == 2 && c.stereo == 1;
+		return c.ns == 1 ? launch_form<BITS, CH, 1>(p, staged, st) :
+		    launch_form<BITS, CH, kDecWide>(p, staged, st);
+	}
+	xa_census_kernel<<<1, kCensusThreads, 0, st>>>(p.src, p.streams, c.d_order, c.n_streams,
+	    (uint32_t)block_bytes(BITS), (uint32_t)CH,
+	    pick_form ? kStagedPermille : c.stereo == 1 && CH == 2 ? 0u : kNever,
+	    alt ? (CH == 2 ? kWidePermilleStereo : kWidePermilleMono)[c.n_streams >= kWideManyStreams] :
+	    kNever, c.d_choice);
+	if ((e = cudaGetLastError()) != cudaSuccess)
+		return e;
+	p.choice = c.d_choice;
+	/* long strips: direct and/or staged */
+	for (int staged = 0; staged < 2; staged++) {
+		if (CH == 1 ? staged == 1 : !pick_form && staged != c.stereo)
+			continue;
+		/* with a wide list, chain-heavy stereo data goes to its staged form
+		 * only: "staged, long strips" then means bit 0 without bit 1 */
+		p.want = staged ? kFormStaged : 0u;
+		e = c.ns == 1 ? launch_form<BITS, CH, 1>(p, staged != 0, st) :
+		    launch_form<BITS, CH, kDecWide>(p, staged != 0, st);
+		if (e != cudaSuccess)
+			return e;
+	}
+	if (alt) {
+		/* the wide list: mono direct; stereo staged (the share that selects
+		 * wide tiles is far above the one that selects the staged form) */
+		p.tiles = c.alt_tiles;
+		p.n_tiles = c.alt_n;
+		const bool staged = CH == 2 && c.stereo != 0;
+		p.want = kFormWide | (staged ? kFormStaged : 0u);
+		e = launch_form<BITS, CH, kDecWide>(p, staged, st);
+	}
+	return e;
 }
 
 template <int BITS, int CH>
@@ -948,16 +1006,22 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 			p.epoch = pl->epoch;
 			p.choice = NULL;
 			p.want = 0;
-			uint32_t *choice = pl->d_first_bad.p + ((n + 3) & ~(size_t)3) + 12 + b;
-			const uint32_t *ord = pl->d_order.p + hp.order_begin[b];
-			const uint32_t cnt = hp.order_begin[b + 1] - hp.order_begin[b];
+			DecodeClass c;
+			c.p = p;
+			c.alt_tiles = hp.alt_ns[b] != 0 ? pl->d_tiles.p + hp.alt_begin[b] : NULL;
+			c.alt_n = hp.alt_begin[b + 1] - hp.alt_begin[b];
+			c.ns = hp.ns[b];
+			c.stereo = pl->stereo;
+			c.d_choice = pl->d_first_bad.p + ((n + 3) & ~(size_t)3) + 12 + b;
+			c.d_order = pl->d_order.p + hp.order_begin[b];
+			c.n_streams = hp.order_begin[b + 1] - hp.order_begin[b];
 			switch (b) {
-			case 0: e = launch_decode<4, 1>(p, hp.ns[b], pl->stereo, choice, ord, cnt, st); break;
-			case 1: e = launch_decode<4, 2>(p, hp.ns[b], pl->stereo, choice, ord, cnt, st); break;
-			case 2: e = launch_decode<6, 1>(p, hp.ns[b], pl->stereo, choice, ord, cnt, st); break;
-			case 3: e = launch_decode<6, 2>(p, hp.ns[b], pl->stereo, choice, ord, cnt, st); break;
-			case 4: e = launch_decode<8, 1>(p, hp.ns[b], pl->stereo, choice, ord, cnt, st); break;
-			default: e = launch_decode<8, 2>(p, hp.ns[b], pl->stereo, choice, ord, cnt, st); break;
+			case 0: e = decode_class<4, 1>(c, st); break;
+			case 1: e = decode_class<4, 2>(c, st); break;
+			case 2: e = decode_class<6, 1>(c, st); break;
+			case 3: e = decode_class<6, 2>(c, st); break;
+			case 4: e = decode_class<8, 1>(c, st); break;
+			default: e = decode_class<8, 2>(c, st); break;
 			}
 		} else {
 			EncodeParams p;

@@ -61,6 +61,8 @@ struct HostPlan {
 	std::vector<uint32_t> order;		/* streams in issue order, by bucket */
 	std::vector<TileEnt> tiles;		/* all buckets, concatenated */
 	uint32_t tile_begin[7];			/* bucket b owns [b], [b+1]) */
+	uint32_t alt_begin[7];			/* decode: its list in the other tile shape */
+	int alt_ns[6];				/* strips per tile there, 0 = no such list */
 	uint32_t order_begin[7];		/* likewise, into order */
 	int ns[6];				/* decode: strips per tile of bucket b */
 	uint32_t n_slots;
@@ -68,29 +70,46 @@ struct HostPlan {
 };
 
 /*
- * Strips per decode tile for a bucket of n streams.  kDecWide short strips of
+ * Strips per decode tile.  One long strip (kDecTBQ block-channels of one
+ * stream) is the shape for streams with cut blocks; kDecWide short strips of
  * different streams give every tile kDecWide independent chains even when the
- * streams have no cut block at all, but only pay off when the batch is large
- * enough that a strip's predecessor (n/kDecWide tickets earlier) has left the
- * device before the strip starts -- about 2 * resident CTAs * kDecWide
- * streams; measured on B200 (profiles/): at 4096 streams the wide shape is
- * 6x faster on all-chain data and 1.4-1.6x slower on cut-rich data, so the
- * automatic choice keeps one long strip per tile below kDecWideMinStreams.
- * `force` (0 = automatic) is a tuning/testing override.
+ * streams have no cut block at all, which is the only parallelism such data
+ * has.  Measured on B200 (profiles/history_r1.md): the wide shape wins only
+ * when nearly every block is a chain block (about 6x on all-chain data) and
+ * loses 1.3-1.8x otherwise, so a class of at least kDecWideMinStreams streams
+ * gets BOTH tile lists and the census kernel picks per launch; smaller classes
+ * already have every stream in flight with one strip per tile.  `force`
+ * (1 or kDecWide; 0 = automatic) builds that shape only: a tuning/testing
+ * override.
  */
-constexpr size_t kDecWideMinStreams = 16384;
-
-inline int choose_strips(size_t n_streams, int force)
-{
-	if (force == 1 || force == kDecWide)
-		return force;
-	return n_streams >= kDecWideMinStreams ? kDecWide : 1;
-}
+constexpr size_t kDecWideMinStreams = 1024;
 
 /* effective blocks per strip */
 inline uint32_t strip_blocks(int ns, int ch)
 {
 	return (uint32_t)(kDecTBQ / ns / ch);
+}
+
+/*
+ * The decode tiles of one class in one shape, time-major: strip j of every
+ * stream before strip j+1 of any, so a strip's predecessor in its stream always
+ * holds a lower ticket.  `o` = the class's streams, longest first (the streams
+ * still active at step j are a prefix); they sit at order[order0...].
+ */
+inline void emit_decode_tiles(HostPlan &hp, const std::vector<uint32_t> &o, uint32_t order0,
+    int ns, int ch)
+{
+	const uint32_t sbe = strip_blocks(ns, ch);
+	size_t active = o.size();
+	for (uint32_t j = 0; active > 0; j++) {
+		while (active > 0 && (uint64_t)j * sbe >= hp.streams[o[active - 1]].blocks)
+			active--;
+		for (size_t base = 0; base < active; base += (size_t)ns) {
+			size_t cnt = std::min(active - base, (size_t)ns);
+			TileEnt te = { order0 + (uint32_t)base, (uint32_t)cnt, j, 0u };
+			hp.tiles.push_back(te);
+		}
+	}
 }
 
 /*
@@ -149,6 +168,7 @@ inline int build_plan(HostPlan &hp, int kind, const Desc *d, size_t n,
 	for (int b = 0; b < 6; b++) {
 		hp.tile_begin[b] = (uint32_t)hp.tiles.size();
 		hp.ns[b] = 1;
+		hp.alt_ns[b] = 0;
 		hp.order_begin[b] = (uint32_t)hp.order.size();
 		std::vector<uint32_t> &o = members[b];
 		if (o.empty())
@@ -175,30 +195,27 @@ inline int build_plan(HostPlan &hp, int kind, const Desc *d, size_t n,
 			continue;
 		}
 
-		const int ns = choose_strips(o.size(), force_strips);
-		const uint32_t sbe = strip_blocks(ns, bucket_ch(b));
-		hp.ns[b] = ns;
+		const bool forced = force_strips == 1 || force_strips == kDecWide;
+		hp.ns[b] = forced ? force_strips : 1;
+		hp.alt_ns[b] = !forced && o.size() >= kDecWideMinStreams ? kDecWide : 0;
+		/* carry slots: one per strip of the finest shape in use; strip j of
+		 * a stream uses slot_base + j in either shape */
+		const uint32_t fine = strip_blocks(std::max(hp.ns[b], hp.alt_ns[b]), bucket_ch(b));
 		for (size_t k = 0; k < o.size(); k++) {
 			StreamDev &sd = hp.streams[o[k]];
 			sd.slot_base = hp.n_slots;
-			hp.n_slots += (sd.blocks + sbe - 1) / sbe;
+			hp.n_slots += (sd.blocks + fine - 1) / fine;
 		}
-		/* time-major: strip j of every stream before strip j+1 of any, so a
-		 * strip's predecessor in its stream always holds a lower ticket */
-		size_t active = o.size();
-		for (uint32_t j = 0; active > 0; j++) {
-			while (active > 0 &&
-			    (uint64_t)j * sbe >= hp.streams[o[active - 1]].blocks)
-				active--;
-			for (size_t base = 0; base < active; base += (size_t)ns) {
-				size_t cnt = std::min(active - base, (size_t)ns);
-				TileEnt te = { order0 + (uint32_t)base, (uint32_t)cnt, j, 0u };
-				hp.tiles.push_back(te);
-			}
-		}
+		emit_decode_tiles(hp, o, order0, hp.ns[b], bucket_ch(b));
 	}
 	hp.tile_begin[6] = (uint32_t)hp.tiles.size();
 	hp.order_begin[6] = (uint32_t)hp.order.size();
+	for (int b = 0; b < 6; b++) {
+		hp.alt_begin[b] = (uint32_t)hp.tiles.size();
+		if (kind == kKindDecode && hp.alt_ns[b] != 0)
+			emit_decode_tiles(hp, members[b], hp.order_begin[b], hp.alt_ns[b], bucket_ch(b));
+	}
+	hp.alt_begin[6] = (uint32_t)hp.tiles.size();
 	return 0;
 }
 

@@ -19,6 +19,7 @@
 
 using namespace xa;
 
+static int g_use_alt = 0;
 static int g_stereo_direct = 0;
 
 /* thread visiting order inside a phase: 0 ascending, 1 descending, 2 strided */
@@ -191,6 +192,13 @@ xa_emul_decode(const bjxa_stream_desc_t *descs, size_t n, const uint8_t *src,
 		uint32_t t0 = hp.tile_begin[b], t1 = hp.tile_begin[b + 1];
 		if (t0 == t1)
 			continue;
+		int ns = hp.ns[b];
+		if (g_use_alt && hp.alt_ns[b] != 0) {
+			/* the class's list in the other tile shape, as the census would pick */
+			t0 = hp.alt_begin[b];
+			t1 = hp.alt_begin[b + 1];
+			ns = hp.alt_ns[b];
+		}
 		DecodeParams p;
 		p.src = src;
 		p.src_bytes = src_bytes;
@@ -206,12 +214,12 @@ xa_emul_decode(const bjxa_stream_desc_t *descs, size_t n, const uint8_t *src,
 		p.fault = &fault;
 		p.epoch = 7;
 		switch (b) {
-		case 0: emul_decode_bucket<4, 1>(p, hp.ns[b], order); break;
-		case 1: emul_decode_bucket<4, 2>(p, hp.ns[b], order); break;
-		case 2: emul_decode_bucket<6, 1>(p, hp.ns[b], order); break;
-		case 3: emul_decode_bucket<6, 2>(p, hp.ns[b], order); break;
-		case 4: emul_decode_bucket<8, 1>(p, hp.ns[b], order); break;
-		default: emul_decode_bucket<8, 2>(p, hp.ns[b], order); break;
+		case 0: emul_decode_bucket<4, 1>(p, ns, order); break;
+		case 1: emul_decode_bucket<4, 2>(p, ns, order); break;
+		case 2: emul_decode_bucket<6, 1>(p, ns, order); break;
+		case 3: emul_decode_bucket<6, 2>(p, ns, order); break;
+		case 4: emul_decode_bucket<8, 1>(p, ns, order); break;
+		default: emul_decode_bucket<8, 2>(p, ns, order); break;
 		}
 	}
 	memcpy(prev_out, res.data(), n * sizeof(StreamRes));
@@ -256,7 +264,8 @@ xa_emul_encode(const bjxa_stream_desc_t *descs, size_t n, const uint8_t *src,
 int
 xa_emul_plan(int kind, const bjxa_stream_desc_t *descs, size_t n, int force_strips,
     uint32_t *tile_stream, uint32_t *tile_count, uint32_t *tile_j, uint32_t cap,
-    uint32_t *tile_begin /* 7 */, uint32_t *n_slots, int *ns /* 6 */)
+    uint32_t *tile_begin /* 7 */, uint32_t *n_slots, int *ns /* 6 */,
+    uint32_t *alt_begin /* 7 */, int *alt_ns /* 6 */)
 {
 	HostPlan hp;
 	size_t bad = 0;
@@ -272,11 +281,14 @@ xa_emul_plan(int kind, const bjxa_stream_desc_t *descs, size_t n, int force_stri
 	}
 	memcpy(tile_begin, hp.tile_begin, 7 * sizeof(uint32_t));
 	memcpy(ns, hp.ns, 6 * sizeof(int));
+	memcpy(alt_begin, hp.alt_begin, 7 * sizeof(uint32_t));
+	memcpy(alt_ns, hp.alt_ns, 6 * sizeof(int));
 	*n_slots = hp.n_slots;
 	return (int)nt;
 }
 
 void xa_emul_stereo_direct(int on) { g_stereo_direct = on; }
+void xa_emul_use_alt(int on) { g_use_alt = on; }
 int xa_emul_strip_blocks(int ns, int ch) { return (int)strip_blocks(ns, ch); }
 int xa_emul_wide(void) { return kDecWide; }
 int xa_emul_enc_tile_blocks(void) { return kEncTBE; }

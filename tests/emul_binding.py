@@ -30,6 +30,7 @@ class Emul:
         self.wide = d.xa_emul_wide()
         self.enc_tile_blocks = d.xa_emul_enc_tile_blocks
         self.stereo_direct = d.xa_emul_stereo_direct    # (0|1): which stereo form to step
+        self.use_alt = d.xa_emul_use_alt                # (0|1): step the alternative tile lists
 
     def dec_tile_blocks(self, ch):
         """effective blocks of one long (NS = 1) strip"""
@@ -55,16 +56,21 @@ class Emul:
 
     def plan(self, kind, descs, strips=0, cap=1 << 20):
         """-> (n_tiles, first stream of each tile, strip counts, j, tile_begin,
-        n_slots, strips per tile of each bucket)"""
+        n_slots, strips per tile of each bucket); the lists in the alternative
+        tile shape, if any, are left in self.alt = (alt_begin, alt_ns)"""
         ts = np.zeros(cap, dtype=np.uint32)
         tc = np.zeros(cap, dtype=np.uint32)
         tj = np.zeros(cap, dtype=np.uint32)
         tb = np.zeros(7, dtype=np.uint32)
         nsb = np.zeros(6, dtype=np.int32)
         ns = C.c_uint32(0)
+        ab = np.zeros(7, dtype=np.uint32)
+        an = np.zeros(6, dtype=np.int32)
         n = self.dll.xa_emul_plan(kind, descs.ctypes.data, descs.size, strips,
                                   ts.ctypes.data, tc.ctypes.data, tj.ctypes.data, cap,
-                                  tb.ctypes.data, C.byref(ns), nsb.ctypes.data)
+                                  tb.ctypes.data, C.byref(ns), nsb.ctypes.data,
+                                  ab.ctypes.data, an.ctypes.data)
+        self.alt = (ab, an)
         if n < 0:
             return n, None, None, None, None, None, None
         return n, ts[:n], tc[:n], tj[:n], tb, ns.value, nsb

@@ -53,6 +53,20 @@ def test_decode_many_streams_wide(emul, oracle, mix):
     _run_decode(emul, oracle, specs, strips=32, xa_gap=4)
 
 
+@pytest.mark.parametrize("alt", [0, 1])
+def test_decode_class_with_both_tile_lists(emul, oracle, alt):
+    """A class large enough to get both tile shapes: the carry slots are sized for
+    the finer shape and must serve either list."""
+    specs = [dict(bits=8 if i % 5 else 4, channels=1, samples=32 * (1 + (i * 13) % 90 + (1100 if i % 97 == 0 else 0)) + i % 32,
+                  mix=("P3", "P2", "P1")[i % 3], key=4000 + i, prev=((i, -i), (0, 0)))
+             for i in range(1400)]
+    emul.use_alt(alt)
+    try:
+        _run_decode(emul, oracle, specs, strips=0, xa_gap=1)
+    finally:
+        emul.use_alt(0)
+
+
 @pytest.mark.parametrize("order", [0, 1, 2])
 @pytest.mark.parametrize("strips", STRIP_MODES)
 def test_decode_mixed_batch(emul, oracle, order, strips):
@@ -213,4 +227,12 @@ def test_plan_order_and_validation(emul):
     assert slots == (w + 2) * 3 + (w + 3) * 2
     big = batchgen.make_descs(20000)
     big["bits"], big["channels"], big["blocks"], big["pcm_len"] = 4, 2, 3, 3 * 128
-    assert emul.plan(0, big)[6][1] == w     # a corpus-sized batch goes wide by itself
+    # a large class gets both shapes (the census picks at launch): the long-strip
+    # list first, the wide one after every primary list; slots fit the finer shape
+    n, ts, tc, tj, tb, slots, nsb = emul.plan(0, big)
+    ab, an = emul.alt
+    assert nsb[1] == 1 and an[1] == w and list(an[[0, 2, 3, 4, 5]]) == [0] * 5
+    assert tb[2] - tb[1] == 20000 and ab[1] == tb[6] and ab[2] == n
+    sb2 = emul.strip_blocks(w, 2)
+    assert (tc[ab[1]:ab[2]] == w).all() and ab[2] - ab[1] == (20000 // w) * -(-3 // sb2)
+    assert slots == 20000 * -(-3 // sb2)

@@ -215,7 +215,7 @@ def leg_corpus(lib, orc, strips):
     ebest = min(ems)
     return {"config": "configs[4] corpus: 262144 streams (mono/stereo, 4/6/8 bit, 0.25-4 s "
                       "log-uniform, mix P1), decode then encode, 1 GPU",
-            "tile_shape": "forced NS=%d" % strips if strips else "automatic (wide, >= 16384 streams per class)",
+            "tile_shape": "forced NS=%d" % strips if strips else "automatic (census picks long strips or wide tiles per class)",
             "launches_per_step": launches,
             "decode": {"ms": [round(m, 3) for m in ms], "Msamples_per_s": round(nsamp / best / 1e3, 1),
                        "GBps": round(algo / best / 1e6, 1),

@@ -1,0 +1,21 @@
+#!/bin/bash
+# Runs on the GPU box (through gpurun): the bench, the reference arm, the
+# BASELINE configs and the two ncu passes, all into gpurun_out/.  Every ncu
+# command runs only after the same command exited 0 without ncu.
+# tools/summarize_profiles.py turns the results into profiles/.
+#   usage: bash tools/refresh_profiles.sh <round-tag>      e.g. r1
+tag=${1:-r1}
+mkdir -p gpurun_out
+set -x
+timeout 900 python bench.py --steps 10 > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err || exit 1
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$tag.json 2> gpurun_out/bench_ref_$tag.err
+timeout 900 python tools/bench_configs.py > gpurun_out/configs_$tag.json 2> gpurun_out/configs_$tag.err
+A="bench.py --steps 2 --warmup 3 --no-extras"
+timeout 300 python $A > gpurun_out/plain_$tag.json 2>/dev/null || exit 2
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file gpurun_out/launches_$tag.csv python $A > gpurun_out/ncu_launches_$tag.log 2>&1
+B="bench.py --steps 1 --warmup 3 --no-extras"
+timeout 300 python $B > /dev/null 2>&1 || exit 3
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:xa_decode -c 1 \
+    -f -o gpurun_out/decode_p1_4096_$tag python $B > gpurun_out/ncu_full_$tag.log 2>&1
+echo done

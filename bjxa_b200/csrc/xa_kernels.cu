@@ -175,7 +175,10 @@ template <class Tile>
 __device__ __forceinline__ typename std::enable_if<!Tile::kStaged>::type
 consume_tile(Tile &t, typename Tile::Smem &sm, int s, uint32_t it, uint32_t tid)
 {
-	t.phase_walk(tid, kDecThreads, sm.heads[s], sm.n_heads[s], it * 96u);
+	/* the warps take turns at walking a tile's chains: up to kStages tiles, and
+	 * so kStages walker warps, are in flight in a CTA */
+	if ((tid >> 5) == it % (kDecThreads / 32u))
+		t.phase_walk_warp(tid & 31u, sm.heads[s], sm.n_heads[s], &sm.next_head[s]);
 	t.phase_units(tid, kDecThreads);
 	__syncwarp();
 	if ((tid & 31u) == 0)
@@ -210,7 +213,7 @@ consume_tile(Tile &t, typename Tile::Smem &sm, int s, uint32_t it, uint32_t tid)
 }
 
 template <class Tile>
-__global__ void __launch_bounds__(kDecBlock)
+__global__ void __launch_bounds__(kDecBlock, Tile::kMinCtas)
 xa_decode_kernel(const DecodeParams p)
 {
 	typedef typename Tile::G G;
@@ -354,6 +357,7 @@ xa_decode_kernel(const DecodeParams p)
 			__syncwarp();
 			if (lane == 0) {
 				sm.n_heads[s] = count;
+				sm.next_head[s] = 32;	/* chains 0..31 start with the lanes */
 				mbar_arrive(smem_u32(&sm.ready[s]));
 			}
 		}

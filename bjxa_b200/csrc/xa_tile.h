@@ -210,6 +210,16 @@ XA_HD void make_strip_ctx(StripCtx &c, const DecodeParams &p, uint32_t stream,
 	c.pad = 0;
 }
 
+/* draw the next index from a shared-memory counter */
+XA_HD uint32_t take_next(uint32_t *ctr)
+{
+#if defined(__CUDA_ARCH__)
+	return atomicAdd(ctr, 1u);
+#else
+	return (*ctr)++;
+#endif
+}
+
 /* ---- decode, direct form (mono) -------------------------------------------- */
 
 template <int BITS, int CH, int TBQ, int NS, int STAGES>
@@ -222,6 +232,7 @@ struct DecSmem {
 	uint32_t n_strips[STAGES];
 	uint16_t heads[STAGES][TBQ];		/* first block of every chain of the tile */
 	uint32_t n_heads[STAGES];
+	uint32_t next_head[STAGES];		/* first chain no walker lane has taken yet */
 	alignas(8) unsigned long long full[STAGES];	/* source bytes have landed */
 	alignas(8) unsigned long long ready[STAGES];	/* ... and have been scanned */
 	alignas(8) unsigned long long empty[STAGES];	/* every consumer warp is done */
@@ -260,6 +271,7 @@ struct DecTile {
 	static constexpr int kLag = 1;
 	static constexpr bool kStaged = false;
 	static constexpr int kStages = STAGES;
+	static constexpr int kMinCtas = 4;	/* per SM: caps the registers at 48 */
 	static constexpr uint32_t UPS = SBQ * 4;	/* 16-byte units per strip */
 
 	const DecodeParams &p;
@@ -481,26 +493,43 @@ struct DecTile {
 		}
 	}
 
-	/* walk the chain that starts at block q (strip-major numbering) */
-	XA_HD void walk(uint32_t q) const
+	/*
+	 * One warp walks all the chains of a tile: lane l starts with chain l and,
+	 * whenever its chain ends, draws the next one nobody has taken (*next, preset
+	 * to 32 by the scanner).  One flat loop -- pick up a chain if idle, then
+	 * decode ONE block -- keeps the lanes that still have blocks converged on the
+	 * block decode while the others pick up their next chain; a loop over whole
+	 * chains would idle every lane until the longest of 32 chains is through.
+	 */
+	XA_HD void phase_walk_warp(uint32_t lane, const uint16_t *heads, uint32_t n,
+	    uint32_t *next) const
 	{
-		const StripCtx &c = ctx[q / SBQ];
-		uint32_t lq = q % SBQ;
-		uint32_t at = block_at(c, lq);
-		int p0, p1;
-		if (lq == 0) {
-			carried_in(c, p0, p1);
-		} else {
-			/* the block in front is a cut block: its last two samples are
-			 * codes 2 and 3 of its last quad, shifted by its range */
-			const uint32_t pa = at - BS;
-			const int sh = 16 + (int)(in[pa] & 15u);
-			int x[4];
-			quad_codes<BITS>(bytes_at(pa + 1 + 7 * QB), x);
-			p1 = x[2] >> sh;
-			p0 = x[3] >> sh;
-		}
+		uint32_t i = lane, lq = 0, at = 0;
+		const StripCtx *c = ctx;
+		int p0 = 0, p1 = 0;
+		bool have = false;
 		for (;;) {
+			if (!have) {
+				if (i >= n)
+					break;
+				const uint32_t q = heads[i];
+				c = &ctx[q / SBQ];
+				lq = q % SBQ;
+				at = block_at(*c, lq);
+				if (lq == 0) {
+					carried_in(*c, p0, p1);
+				} else {
+					/* the block in front is a cut block: its last two
+					 * samples are codes 2 and 3 of its last quad */
+					const uint32_t pa = at - BS;
+					const int sh = 16 + (int)(in[pa] & 15u);
+					int x[4];
+					quad_codes<BITS>(bytes_at(pa + 1 + 7 * QB), x);
+					p1 = x[2] >> sh;
+					p0 = x[3] >> sh;
+				}
+				have = true;
+			}
 			uint32_t pw[BITS], o[16];
 			fetch_block(at, pw);
 			decode_block_chain<BITS>(o, pw, in[at], p0, p1);
@@ -509,26 +538,21 @@ struct DecTile {
 				uint4 v;
 				v.x = o[4 * j]; v.y = o[4 * j + 1];
 				v.z = o[4 * j + 2]; v.w = o[4 * j + 3];
-				put_unit(c, (lq * 4u + (uint32_t)j) * 16u, v);
+				put_unit(*c, (lq * 4u + (uint32_t)j) * 16u, v);
 			}
-			if (lq + 1 >= c.nq) {
-				publish(c, p0, p1);
-				break;
+			bool more = false;
+			if (lq + 1 >= c->nq) {
+				publish(*c, p0, p1);
+			} else {
+				lq++;
+				at += BS;
+				more = block_kind(in[at]) == kChain;
 			}
-			lq++;
-			at += BS;
-			if (block_kind(in[at]) != kChain)
-				break;
+			if (!more) {
+				have = false;
+				i = take_next(next);
+			}
 		}
-	}
-
-	/* walkers: chain i of the tile goes to thread (i + rot) mod nt, so that
-	 * over the tiles every warp takes its turn at the (slow) chains */
-	XA_HD void phase_walk(uint32_t tid, uint32_t nt, const uint16_t *heads, uint32_t n,
-	    uint32_t rot) const
-	{
-		for (uint32_t i = (tid + nt - rot % nt) % nt; i < n; i += nt)
-			walk(heads[i]);
 	}
 };
 
@@ -560,6 +584,7 @@ struct DecTileStereo {
 	static constexpr int kLag = 1;
 	static constexpr bool kStaged = false;
 	static constexpr int kStages = STAGES;
+	static constexpr int kMinCtas = 1;
 	static constexpr uint32_t UPS = SBE * 8;	/* 16-byte units per strip */
 
 	const DecodeParams &p;
@@ -805,55 +830,72 @@ struct DecTileStereo {
 		}
 	}
 
-	/* walk the run of effective blocks that starts at q = strip * SBE + eb */
-	XA_HD void walk(uint32_t q) const
+	/*
+	 * One warp walks all the runs of a tile, lanes drawing the next run as they
+	 * finish one (see DecTile::phase_walk_warp).  A run starts at the effective
+	 * block heads[i] = strip * SBE + eb and is decoded one effective block per
+	 * turn of the loop.
+	 */
+	XA_HD void phase_walk_warp(uint32_t lane, const uint16_t *heads, uint32_t n,
+	    uint32_t *next) const
 	{
-		const StripCtx &c = ctx[q / SBE];
-		uint32_t eb = q % SBE;
-		uint32_t at = eb_at(c, eb);
+		uint32_t i = lane, eb = 0, at = 0, m = 0;
+		const StripCtx *c = ctx;
 		int p0[2] = { 0, 0 }, p1[2] = { 0, 0 };
-		uint32_t m = chains(c, eb);
-		if (eb == 0) {
-			/* a channel that starts with a cut block needs no history */
-			if (m & 1u)
-				carried_in(c, 0, p0[0], p1[0]);
-			if (m & 2u)
-				carried_in(c, 1, p0[1], p1[1]);
-		} else {
-			/* the blocks in front of this run's chain blocks are not chain
-			 * blocks: their last two samples = codes 2, 3 of the last quad
-			 * (read for both channels; only a chain channel's matter) */
-#pragma unroll
-			for (int ch = 0; ch < 2; ch++) {
-				const uint32_t pa = at - 2 * BS + ch * BS;
-				const int sh = 16 + (int)(in[pa] & 15u);
-				int x[4];
-				quad_codes<BITS>(bytes_at(pa + 1 + 7 * QB), x);
-				p1[ch] = x[2] >> sh;
-				p0[ch] = x[3] >> sh;
-			}
-		}
+		bool have = false;
 		for (;;) {
+			if (!have) {
+				if (i >= n)
+					break;
+				const uint32_t q = heads[i];
+				c = &ctx[q / SBE];
+				eb = q % SBE;
+				at = eb_at(*c, eb);
+				m = chains(*c, eb);
+				if (eb == 0) {
+					/* a channel that starts with a cut block needs no history */
+					if (m & 1u)
+						carried_in(*c, 0, p0[0], p1[0]);
+					if (m & 2u)
+						carried_in(*c, 1, p0[1], p1[1]);
+				} else {
+					/* the blocks in front of this run's chain blocks are not
+					 * chain blocks: their last two samples = codes 2, 3 of
+					 * the last quad (read for both channels; only a chain
+					 * channel's matter) */
+#pragma unroll
+					for (int ch = 0; ch < 2; ch++) {
+						const uint32_t pa = at - 2 * BS + ch * BS;
+						const int sh = 16 + (int)(in[pa] & 15u);
+						int x[4];
+						quad_codes<BITS>(bytes_at(pa + 1 + 7 * QB), x);
+						p1[ch] = x[2] >> sh;
+						p0[ch] = x[3] >> sh;
+					}
+				}
+				have = true;
+			}
 			const uint32_t profl = in[at], profr = in[at + BS];
 			if (profl >> 4 >= 5u)
-				global_min_u32(&p.first_bad[c.stream], (c.first_eb + eb) * 2);
+				global_min_u32(&p.first_bad[c->stream], (c->first_eb + eb) * 2);
 			if (profr >> 4 >= 5u)
-				global_min_u32(&p.first_bad[c.stream], (c.first_eb + eb) * 2 + 1);
+				global_min_u32(&p.first_bad[c->stream], (c->first_eb + eb) * 2 + 1);
 			uint32_t pl[BITS], pr[BITS];
 			fetch_block(at, pl);
 			fetch_block(at + BS, pr);
 			const int shl = 16 + (int)(profl & 15u), shr = 16 + (int)(profr & 15u);
 			const int k0l = gain_k0(profl >> 4), k1l = gain_k1(profl >> 4);
 			const int k0r = gain_k0(profr >> 4), k1r = gain_k1(profr >> 4);
-			/* both channels side by side: two independent dependency chains */
+			/* both channels side by side: two independent dependency chains
+			 * (a cut block inside a run simply has k0 = k1 = 0) */
 #pragma unroll
 			for (int j = 0; j < 8; j++) {
 				int l[4], r[4];
 #pragma unroll
-				for (int i = 0; i < 4; i++) {
-					l[i] = sample_chain(top_code<BITS>(pl, 4 * j + i), shl, k0l, k1l,
+				for (int k = 0; k < 4; k++) {
+					l[k] = sample_chain(top_code<BITS>(pl, 4 * j + k), shl, k0l, k1l,
 					    p0[0], p1[0]);
-					r[i] = sample_chain(top_code<BITS>(pr, 4 * j + i), shr, k0r, k1r,
+					r[k] = sample_chain(top_code<BITS>(pr, 4 * j + k), shr, k0r, k1r,
 					    p0[1], p1[1]);
 				}
 				uint4 v;
@@ -861,27 +903,24 @@ struct DecTileStereo {
 				v.y = pack2(l[1], r[1]);
 				v.z = pack2(l[2], r[2]);
 				v.w = pack2(l[3], r[3]);
-				put_unit(c, (eb * 8u + (uint32_t)j) * 16u, v);
+				put_unit(*c, (eb * 8u + (uint32_t)j) * 16u, v);
 			}
-			if ((eb + 1) * 2 >= c.nq) {
-				publish(c, 0, p0[0], p1[0]);
-				publish(c, 1, p0[1], p1[1]);
-				break;
+			bool more = false;
+			if ((eb + 1) * 2 >= c->nq) {
+				publish(*c, 0, p0[0], p1[0]);
+				publish(*c, 1, p0[1], p1[1]);
+			} else {
+				eb++;
+				at += 2 * BS;
+				const uint32_t nm = chains(*c, eb);
+				more = (nm & m) != 0;	/* else all cut, or the head of another run */
+				m = nm;
 			}
-			eb++;
-			at += 2 * BS;
-			const uint32_t next = chains(c, eb);
-			if ((next & m) == 0)
-				break;		/* all cut, or the head of another run */
-			m = next;
+			if (!more) {
+				have = false;
+				i = take_next(next);
+			}
 		}
-	}
-
-	XA_HD void phase_walk(uint32_t tid, uint32_t nt, const uint16_t *heads, uint32_t n,
-	    uint32_t rot) const
-	{
-		for (uint32_t i = (tid + nt - rot % nt) % nt; i < n; i += nt)
-			walk(heads[i]);
 	}
 };
 
@@ -907,6 +946,7 @@ struct DecSmemStaged {
 	uint32_t n_strips[STAGES];
 	uint16_t heads[STAGES][TBQ];		/* first block of every chain of the tile */
 	uint32_t n_heads[STAGES];
+	uint32_t next_head[STAGES];		/* unused here: heads are dealt out statically */
 	alignas(8) unsigned long long full[STAGES];
 	alignas(8) unsigned long long ready[STAGES];
 	alignas(8) unsigned long long empty[STAGES];
@@ -923,6 +963,7 @@ struct DecTileStaged {
 	static constexpr int kLag = CH;			/* predecessor of item q is q - CH */
 	static constexpr bool kStaged = true;
 	static constexpr int kStages = STAGES;
+	static constexpr int kMinCtas = 1;
 
 	const DecodeParams &p;
 	Smem &sm;

@@ -67,9 +67,11 @@ emul_decode_ns(const DecodeParams &p, int order)
 			if (t.is_head(q))
 				sm->heads[s][count++] = (uint16_t)q;
 		sm->n_heads[s] = count;
-		/* consumers */
-		for (uint32_t i = 0; i < nt; i++)
-			t.phase_walk(visit(i, nt, order), nt, sm->heads[s], count, ticket * 96u);
+		sm->next_head[s] = 32;
+		/* consumers: the tile's walker warp, lane by lane (whichever lane runs
+		 * first picks up every chain left over), then the units */
+		for (uint32_t i = 0; i < 32; i++)
+			t.phase_walk_warp(visit(i, 32, order), sm->heads[s], count, &sm->next_head[s]);
 		for (uint32_t i = 0; i < nt; i++)
 			t.phase_units(visit(i, nt, order), nt);
 	}

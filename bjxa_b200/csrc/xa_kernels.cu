@@ -91,7 +91,7 @@ __device__ __forceinline__ void consumer_sync()
  *   loader     (1 warp) lane 0 draws tile tickets in order; lane i builds the
  *              context of strip i and starts the bulk-async (TMA) copy of that
  *              strip's contiguous XA bytes into the next free stage buffer,
- *              kDecStages tiles ahead;
+ *              Tile::kStages tiles ahead;
  *   scanner    (1 warp) when a tile's bytes have landed, scans its profile
  *              bytes for the heads of chains and publishes the tile on its
  *              "ready" mbarrier;
@@ -120,7 +120,8 @@ constexpr int kDecBlock = kDecThreads + 64;	/* consumers + loader warp + scanner
  * profiles/history_r1.md.
  */
 constexpr uint32_t kCensusThreads = 1024, kCensusPerThread = 8;
-constexpr uint32_t kStagedPermille = 100;		/* stereo: direct below, staged above */
+/* stereo: direct form below this share of chain blocks, staged form above */
+constexpr uint32_t staged_permille(int bits) { return bits == 4 ? 300u : bits == 6 ? 500u : 650u; }
 /* wide tiles: the more streams, the more chains they keep in flight, so the
  * share of chain blocks from which they win drops with the size of the class */
 constexpr uint32_t kWideManyStreams = 8192;
@@ -642,12 +643,12 @@ set_attrs_one(void)
 {
 	cudaError_t e;
 	if (CH == 1) {
-		if ((e = set_dec_attr<DecTile<BITS, kDecTBQ, 1, kDecStages> >()) != cudaSuccess ||
-		    (e = set_dec_attr<DecTile<BITS, kDecTBQ, kDecWide, kDecStages> >()) != cudaSuccess)
+		if ((e = set_dec_attr<DecTile<BITS, kDecTBQ, 1, dec_stages(BITS, 1)> >()) != cudaSuccess ||
+		    (e = set_dec_attr<DecTile<BITS, kDecTBQ, kDecWide, dec_stages(BITS, 1)> >()) != cudaSuccess)
 			return e;
 	} else {
-		if ((e = set_dec_attr<DecTileStereo<BITS, kDecTBQ, 1, kDecStages> >()) != cudaSuccess ||
-		    (e = set_dec_attr<DecTileStereo<BITS, kDecTBQ, kDecWide, kDecStages> >()) != cudaSuccess ||
+		if ((e = set_dec_attr<DecTileStereo<BITS, kDecTBQ, 1, dec_stages(BITS, 2)> >()) != cudaSuccess ||
+		    (e = set_dec_attr<DecTileStereo<BITS, kDecTBQ, kDecWide, dec_stages(BITS, 2)> >()) != cudaSuccess ||
 		    (e = set_dec_attr<DecTileStaged<BITS, 2, kDecTBQ, 1, kDecStagedStages> >()) != cudaSuccess ||
 		    (e = set_dec_attr<DecTileStaged<BITS, 2, kDecTBQ, kDecWide, kDecStagedStages> >()) != cudaSuccess)
 			return e;
@@ -874,10 +875,10 @@ static cudaError_t
 launch_form(const DecodeParams &p, bool staged, cudaStream_t st)
 {
 	if (CH == 1)
-		return launch_persistent<DecTile<BITS, kDecTBQ, NS, kDecStages> >(p, st);
+		return launch_persistent<DecTile<BITS, kDecTBQ, NS, dec_stages(BITS, 1)> >(p, st);
 	if (staged)
 		return launch_persistent<DecTileStaged<BITS, 2, kDecTBQ, NS, kDecStagedStages> >(p, st);
-	return launch_persistent<DecTileStereo<BITS, kDecTBQ, NS, kDecStages> >(p, st);
+	return launch_persistent<DecTileStereo<BITS, kDecTBQ, NS, dec_stages(BITS, 2)> >(p, st);
 }
 
 /* how many kernels decode_class() launches */
@@ -903,7 +904,7 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 	}
 	xa_census_kernel<<<1, kCensusThreads, 0, st>>>(p.src, p.streams, c.d_order, c.n_streams,
 	    (uint32_t)block_bytes(BITS), (uint32_t)CH,
-	    pick_form ? kStagedPermille : c.stereo == 1 && CH == 2 ? 0u : kNever,
+	    pick_form ? staged_permille(BITS) : c.stereo == 1 && CH == 2 ? 0u : kNever,
 	    alt ? (CH == 2 ? kWidePermilleStereo : kWidePermilleMono)[c.n_streams >= kWideManyStreams] :
 	    kNever, c.d_choice);
 	if ((e = cudaGetLastError()) != cudaSuccess)

@@ -33,15 +33,27 @@ namespace xa {
 #ifndef XA_DEC_NT
 #define XA_DEC_NT 256
 #endif
-#ifndef XA_DEC_STAGES
-#define XA_DEC_STAGES 3
-#endif
 #ifndef XA_DEC_WIDE
 #define XA_DEC_WIDE 32
 #endif
 constexpr int kDecTBQ = XA_DEC_TBQ;		/* block-channels per tile */
 constexpr int kDecThreads = XA_DEC_NT;		/* consumer threads (+1 producer warp) */
-constexpr int kDecStages = XA_DEC_STAGES;	/* source buffers in flight per CTA */
+/*
+ * Source buffers (tiles) in flight per CTA of the direct forms.  A tile with
+ * chains stays in flight for as long as its longest chain takes, so the deeper
+ * the ring the more chains run at once; the depth is what fits next to the
+ * occupancy the registers allow (3 or 4 CTAs of 320 threads per SM) in 227 KB
+ * without costing the cut-only case anything (measured: profiles/history_r1.md).
+ * -DXA_DEC_STAGES=n overrides it for geometry sweeps.
+ */
+constexpr int dec_stages(int bits, int ch)
+{
+#ifdef XA_DEC_STAGES
+	return XA_DEC_STAGES;
+#else
+	return ch == 1 ? (bits == 4 ? 4 : 3) : (bits == 4 ? 3 : bits == 6 ? 5 : 4);
+#endif
+}
 constexpr int kDecWide = XA_DEC_WIDE;		/* strips per tile in "wide" mode */
 constexpr int kEncTBE = 256;
 constexpr int kEncThreads = 128;

@@ -584,7 +584,10 @@ struct DecTileStereo {
 	static constexpr int kLag = 1;
 	static constexpr bool kStaged = false;
 	static constexpr int kStages = STAGES;
-	static constexpr int kMinCtas = 1;
+	/* CTAs per SM the registers must allow: 4 (48 registers) for 4-bit streams,
+	 * whose units are the most work per byte; 3 (64 registers) otherwise, where
+	 * the cap costs more in the walkers than the fourth CTA brings (measured) */
+	static constexpr int kMinCtas = BITS == 4 ? 4 : 3;
 	static constexpr uint32_t UPS = SBE * 8;	/* 16-byte units per strip */
 
 	const DecodeParams &p;
@@ -963,7 +966,7 @@ struct DecTileStaged {
 	static constexpr int kLag = CH;			/* predecessor of item q is q - CH */
 	static constexpr bool kStaged = true;
 	static constexpr int kStages = STAGES;
-	static constexpr int kMinCtas = 1;
+	static constexpr int kMinCtas = 3;	/* per SM: caps the registers at 64 */
 
 	const DecodeParams &p;
 	Smem &sm;

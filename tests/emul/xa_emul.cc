@@ -44,7 +44,7 @@ emul_decode_ns(const DecodeParams &p, int order)
 	memset(sm, 0xa5, sizeof *sm);	/* smem is garbage at CTA start */
 	for (uint32_t ticket = 0; ticket < p.n_tiles; ticket++) {
 		/* one persistent CTA draws every ticket; stages rotate as on the GPU */
-		const int s = (int)(ticket % kDecStages);
+		const int s = (int)(ticket % Tile::kStages);
 		memset(sm->in[s], 0xa5, sizeof sm->in[s]);
 		const TileEnt te = p.tiles[ticket];
 		bool tail = false;
@@ -133,13 +133,13 @@ emul_decode_bucket(const DecodeParams &p, int ns, int order)
 			emul_decode_staged_ns<BITS, CH, kDecWide>(p, order);
 	} else if (CH == 2) {
 		if (ns == 1)
-			emul_decode_ns<DecTileStereo<BITS, kDecTBQ, 1, kDecStages> >(p, order);
+			emul_decode_ns<DecTileStereo<BITS, kDecTBQ, 1, dec_stages(BITS, 2)> >(p, order);
 		else
-			emul_decode_ns<DecTileStereo<BITS, kDecTBQ, kDecWide, kDecStages> >(p, order);
+			emul_decode_ns<DecTileStereo<BITS, kDecTBQ, kDecWide, dec_stages(BITS, 2)> >(p, order);
 	} else if (ns == 1) {
-		emul_decode_ns<DecTile<BITS, kDecTBQ, 1, kDecStages> >(p, order);
+		emul_decode_ns<DecTile<BITS, kDecTBQ, 1, dec_stages(BITS, 1)> >(p, order);
 	} else {
-		emul_decode_ns<DecTile<BITS, kDecTBQ, kDecWide, kDecStages> >(p, order);
+		emul_decode_ns<DecTile<BITS, kDecTBQ, kDecWide, dec_stages(BITS, 1)> >(p, order);
 	}
 }
 

@@ -1,0 +1,6 @@
+mkdir -p gpurun_out; rm -f gpurun_out/wide.jsonl gpurun_out/wide.err
+M=P0,P1,C10,C20,C50,P2
+for bits in 4 6 8; do
+BJXA_B200_STEREO=direct timeout 600 python tools/prof_decode.py --mix $M --streams 4096 --seconds 30 --bits $bits --ch 2 --steps 4 --warmup 2 --tag direct >> gpurun_out/wide.jsonl 2>> gpurun_out/wide.err
+done
+BJXA_B200_STEREO=staged timeout 600 python tools/prof_decode.py --mix $M --streams 4096 --seconds 30 --bits 8 --ch 2 --steps 4 --warmup 2 --tag staged >> gpurun_out/wide.jsonl 2>> gpurun_out/wide.err

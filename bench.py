@@ -471,16 +471,19 @@ def main():
         # ---- CPU baseline: the reference on this box's host cores (rank 0, N=1) ---
         if rank == 0 and world == 1:
             cores = os.cpu_count() or 1
-            n = max(2 * cores, 16)
-            base = [xa[i].reshape(-1).cpu().numpy() for i in range(min(n, 16))]
+            # bounded sample: about 10-30 s of CPU work (64 streams = 0.17 Gsamples a core)
+            n = 64 * cores
+            base = [xa[i].reshape(-1).cpu().numpy() for i in range(16)]
             streams = [base[i % len(base)] for i in range(n)]
+            cpu_reference_rate(streams[:cores], steps=1, warmup=0)      # thread start-up, page-in
             rate, dt, info = cpu_reference_rate(streams, steps=1, warmup=0)
             line["cpu_baseline"] = {
                 "value": round(rate, 2), "unit": "Msamples/s", "cores": info["cores"],
                 "kind": info["kind"],
                 "sample": f"{n} streams of this workload ({len(base)} distinct) decoded once, "
                           f"one reference decoder per stream, static partition over "
-                          f"{info['cores']} threads, {dt:.2f} s"}
+                          f"{info['cores']} threads, {dt:.2f} s wall = "
+                          f"{dt * info['cores']:.0f} core-seconds"}
 
     if sampler:
         sampler.stop()

@@ -18,4 +18,5 @@ B="bench.py --steps 1 --warmup 3 --no-extras"
 timeout 300 python $B > /dev/null 2>&1 || exit 3
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:xa_decode -c 1 \
     -f -o gpurun_out/decode_p1_4096_$tag python $B > gpurun_out/ncu_full_$tag.log 2>&1
+timeout 300 python tools/pcie_probe.py > gpurun_out/pcie_$tag.json 2> gpurun_out/pcie_$tag.err
 echo done

@@ -367,7 +367,7 @@ def main():
     achieved = algo_bytes / (avg_launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": ncu_traffic(),
-                "kernel": "xa_decode_kernel<8,1>", "peak_source": peak_src,
+                "kernel": "xa_decode_kernel<DecTile<8,512,1,3>> (mono, long strips, direct form)", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "avg_launch_ms": round(avg_launch_ms, 4),
                 "frac_of_nominal_8000": round(achieved / 8000.0, 4)}

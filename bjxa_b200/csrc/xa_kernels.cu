@@ -96,12 +96,12 @@ __device__ __forceinline__ void consumer_sync()
  *              bytes for the heads of chains and publishes the tile on its
  *              "ready" mbarrier;
  *   consumers  (kDecThreads threads) wait for "ready" and run the tile's
- *              phases (xa_tile.h).  Direct forms: walk their share of the
- *              chains and decode their share of the 16-byte units of the cut
- *              blocks, storing everything straight from registers, then arrive
- *              -- one arrival per warp -- on the stage's "empty" mbarrier; no
- *              CTA barrier at all.  Staged form (stereo): rows, barrier,
- *              interleaving store, barrier.
+ *              phases (xa_tile.h).  Direct forms: the tile's walker warp
+ *              (the warps take turns) walks the chains, every warp decodes its
+ *              share of the 16-byte units of the cut blocks, everything is
+ *              stored straight from registers, then one arrival per warp on the
+ *              stage's "empty" mbarrier; no CTA barrier at all.  Staged form
+ *              (chain-heavy stereo): rows, barrier, interleaving store, barrier.
  */
 #ifndef XA_DEC_STAGED_STAGES
 #define XA_DEC_STAGED_STAGES 2

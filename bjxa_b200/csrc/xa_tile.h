@@ -250,11 +250,12 @@ struct DecSmem {
  *            as filter 0 and reported): it unpacks the 2 * BITS/2 payload bytes
  *            it needs and stores the unit straight from registers --
  *            neighbouring threads write neighbouring 16 bytes;
- *   walkers  one consumer thread per chain: predictor state in registers,
- *            starting from the last two samples of the cut block in front of
- *            the chain -- which the walker recomputes itself from that block's
- *            bytes -- or from the carry mailbox at the start of a strip; it
- *            stores its own 64-byte rows.
+ *   walkers  one consumer WARP per tile (the warps take turns), one lane per
+ *            chain, lanes drawing the next chain as they finish one: predictor
+ *            state in registers, starting from the last two samples of the cut
+ *            block in front of the chain -- which the walker recomputes itself
+ *            from that block's bytes -- or from the carry mailbox at the start
+ *            of a strip; it stores its own 64-byte rows.
  *
  * A consumer warp that is done with its share of a tile arrives on the stage's
  * "empty" mbarrier and moves on; warps may drift up to STAGES tiles apart, so
@@ -929,14 +930,14 @@ struct DecTileStereo {
 
 /* ---- decode, staged variant (used for stereo) ------------------------------ */
 /*
- * The first complete form of the tile algorithm, kept for STEREO streams: every
- * block-channel is decoded into a 64-byte row of a shared-memory image of the
- * tile (cut blocks in phase A, chains by one walker lane each), and a store
- * phase interleaves left and right rows into 16-byte units.  For stereo this is
- * faster than the direct form below whenever chains are present, because a
- * walker that owns only one channel of an effective block would otherwise have
- * to write its int16 samples around the other channel's (measured:
- * profiles/history_r1.md).
+ * The first complete form of the tile algorithm, kept for chain-heavy STEREO
+ * data: every block-channel is decoded into a 64-byte row of a shared-memory
+ * image of the tile (cut blocks in phase A, chains by one walker lane each, all
+ * warps at once), and a store phase interleaves left and right rows into
+ * 16-byte units.  Walking per channel keeps twice as many chains in flight as
+ * the pair walkers of the direct form; the price is two CTA barriers per tile
+ * and the rows' shared-memory traffic, so the census (xa_kernels.cu) picks it
+ * only above a measured share of chain blocks (profiles/history_r1.md).
  */
 template <int BITS, int CH, int TBQ, int NS, int STAGES>
 struct DecSmemStaged {

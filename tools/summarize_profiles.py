@@ -1,0 +1,171 @@
+#!/usr/bin/env python
+"""Turns what tools/refresh_profiles.sh left in gpurun_out/ into the committed
+summaries under profiles/ (run here, after the gpurun call has merged its files):
+
+    python tools/summarize_profiles.py r1
+
+  bench_<tag>.json, bench_ref_<tag>.json, configs_<tag>.json, pcie_<tag>.json   copied
+  launches_<tag>_summary.md        from launches_<tag>.csv (ncu launch list)
+  decode_p1_4096_<tag>_ncu_summary.csv, decode_traffic.json
+                                   from decode_p1_4096_<tag>.ncu-rep (ncu --set full)
+"""
+import csv
+import io
+import json
+import os
+import shutil
+import subprocess
+import sys
+from collections import OrderedDict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+PROF = os.path.join(ROOT, "profiles")
+
+METRICS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_op_write.sum",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum", "smsp__thread_inst_executed.sum",
+    "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "smsp__warps_eligible.avg.per_cycle_active",
+    "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers",
+    "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_warps",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "smsp__cycles_active.avg", "sm__cycles_elapsed.max",
+]
+
+
+def fnum(x):
+    return float(x.replace(",", ""))
+
+
+def copy(name):
+    src = os.path.join(OUT, name)
+    if os.path.exists(src) and os.path.getsize(src):
+        shutil.copy(src, os.path.join(PROF, name))
+        return True
+    print("missing:", name)
+    return False
+
+
+def launches(tag):
+    path = os.path.join(OUT, f"launches_{tag}.csv")
+    if not os.path.exists(path):
+        print("missing:", path)
+        return
+    text = open(path).read()
+    start = text.index('"ID"')
+    rows = list(csv.DictReader(io.StringIO(text[start:])))
+    per, order = OrderedDict(), []
+    for r in rows:
+        if r.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        v = fnum(r["Metric Value"])
+        unit = r["Metric Unit"]
+        ms = v / 1e6 if unit in ("ns", "nsecond") else v / 1e3 if unit in ("us", "usecond") else v
+        k = r["Kernel Name"]
+        per.setdefault(k, [0, 0.0])
+        per[k][0] += 1
+        per[k][1] += ms
+        order.append((k, ms))
+    total = sum(v[1] for v in per.values())
+    cmd = "python bench.py --steps 2 --warmup 3 --no-extras"
+    L = [f"# ncu launch list, round {tag} -- `{cmd}`", "",
+         f"Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file "
+         f"gpurun_out/launches_{tag}.csv {cmd}` on one B200 (tools/refresh_profiles.sh); the same "
+         "command had exited 0 without ncu directly before.",
+         "Times are ncu's serialised, cold-cache per-launch durations: compare SHARES, not absolutes.",
+         "",
+         f"{len(order)} launches, {total:.2f} ms in total. Everything that is not `xa_*` is the "
+         "synthetic-input generator (torch RNG / indexing kernels that build the 11.2 GB XA arena and "
+         "its profile bytes) and runs BEFORE the timed region.", "",
+         "| kernel | launches | total ms | share of all launches |", "|---|---:|---:|---:|"]
+    for k, (n, ms) in sorted(per.items(), key=lambda kv: -kv[1][1])[:10]:
+        L.append(f"| `{k[:90]}` | {n} | {ms:.3f} | {100 * ms / total:.1f} % |")
+    ours = [(k, ms) for k, ms in order if "xa_" in k]
+    L += ["", "## The timed region", "",
+          "One step = one `bjxa_plan_run()` = one `cudaMemsetAsync` (arms first_bad[], the ticket "
+          "counters and the census words; a memset node, not a kernel) + the launches below. The "
+          "4096-stream class carries both tile shapes, so the census kernel runs and the tile form "
+          "it does not pick returns at once:", "",
+          "| launch | kernel | ms under ncu |", "|---|---|---:|"]
+    per_step = len(ours) // 5 if len(ours) % 5 == 0 else None
+    for i, (k, ms) in enumerate(ours):
+        step = i // per_step if per_step else i
+        kind = "warm-up" if step < 3 else "timed"
+        L.append(f"| {i} ({kind} step {step}) | `{k[:100]}` | {ms:.4f} |")
+    if per_step:
+        timed = ours[3 * per_step:]
+        tot = sum(ms for _, ms in timed)
+        dec = sum(ms for k, ms in timed if "xa_decode_kernel" in k)
+        big = max(ms for _, ms in timed)
+        L += ["", f"Share of the dominant `xa_decode_kernel` launch in a timed step: "
+              f"{100 * big * 2 / tot:.1f} % of the step's kernel time "
+              f"(all `xa_decode_kernel` launches {100 * dec / tot:.1f} %, census the rest)."]
+    try:
+        b = json.loads(open(os.path.join(PROF, f"bench_{tag}.json")).read().strip().splitlines()[-1])
+        L += [f"bench.py's CUDA-event time for the same step, not under a profiler, is "
+              f"{b['ms_per_step']} ms (profiles/bench_{tag}.json)."]
+    except (OSError, ValueError, KeyError):
+        pass
+    open(os.path.join(PROF, f"launches_{tag}_summary.md"), "w").write("\n".join(L) + "\n")
+
+
+def full(tag):
+    rep = os.path.join(OUT, f"decode_p1_4096_{tag}.ncu-rep")
+    if not os.path.exists(rep):
+        print("missing:", rep)
+        return
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True,
+                         text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, d = rows[0], rows[1], rows[2]
+    idx = {h: i for i, h in enumerate(hdr)}
+    name = d[idx["Kernel Name"]]
+    L = ["# ncu --set full --clock-control none --import-source on -k regex:xa_decode -c 1 "
+         "python bench.py --steps 1 --warmup 3 --no-extras",
+         f"# kernel: {name}, BASELINE.json configs[1] (4096 mono 8-bit streams x 60 s), profile mix "
+         f"P1, one B200; round {tag}", "metric,unit,value"]
+    for m in METRICS:
+        if m in idx:
+            L.append(f"{m},{units[idx[m]]},{d[idx[m]]}")
+    stalls = []
+    for h in hdr:
+        if "average_warp_latency_issue_stalled" in h or ("warp_issue_stalled" in h and h.endswith("_per_warp_active.pct")):
+            try:
+                stalls.append((fnum(d[idx[h]]), h, units[idx[h]]))
+            except ValueError:
+                pass
+    for v, h, u in sorted(stalls, reverse=True)[:8]:
+        L.append(f"{h},{u},{v}")
+    open(os.path.join(PROF, f"decode_p1_4096_{tag}_ncu_summary.csv"), "w").write("\n".join(L) + "\n")
+
+    def gb(m):
+        v, u = fnum(d[idx[m]]), units[idx[m]]
+        return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u]
+    rd, wr = gb("dram__bytes_read.sum"), gb("dram__bytes_write.sum")
+    algo = 4096 * (2728704 + 5292000)
+    json.dump({"kernel": name, "workload": "4096 mono 8-bit streams x 60 s, mix P1",
+               "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
+               "algorithmic_bytes_per_launch": algo,
+               "traffic_over_algorithmic": round((rd + wr) / algo, 4),
+               "source": f"profiles/decode_p1_4096_{tag}_ncu_summary.csv (ncu --set full, one launch)"},
+              open(os.path.join(PROF, "decode_traffic.json"), "w"), indent=1)
+
+
+def main():
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+    for n in (f"bench_{tag}.json", f"bench_ref_{tag}.json", f"configs_{tag}.json", f"pcie_{tag}.json"):
+        copy(n)
+    launches(tag)
+    full(tag)
+
+
+if __name__ == "__main__":
+    main()

@@ -15,6 +15,7 @@ from .capi import BjxaLib, _addr
 
 PLAN_DECODE = 0
 PLAN_ENCODE = 1
+PLAN_ENCODE_SEARCH = 2     # extension: per-block filter/range search (include/bjxa_batch.h)
 
 
 class StreamDesc(C.Structure):

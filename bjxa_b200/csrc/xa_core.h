@@ -291,5 +291,68 @@ XA_HD uint32_t pack4(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3)
 	}
 }
 
+/* ---- searching encoder (an extension: SURVEY.md section 8, row E4) -------- */
+
+/*
+ * The reference encoder writes profile 0 and the top bits of every sample
+ * (src/libbjxa.c:679); nothing in the reference searches.  This extension picks
+ * a filter and a range per block, closed loop: for every candidate
+ *     filter f = 0..4,  range r = 0..16-BITS      (profile byte f << 4 | r)
+ * the block is encoded and decoded again exactly as the reference DEcoder would
+ * (src/libbjxa.c:556-571), starting from the decoder state the previous block's
+ * winner left behind:
+ *     pred  = (q0*k0 + q1*k1) / 256                    truncating toward zero
+ *     step  = 1 << (16 - BITS - r)
+ *     code  = clamp(floor((x - pred + step/2) / step), -2^(BITS-1), 2^(BITS-1)-1)
+ *     s     = clamp_int16(code * step + pred);   err += (x - s)^2;   q1 = q0; q0 = s
+ * and the candidate with the smallest (err, profile byte) wins.  Candidate
+ * index c = f * (17 - BITS) + r orders the candidates by profile byte.  The
+ * candidate (f, r) = (0, 0) never does worse than the reference's truncation,
+ * whatever the state, so the result never has a larger error than the
+ * reference encoder's.  (The test suite holds a plain-C restatement.)
+ */
+XA_HD constexpr int search_ranges(int bits) { return 17 - bits; }
+XA_HD constexpr int search_candidates(int bits) { return 5 * (17 - bits); }
+
+template <int BITS>
+XA_HD int search_sample(int x, int k0, int k1, int shift, int &q0, int &q1,
+    unsigned long long &err)
+{
+	const int g = q0 * k0 + q1 * k1;
+	const int pred = (g + ((g >> 31) & 255)) >> 8;
+	int code = (x - pred + ((1 << shift) >> 1)) >> shift;
+	const int lo = -(1 << (BITS - 1)), hi = (1 << (BITS - 1)) - 1;
+	code = code < lo ? lo : code;
+	code = code > hi ? hi : code;
+	int s = code * (1 << shift) + pred;
+	s = s < -32768 ? -32768 : s;
+	s = s > 32767 ? 32767 : s;
+	const long long e = (long long)(x - s);
+	err += (unsigned long long)(e * e);
+	q1 = q0;
+	q0 = s;
+	return code;
+}
+
+/*
+ * Puts code i (i = 0..31, a compile-time constant once the caller's loop is
+ * unrolled) into the payload's byte image, BITS little-endian words: the codes
+ * form one MSB-first bit stream (bjxa.5.rst: high nibble first; 6-bit codes
+ * four to three bytes, big endian).
+ */
+template <int BITS>
+XA_HD void put_code(uint32_t (&w)[BITS], int i, int code)
+{
+	const uint32_t c = (uint32_t)code & ((1u << BITS) - 1u);
+	const int bit = BITS * i, byte = bit >> 3, top = bit & 7;
+	if (top + BITS <= 8) {
+		w[byte >> 2] |= (c << (8 - top - BITS)) << (8 * (byte & 3));
+	} else {
+		const int spill = top + BITS - 8;	/* bits that go to the next byte */
+		w[byte >> 2] |= (c >> spill) << (8 * (byte & 3));
+		w[(byte + 1) >> 2] |= ((c << (8 - spill)) & 0xffu) << (8 * ((byte + 1) & 3));
+	}
+}
+
 } /* namespace xa */
 #endif

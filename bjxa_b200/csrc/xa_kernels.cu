@@ -410,6 +410,136 @@ xa_encode_kernel(const EncodeParams p)
 	t.phase_store(tid, kEncThreads);
 }
 
+/*
+ * Searching encoder (an extension, not in the reference: xa_core.h spells out
+ * the rule, the test suite holds a plain-C restatement).  A stream-channel is one serial
+ * chain over all of its blocks -- every block starts from the decoder state
+ * its predecessor's winner left -- so the parallelism is streams x channels x
+ * candidates: ONE WARP PER STREAM-CHANNEL, lane l simulating candidates l,
+ * l + 32, (l + 64) side by side (independent dependency chains, which hides
+ * the latency of the predictor step), the block's 32 samples going round by
+ * shuffle; warp-wide argmin on (error, candidate); the winner's packed codes
+ * are handed to the lanes that store them, one payload byte per lane.
+ * Compute-bound by design: 45-65 closed-loop simulations per sample.
+ */
+constexpr int kSearchThreads = 128;
+
+template <int BITS, int CH>
+__global__ void __launch_bounds__(kSearchThreads)
+xa_search_kernel(const EncodeParams p)
+{
+	constexpr int NR = search_ranges(BITS), NC = search_candidates(BITS);
+	constexpr int SLOTS = (NC + 31) / 32, BS = block_bytes(BITS);
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t warp = (blockIdx.x * kSearchThreads + threadIdx.x) >> 5;
+	if (warp >= p.n_streams * CH)
+		return;
+	const uint32_t stream = p.order[warp / CH], ch = warp % CH;
+	const StreamDev sd = p.streams[stream];
+	const uint8_t *pcm = p.src + sd.pcm_off;
+	uint8_t *xa = p.dst + sd.xa_off + ch * BS;
+	const uint32_t frames = sd.pcm_len / (2u * CH);
+	int s0 = sd.prev[ch][0], s1 = sd.prev[ch][1];
+
+	int k0[SLOTS], k1[SLOTS], sh[SLOTS];
+#pragma unroll
+	for (int j = 0; j < SLOTS; j++) {
+		const uint32_t c = lane + 32u * j;
+		const uint32_t f = c < (uint32_t)NC ? c / NR : 0u, r = c < (uint32_t)NC ? c % NR : 0u;
+		k0[j] = gain_k0(f);
+		k1[j] = gain_k1(f);
+		sh[j] = 16 - BITS - (int)r;
+	}
+	/* lane i holds sample i of the block; frames past the end are zero
+	 * (src/libbjxa.c:686-690) */
+	auto sample = [&](uint32_t eb) -> int {
+		const uint32_t fr = eb * 32u + lane;
+		return fr < frames ?
+		    *reinterpret_cast<const int16_t *>(pcm + ((uint64_t)fr * CH + ch) * 2u) : 0;
+	};
+	int xn = sample(0);
+	for (uint32_t eb = 0; eb < sd.blocks; eb++) {
+		const int x = xn;
+		if (eb + 1 < sd.blocks)
+			xn = sample(eb + 1);
+		int q0[SLOTS], q1[SLOTS];
+		unsigned long long err[SLOTS];
+		uint32_t w[SLOTS][BITS];
+#pragma unroll
+		for (int j = 0; j < SLOTS; j++) {
+			q0[j] = s0;
+			q1[j] = s1;
+			err[j] = 0;
+#pragma unroll
+			for (int k = 0; k < BITS; k++)
+				w[j][k] = 0;
+		}
+#pragma unroll
+		for (int i = 0; i < 32; i++) {
+			const int xi = __shfl_sync(0xffffffffu, x, i);
+#pragma unroll
+			for (int j = 0; j < SLOTS; j++)
+				put_code<BITS>(w[j], i,
+				    search_sample<BITS>(xi, k0[j], k1[j], sh[j], q0[j], q1[j], err[j]));
+		}
+		/* this lane's best, then the warp's: smallest (error, candidate) */
+		unsigned long long be = ~0ULL;
+		uint32_t bc = 0xffffffffu;
+#pragma unroll
+		for (int j = 0; j < SLOTS; j++) {
+			const uint32_t c = lane + 32u * j;
+			if (c < (uint32_t)NC && (err[j] < be || (err[j] == be && c < bc))) {
+				be = err[j];
+				bc = c;
+			}
+		}
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			const unsigned long long oe = __shfl_xor_sync(0xffffffffu, be, o);
+			const uint32_t oc = __shfl_xor_sync(0xffffffffu, bc, o);
+			if (oe < be || (oe == be && oc < bc)) {
+				be = oe;
+				bc = oc;
+			}
+		}
+		const uint32_t wl = bc & 31u, ws = bc >> 5;
+		int wq0 = q0[0], wq1 = q1[0];
+		uint32_t ww[BITS];
+#pragma unroll
+		for (int k = 0; k < BITS; k++)
+			ww[k] = w[0][k];
+#pragma unroll
+		for (int j = 1; j < SLOTS; j++) {
+			if (ws == (uint32_t)j) {
+				wq0 = q0[j];
+				wq1 = q1[j];
+#pragma unroll
+				for (int k = 0; k < BITS; k++)
+					ww[k] = w[j][k];
+			}
+		}
+		s0 = __shfl_sync(0xffffffffu, wq0, wl);
+		s1 = __shfl_sync(0xffffffffu, wq1, wl);
+		/* payload byte `lane` (and lane + 32 is never needed: 4 * BITS <= 32) */
+		uint32_t mine = 0;
+#pragma unroll
+		for (int k = 0; k < BITS; k++) {
+			const uint32_t wk = __shfl_sync(0xffffffffu, ww[k], wl);
+			if (lane >> 2 == (uint32_t)k)
+				mine = wk;
+		}
+		uint8_t *blk = xa + (uint64_t)eb * (CH * BS);
+		if (lane < 4u * BITS)
+			blk[1 + lane] = (uint8_t)(mine >> (8u * (lane & 3u)));
+		if (lane == 0)
+			blk[0] = (uint8_t)((bc / NR) << 4 | (bc % NR));
+	}
+	if (lane == 0) {
+		p.results[stream].prev[ch][0] = (int16_t)s0;
+		p.results[stream].prev[ch][1] = (int16_t)s1;
+	}
+}
+
 /* ---- error mapping -------------------------------------------------------- */
 
 static int
@@ -714,7 +844,7 @@ plan_build(bjxa_plan *pl, int kind, const bjxa_stream_desc_t *descs, size_t n)
 {
 	size_t bad = 0;
 
-	if (kind != BJXA_PLAN_DECODE && kind != BJXA_PLAN_ENCODE) {
+	if (kind != BJXA_PLAN_DECODE && kind != BJXA_PLAN_ENCODE && kind != BJXA_PLAN_ENCODE_SEARCH) {
 		errno = EINVAL;
 		return (-1);
 	}
@@ -734,7 +864,7 @@ plan_build(bjxa_plan *pl, int kind, const bjxa_stream_desc_t *descs, size_t n)
 	pl->launches = 0;
 	pl->stereo = stereo_mode();
 	for (int b = 0; b < 6; b++)
-		if (pl->hp.tile_begin[b + 1] > pl->hp.tile_begin[b])
+		if (pl->hp.order_begin[b + 1] > pl->hp.order_begin[b])
 			pl->launches += kind == kKindDecode ? decode_class_launches(bucket_ch(b),
 			    pl->stereo, pl->hp.alt_ns[b] != 0) : 1;
 	return (plan_upload(pl));
@@ -951,7 +1081,7 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 	HostPlan &hp = pl->hp;
 	cudaStream_t st = (cudaStream_t)cuda_stream;
 
-	if (hp.tiles.empty()) {
+	if (hp.order.empty()) {		/* no stream has any block */
 		pl->ran = true;
 		pl->last_stream = st;
 		pl->last_dst = (uint8_t *)dst;
@@ -990,10 +1120,34 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 
 	for (int b = 0; b < 6; b++) {
 		uint32_t t0 = hp.tile_begin[b], t1 = hp.tile_begin[b + 1];
-		if (t1 == t0)
+		const uint32_t n_class = hp.order_begin[b + 1] - hp.order_begin[b];
+		if (n_class == 0)
 			continue;
 		cudaError_t e;
-		if (hp.kind == kKindDecode) {
+		if (hp.kind == kKindSearch) {
+			EncodeParams p;
+			p.src = (const uint8_t *)src;
+			p.src_bytes = src_bytes;
+			p.dst = (uint8_t *)dst;
+			p.dst_bytes = dst_bytes;
+			p.streams = pl->d_streams.p;
+			p.tiles = NULL;
+			p.n_tiles = 0;
+			p.results = pl->d_results.p;
+			p.order = pl->d_order.p + hp.order_begin[b];
+			p.n_streams = n_class;
+			const uint32_t warps = n_class * (uint32_t)bucket_ch(b);
+			const uint32_t grid = (warps * 32u + kSearchThreads - 1) / kSearchThreads;
+			switch (b) {
+			case 0: xa_search_kernel<4, 1><<<grid, kSearchThreads, 0, st>>>(p); break;
+			case 1: xa_search_kernel<4, 2><<<grid, kSearchThreads, 0, st>>>(p); break;
+			case 2: xa_search_kernel<6, 1><<<grid, kSearchThreads, 0, st>>>(p); break;
+			case 3: xa_search_kernel<6, 2><<<grid, kSearchThreads, 0, st>>>(p); break;
+			case 4: xa_search_kernel<8, 1><<<grid, kSearchThreads, 0, st>>>(p); break;
+			default: xa_search_kernel<8, 2><<<grid, kSearchThreads, 0, st>>>(p); break;
+			}
+			e = cudaGetLastError();
+		} else if (hp.kind == kKindDecode) {
 			DecodeParams p;
 			p.src = (const uint8_t *)src;
 			p.src_bytes = src_bytes;
@@ -1037,6 +1191,9 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 			p.streams = pl->d_streams.p;
 			p.tiles = pl->d_tiles.p + t0;
 			p.n_tiles = t1 - t0;
+			p.results = NULL;
+			p.order = NULL;
+			p.n_streams = 0;
 			switch (b) {
 			case 0: e = launch_encode<4, 1>(p, st); break;
 			case 1: e = launch_encode<4, 2>(p, st); break;
@@ -1130,12 +1287,21 @@ bjxa_plan_fetch(bjxa_plan_t *pl, bjxa_stream_desc_t *out, size_t n)
 	XA_CUDA(cudaStreamSynchronize(pl->last_stream));
 	XA_CUDA(cudaGetLastError());
 
-	if (pl->hp.kind == kKindEncode) {
+	if (pl->hp.kind != kKindDecode) {
+		std::vector<StreamRes> after;
+		if (pl->hp.kind == kKindSearch && n) {
+			/* the decoder state the encoded blocks leave behind */
+			after.resize(n);
+			XA_CUDA(cudaMemcpy(after.data(), pl->d_results.p, n * sizeof(StreamRes),
+			    cudaMemcpyDeviceToHost));
+		}
 		for (size_t i = 0; i < n; i++) {
 			out[i] = pl->descs[i];
 			out[i].done = out[i].blocks;
 			out[i].result = (int32_t)out[i].blocks;
 			out[i].error = 0;
+			if (!after.empty() && out[i].blocks != 0)
+				memcpy(out[i].prev, after[i].prev, sizeof after[i].prev);
 		}
 		return (0);
 	}

@@ -60,7 +60,7 @@ constexpr int kEncThreads = 128;
 static_assert(kDecThreads % 32 == 0 && kDecTBQ % 2 == 0, "tile geometry");
 static_assert(kDecWide <= 32, "one producer lane per strip");
 
-enum { kKindDecode = 0, kKindEncode = 1 };
+enum { kKindDecode = 0, kKindEncode = 1, kKindSearch = 2 };	/* = BJXA_PLAN_* */
 
 XA_HD int bucket_of(int bits, int ch) { return (bits / 2 - 2) * 2 + (ch - 1); }
 XA_HD int bucket_bits(int b) { return 4 + 2 * (b / 2); }
@@ -192,6 +192,8 @@ inline int build_plan(HostPlan &hp, int kind, const Desc *d, size_t n,
 		const uint32_t order0 = (uint32_t)hp.order.size();
 		hp.order.insert(hp.order.end(), o.begin(), o.end());
 
+		if (kind == kKindSearch)
+			continue;	/* one warp per stream-channel, in this order: no tiles */
 		if (kind == kKindEncode) {
 			const uint32_t tbe = (uint32_t)kEncTBE;
 			size_t active = o.size();

@@ -87,6 +87,10 @@ struct EncodeParams {
 	const StreamDev *streams;
 	const TileEnt *tiles;
 	uint32_t n_tiles;
+	/* searching encoder only */
+	StreamRes *results;	/* decoder state after the last block */
+	const uint32_t *order;	/* the class's streams, longest first */
+	uint32_t n_streams;
 };
 
 /* ---- environment shims -------------------------------------------------- */

@@ -73,6 +73,20 @@ typedef struct bjxa_stream_desc {
 
 #define BJXA_PLAN_DECODE 0
 #define BJXA_PLAN_ENCODE 1
+/*
+ * EXTENSION, not in the reference (whose encoder writes profile 0 and the top
+ * bits of every sample, src/libbjxa.c:679): encode with a per-block search
+ * over filter 0..4 x range 0..16-bits, closed loop against the reference
+ * decoder's arithmetic (src/libbjxa.c:556-571), smallest squared error wins,
+ * ties go to the lowest profile byte.  Same arenas and descriptors as
+ * BJXA_PLAN_ENCODE; `prev` is the DEcoder state the stream's first block will
+ * be decoded from (0 for a file: bjxa_dump_header writes no history) and, out
+ * of bjxa_plan_fetch, the state after the last block, so a stream may be
+ * encoded in several calls.  The output decodes with the reference decoder and
+ * never has a larger error than BJXA_PLAN_ENCODE's.  Opt-in only: bjxa_encode
+ * and bjxa_batch_encode stay reference-exact.
+ */
+#define BJXA_PLAN_ENCODE_SEARCH 2
 
 typedef struct bjxa_plan bjxa_plan_t;
 

@@ -79,6 +79,23 @@ class Oracle:
         assert done == blocks
         return out
 
+    def encode_search_blocks(self, bits, channels, prev, pcm: np.ndarray):
+        """The searching encoder (an extension, see bjxa_oracle.h).
+        -> (xa bytes, decoder state after the last block [[n-1, n-2], ...])"""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        frames = pcm.size // channels
+        blocks = (frames + 31) // 32
+        out = np.zeros(blocks * channels * (4 * bits + 1), dtype=np.uint8)
+        st = ((C.c_int16 * 2) * 2)()
+        for c in range(2):
+            st[c][0], st[c][1] = int(prev[c][0]), int(prev[c][1])
+        self.dll.xao_encode_search_blocks.restype = C.c_long
+        done = self.dll.xao_encode_search_blocks(
+            C.c_uint(bits), C.c_uint(channels), st, C.c_void_p(pcm.ctypes.data),
+            C.c_uint32(pcm.size * 2), C.c_void_p(out.ctypes.data))
+        assert done == blocks, done
+        return out, [[st[c][0], st[c][1]] for c in range(2)]
+
     def parse_xa_header(self, hdr: bytes):
         st = _Stream()
         buf = (C.c_char * 32).from_buffer_copy(hdr[:32])

@@ -221,6 +221,116 @@ xao_encode_blocks(unsigned bits, unsigned channels, const int16_t *pcm,
 }
 
 /* ---------------------------------------------------------------------- */
+/* searching encoder -- an EXTENSION, see bjxa_oracle.h                      */
+
+static long
+floor_div(long a, long b)				/* b > 0 */
+{
+	return (a >= 0 ? a / b : -((-a + b - 1) / b));
+}
+
+/* MSB-first bit stream of 32 codes of `bits` bits each (bjxa.5.rst) */
+static void
+pack_codes(unsigned bits, uint8_t *payload, const int codes[XAO_BLOCK_SAMPLES])
+{
+	unsigned n, k, pos = 0;
+
+	memset(payload, 0, 4 * bits);
+	for (n = 0; n < XAO_BLOCK_SAMPLES; n++)
+		for (k = 0; k < bits; k++, pos++)
+			if (((unsigned)codes[n] >> (bits - 1 - k)) & 1u)
+				payload[pos >> 3] |= (uint8_t)(0x80u >> (pos & 7));
+}
+
+long
+xao_encode_search_blocks(unsigned bits, unsigned channels, int16_t prev[2][2],
+    const int16_t *pcm, uint32_t pcm_bytes, uint8_t *xa)
+{
+	const unsigned bsize = 4 * bits + 1;
+	const int lo = -(1 << (bits - 1)), hi = (1 << (bits - 1)) - 1;
+	uint32_t frames = pcm_bytes / (2u * channels);
+	long done = 0;
+	unsigned c, n, f, r;
+
+	while (frames > 0) {
+		uint32_t take = frames < XAO_BLOCK_SAMPLES ? frames :
+		    XAO_BLOCK_SAMPLES;
+
+		for (c = 0; c < channels; c++) {
+			int16_t one[XAO_BLOCK_SAMPLES], back[XAO_BLOCK_SAMPLES];
+			int16_t best_rec[XAO_BLOCK_SAMPLES], st[2];
+			int best_codes[XAO_BLOCK_SAMPLES];
+			uint64_t best_err = UINT64_MAX;
+			unsigned best_profile = 0;
+
+			for (n = 0; n < take; n++)
+				one[n] = pcm[n * channels + c];
+			for (; n < XAO_BLOCK_SAMPLES; n++)
+				one[n] = 0;
+
+			/* ascending profile byte, strict "<": ties keep the lowest */
+			for (f = 0; f < 5; f++) {
+				for (r = 0; r <= 16 - bits; r++) {
+					const long step = 1L << (16 - bits - r);
+					long q0 = prev[c][0], q1 = prev[c][1];
+					int codes[XAO_BLOCK_SAMPLES];
+					int16_t rec[XAO_BLOCK_SAMPLES];
+					uint64_t err = 0;
+
+					for (n = 0; n < XAO_BLOCK_SAMPLES; n++) {
+						long pred = (q0 * xao_gain[f][0] +
+						    q1 * xao_gain[f][1]) / 256;	/* C: toward 0 */
+						long code = floor_div(one[n] - pred + step / 2, step);
+						long s, e;
+
+						if (code < lo)
+							code = lo;
+						if (code > hi)
+							code = hi;
+						s = code * step + pred;
+						if (s < INT16_MIN)
+							s = INT16_MIN;
+						if (s > INT16_MAX)
+							s = INT16_MAX;
+						e = one[n] - s;
+						err += (uint64_t)(e * e);
+						codes[n] = (int)code;
+						rec[n] = (int16_t)s;
+						q1 = q0;
+						q0 = s;
+					}
+					if (err < best_err) {
+						best_err = err;
+						best_profile = f << 4 | r;
+						memcpy(best_codes, codes, sizeof codes);
+						memcpy(best_rec, rec, sizeof rec);
+					}
+				}
+			}
+
+			xa[0] = (uint8_t)best_profile;
+			pack_codes(bits, xa + 1, best_codes);
+
+			/* what the (pinned) decoder makes of this block must be what
+			 * the search thought it would be */
+			st[0] = prev[c][0];
+			st[1] = prev[c][1];
+			if (xao_inflate(bits, back, 1, xa) != best_profile ||
+			    xao_predict(back, 1, xa[0], st) != 0 ||
+			    memcmp(back, best_rec, sizeof back) != 0)
+				return (-1);
+			prev[c][0] = st[0];
+			prev[c][1] = st[1];
+			xa += bsize;
+		}
+		pcm += take * channels;
+		frames -= take;
+		done++;
+	}
+	return (done);
+}
+
+/* ---------------------------------------------------------------------- */
 /* containers                                                               */
 
 /* ref: src/libbjxa.c:395-453 */

@@ -75,6 +75,19 @@ long xao_decode_blocks(unsigned bits, unsigned channels, int16_t prev[2][2],
 long xao_encode_blocks(unsigned bits, unsigned channels, const int16_t *pcm,
     uint32_t pcm_bytes, uint8_t *xa);
 
+/* EXTENSION, not in the reference (the reference
+ * hard-codes profile 0, src/libbjxa.c:679): per-block search over filter 0..4 x
+ * range 0..16-bits, closed loop against the reference decoder's arithmetic
+ * (src/libbjxa.c:556-571), error = sum (x - decoded)^2, ties -> lowest profile
+ * byte; the exact rule is spelled out in bjxa_b200/csrc/xa_core.h.  prev is the
+ * decoder state on entry and on return.  Every emitted block is decoded again
+ * with xao_inflate + xao_predict and compared with the search's own
+ * reconstruction: returns -1 if they ever differ, else the number of effective
+ * blocks written.  Parity for this function is pinned by properties only
+ * (tests/test_search.py): there is no reference implementation. */
+long xao_encode_search_blocks(unsigned bits, unsigned channels,
+    int16_t prev[2][2], const int16_t *pcm, uint32_t pcm_bytes, uint8_t *xa);
+
 /* Container helpers (cold path; only here so the oracle can be checked
  * against the reference's whole-file goldens). */
 

@@ -165,6 +165,60 @@ emul_encode_bucket(const EncodeParams &p, int order)
 	delete sm;
 }
 
+/*
+ * Searching encoder: the candidate arithmetic of xa_core.h (search_sample,
+ * put_code) driven by plain loops -- candidates in ascending order, strict
+ * "<", which is the key order (error, candidate) of the kernel's warp-wide
+ * argmin.  prev_out: [n][2][2] decoder state after the last block.
+ */
+template <int BITS>
+static void
+emul_search_stream(const bjxa_stream_desc_t &d, const uint8_t *src, uint8_t *dst,
+    int16_t *prev_out)
+{
+	constexpr int NR = search_ranges(BITS), NC = search_candidates(BITS);
+	constexpr int BS = block_bytes(BITS);
+	const uint32_t ch_n = d.channels, frames = d.pcm_len / (2u * ch_n);
+	const int16_t *pcm = reinterpret_cast<const int16_t *>(src + d.pcm_off);
+	for (uint32_t ch = 0; ch < ch_n; ch++) {
+		int s0 = d.prev[ch][0], s1 = d.prev[ch][1];
+		for (uint32_t eb = 0; eb < d.blocks; eb++) {
+			int x[32];
+			for (uint32_t i = 0; i < 32; i++) {
+				uint32_t fr = eb * 32 + i;
+				x[i] = fr < frames ? pcm[(uint64_t)fr * ch_n + ch] : 0;
+			}
+			unsigned long long best = ~0ULL;
+			uint32_t bw[BITS] = { 0 };
+			int bq0 = 0, bq1 = 0, bc = 0;
+			for (int c = 0; c < NC; c++) {
+				const unsigned f = (unsigned)(c / NR);
+				int q0 = s0, q1 = s1;
+				unsigned long long err = 0;
+				uint32_t w[BITS] = { 0 };
+				for (int i = 0; i < 32; i++)
+					put_code<BITS>(w, i, search_sample<BITS>(x[i], gain_k0(f),
+					    gain_k1(f), 16 - BITS - c % NR, q0, q1, err));
+				if (err < best) {
+					best = err;
+					bc = c;
+					bq0 = q0;
+					bq1 = q1;
+					memcpy(bw, w, sizeof w);
+				}
+			}
+			uint8_t *blk = dst + d.xa_off + ((uint64_t)eb * ch_n + ch) * BS;
+			blk[0] = (uint8_t)((bc / NR) << 4 | (bc % NR));
+			for (int j = 0; j < 4 * BITS; j++)
+				blk[1 + j] = (uint8_t)(bw[j >> 2] >> (8 * (j & 3)));
+			s0 = bq0;
+			s1 = bq1;
+		}
+		prev_out[ch * 2] = (int16_t)s0;
+		prev_out[ch * 2 + 1] = (int16_t)s1;
+	}
+}
+
 extern "C" {
 
 /*
@@ -249,6 +303,9 @@ xa_emul_encode(const bjxa_stream_desc_t *descs, size_t n, const uint8_t *src,
 		p.streams = hp.streams.data();
 		p.tiles = hp.tiles.data() + t0;
 		p.n_tiles = t1 - t0;
+		p.results = NULL;
+		p.order = NULL;
+		p.n_streams = 0;
 		switch (b) {
 		case 0: emul_encode_bucket<4, 1>(p, order); break;
 		case 1: emul_encode_bucket<4, 2>(p, order); break;
@@ -256,6 +313,29 @@ xa_emul_encode(const bjxa_stream_desc_t *descs, size_t n, const uint8_t *src,
 		case 3: emul_encode_bucket<6, 2>(p, order); break;
 		case 4: emul_encode_bucket<8, 1>(p, order); break;
 		default: emul_encode_bucket<8, 2>(p, order); break;
+		}
+	}
+	return 0;
+}
+
+int
+xa_emul_search(const bjxa_stream_desc_t *descs, size_t n, const uint8_t *src,
+    uint8_t *dst, int16_t *prev_out)
+{
+	HostPlan hp;
+	size_t bad = 0;
+	int rc = build_plan(hp, kKindSearch, descs, n, &bad);
+	if (rc)
+		return rc;
+	if (!hp.tiles.empty())
+		return -1;		/* a search plan has no tiles */
+	for (size_t i = 0; i < n; i++) {
+		if (descs[i].blocks == 0)
+			continue;
+		switch (descs[i].bits) {
+		case 4: emul_search_stream<4>(descs[i], src, dst, prev_out + 4 * i); break;
+		case 6: emul_search_stream<6>(descs[i], src, dst, prev_out + 4 * i); break;
+		default: emul_search_stream<8>(descs[i], src, dst, prev_out + 4 * i); break;
 		}
 	}
 	return 0;

@@ -54,6 +54,18 @@ class Emul:
                                      src.size, dst.ctypes.data, dst.size, order)
         return rc, dst
 
+    def search(self, descs, src, dst_bytes):
+        """The searching encoder's arithmetic (xa_core.h) in plain loops.
+        -> (rc, xa arena, decoder state after the last block [n][2][2])"""
+        src = np.ascontiguousarray(src).view(np.uint8)
+        dst = np.full(dst_bytes, 0xCD, dtype=np.uint8)
+        prev = np.zeros((descs.size, 2, 2), dtype=np.int16)
+        self.dll.xa_emul_search.restype = C.c_int
+        rc = self.dll.xa_emul_search(C.c_void_p(descs.ctypes.data), C.c_size_t(descs.size),
+                                     C.c_void_p(src.ctypes.data), C.c_void_p(dst.ctypes.data),
+                                     C.c_void_p(prev.ctypes.data))
+        return rc, dst, prev
+
     def plan(self, kind, descs, strips=0, cap=1 << 20):
         """-> (n_tiles, first stream of each tile, strip counts, j, tile_begin,
         n_slots, strips per tile of each bucket); the lists in the alternative

@@ -29,7 +29,7 @@ import torch  # noqa: E402
 
 import bench  # noqa: E402
 import bjxa_b200  # noqa: E402
-from bjxa_b200.api import PLAN_DECODE, PLAN_ENCODE, make_descs  # noqa: E402
+from bjxa_b200.api import PLAN_DECODE, PLAN_ENCODE, PLAN_ENCODE_SEARCH, make_descs  # noqa: E402
 from oracle import binding  # noqa: E402
 
 DEV = torch.device("cuda", 0)
@@ -181,6 +181,29 @@ def leg_encode(lib, orc):
            "Msamples_per_s": round(n * samples * ch / best / 1e3, 1),
            "GBps": round(algo / best / 1e6, 1), "hbm_frac": round(algo / best / 1e6 / PEAK, 4),
            "bytes": {"pcm": n * pcm_bytes, "xa": n * xa_bytes}, "parity": "3 streams vs oracle ok"}
+    lib.plan_free(plan)
+
+    # The same batch through the searching encoder (an extension: filter 0-4 x
+    # range 0-12 per block, closed loop; include/bjxa_batch.h).  Compute-bound --
+    # 65 simulations per sample -- so one step, and the oracle check on the first
+    # seconds of three streams (the CPU restatement manages 0.8 Msamples/s a core).
+    plan = lib.plan_create(PLAN_ENCODE_SEARCH, d)
+    sms = timed(lambda: lib.plan_run(plan, xa.data_ptr(), xa.numel(), raw.data_ptr(),
+                                     raw.numel(), st), 1, warmup=0)
+    res = lib.plan_fetch(plan, n)
+    assert (res["result"] == d["blocks"]).all()
+    head = 32 * 400
+    for i in (0, n // 3, n - 1):
+        want, _ = orc.encode_search_blocks(bits, ch, [[0, 0], [0, 0]],
+                                           pcm[i].cpu().numpy()[:head * ch])
+        got = xa[i * xa_bytes:i * xa_bytes + want.size].cpu().numpy()
+        assert np.array_equal(got, want), f"searched stream {i} differs from the oracle"
+    sbest = min(sms)
+    out["search"] = {"what": "same batch, BJXA_PLAN_ENCODE_SEARCH (extension; 65 candidates per block)",
+                     "ms": [round(m, 2) for m in sms],
+                     "Msamples_per_s": round(n * samples * ch / sbest / 1e3, 1),
+                     "Gcandidate_samples_per_s": round(65 * n * samples * ch / sbest / 1e6, 1),
+                     "parity": "first 400 blocks of 3 streams vs oracle ok"}
     lib.plan_free(plan)
     return out
 

@@ -35,9 +35,13 @@ $(OBJDIR)/bjxa_host.o: $(SRC)/bjxa_host.c include/bjxa.h include/bjxa_batch.h
 	@mkdir -p $(OBJDIR)
 	$(CC) $(CFLAGS) -c -o $@ $<
 
-$(LIB): $(OBJDIR)/xa_kernels.o $(OBJDIR)/bjxa_host.o $(SRC)/libbjxa.map
+$(OBJDIR)/bjxa_corpus.o: $(SRC)/bjxa_corpus.c include/bjxa.h include/bjxa_batch.h
+	@mkdir -p $(OBJDIR)
+	$(CC) $(CFLAGS) -c -o $@ $<
+
+$(LIB): $(OBJDIR)/xa_kernels.o $(OBJDIR)/bjxa_host.o $(OBJDIR)/bjxa_corpus.o $(SRC)/libbjxa.map
 	@mkdir -p $(LIBDIR)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJDIR)/xa_kernels.o $(OBJDIR)/bjxa_host.o \
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJDIR)/xa_kernels.o $(OBJDIR)/bjxa_host.o $(OBJDIR)/bjxa_corpus.o \
 	    -Xlinker --version-script=$(SRC)/libbjxa.map -Xlinker -soname=libbjxa_b200.so \
 	    -cudart static -lpthread -ldl -lrt
 

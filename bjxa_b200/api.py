@@ -45,6 +45,16 @@ DESC_DTYPE = np.dtype({
 })
 assert C.sizeof(StreamDesc) == DESC_DTYPE.itemsize == 48
 
+FILE_DTYPE = np.dtype({
+    "names": ["in_off", "in_len", "out_off", "out_len", "error", "blocks", "bits",
+              "channels", "rate", "reserved"],
+    "formats": ["<u8", "<u8", "<u8", "<u8", "<i4", "<u4", "u1", "u1", "<u2", "<u4"],
+    "offsets": [0, 8, 16, 24, 32, 36, 40, 41, 42, 44],
+    "itemsize": 48,
+})      # bjxa_file_desc_t
+CORPUS_XA_TO_WAV = 0
+CORPUS_WAV_TO_XA = 1
+
 _VP, _SZ = C.c_void_p, C.c_size_t
 
 BATCH_SYMBOLS = {
@@ -76,6 +86,9 @@ BATCH_SYMBOLS = {
     "bjxa_gpu_download_async": (C.c_int, [_VP, _VP, _SZ, _VP]),
     "bjxa_shard_range": (C.c_int, [_VP, _SZ, C.c_int, C.c_int,
                                    C.POINTER(_SZ), C.POINTER(_SZ)]),
+    "bjxa_gpu_scatter_async": (C.c_int, [_VP, _VP, C.c_uint32, _SZ, _VP]),
+    "bjxa_corpus_extent": (C.c_int, [C.c_int, _VP, _SZ, _VP, _SZ, C.POINTER(C.c_uint64)]),
+    "bjxa_corpus_run": (C.c_int, [C.c_int, _VP, _SZ, _VP, _SZ, _VP, _SZ]),
 }
 
 
@@ -192,6 +205,53 @@ class Bjxa(BjxaLib):
 
     def batch_encode(self, encs, dsts, srcs):
         return self._batch(self._bjxa_batch_encode, encs, dsts, srcs)
+
+    # -- whole files ----------------------------------------------------------------
+    def corpus(self, kind: int, files, bits: int = 0):
+        """files: list of bytes (whole .xa or .wav files).  Lays them out in one
+        pinned arena, runs bjxa_corpus_run, returns (table, list of produced
+        files as bytes -- empty where the table's error is set and nothing was
+        produced)."""
+        table = np.zeros(len(files), dtype=FILE_DTYPE)
+        off = 0
+        for i, f in enumerate(files):
+            if kind == CORPUS_WAV_TO_XA:
+                off += (-(off + 44)) % 16          # PCM data 16-byte aligned
+            table[i]["in_off"], table[i]["in_len"] = off, len(f)
+            off += len(f)
+        table["bits"] = bits
+        in_bytes = max(off, 16)
+        h_in = self._bjxa_host_alloc(in_bytes)
+        if not h_in:
+            raise MemoryError("bjxa_host_alloc")
+        h_out = None
+        try:
+            arena = np.ctypeslib.as_array((C.c_uint8 * in_bytes).from_address(h_in))
+            arena[:] = 0xEE
+            for i, f in enumerate(files):
+                o = int(table[i]["in_off"])
+                arena[o:o + len(f)] = np.frombuffer(f, dtype=np.uint8)
+            need = C.c_uint64(0)
+            self._check(self._bjxa_corpus_extent(kind, h_in, in_bytes, table.ctypes.data,
+                                                 len(files), C.byref(need)),
+                        "bjxa_corpus_extent")
+            out_bytes = int(need.value)
+            h_out = self._bjxa_host_alloc(out_bytes)
+            if not h_out:
+                raise MemoryError("bjxa_host_alloc")
+            out = np.ctypeslib.as_array((C.c_uint8 * out_bytes).from_address(h_out))
+            out[:] = 0xCD
+            self._check(self._bjxa_corpus_run(kind, h_in, in_bytes, h_out, out_bytes,
+                                              table.ctypes.data, len(files)),
+                        "bjxa_corpus_run")
+            made = [out[int(t["out_off"]):int(t["out_off"] + t["out_len"])].tobytes()
+                    for t in table]
+            self.last_corpus_out = out.copy()
+            return table, made
+        finally:
+            self._bjxa_host_free(h_in)
+            if h_out:
+                self._bjxa_host_free(h_out)
 
     # -- sharding ------------------------------------------------------------------
     def shard_range(self, n: int, rank: int, world: int, nbytes=None):

@@ -1360,6 +1360,42 @@ bjxa_plan_fetch(bjxa_plan_t *pl, bjxa_stream_desc_t *out, size_t n)
 
 /* ---- sharding ------------------------------------------------------------- */
 
+/* ---- header scatter (file assembly on the device) --------------------------- */
+
+__global__ void
+xa_scatter_kernel(uint8_t *dst, const uint8_t *table, uint32_t rec_len, uint32_t n)
+{
+	/* one 64-byte record per 64 threads: thread b moves byte b */
+	const uint32_t i = blockIdx.x * (blockDim.x / 64u) + threadIdx.x / 64u;
+	const uint32_t b = threadIdx.x % 64u;
+	if (i >= n || b >= rec_len)
+		return;
+	const uint8_t *rec = table + (uint64_t)i * 64u;
+	const uint64_t off = *reinterpret_cast<const uint64_t *>(rec);
+	dst[off + b] = rec[8 + b];
+}
+
+extern "C" int
+bjxa_gpu_scatter_async(void *dst, const void *d_table, uint32_t rec_len, size_t n,
+    void *cuda_stream)
+{
+	if (n == 0)
+		return (0);
+	if (dst == NULL || d_table == NULL) {
+		errno = EFAULT;
+		return (-1);
+	}
+	if (rec_len > 56 || n > 0xffffffffu) {
+		errno = EINVAL;
+		return (-1);
+	}
+	const uint32_t per = 256 / 64;
+	xa_scatter_kernel<<<(unsigned)((n + per - 1) / per), 256, 0, (cudaStream_t)cuda_stream>>>(
+	    (uint8_t *)dst, (const uint8_t *)d_table, rec_len, (uint32_t)n);
+	XA_CUDA(cudaGetLastError());
+	return (0);
+}
+
 extern "C" int
 bjxa_shard_range(const uint64_t *bytes, size_t n, int rank, int world,
     size_t *first, size_t *count)

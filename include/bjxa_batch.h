@@ -152,6 +152,69 @@ int    bjxa_gpu_download_async(void *hptr, const void *dptr, size_t bytes,
 	    void *cuda_stream);
 
 /*
+ * Scatter of small fixed-size records on the device: record i is a 64-byte
+ * slot of d_table, { uint64 offset; uint8 bytes[56] }, whose first rec_len
+ * (<= 56) bytes go to (uint8_t *)dst + offset.  Used to put the 44-byte RIFF /
+ * 32-byte XA headers in front of the data a plan produced, so that whole files
+ * leave the device in one copy.  All pointers are device pointers.
+ */
+int    bjxa_gpu_scatter_async(void *dst, const void *d_table, uint32_t rec_len,
+	    size_t n, void *cuda_stream);
+
+/* ---- whole files: a corpus in, a corpus out -------------------------------- */
+
+/*
+ * What `bjxa decode` / `bjxa encode` do to one file (src/bjxa_decode.c:38-93,
+ * src/bjxa_encode.c: read the header, write the other header, run the block
+ * loop, write the data), for n files that lie in one host arena, producing n
+ * files in another: header parse and validation are bjxa_parse_header /
+ * bjxa_parse_riff_header (src/libbjxa.c:396-453, 827-896), the emitted headers
+ * are bjxa_dump_riff_header / bjxa_dump_header (:899-927, :479-503), byte for
+ * byte.  Consecutive files travel to the device in ONE copy per chunk, the
+ * produced files are assembled on the device (data by the block-loop kernels,
+ * headers by bjxa_gpu_scatter_async) and come back in ONE copy per chunk;
+ * chunks are pipelined over CUDA streams.  Pinned arenas (bjxa_host_alloc)
+ * make the copies asynchronous.
+ *
+ * in:  in_off / in_len -- where file i lies in the input arena; files must be
+ *      in ascending, non-overlapping order.  wav_to_xa additionally wants the
+ *      PCM data of each WAV file 16-byte aligned in the arena, (in_off + 44) %
+ *      16 == 0 (ENOTSUP otherwise: lay the corpus out accordingly).
+ * out: out_off / out_len -- where the produced file lies in the output arena
+ *      and how long it is.  Decoded WAV files start at offsets = 4 (mod 16), so
+ *      there are up to 15 bytes of padding between two files (content
+ *      unspecified).
+ *      error -- 0, or the errno the reference would have stopped at: EPROTO /
+ *      EINVAL for a header it rejects, EIO for a file shorter than its header
+ *      says, EPROTO for a bad block profile (out_len then covers the header and
+ *      the blocks in front of the bad one, which is what the reference CLI has
+ *      written when it gives up).
+ * Returns 0 when every file was looked at (see error for each), -1 with errno
+ * for a failure of the call itself (EFAULT, ENOBUFS: output arena too small --
+ * bjxa_corpus_extent tells how much is needed --, ENODEV, ENOMEM).
+ */
+typedef struct bjxa_file_desc {
+	uint64_t in_off, in_len;
+	uint64_t out_off, out_len;
+	int32_t  error;
+	uint32_t blocks;	/* out: effective blocks processed */
+	uint8_t  bits;		/* wav_to_xa in: 4, 6 or 8; xa_to_wav out: the file's */
+	uint8_t  channels;	/* out */
+	uint16_t rate;		/* out: samples per second */
+	uint32_t reserved;
+} bjxa_file_desc_t;
+
+#define BJXA_CORPUS_XA_TO_WAV 0
+#define BJXA_CORPUS_WAV_TO_XA 1
+
+/* bytes of output arena bjxa_corpus_run will use for these files (headers are
+ * read; nothing is decoded) */
+int bjxa_corpus_extent(int kind, const void *in_arena, size_t in_bytes,
+    const bjxa_file_desc_t *files, size_t n, uint64_t *out_bytes);
+int bjxa_corpus_run(int kind, const void *in_arena, size_t in_bytes,
+    void *out_arena, size_t out_bytes, bjxa_file_desc_t *files, size_t n);
+
+/*
  * Contiguous shard of n streams for `rank` of `world` (one process per GPU),
  * balanced by bytes[] (per-stream work; NULL = by count).  No collective is
  * involved: shards are independent.

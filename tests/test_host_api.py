@@ -280,3 +280,45 @@ def test_shard_range(lib):
         assert first + count == 1000
     with pytest.raises(OSError):
         lib.shard_range(10, 3, 3)
+
+
+def test_corpus_extent_and_argument_errors(lib, vectors, oracle):
+    """bjxa_corpus_extent only reads headers, so it runs without a GPU: the size
+    it reports is the layout bjxa_corpus_run uses (WAV files at offsets = 4 mod
+    16); argument errors; and without a CUDA device bjxa_corpus_run refuses."""
+    import ctypes as C
+
+    from bjxa_b200.api import FILE_DTYPE
+    names = ["square-stereo-8.xa", "square-mono-4.xa", "square-mono-6.xa"]
+    files = [vectors[n] for n in names] + [b"KWD1" + bytes(10)]      # + one too short
+    table = np.zeros(len(files), dtype=FILE_DTYPE)
+    off = 3
+    for i, f in enumerate(files):
+        table[i]["in_off"], table[i]["in_len"] = off, len(f)
+        off += len(f) + i
+    arena = np.zeros(off + 16, dtype=np.uint8)
+    for t, f in zip(table, files):
+        arena[int(t["in_off"]):int(t["in_off"]) + len(f)] = np.frombuffer(f, dtype=np.uint8)
+    need = C.c_uint64(0)
+
+    def extent(kind, tab):
+        return lib._bjxa_corpus_extent(kind, arena.ctypes.data, arena.size, tab.ctypes.data,
+                                       tab.size, C.byref(need))
+    assert extent(0, table) == 0
+    cur = 0
+    for f in files[:3]:
+        cur = ((cur + 44 + 15) & ~15) - 44 + len(oracle.xa_to_wav(f))
+    assert need.value == cur + 16
+    swapped = table.copy()
+    swapped[[0, 1]] = swapped[[1, 0]]
+    assert extent(0, swapped) == -1 and lib.errno() == errno.EINVAL
+    beyond = table.copy()
+    beyond[3]["in_len"] = arena.size
+    assert extent(0, beyond) == -1 and lib.errno() == errno.ENOBUFS
+    assert extent(7, table) == -1 and lib.errno() == errno.EINVAL
+    assert extent(1, table) == -1 and lib.errno() == errno.ENOTSUP   # WAV data not 16-aligned
+    if lib.gpu_count() <= 0:
+        out = np.full(int(need.value) + 64, 0xEE, dtype=np.uint8)
+        rc = lib._bjxa_corpus_run(0, arena.ctypes.data, arena.size, out.ctypes.data, out.size,
+                                  table.ctypes.data, table.size)
+        assert rc == -1 and lib.errno() == errno.ENODEV and (out == 0xEE).all()

@@ -251,9 +251,67 @@ def leg_corpus(lib, orc, strips):
             "parity": "3 decoded streams vs oracle ok"}
 
 
+def leg_files(lib, orc):
+    """Whole .xa files in a pinned host arena -> whole .wav files in another
+    (bjxa_corpus_run): header parse, one copy per chunk each way, files
+    assembled on the device.  Wall clock of the call, copies included."""
+    import ctypes as C
+    import time
+
+    from bjxa_b200 import synth
+    from bjxa_b200.api import CORPUS_XA_TO_WAV, FILE_DTYPE
+    rng = np.random.default_rng(11)
+    protos = []
+    for i in range(48):
+        bits, ch = (4, 6, 8)[i % 3], 1 + (i // 3) % 2
+        secs = float(np.exp(rng.uniform(np.log(0.25), np.log(4.0))))
+        protos.append(synth.make_xa(0xB7A, 5000 + i, bits, ch, int(secs * 44100), mix="P1"))
+    n = 40000
+    pick = rng.integers(0, len(protos), n)
+    table = np.zeros(n, dtype=FILE_DTYPE)
+    lens = np.array([len(protos[k]) for k in pick], dtype=np.uint64)
+    table["in_len"] = lens
+    table["in_off"] = np.concatenate(([0], np.cumsum(lens)[:-1]))
+    in_bytes = int(lens.sum())
+    h_in = lib._bjxa_host_alloc(in_bytes)
+    arena = np.ctypeslib.as_array((C.c_uint8 * in_bytes).from_address(h_in))
+    for k, t in zip(pick, table):
+        o = int(t["in_off"])
+        arena[o:o + int(t["in_len"])] = np.frombuffer(protos[k], dtype=np.uint8)
+    need = C.c_uint64(0)
+    assert lib._bjxa_corpus_extent(CORPUS_XA_TO_WAV, h_in, in_bytes, table.ctypes.data, n,
+                                   C.byref(need)) == 0
+    out_bytes = int(need.value)
+    h_out = lib._bjxa_host_alloc(out_bytes)
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        rc = lib._bjxa_corpus_run(CORPUS_XA_TO_WAV, h_in, in_bytes, h_out, out_bytes,
+                                  table.ctypes.data, n)
+        times.append(time.perf_counter() - t0)
+        assert rc == 0 and (table["error"] == 0).all()
+    out = np.ctypeslib.as_array((C.c_uint8 * out_bytes).from_address(h_out))
+    for i in (0, n // 2, n - 1):
+        t = table[i]
+        got = out[int(t["out_off"]):int(t["out_off"] + t["out_len"])].tobytes()
+        assert got == orc.xa_to_wav(protos[pick[i]]), f"file {i} differs from the oracle"
+    samples = int(((table["out_len"].astype(np.int64) - 44) // 2).sum())
+    best = min(times)
+    res = {"config": "files: 40000 whole .xa files (mono/stereo, 4/6/8 bit, 0.25-4 s, mix P1) in a "
+                     "pinned arena -> whole .wav files, bjxa_corpus_run, wall clock incl. copies",
+           "s": [round(t, 4) for t in times], "in_GB": round(in_bytes / 1e9, 3),
+           "out_GB": round(out_bytes / 1e9, 3),
+           "Msamples_per_s": round(samples / best / 1e6, 1),
+           "pcie_GBps_in_plus_out": round((in_bytes + out_bytes) / best / 1e9, 2),
+           "files_per_s": round(n / best), "parity": "3 files vs oracle ok"}
+    lib._bjxa_host_free(h_in)
+    lib._bjxa_host_free(h_out)
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="mixed,encode,corpus")
+    ap.add_argument("--only", default="mixed,encode,corpus,files")
     a = ap.parse_args()
     lib = bjxa_b200.load()
     orc = binding.Oracle()
@@ -265,6 +323,8 @@ def main():
     if "encode" in legs:
         print(json.dumps(leg_encode(lib, orc)), flush=True)
         torch.cuda.empty_cache()
+    if "files" in legs:
+        print(json.dumps(leg_files(lib, orc)), flush=True)
     if "corpus" in legs:
         for strips in (0, 1):
             print(json.dumps(leg_corpus(lib, orc, strips)), flush=True)

@@ -9,6 +9,7 @@ mkdir -p $d
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC $defs \
     -c -o $d/xa_kernels.o bjxa_b200/csrc/xa_kernels.cu
 gcc -std=c99 -O2 -fPIC -c -o $d/bjxa_host.o bjxa_b200/csrc/bjxa_host.c
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $d/libbjxa_b200.so $d/xa_kernels.o $d/bjxa_host.o \
+gcc -std=c99 -O2 -fPIC -c -o $d/bjxa_corpus.o bjxa_b200/csrc/bjxa_corpus.c
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $d/libbjxa_b200.so $d/xa_kernels.o $d/bjxa_host.o $d/bjxa_corpus.o \
     -Xlinker --version-script=bjxa_b200/csrc/libbjxa.map -cudart static -lpthread -ldl -lrt
 echo built $d

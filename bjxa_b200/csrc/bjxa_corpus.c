@@ -25,6 +25,16 @@
 
 #define DEPTH		3			/* chunks in flight */
 #define CHUNK_IN	((uint64_t)48 << 20)	/* input bytes per chunk, about */
+
+/* BJXA_B200_CORPUS_CHUNK=bytes: smaller chunks, for tests of the pipeline */
+static uint64_t
+chunk_in(void)
+{
+	const char *e = getenv("BJXA_B200_CORPUS_CHUNK");
+	uint64_t v = e != NULL ? strtoull(e, NULL, 0) : 0;
+
+	return (v != 0 ? v : CHUNK_IN);
+}
 #define ALIGN16(x)	(((x) + 15u) & ~(uint64_t)15u)
 
 struct rec {				/* bjxa_gpu_scatter_async's 64-byte slot */
@@ -265,6 +275,7 @@ bjxa_corpus_run(int kind, const void *in_arena, size_t in_bytes, void *out_arena
 	struct parsed p;
 	uint64_t cur = 0;
 	size_t first = 0, turn = 0, i, k;
+	const uint64_t chunk = chunk_in();
 	int rc = -1, d;
 
 	if (check_args(kind, in_arena, files, n) < 0)
@@ -305,7 +316,7 @@ bjxa_corpus_run(int kind, const void *in_arena, size_t in_bytes, void *out_arena
 		in_end = in0;
 		while (first + count < n &&
 		    (count == 0 || files[first + count].in_off +
-		    files[first + count].in_len - in0 <= CHUNK_IN)) {
+		    files[first + count].in_len - in0 <= chunk)) {
 			const bjxa_file_desc_t *f = &files[first + count];
 			if (f->in_off + f->in_len > in_bytes) {
 				errno = ENOBUFS;
@@ -408,6 +419,12 @@ bjxa_corpus_run(int kind, const void *in_arena, size_t in_bytes, void *out_arena
 		}
 		first += count;
 		turn++;
+		/* while this chunk's upload is under way: the results of the chunk
+		 * before it, and its download queued, so that the device-to-host
+		 * engine never waits for this loop */
+		if (turn >= 2 &&
+		    slot_finish(&ring[(turn - 2) % DEPTH], kind, out_arena, files) < 0)
+			goto out;
 	}
 	rc = 0;
 out:

@@ -637,6 +637,9 @@ extern "C" int
 bjxa_gpu_upload(void *dptr, const void *hptr, size_t bytes)
 {
 	XA_CUDA(cudaMemcpy(dptr, hptr, bytes, cudaMemcpyHostToDevice));
+	/* from pageable memory the call returns when the bytes are staged: wait
+	 * for the DMA, streams that do not sync with the default one may follow */
+	XA_CUDA(cudaStreamSynchronize(0));
 	return (0);
 }
 
@@ -707,7 +710,13 @@ struct DevBuf {
 			return cuda_errno(e);
 		}
 		if (zero) {
+			/* cudaMemset only QUEUES the fill on the default stream, and
+			 * the plan's kernels run on streams that do not wait for
+			 * that one: a fill that lands late would wipe mailboxes
+			 * already in use -- so wait for it here */
 			e = cudaMemset(p, 0, want * sizeof(T));
+			if (e == cudaSuccess)
+				e = cudaStreamSynchronize(0);
 			if (e != cudaSuccess)
 				return cuda_errno(e);
 		}
@@ -836,6 +845,10 @@ plan_upload(bjxa_plan *pl)
 	if (!hp.order.empty())
 		XA_CUDA(cudaMemcpy(pl->d_order.p, hp.order.data(),
 		    hp.order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+	/* a copy from pageable memory returns once the bytes are staged; the DMA
+	 * runs on the default stream, which the caller's (non-blocking) stream does
+	 * not wait for: the tables must have landed before a kernel reads them */
+	XA_CUDA(cudaStreamSynchronize(0));
 	return (0);
 }
 
@@ -1314,6 +1327,7 @@ bjxa_plan_fetch(bjxa_plan_t *pl, bjxa_stream_desc_t *out, size_t n)
 		/* a tile gave up waiting for its predecessor's state: internal
 		 * error, the output is not trustworthy */
 		(void)cudaMemset(pl->d_fault.p, 0, sizeof fault);
+		(void)cudaStreamSynchronize(0);
 		errno = EIO;
 		return (-1);
 	}

@@ -110,6 +110,20 @@ def test_many_files_span_several_chunks(lib, oracle):
         assert wav == want[i % 12], i
 
 
+def test_pipeline_slots_are_reused(lib, oracle, monkeypatch):
+    """Tiny chunks: dozens of turns through the three pipeline slots, every plan
+    reset and re-run many times."""
+    monkeypatch.setenv("BJXA_B200_CORPUS_CHUNK", str(300 << 10))
+    protos = [_xa_file(92, i, (4, 6, 8)[i % 3], 1 + i % 2, 32 * (900 + 211 * i) + i,
+                       mix=("P1", "P2", "P3")[i % 3]) for i in range(9)]
+    files = [protos[(i * 5) % 9] for i in range(400)]
+    table, wavs = lib.corpus(CORPUS_XA_TO_WAV, files)
+    assert (table["error"] == 0).all()
+    want = [oracle.xa_to_wav(p) for p in protos]
+    for i, wav in enumerate(wavs):
+        assert wav == want[(i * 5) % 9], i
+
+
 def test_wav_corpus_vs_oracle(lib, oracle):
     files = []
     for i, (bits, ch) in enumerate([(4, 1), (4, 2), (6, 1), (6, 2), (8, 1), (8, 2)] * 3):

@@ -289,7 +289,8 @@ def leg_files(lib, orc):
         rc = lib._bjxa_corpus_run(CORPUS_XA_TO_WAV, h_in, in_bytes, h_out, out_bytes,
                                   table.ctypes.data, n)
         times.append(time.perf_counter() - t0)
-        assert rc == 0 and (table["error"] == 0).all()
+        assert rc == 0, f"bjxa_corpus_run: errno {lib.errno()}"
+        assert (table["error"] == 0).all(), np.unique(table["error"], return_counts=True)
     out = np.ctypeslib.as_array((C.c_uint8 * out_bytes).from_address(h_out))
     for i in (0, n // 2, n - 1):
         t = table[i]

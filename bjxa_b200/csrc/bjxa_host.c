@@ -596,7 +596,9 @@ bjxa_encoder_commit(bjxa_encoder_t *enc, const bjxa_stream_desc_t *d)
  * download of another (PCIe is full duplex) and both overlap the kernels.
  * The results of a chunk are fetched BEFORE its download is queued because a
  * stream that met a bad profile must only deliver the blocks in front of it
- * (libbjxa.c:634-648 leaves the rest of dst untouched).
+ * (libbjxa.c:634-648 leaves the rest of dst untouched); that happens as soon as
+ * the next chunk has been queued, so the downloads of chunk c run under the
+ * upload and the kernels of chunk c+1.
  */
 #define PIPE_DEPTH	3
 #define CHUNK_BYTES	((uint64_t)96 << 20)	/* PCM bytes per chunk, about */
@@ -769,6 +771,13 @@ run_host_batch(int kind, bjxa_stream_desc_t *work, void *const *dsts,
 		queued++;
 		first = i + 1;
 		in_chunk = 0;
+		/* while this chunk uploads: the results of the one before it, and
+		 * its downloads queued -- the device-to-host engine is the
+		 * bottleneck of the whole call and must never wait for this loop */
+		while (rc == 0 && queued - finished >= 2) {
+			rc = chunk_finish(sg, kind, &ring[finished % PIPE_DEPTH], work, dsts);
+			finished++;
+		}
 	}
 	while (rc == 0 && finished < queued) {
 		rc = chunk_finish(sg, kind, &ring[finished % PIPE_DEPTH], work, dsts);

@@ -7,6 +7,7 @@
 tag=${1:-r1}
 mkdir -p gpurun_out
 set -x
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$tag.log 2>&1 || exit 9
 timeout 900 python bench.py --steps 10 > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err || exit 1
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$tag.json 2> gpurun_out/bench_ref_$tag.err
 timeout 900 python tools/bench_configs.py > gpurun_out/configs_$tag.json 2> gpurun_out/configs_$tag.err

@@ -96,7 +96,6 @@ struct EncodeParams {
 /* ---- environment shims -------------------------------------------------- */
 
 #if defined(__CUDA_ARCH__)
-XA_HD int smem_inc(int *p) { return atomicAdd(p, 1); }
 XA_HD void global_min_u32(uint32_t *p, uint32_t v) { atomicMin(p, v); }
 XA_HD void mailbox_put(unsigned long long *p, unsigned long long v)
 {
@@ -122,7 +121,6 @@ XA_HD unsigned long long mailbox_get(const unsigned long long *p, uint32_t epoch
 	return 0;
 }
 #else
-XA_HD int smem_inc(int *p) { return (*p)++; }
 XA_HD void global_min_u32(uint32_t *p, uint32_t v) { if (v < *p) *p = v; }
 XA_HD void mailbox_put(unsigned long long *p, unsigned long long v) { *p = v; }
 XA_HD unsigned long long mailbox_get(const unsigned long long *p, uint32_t epoch,
@@ -722,8 +720,9 @@ struct DecTileStereo {
 		return v;
 	}
 
+	/* one unit of a tile of several strips (the one-strip loop is phase_units') */
 	XA_HD void unit_body(const StripCtx &c, uint32_t eb, uint32_t k, uint32_t at,
-	    uint32_t u_in_strip, uint8_t *out, bool whole) const
+	    uint32_t u_in_strip) const
 	{
 		const uint32_t profl = in[at], profr = in[at + BS];
 		const uint32_t fl = profl >> 4, fr = profr >> 4;
@@ -736,10 +735,7 @@ struct DecTileStereo {
 				global_min_u32(&p.first_bad[c.stream], (c.first_eb + eb) * 2 + 1);
 		}
 		const uint4 v = decode_unit(at, k, profl, profr);
-		if (whole)
-			*reinterpret_cast<uint4 *>(out) = v;
-		else
-			put_unit(c, u_in_strip * 16u, v);
+		put_unit(c, u_in_strip * 16u, v);
 		if (k == 7 && (eb + 1) * 2 >= c.nq) {
 			/* frames 30 and 31: v.z = L30 | R30 << 16, v.w = L31 | R31 << 16 */
 			publish(c, 0, (int)(int16_t)(v.w & 0xffffu), (int)(int16_t)(v.z & 0xffffu));
@@ -834,7 +830,7 @@ struct DecTileStereo {
 			const uint32_t eb = lu / 8u, k = lu % 8u;
 			if (eb * 2 >= c.nq)
 				continue;
-			unit_body(c, eb, k, eb_at(c, eb), lu, NULL, false);
+			unit_body(c, eb, k, eb_at(c, eb), lu);
 		}
 	}
 

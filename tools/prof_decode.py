@@ -21,7 +21,7 @@ import torch  # noqa: E402
 
 import bench  # noqa: E402
 import bjxa_b200  # noqa: E402
-from bjxa_b200.api import PLAN_DECODE, PLAN_ENCODE, Bjxa, make_descs  # noqa: E402
+from bjxa_b200.api import PLAN_DECODE, PLAN_ENCODE, PLAN_ENCODE_SEARCH, Bjxa, make_descs  # noqa: E402
 
 
 def main():
@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--encode", action="store_true")
+    ap.add_argument("--search", action="store_true",
+                    help="also run the searching encoder (BJXA_PLAN_ENCODE_SEARCH) on the decoded PCM")
     ap.add_argument("--tag", default="")
     a = ap.parse_args()
 
@@ -113,6 +115,22 @@ def main():
                           "GBps": round(algo / best / 1e6, 1),
                           "frac_6550": round(algo / best / 1e6 / 6550.4, 4)}), flush=True)
         lib.plan_free(eplan)
+
+    if a.search:
+        splan = lib.plan_create(PLAN_ENCODE_SEARCH, descs)
+        xo = torch.empty(S * xa_bytes + 16, dtype=torch.uint8, device=dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record()
+        lib.plan_run(splan, xo.data_ptr(), xo.numel(), pcm.data_ptr(), pcm.numel(), stream)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        print(json.dumps({"tag": a.tag, "kind": "search", "bits": bits, "ch": ch, "streams": S,
+                          "ms": round(ms, 2), "Gsamples_s": round(S * samples * ch / ms / 1e6, 2),
+                          "Gcandidate_samples_s": round(5 * (17 - bits) * S * samples * ch / ms / 1e6, 1)}),
+              flush=True)
+        lib.plan_free(splan)
 
 
 if __name__ == "__main__":

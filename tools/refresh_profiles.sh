@@ -19,5 +19,18 @@ B="bench.py --steps 1 --warmup 3 --no-extras"
 timeout 300 python $B > /dev/null 2>&1 || exit 3
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:xa_decode -c 1 \
     -f -o gpurun_out/decode_p1_4096_$tag python $B > gpurun_out/ncu_full_$tag.log 2>&1
+# secondary kernels: stereo decode (direct form), encode, searching encoder
+C="tools/prof_decode.py --mix P1 --streams 2048 --seconds 30 --bits 8 --ch 2 --steps 1 --warmup 0"
+timeout 300 python $C > gpurun_out/prof_stereo_$tag.json 2>/dev/null && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:xa_decode_kernel -c 1 \
+    -f -o gpurun_out/decode_stereo8_p1_$tag python $C > gpurun_out/ncu_stereo_$tag.log 2>&1
+D="tools/prof_decode.py --mix P0 --streams 2048 --seconds 30 --bits 4 --ch 2 --steps 1 --warmup 0 --encode"
+timeout 300 python $D > gpurun_out/prof_encode_$tag.json 2>/dev/null && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:xa_encode_kernel -c 1 \
+    -f -o gpurun_out/encode_stereo4_$tag python $D > gpurun_out/ncu_encode_$tag.log 2>&1
+E="tools/prof_decode.py --mix P0 --streams 1024 --seconds 4 --bits 4 --ch 2 --steps 1 --warmup 0 --search"
+timeout 300 python $E > gpurun_out/prof_search_$tag.json 2>/dev/null && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:xa_search_kernel -c 1 \
+    -f -o gpurun_out/search_stereo4_$tag python $E > gpurun_out/ncu_search_$tag.log 2>&1
 timeout 300 python tools/pcie_probe.py > gpurun_out/pcie_$tag.json 2> gpurun_out/pcie_$tag.err
 echo done

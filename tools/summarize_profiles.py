@@ -159,8 +159,39 @@ def full(tag):
               open(os.path.join(PROF, "decode_traffic.json"), "w"), indent=1)
 
 
+def secondary(tag, stem, cmd, what):
+    """ncu --set full of one launch of a secondary kernel -> <stem>_<tag>_ncu_summary.csv"""
+    rep = os.path.join(OUT, f"{stem}_{tag}.ncu-rep")
+    if not os.path.exists(rep):
+        print("missing:", rep)
+        return
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True,
+                         text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    if len(rows) < 3:
+        print("empty:", rep)
+        return
+    hdr, units, d = rows[0], rows[1], rows[2]
+    idx = {h: i for i, h in enumerate(hdr)}
+    L = [f"# ncu --set full --clock-control none --import-source on -c 1 python {cmd}",
+         f"# kernel: {d[idx['Kernel Name']]}; {what}; one B200; round {tag}", "metric,unit,value"]
+    for m in METRICS:
+        if m in idx:
+            L.append(f"{m},{units[idx[m]]},{d[idx[m]]}")
+    open(os.path.join(PROF, f"{stem}_{tag}_ncu_summary.csv"), "w").write("\n".join(L) + "\n")
+
+
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+    secondary(tag, "decode_stereo8_p1",
+              "tools/prof_decode.py --mix P1 --streams 2048 --seconds 30 --bits 8 --ch 2 --steps 1 --warmup 0",
+              "stereo decode, direct form, 2048 stereo 8-bit streams x 30 s, mix P1")
+    secondary(tag, "encode_stereo4",
+              "tools/prof_decode.py --mix P0 --streams 2048 --seconds 30 --bits 4 --ch 2 --steps 1 --warmup 0 --encode",
+              "reference-exact encode, 2048 stereo streams x 30 s -> 4-bit XA")
+    secondary(tag, "search_stereo4",
+              "tools/prof_decode.py --mix P0 --streams 1024 --seconds 4 --bits 4 --ch 2 --steps 1 --warmup 0 --search",
+              "searching encoder (extension), 1024 stereo streams x 4 s -> 4-bit XA, 65 candidates per block")
     for n in (f"bench_{tag}.json", f"bench_ref_{tag}.json", f"configs_{tag}.json", f"pcie_{tag}.json"):
         copy(n)
     launches(tag)

@@ -764,6 +764,9 @@ struct bjxa_plan {
 	cudaStream_t last_stream;
 	int launches;
 	int stereo;			/* stereo_mode() when the plan was built */
+	/* a plan with several classes runs them side by side (bjxa_plan_run) */
+	cudaStream_t cls_stream[6];
+	cudaEvent_t ev_start, ev_done[6];
 };
 
 static bool g_attr_done = false;
@@ -941,6 +944,14 @@ bjxa_plan_free(bjxa_plan_t **planp)
 	pl->d_order.release();
 	pl->d_carry.release();
 	pl->d_fault.release();
+	for (int b = 0; b < 6; b++) {
+		if (pl->cls_stream[b] != NULL)
+			(void)cudaStreamDestroy(pl->cls_stream[b]);
+		if (pl->ev_done[b] != NULL)
+			(void)cudaEventDestroy(pl->ev_done[b]);
+	}
+	if (pl->ev_start != NULL)
+		(void)cudaEventDestroy(pl->ev_start);
 	pl->magic = 0;
 	delete pl;
 	*planp = NULL;
@@ -1131,11 +1142,40 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 		    (n + 24) * sizeof(uint32_t), st));
 	}
 
+	/*
+	 * The classes of a plan are independent (different streams of the batch,
+	 * disjoint bytes), so with more than one they run side by side on streams
+	 * of the plan's own, forked from and joined to the caller's stream by
+	 * events: the censuses all run at once, and the tail of one class's
+	 * persistent kernel fills up with the next class's CTAs instead of
+	 * draining the device six times.
+	 */
+	int n_active = 0;
+	for (int b = 0; b < 6; b++)
+		n_active += hp.order_begin[b + 1] > hp.order_begin[b];
+	const bool fork = n_active > 1;
+	const cudaStream_t user_st = st;
+	if (fork) {
+		if (pl->ev_start == NULL)
+			XA_CUDA(cudaEventCreateWithFlags(&pl->ev_start, cudaEventDisableTiming));
+		XA_CUDA(cudaEventRecord(pl->ev_start, user_st));
+	}
+
 	for (int b = 0; b < 6; b++) {
 		uint32_t t0 = hp.tile_begin[b], t1 = hp.tile_begin[b + 1];
 		const uint32_t n_class = hp.order_begin[b + 1] - hp.order_begin[b];
 		if (n_class == 0)
 			continue;
+		if (fork) {
+			if (pl->cls_stream[b] == NULL) {
+				XA_CUDA(cudaStreamCreateWithFlags(&pl->cls_stream[b],
+				    cudaStreamNonBlocking));
+				XA_CUDA(cudaEventCreateWithFlags(&pl->ev_done[b],
+				    cudaEventDisableTiming));
+			}
+			st = pl->cls_stream[b];
+			XA_CUDA(cudaStreamWaitEvent(st, pl->ev_start, 0));
+		}
 		cudaError_t e;
 		if (hp.kind == kKindSearch) {
 			EncodeParams p;
@@ -1217,7 +1257,12 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 			}
 		}
 		XA_CUDA(e);
+		if (fork) {
+			XA_CUDA(cudaEventRecord(pl->ev_done[b], st));
+			XA_CUDA(cudaStreamWaitEvent(user_st, pl->ev_done[b], 0));
+		}
 	}
+	st = user_st;
 	pl->ran = true;
 	pl->last_stream = st;
 	pl->last_dst = (uint8_t *)dst;

@@ -177,10 +177,16 @@ __device__ __forceinline__ typename std::enable_if<!Tile::kStaged>::type
 consume_tile(Tile &t, typename Tile::Smem &sm, int s, uint32_t it, uint32_t tid)
 {
 	/* the warps take turns at walking a tile's chains: up to kStages tiles, and
-	 * so kStages walker warps, are in flight in a CTA */
-	if ((tid >> 5) == it % (kDecThreads / 32u))
+	 * so kStages walker warps, are in flight in a CTA.  A tile with chains has
+	 * its units decoded by the other seven warps, so that the walker warp is
+	 * not the last one to let go of the stage by a whole share of units. */
+	const uint32_t walker = it % (kDecThreads / 32u), warp = tid >> 5;
+	if (sm.n_heads[s] == 0)
+		t.phase_units(tid, kDecThreads);
+	else if (warp == walker)
 		t.phase_walk_warp(tid & 31u, sm.heads[s], sm.n_heads[s], &sm.next_head[s]);
-	t.phase_units(tid, kDecThreads);
+	else
+		t.phase_units(warp < walker ? tid : tid - 32u, kDecThreads - 32u);
 	__syncwarp();
 	if ((tid & 31u) == 0)
 		mbar_arrive(smem_u32(&sm.empty[s]));

@@ -72,8 +72,11 @@ emul_decode_ns(const DecodeParams &p, int order)
 		 * first picks up every chain left over), then the units */
 		for (uint32_t i = 0; i < 32; i++)
 			t.phase_walk_warp(visit(i, 32, order), sm->heads[s], count, &sm->next_head[s]);
-		for (uint32_t i = 0; i < nt; i++)
-			t.phase_units(visit(i, nt, order), nt);
+		/* as in consume_tile: a tile with chains leaves its units to the
+		 * seven warps that do not walk */
+		const uint32_t ut = count == 0 ? nt : nt - 32;
+		for (uint32_t i = 0; i < ut; i++)
+			t.phase_units(visit(i, ut, order), ut);
 	}
 	delete sm;
 }

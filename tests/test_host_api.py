@@ -322,3 +322,13 @@ def test_corpus_extent_and_argument_errors(lib, vectors, oracle):
         rc = lib._bjxa_corpus_run(0, arena.ctypes.data, arena.size, out.ctypes.data, out.size,
                                   table.ctypes.data, table.size)
         assert rc == -1 and lib.errno() == errno.ENODEV and (out == 0xEE).all()
+
+
+def test_scatter_argument_errors(lib):
+    """bjxa_gpu_scatter_async checks its arguments before it touches the device."""
+    buf = np.zeros(128, dtype=np.uint8)
+    assert lib._bjxa_gpu_scatter_async(None, None, 44, 0, None) == 0          # nothing to do
+    assert lib._bjxa_gpu_scatter_async(None, buf.ctypes.data, 44, 1, None) == -1
+    assert lib.errno() == errno.EFAULT
+    assert lib._bjxa_gpu_scatter_async(buf.ctypes.data, buf.ctypes.data, 57, 1, None) == -1
+    assert lib.errno() == errno.EINVAL

@@ -207,7 +207,7 @@ class Bjxa(BjxaLib):
         return self._batch(self._bjxa_batch_encode, encs, dsts, srcs)
 
     # -- whole files ----------------------------------------------------------------
-    def corpus(self, kind: int, files, bits: int = 0):
+    def corpus(self, kind: int, files, bits: int = 0, align: bool = True):
         """files: list of bytes (whole .xa or .wav files).  Lays them out in one
         pinned arena, runs bjxa_corpus_run, returns (table, list of produced
         files as bytes -- empty where the table's error is set and nothing was
@@ -215,7 +215,7 @@ class Bjxa(BjxaLib):
         table = np.zeros(len(files), dtype=FILE_DTYPE)
         off = 0
         for i, f in enumerate(files):
-            if kind == CORPUS_WAV_TO_XA:
+            if kind == CORPUS_WAV_TO_XA and align:
                 off += (-(off + 44)) % 16          # PCM data 16-byte aligned
             table[i]["in_off"], table[i]["in_len"] = off, len(f)
             off += len(f)

@@ -127,11 +127,15 @@ place(int kind, uint64_t cur)
 	return (cur);
 }
 
+/* *packed: every file's data keeps its 16-byte phase when the arena travels as
+ * one piece (always true for XA input, whose blocks may start anywhere) */
 static int
-check_args(int kind, const void *in, const bjxa_file_desc_t *files, size_t n)
+check_args(int kind, const void *in, const bjxa_file_desc_t *files, size_t n,
+    int *packed)
 {
 	size_t i;
 
+	*packed = 1;
 	if (kind != BJXA_CORPUS_XA_TO_WAV && kind != BJXA_CORPUS_WAV_TO_XA) {
 		errno = EINVAL;
 		return (-1);
@@ -146,10 +150,8 @@ check_args(int kind, const void *in, const bjxa_file_desc_t *files, size_t n)
 			return (-1);
 		}
 		if (kind == BJXA_CORPUS_WAV_TO_XA &&
-		    (files[i].in_off + BJXA_HEADER_SIZE_RIFF) % 16 != 0) {
-			errno = ENOTSUP;
-			return (-1);
-		}
+		    (files[i].in_off + BJXA_HEADER_SIZE_RIFF) % 16 != 0)
+			*packed = 0;	/* the encode kernels load PCM 16 bytes at a time */
 	}
 	return (0);
 }
@@ -163,12 +165,13 @@ bjxa_corpus_extent(int kind, const void *in_arena, size_t in_bytes,
 	struct parsed p;
 	uint64_t cur = 0;
 	size_t i;
+	int packed;
 
 	if (out_bytes == NULL) {
 		errno = EFAULT;
 		return (-1);
 	}
-	if (check_args(kind, in_arena, files, n) < 0)
+	if (check_args(kind, in_arena, files, n, &packed) < 0)
 		return (-1);
 	dec = bjxa_decoder();
 	enc = bjxa_encoder();
@@ -276,9 +279,9 @@ bjxa_corpus_run(int kind, const void *in_arena, size_t in_bytes, void *out_arena
 	uint64_t cur = 0;
 	size_t first = 0, turn = 0, i, k;
 	const uint64_t chunk = chunk_in();
-	int rc = -1, d;
+	int rc = -1, d, packed;
 
-	if (check_args(kind, in_arena, files, n) < 0)
+	if (check_args(kind, in_arena, files, n, &packed) < 0)
 		return (-1);
 	if (out_arena == NULL && n != 0) {
 		errno = EFAULT;
@@ -302,6 +305,7 @@ bjxa_corpus_run(int kind, const void *in_arena, size_t in_bytes, void *out_arena
 		struct slot *s = &ring[turn % DEPTH];
 		uint64_t in0, in_end, want_in, want_out;
 		size_t count = 0, live = 0;
+		uint64_t dcur = 0;		/* unpacked input: next free device byte */
 
 		/* the slot's previous chunk: results, download, and only then reuse */
 		if (slot_finish(s, kind, out_arena, files) < 0)
@@ -379,7 +383,12 @@ bjxa_corpus_run(int kind, const void *in_arena, size_t in_bytes, void *out_arena
 				sd->xa_off = rel + BJXA_HEADER_SIZE_XA;
 				sd->pcm_off = f->out_off - s->out0 + (s->out0 & 15u) + p.hdr_len;
 			} else {
-				sd->pcm_off = rel + BJXA_HEADER_SIZE_RIFF;
+				if (packed) {
+					sd->pcm_off = rel + BJXA_HEADER_SIZE_RIFF;
+				} else {
+					sd->pcm_off = dcur;	/* its own, aligned place */
+					dcur += ALIGN16(p.data_in);
+				}
 				sd->xa_off = f->out_off - s->out0 + (s->out0 & 15u) + p.hdr_len;
 			}
 			s->tab[live].off = f->out_off - s->out0 + (s->out0 & 15u);
@@ -390,15 +399,27 @@ bjxa_corpus_run(int kind, const void *in_arena, size_t in_bytes, void *out_arena
 		s->out_len = live != 0 ? cur - s->out0 : 0;
 
 		if (live != 0) {
-			want_in = (in0 & 15u) + (in_end - in0) + 64;
+			want_in = (packed ? (in0 & 15u) + (in_end - in0) : dcur) + 64;
 			want_out = (s->out0 & 15u) + s->out_len + 64;
 			if (grow_dev(&s->d_in, &s->cap_in, want_in) < 0 ||
 			    grow_dev(&s->d_out, &s->cap_out, want_out) < 0 ||
 			    grow_dev(&s->d_tab, &s->cap_tab, live * sizeof *s->tab) < 0)
 				goto out;
-			if (bjxa_gpu_upload_async((uint8_t *)s->d_in + (in0 & 15u),
-			    (const uint8_t *)in_arena + in0, in_end - in0, s->stream) < 0 ||
-			    bjxa_gpu_upload_async(s->d_tab, s->tab, live * sizeof *s->tab,
+			if (packed) {
+				if (bjxa_gpu_upload_async((uint8_t *)s->d_in + (in0 & 15u),
+				    (const uint8_t *)in_arena + in0, in_end - in0, s->stream) < 0)
+					goto out;
+			} else {
+				/* WAV data that is not 16-byte aligned in the arena: every
+				 * file's PCM travels on its own to an aligned place */
+				for (k = 0; k < count; k++)
+					if (s->desc[k].blocks != 0 && bjxa_gpu_upload_async(
+					    (uint8_t *)s->d_in + s->desc[k].pcm_off,
+					    (const uint8_t *)in_arena + files[first + k].in_off +
+					    BJXA_HEADER_SIZE_RIFF, s->desc[k].pcm_len, s->stream) < 0)
+						goto out;
+			}
+			if (bjxa_gpu_upload_async(s->d_tab, s->tab, live * sizeof *s->tab,
 			    s->stream) < 0)
 				goto out;
 			d = kind == BJXA_CORPUS_XA_TO_WAV ? BJXA_PLAN_DECODE : BJXA_PLAN_ENCODE;

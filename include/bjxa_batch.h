@@ -177,9 +177,10 @@ int    bjxa_gpu_scatter_async(void *dst, const void *d_table, uint32_t rec_len,
  * make the copies asynchronous.
  *
  * in:  in_off / in_len -- where file i lies in the input arena; files must be
- *      in ascending, non-overlapping order.  wav_to_xa additionally wants the
- *      PCM data of each WAV file 16-byte aligned in the arena, (in_off + 44) %
- *      16 == 0 (ENOTSUP otherwise: lay the corpus out accordingly).
+ *      in ascending, non-overlapping order.  wav_to_xa is fastest when the PCM
+ *      data of every WAV file is 16-byte aligned in the arena, (in_off + 44) %
+ *      16 == 0: then a chunk travels in one copy; otherwise every file's PCM is
+ *      copied on its own.
  * out: out_off / out_len -- where the produced file lies in the output arena
  *      and how long it is.  Decoded WAV files start at offsets = 4 (mod 16), so
  *      there are up to 15 bytes of padding between two files (content

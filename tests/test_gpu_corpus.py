@@ -135,6 +135,12 @@ def test_wav_corpus_vs_oracle(lib, oracle):
         assert (table["error"] == 0).all()
         for f, xa in zip(sel, xas):
             assert xa == oracle.wav_to_xa(f, bits)
+        # the same files packed back to back: their PCM is no longer 16-byte
+        # aligned in the arena and travels file by file
+        table, xas = lib.corpus(CORPUS_WAV_TO_XA, sel, bits=bits, align=False)
+        assert (table["error"] == 0).all() and (table["in_off"][1:] % 16 != 4).any()
+        for f, xa in zip(sel, xas):
+            assert xa == oracle.wav_to_xa(f, bits)
     # a WAV the reference rejects (8-bit PCM) and one cut short
     bad = bytearray(files[0][1])
     bad[34] = 8

@@ -216,6 +216,14 @@ grow_dev(void **p, size_t *cap, size_t need)
 	return (0);
 }
 
+/*
+ * The pipeline's buffers, streams and plans stay with the calling thread from
+ * one call to the next (allocating and freeing a few hundred MB of device and
+ * pinned memory costs more than moving a small corpus); a failed call gives
+ * them back.
+ */
+static __thread struct slot tls_ring[DEPTH];
+
 static void
 slot_release(struct slot *s)
 {
@@ -272,7 +280,7 @@ int
 bjxa_corpus_run(int kind, const void *in_arena, size_t in_bytes, void *out_arena,
     size_t out_bytes, bjxa_file_desc_t *files, size_t n)
 {
-	struct slot ring[DEPTH];
+	struct slot *ring = tls_ring;
 	bjxa_decoder_t *dec = NULL;
 	bjxa_encoder_t *enc = NULL;
 	struct parsed p;
@@ -293,7 +301,8 @@ bjxa_corpus_run(int kind, const void *in_arena, size_t in_bytes, void *out_arena
 		errno = ENODEV;		/* no CPU path */
 		return (-1);
 	}
-	memset(ring, 0, sizeof ring);
+	for (i = 0; i < DEPTH; i++)
+		ring[i].busy = 0;
 	dec = bjxa_decoder();
 	enc = bjxa_encoder();
 	if (dec == NULL || enc == NULL) {
@@ -464,7 +473,8 @@ out:
 				rc = -1;
 				saved = errno;
 			}
-			slot_release(&ring[i]);
+			if (rc != 0)
+				slot_release(&ring[i]);	/* start clean after a failure */
 		}
 		(void)bjxa_free_decoder(&dec);
 		(void)bjxa_free_encoder(&enc);

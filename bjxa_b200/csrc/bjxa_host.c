@@ -663,18 +663,40 @@ chunk_start(struct stage *sg, int kind, const struct chunk *ck,
 	if (stage_plan(sg, ck->slot, kind, work + ck->first, ck->count) < 0)
 		return (-1);
 	st = sg->stream[ck->slot];
-	for (i = ck->first; i < ck->first + ck->count; i++) {
-		if (work[i].blocks == 0)
-			continue;
-		if (kind == BJXA_PLAN_DECODE) {
-			if (bjxa_gpu_upload_async((uint8_t *)sg->d_xa + work[i].xa_off,
-			    srcs[i], xa_bytes[i], st) < 0)
+	/* one copy per run of streams whose source buffers follow each other in
+	 * host memory exactly as their places do in the device arena (callers
+	 * that keep a batch in one allocation get one copy per chunk) */
+	{
+		const uint8_t *run_src = NULL;
+		uint8_t *run_dst = NULL;
+		size_t run_len = 0;
+
+		for (i = ck->first; i < ck->first + ck->count; i++) {
+			uint8_t *d;
+			size_t len;
+
+			if (work[i].blocks == 0)
+				continue;
+			if (kind == BJXA_PLAN_DECODE) {
+				d = (uint8_t *)sg->d_xa + work[i].xa_off;
+				len = xa_bytes[i];
+			} else {
+				d = (uint8_t *)sg->d_pcm + work[i].pcm_off;
+				len = work[i].pcm_len;
+			}
+			if (run_len != 0 && (const uint8_t *)srcs[i] == run_src + run_len &&
+			    d == run_dst + run_len) {
+				run_len += len;
+				continue;
+			}
+			if (run_len != 0 && bjxa_gpu_upload_async(run_dst, run_src, run_len, st) < 0)
 				return (-1);
-		} else {
-			if (bjxa_gpu_upload_async((uint8_t *)sg->d_pcm + work[i].pcm_off,
-			    srcs[i], work[i].pcm_len, st) < 0)
-				return (-1);
+			run_src = srcs[i];
+			run_dst = d;
+			run_len = len;
 		}
+		if (run_len != 0 && bjxa_gpu_upload_async(run_dst, run_src, run_len, st) < 0)
+			return (-1);
 	}
 	if (kind == BJXA_PLAN_DECODE)
 		return (bjxa_plan_run(sg->plan[ck->slot], sg->d_pcm, sg->cap_pcm,
@@ -693,24 +715,44 @@ chunk_finish(struct stage *sg, int kind, const struct chunk *ck,
 
 	if (bjxa_plan_fetch(sg->plan[ck->slot], work + ck->first, ck->count) < 0)
 		return (-1);
-	for (i = ck->first; i < ck->first + ck->count; i++) {
-		size_t bytes;
+	/* downloads, again one copy per run of buffers that follow each other in
+	 * host memory as their contents do on the device -- and never a byte
+	 * more than a stream delivers */
+	{
+		uint8_t *run_dst = NULL;
+		const uint8_t *run_src = NULL;
+		size_t run_len = 0;
 
-		if (work[i].blocks == 0)
-			continue;
-		if (kind == BJXA_PLAN_DECODE) {
-			bytes = work[i].done == work[i].blocks ? work[i].pcm_len :
-			    (size_t)work[i].done * 64u * work[i].channels;
-			if (bytes != 0 && bjxa_gpu_download_async(dsts[i],
-			    (uint8_t *)sg->d_pcm + work[i].pcm_off, bytes, st) < 0)
+		for (i = ck->first; i < ck->first + ck->count; i++) {
+			const uint8_t *d;
+			size_t bytes;
+
+			if (work[i].blocks == 0)
+				continue;
+			if (kind == BJXA_PLAN_DECODE) {
+				bytes = work[i].done == work[i].blocks ? work[i].pcm_len :
+				    (size_t)work[i].done * 64u * work[i].channels;
+				d = (const uint8_t *)sg->d_pcm + work[i].pcm_off;
+			} else {
+				bytes = (size_t)work[i].done * (4u * work[i].bits + 1u) *
+				    work[i].channels;
+				d = (const uint8_t *)sg->d_xa + work[i].xa_off;
+			}
+			if (bytes == 0)
+				continue;
+			if (run_len != 0 && (uint8_t *)dsts[i] == run_dst + run_len &&
+			    d == run_src + run_len) {
+				run_len += bytes;
+				continue;
+			}
+			if (run_len != 0 && bjxa_gpu_download_async(run_dst, run_src, run_len, st) < 0)
 				return (-1);
-		} else {
-			bytes = (size_t)work[i].done * (4u * work[i].bits + 1u) *
-			    work[i].channels;
-			if (bytes != 0 && bjxa_gpu_download_async(dsts[i],
-			    (uint8_t *)sg->d_xa + work[i].xa_off, bytes, st) < 0)
-				return (-1);
+			run_dst = dsts[i];
+			run_src = d;
+			run_len = bytes;
 		}
+		if (run_len != 0 && bjxa_gpu_download_async(run_dst, run_src, run_len, st) < 0)
+			return (-1);
 	}
 	return (0);
 }

@@ -115,6 +115,7 @@ constexpr int kDecBlock = kDecThreads + 64;	/* consumers + loader warp + scanner
  * chain blocks (filters 1..4) among them:
  *   bit 0  the staged stereo form instead of the direct one (share >= staged)
  *   bit 1  the wide tile list instead of the long-strip one  (share >= wide)
+ *   bit 2  (alone) the pooled form over the long-strip list  (pool <= share < wide)
  * A threshold above 1000 permille switches that choice off.  One CTA, no
  * atomics, nothing to clear; all of a thread's loads in flight together.  Measured crossovers:
  * profiles/history_r1.md.
@@ -127,12 +128,23 @@ constexpr uint32_t staged_permille(int bits) { return bits == 4 ? 300u : bits ==
 constexpr uint32_t kWideManyStreams = 8192;
 constexpr uint32_t kWidePermilleMono[2] = { 985, 930 }, kWidePermilleStereo[2] = { 920, 700 };
 constexpr uint32_t kNever = 1001;
-enum { kFormStaged = 1, kFormWide = 2 };
+enum { kFormStaged = 1, kFormWide = 2, kFormPool = 4 };
+/* pooled walkers instead of one walker warp per tile: from this share of chain
+ * blocks (measured crossovers: profiles/history_r1.md), for classes of at least
+ * kPoolMinTiles tiles -- below that the launch is too short to care */
+#ifndef XA_POOL_PERMILLE_MONO
+#define XA_POOL_PERMILLE_MONO 1001
+#endif
+#ifndef XA_POOL_PERMILLE_STEREO
+#define XA_POOL_PERMILLE_STEREO 1001
+#endif
+constexpr uint32_t kPoolPermilleMono = XA_POOL_PERMILLE_MONO, kPoolPermilleStereo = XA_POOL_PERMILLE_STEREO;
+constexpr uint32_t kPoolMinTiles = 296;
 
 __global__ void __launch_bounds__(kCensusThreads)
 xa_census_kernel(const uint8_t *src, const StreamDev *streams, const uint32_t *order,
     uint32_t n_streams, uint32_t block_bytes_one, uint32_t ch, uint32_t staged_permille,
-    uint32_t wide_permille, uint32_t *choice)
+    uint32_t wide_permille, uint32_t pool_permille, uint32_t *choice)
 {
 	__shared__ uint32_t warp_sum[kCensusThreads / 32];
 	const uint32_t tid = threadIdx.x;
@@ -166,8 +178,9 @@ xa_census_kernel(const uint8_t *src, const StreamDev *streams, const uint32_t *o
 		for (uint32_t w = 0; w < kCensusThreads / 32; w++)
 			total += warp_sum[w];
 		const uint32_t permille = total * 1000u / (kCensusThreads * kCensusPerThread);
-		*choice = (permille >= staged_permille ? kFormStaged : 0u) |
-		    (permille >= wide_permille ? kFormWide : 0u);
+		const uint32_t staged = permille >= staged_permille ? kFormStaged : 0u;
+		*choice = permille >= wide_permille ? kFormWide | staged :
+		    permille >= pool_permille ? (uint32_t)kFormPool : staged;
 	}
 }
 
@@ -219,12 +232,210 @@ consume_tile(Tile &t, typename Tile::Smem &sm, int s, uint32_t it, uint32_t tid)
 	}
 }
 
+/* ---- the pooled form's shared-memory protocol (xa_decode_pool_kernel below) ---- */
+#ifndef XA_POOL_UNIT_WARPS
+#define XA_POOL_UNIT_WARPS 2
+#endif
+#ifndef XA_POOL_WALK_WARPS
+#define XA_POOL_WALK_WARPS 6
+#endif
+constexpr int kPoolUnitWarps = XA_POOL_UNIT_WARPS, kPoolWalkWarps = XA_POOL_WALK_WARPS;
+constexpr int kPoolCtas = XA_POOL_CTAS;			/* per SM */
+constexpr int kPoolConsumers = (kPoolUnitWarps + kPoolWalkWarps) * 32;
+constexpr int kPoolBlock = kPoolConsumers + 64;		/* + scanner warp + loader warp */
+
+template <class Tile>
+struct PoolSmem : Tile::Smem {
+	uint32_t draw[Tile::kStages];
+	uint32_t pending[Tile::kStages];	/* chains of the tile not finished yet */
+	uint32_t oldest;			/* the stage the loader waits for */
+	uint32_t done;				/* every tile has been offered */
+};
+
+template <class SM>
+__device__ __forceinline__ void pool_set_oldest(SM &sm, uint32_t s)
+{
+	*(volatile uint32_t *)&sm.oldest = s;
+}
+
+template <class SM>
+__device__ __forceinline__ void pool_finish(SM &sm)
+{
+	__threadfence_block();
+	*(volatile uint32_t *)&sm.done = 1u;
+}
+
+/* scanner lane 0: the tile in stage s has `count` chains (heads[] written) */
+template <class SM>
+__device__ __forceinline__ void pool_offer(SM &sm, int s, uint32_t gen, uint32_t count)
+{
+	if (count == 0) {
+		mbar_arrive(smem_u32(&sm.empty[s]));	/* on behalf of the chains */
+		return;
+	}
+	*(volatile uint32_t *)&sm.pending[s] = count;
+	__threadfence_block();		/* heads[], pending before the offer */
+	*(volatile uint32_t *)&sm.draw[s] = (gen & 0xffu) << 24 | count << 12;
+}
+
+/*
+ * Loader warp: tickets, strip contexts, bulk-async copies.  The ticket and the
+ * records of the NEXT tile (ticket -> tile table -> issue order -> stream
+ * record: four dependent global round trips) are fetched while the warp waits
+ * for a free stage.  POOL: the stage the loader wants back next is made known to
+ * the pooled walkers, who then finish that tile's chains first.
+ */
+template <class Tile, bool POOL, class SM>
+__device__ __forceinline__ void
+loader_warp(const DecodeParams &p, SM &sm, const uint32_t lane)
+{
+	typedef typename Tile::G G;
+	constexpr int NS = G::kNS;
+	constexpr int kStages = Tile::kStages;
+	unsigned long long t = 0;
+	TileEnt te = { 0u, 0u, 0u, 0u };
+	StripCtx c;
+	auto prefetch = [&]() {
+		/* the counter is preset to ~0 with first_bad[]: old + 1 = ticket */
+		if (lane == 0)
+			t = atomicAdd(p.ticket, 1ULL) + 1ULL;
+		t = __shfl_sync(0xffffffffu, t, 0);
+		if (t < p.n_tiles) {
+			te = p.tiles[t];
+			if (lane < te.count)
+				make_strip_ctx<G::kBits, G::kCh, G::kTBQ, NS>(c, p,
+				    p.order[te.first + lane], te.j, lane);
+		}
+	};
+	prefetch();
+	for (uint32_t it = 0;; it++) {
+		const int s = (int)(it % kStages);
+		if (it >= (uint32_t)kStages) {
+			if constexpr (POOL) {
+				if (lane == 0)
+					pool_set_oldest(sm, (uint32_t)s);
+			}
+			mbar_wait(smem_u32(&sm.empty[s]), (it / kStages - 1) & 1);
+		}
+		const uint32_t full = smem_u32(&sm.full[s]);
+		if (t >= p.n_tiles) {
+			if (lane == 0) {
+				sm.tile_flags[s] = kCtxEnd;
+				mbar_arrive(full);
+			}
+			return;
+		}
+		uint32_t bulk = 0, tail = 0;
+		const unsigned char *src = p.src;
+		if (lane < te.count) {
+			sm.ctx[s][lane] = c;
+			bulk = c.bulk;
+			tail = c.flags & kCtxTail;
+			src += c.a0;
+		}
+		uint32_t total = bulk;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1)
+			total += __shfl_xor_sync(0xffffffffu, total, o);
+		const uint32_t any_tail = __ballot_sync(0xffffffffu, tail != 0);
+		if (lane == 0) {
+			sm.tile_flags[s] = any_tail ? kCtxTail : 0u;
+			sm.n_strips[s] = te.count;
+			if (total)
+				mbar_expect_tx(full, total);
+			else
+				mbar_arrive(full);
+		}
+		__syncwarp();
+		if (bulk)
+			bulk_g2s(smem_u32(sm.in[s]) + lane * G::SLOT, src, bulk, full);
+		prefetch();
+	}
+}
+
+/*
+ * Scanner warp: the heads of chains of every landed tile.  POOL: the tile's
+ * chains are then put up for the pooled walkers (pool_offer).
+ */
+template <class Tile, bool POOL, class SM>
+__device__ __forceinline__ void
+scanner_warp(const DecodeParams &p, SM &sm, const uint32_t lane)
+{
+	typedef typename Tile::G G;
+	constexpr int NS = G::kNS;
+	constexpr int kStages = Tile::kStages;
+	for (uint32_t it = 0;; it++) {
+		const int s = (int)(it % kStages);
+		mbar_wait(smem_u32(&sm.full[s]), (it / kStages) & 1);
+		const uint32_t tf = sm.tile_flags[s];
+		if (tf & kCtxEnd) {
+			if (lane == 0) {
+				if constexpr (POOL)
+					pool_finish(sm);
+				mbar_arrive(smem_u32(&sm.ready[s]));
+			}
+			return;
+		}
+		Tile t(p, sm, s);
+		if (tf & kCtxTail) {	/* only at the very end of the arena */
+			t.load_tail(lane, 32, sm.in[s]);
+			__syncwarp();
+		}
+		uint32_t count = 0;
+		if (NS == 1) {
+			/* one strip: one item (block, or pair of blocks) per lane
+			 * and step; "the item in front is a walker's too" comes out
+			 * of the ballots */
+			constexpr int LAG = Tile::kLag;	/* item q follows item q - LAG */
+			const uint32_t nq = Tile::kStaged ? sm.ctx[s][0].nq :
+			    sm.ctx[s][0].nq / G::kCh;
+			uint32_t prev = 0;	/* items -LAG..-1: no chain channels */
+			for (uint32_t base = 0; base < nq; base += 32) {
+				const uint32_t q = base + lane;
+				/* chain channels of item q and of the item in front;
+				 * a head continues none of that one's chains */
+				const uint32_t cm = t.chain_mask(q);
+				const uint32_t up = __shfl_up_sync(0xffffffffu, cm, LAG);
+				const uint32_t old = __shfl_sync(0xffffffffu, prev,
+				    (32 - LAG + lane) & 31u);
+				const uint32_t before = lane >= (uint32_t)LAG ? up : old;
+				const bool h = cm != 0 && (cm & before) == 0;
+				const uint32_t mh = __ballot_sync(0xffffffffu, h);
+				if (h)
+					sm.heads[s][count + __popc(mh & ((1u << lane) - 1u))] =
+					    (uint16_t)q;
+				count += __popc(mh);
+				prev = cm;
+			}
+		} else {
+			const uint32_t nq = t.n_strips * Tile::SCAN;
+			for (uint32_t base = 0; base < nq; base += 32) {
+				const uint32_t q = base + lane;
+				const bool h = q < nq && t.is_head(q);
+				const uint32_t m = __ballot_sync(0xffffffffu, h);
+				if (h)
+					sm.heads[s][count + __popc(m & ((1u << lane) - 1u))] =
+					    (uint16_t)q;
+				count += __popc(m);
+			}
+		}
+		__syncwarp();
+		if (lane == 0) {
+			sm.n_heads[s] = count;
+			if constexpr (POOL) {
+				pool_offer(sm, s, it / kStages, count);
+			} else {
+				sm.next_head[s] = 32;	/* chains 0..31 start with the lanes */
+			}
+			mbar_arrive(smem_u32(&sm.ready[s]));
+		}
+	}
+}
+
 template <class Tile>
 __global__ void __launch_bounds__(kDecBlock, Tile::kMinCtas)
 xa_decode_kernel(const DecodeParams p)
 {
-	typedef typename Tile::G G;
-	constexpr int NS = G::kNS;
 	constexpr int kStages = Tile::kStages;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	typename Tile::Smem &sm = *reinterpret_cast<typename Tile::Smem *>(smem_raw);
@@ -245,129 +456,12 @@ xa_decode_kernel(const DecodeParams p)
 	__syncthreads();
 
 	if (tid >= kDecThreads + 32) {
-		/* ---- loader warp: tickets, strip contexts, bulk-async copies ----
-		 * The ticket and the records of the NEXT tile (ticket -> tile table ->
-		 * issue order -> stream record: four dependent global round trips)
-		 * are fetched while the warp waits for a free stage. */
-		const uint32_t lane = tid - (kDecThreads + 32);
-		unsigned long long t = 0;
-		TileEnt te = { 0u, 0u, 0u, 0u };
-		StripCtx c;
-		auto prefetch = [&]() {
-			/* the counter is preset to ~0 with first_bad[]: old + 1 = ticket */
-			if (lane == 0)
-				t = atomicAdd(p.ticket, 1ULL) + 1ULL;
-			t = __shfl_sync(0xffffffffu, t, 0);
-			if (t < p.n_tiles) {
-				te = p.tiles[t];
-				if (lane < te.count)
-					make_strip_ctx<G::kBits, G::kCh, G::kTBQ, NS>(c, p,
-					    p.order[te.first + lane], te.j, lane);
-			}
-		};
-		prefetch();
-		for (uint32_t it = 0;; it++) {
-			const int s = (int)(it % kStages);
-			if (it >= (uint32_t)kStages)
-				mbar_wait(smem_u32(&sm.empty[s]), (it / kStages - 1) & 1);
-			const uint32_t full = smem_u32(&sm.full[s]);
-			if (t >= p.n_tiles) {
-				if (lane == 0) {
-					sm.tile_flags[s] = kCtxEnd;
-					mbar_arrive(full);
-				}
-				return;
-			}
-			uint32_t bulk = 0, tail = 0;
-			const unsigned char *src = p.src;
-			if (lane < te.count) {
-				sm.ctx[s][lane] = c;
-				bulk = c.bulk;
-				tail = c.flags & kCtxTail;
-				src += c.a0;
-			}
-			uint32_t total = bulk;
-#pragma unroll
-			for (int o = 16; o > 0; o >>= 1)
-				total += __shfl_xor_sync(0xffffffffu, total, o);
-			const uint32_t any_tail = __ballot_sync(0xffffffffu, tail != 0);
-			if (lane == 0) {
-				sm.tile_flags[s] = any_tail ? kCtxTail : 0u;
-				sm.n_strips[s] = te.count;
-				if (total)
-					mbar_expect_tx(full, total);
-				else
-					mbar_arrive(full);
-			}
-			__syncwarp();
-			if (bulk)
-				bulk_g2s(smem_u32(sm.in[s]) + lane * G::SLOT, src, bulk, full);
-			prefetch();
-		}
+		loader_warp<Tile, false>(p, sm, tid - (kDecThreads + 32));
+		return;
 	}
-
 	if (tid >= kDecThreads) {
-		/* ---- scanner warp: heads of chains of every landed tile ---- */
-		const uint32_t lane = tid - kDecThreads;
-		for (uint32_t it = 0;; it++) {
-			const int s = (int)(it % kStages);
-			mbar_wait(smem_u32(&sm.full[s]), (it / kStages) & 1);
-			const uint32_t tf = sm.tile_flags[s];
-			if (tf & kCtxEnd) {
-				if (lane == 0)
-					mbar_arrive(smem_u32(&sm.ready[s]));
-				return;
-			}
-			Tile t(p, sm, s);
-			if (tf & kCtxTail) {	/* only at the very end of the arena */
-				t.load_tail(lane, 32, sm.in[s]);
-				__syncwarp();
-			}
-			uint32_t count = 0;
-			if (NS == 1) {
-				/* one strip: one item (block, or pair of blocks) per lane
-				 * and step; "the item in front is a walker's too" comes out
-				 * of the ballots */
-				constexpr int LAG = Tile::kLag;	/* item q follows item q - LAG */
-				const uint32_t nq = Tile::kStaged ? sm.ctx[s][0].nq :
-				    sm.ctx[s][0].nq / G::kCh;
-				uint32_t prev = 0;	/* items -LAG..-1: no chain channels */
-				for (uint32_t base = 0; base < nq; base += 32) {
-					const uint32_t q = base + lane;
-					/* chain channels of item q and of the item in front;
-					 * a head continues none of that one's chains */
-					const uint32_t cm = t.chain_mask(q);
-					const uint32_t up = __shfl_up_sync(0xffffffffu, cm, LAG);
-					const uint32_t old = __shfl_sync(0xffffffffu, prev,
-					    (32 - LAG + lane) & 31u);
-					const uint32_t before = lane >= (uint32_t)LAG ? up : old;
-					const bool h = cm != 0 && (cm & before) == 0;
-					const uint32_t mh = __ballot_sync(0xffffffffu, h);
-					if (h)
-						sm.heads[s][count + __popc(mh & ((1u << lane) - 1u))] =
-						    (uint16_t)q;
-					count += __popc(mh);
-					prev = cm;
-				}
-			} else {
-				const uint32_t nq = t.n_strips * Tile::SCAN;
-				for (uint32_t base = 0; base < nq; base += 32) {
-					const uint32_t q = base + lane;
-					const bool h = q < nq && t.is_head(q);
-					const uint32_t m = __ballot_sync(0xffffffffu, h);
-					if (h)
-						sm.heads[s][count + __popc(m & ((1u << lane) - 1u))] =
-						    (uint16_t)q;
-					count += __popc(m);
-				}
-			}
-			__syncwarp();
-			if (lane == 0) {
-				sm.n_heads[s] = count;
-				sm.next_head[s] = 32;	/* chains 0..31 start with the lanes */
-				mbar_arrive(smem_u32(&sm.ready[s]));
-			}
-		}
+		scanner_warp<Tile, false>(p, sm, tid - kDecThreads);
+		return;
 	}
 
 	/* ---- consumer warps ---- */
@@ -380,6 +474,149 @@ xa_decode_kernel(const DecodeParams p)
 		mbar_wait(smem_u32(&sm.full[s]), (it / kStages) & 1);
 		Tile t(p, sm, s);
 		consume_tile(t, sm, s, it, tid);
+	}
+}
+
+/*
+ * Pooled form, for data with many chain blocks.  In xa_decode_kernel a tile's
+ * chains are walked by ONE warp, and a CTA has as many walker warps at work as
+ * it has tiles in its ring; on chain-heavy data most lanes of those warps idle
+ * behind the longest chains while five of eight warps wait for a stage.  Here
+ * the roles are fixed and the chains of ALL tiles in the ring form one pool:
+ *   unit warps    (kPoolUnitWarps) decode the cut blocks of every tile, in order;
+ *   walker warps  (kPoolWalkWarps) never look at tiles: every idle LANE draws
+ *                 the next chain of any tile on offer (oldest stage first) and
+ *                 walks it one block per turn of the warp's loop, so lanes of
+ *                 one warp hold chains of different tiles side by side.
+ * A stage goes back to the loader when the unit warps have arrived and the
+ * tile's last chain has been finished (a countdown in shared memory).
+ *
+ * sm.draw[s] = generation:8 | chains:12 | next:12 -- one atomicAdd both draws a
+ * chain and tells whether the draw was good, whichever tile the stage holds by
+ * then; a good draw pins the tile (its countdown cannot reach zero before the
+ * drawn chain is finished).
+ */
+template <class Tile>
+__device__ __forceinline__ void
+pool_walker_warp(const DecodeParams &p, PoolSmem<Tile> &sm)
+{
+	constexpr int kStages = Tile::kStages;
+	typename Tile::Walk w;
+	int ls = 0;			/* the stage this lane's chain lives in */
+	uint32_t vain = 0;		/* turns spent waiting for a carry */
+	bool have = false, saw_done = false;
+
+	for (;;) {
+		if (!have) {
+			const uint32_t s0 = *(volatile uint32_t *)&sm.oldest;
+			for (int k = 0; k < kStages; k++) {
+				int s = (int)s0 + k;
+				if (s >= kStages)
+					s -= kStages;
+				const uint32_t peek = *(volatile uint32_t *)&sm.draw[s];
+				if ((peek & 0xfffu) >= (peek >> 12 & 0xfffu))
+					continue;
+				const uint32_t got = atomicAdd(&sm.draw[s], 1u);
+				if ((got & 0xfffu) >= (got >> 12 & 0xfffu))
+					continue;
+				/* a good draw: the tile of generation got >> 24 is pinned.
+				 * Its barriers have completed; waiting on "full" orders the
+				 * bulk copy's bytes for this thread, the fence the scanner's */
+				mbar_wait(smem_u32(&sm.full[s]), (got >> 24) & 1u);
+				__threadfence_block();
+				ls = s;
+				Tile t(p, sm, s);
+				t.walk_begin(w, sm.heads[s][got & 0xfffu]);
+				have = true;
+				vain = 0;
+				break;
+			}
+		}
+		if (!__any_sync(0xffffffffu, have)) {
+			if (saw_done)
+				return;		/* nothing on offer after the last tile was */
+			saw_done = *(volatile uint32_t *)&sm.done != 0;
+			if (!saw_done)
+				__nanosleep(64);
+			continue;
+		}
+		bool moved = false;
+		if (have) {
+			Tile t(p, sm, ls);
+			if (w.need != 0) {
+				/* the strip's carry: looked for once per turn, never waited
+				 * for -- the lane that produces it may be in this very warp.
+				 * Bounded like mailbox_get. */
+				t.walk_carry(w);
+				if (w.need != 0 && ++vain > (1u << 25))
+					t.walk_give_up(w);
+			}
+			if (w.need == 0) {
+				moved = true;
+				if (!t.walk_block(w)) {
+					have = false;
+					/* the chain's reads of the stage are over */
+					if (atomicSub(&sm.pending[ls], 1u) == 1u)
+						mbar_arrive(smem_u32(&sm.empty[ls]));
+				}
+			}
+		}
+		if (!__any_sync(0xffffffffu, moved))
+			__nanosleep(128);	/* every chain of the warp waits for its carry */
+	}
+}
+
+template <class Tile>
+__global__ void __launch_bounds__(kPoolBlock, kPoolCtas)
+xa_decode_pool_kernel(const DecodeParams p)
+{
+	constexpr int kStages = Tile::kStages;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	PoolSmem<Tile> &sm = *reinterpret_cast<PoolSmem<Tile> *>(smem_raw);
+	const uint32_t tid = threadIdx.x;
+
+	if (p.choice != NULL && *p.choice != p.want)
+		return;		/* the census picked another tile form */
+
+	if (tid == 0) {
+		for (int s = 0; s < kStages; s++) {
+			mbar_init(smem_u32(&sm.full[s]), 1);
+			mbar_init(smem_u32(&sm.ready[s]), 1);
+			/* one arrival per unit warp, one for the tile's chains */
+			mbar_init(smem_u32(&sm.empty[s]), kPoolUnitWarps + 1);
+			sm.draw[s] = 0;
+			sm.pending[s] = 0;
+		}
+		sm.oldest = 0;
+		sm.done = 0;
+	}
+	__syncthreads();
+
+	if (tid >= kPoolConsumers + 32) {
+		loader_warp<Tile, true>(p, sm, tid - (kPoolConsumers + 32));
+		return;
+	}
+	if (tid >= kPoolConsumers) {
+		scanner_warp<Tile, true>(p, sm, tid - kPoolConsumers);
+		return;
+	}
+	if (tid >= kPoolUnitWarps * 32) {
+		pool_walker_warp<Tile>(p, sm);
+		return;
+	}
+
+	/* ---- unit warps ---- */
+	for (uint32_t it = 0;; it++) {
+		const int s = (int)(it % kStages);
+		mbar_wait(smem_u32(&sm.ready[s]), (it / kStages) & 1);
+		if (sm.tile_flags[s] & kCtxEnd)
+			return;
+		mbar_wait(smem_u32(&sm.full[s]), (it / kStages) & 1);
+		Tile t(p, sm, s);
+		t.phase_units(tid, kPoolUnitWarps * 32);
+		__syncwarp();
+		if ((tid & 31u) == 0)
+			mbar_arrive(smem_u32(&sm.empty[s]));
 	}
 }
 
@@ -747,7 +984,9 @@ stereo_mode(void)
 	return e == NULL ? 2 : strcmp(e, "direct") == 0 ? 0 : strcmp(e, "staged") == 0 ? 1 : 2;
 }
 
-static int decode_class_launches(int ch, int stereo, bool alt);
+static int pool_mode(void);
+static int pool_candidate(int pool, int ns, uint32_t n_tiles);
+static int decode_class_launches(int ch, int stereo, bool alt, int poolc);
 
 struct bjxa_plan {
 	uint32_t magic;
@@ -770,6 +1009,7 @@ struct bjxa_plan {
 	cudaStream_t last_stream;
 	int launches;
 	int stereo;			/* stereo_mode() when the plan was built */
+	int pool;			/* pool_mode() likewise */
 	/* a plan with several classes runs them side by side (bjxa_plan_run) */
 	cudaStream_t cls_stream[6];
 	cudaEvent_t ev_start, ev_done[6];
@@ -785,11 +1025,24 @@ set_dec_attr(void)
 	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(typename Tile::Smem));
 }
 
+/* the pooled form's tile type: the direct tile over a deeper ring */
+template <int BITS, int CH> struct PoolTile;
+template <int BITS> struct PoolTile<BITS, 1> {
+	typedef DecTile<BITS, kDecTBQ, 1, pool_stages(BITS, 1)> type;
+};
+template <int BITS> struct PoolTile<BITS, 2> {
+	typedef DecTileStereo<BITS, kDecTBQ, 1, pool_stages(BITS, 2)> type;
+};
+
 template <int BITS, int CH>
 static cudaError_t
 set_attrs_one(void)
 {
 	cudaError_t e;
+	typedef typename PoolTile<BITS, CH>::type PT;
+	if ((e = cudaFuncSetAttribute(xa_decode_pool_kernel<PT>,
+	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PoolSmem<PT>))) != cudaSuccess)
+		return e;
 	if (CH == 1) {
 		if ((e = set_dec_attr<DecTile<BITS, kDecTBQ, 1, dec_stages(BITS, 1)> >()) != cudaSuccess ||
 		    (e = set_dec_attr<DecTile<BITS, kDecTBQ, kDecWide, dec_stages(BITS, 1)> >()) != cudaSuccess)
@@ -885,10 +1138,12 @@ plan_build(bjxa_plan *pl, int kind, const bjxa_stream_desc_t *descs, size_t n)
 	pl->ran = false;
 	pl->launches = 0;
 	pl->stereo = stereo_mode();
+	pl->pool = pool_mode();
 	for (int b = 0; b < 6; b++)
 		if (pl->hp.order_begin[b + 1] > pl->hp.order_begin[b])
 			pl->launches += kind == kKindDecode ? decode_class_launches(bucket_ch(b),
-			    pl->stereo, pl->hp.alt_ns[b] != 0) : 1;
+			    pl->stereo, pl->hp.alt_ns[b] != 0, pool_candidate(pl->pool, pl->hp.ns[b],
+			    pl->hp.tile_begin[b + 1] - pl->hp.tile_begin[b])) : 1;
 	return (plan_upload(pl));
 }
 
@@ -1012,6 +1267,35 @@ launch_persistent(const DecodeParams &p, cudaStream_t st)
 	return cudaGetLastError();
 }
 
+template <class Tile>
+static cudaError_t
+launch_pool(const DecodeParams &p, cudaStream_t st)
+{
+	static thread_local int grid_cache[2] = { -1, 0 };
+	const size_t smem = sizeof(PoolSmem<Tile>);
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess)
+		return e;
+	if (grid_cache[0] != dev) {
+		int per_sm = 0, sms = 0;
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm,
+		    xa_decode_pool_kernel<Tile>, kPoolBlock, smem);
+		if (e != cudaSuccess)
+			return e;
+		e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		if (e != cudaSuccess)
+			return e;
+		grid_cache[0] = dev;
+		grid_cache[1] = per_sm * sms > 0 ? per_sm * sms : sms;
+	}
+	uint32_t grid = (uint32_t)grid_cache[1];
+	if (grid > p.n_tiles)
+		grid = p.n_tiles;
+	xa_decode_pool_kernel<Tile><<<grid, kPoolBlock, smem, st>>>(p);
+	return cudaGetLastError();
+}
+
 /*
  * One class of a decode plan.  Up to four tile forms can serve it -- long-strip
  * or wide tiles, and for stereo the direct or the staged form (xa_tile.h
@@ -1025,6 +1309,7 @@ struct DecodeClass {
 	uint32_t alt_n;
 	int ns;				/* strips per tile of the primary list */
 	int stereo;			/* 0 direct, 1 staged, 2 census (stereo classes) */
+	int pool;			/* 0 never, 1 always, 2 census */
 	uint32_t *d_choice;
 	const uint32_t *d_order;	/* the class's streams */
 	uint32_t n_streams;
@@ -1041,11 +1326,31 @@ launch_form(const DecodeParams &p, bool staged, cudaStream_t st)
 	return launch_persistent<DecTileStereo<BITS, kDecTBQ, NS, dec_stages(BITS, 2)> >(p, st);
 }
 
+/* pooled form: 0 = never, 1 = always (long-strip lists), 2 = let the census decide
+ * (BJXA_B200_POOL=off|on|auto, default auto) */
+static int
+pool_mode(void)
+{
+	const char *e = getenv("BJXA_B200_POOL");
+	return e == NULL ? 2 : strcmp(e, "off") == 0 ? 0 : strcmp(e, "on") == 0 ? 1 : 2;
+}
+
+/* is the pooled form a candidate for this class, and the only one? */
+static int
+pool_candidate(int pool, int ns, uint32_t n_tiles)
+{
+	if (ns != 1 || pool == 0)
+		return 0;
+	return pool == 1 ? 1 : n_tiles >= kPoolMinTiles ? 2 : 0;
+}
+
 /* how many kernels decode_class() launches */
 static int
-decode_class_launches(int ch, int stereo, bool alt)
+decode_class_launches(int ch, int stereo, bool alt, int poolc)
 {
-	const int forms = (ch == 2 && stereo == 2 ? 2 : 1) + (alt ? 1 : 0);
+	if (poolc == 1)
+		return 1;
+	const int forms = (ch == 2 && stereo == 2 ? 2 : 1) + (alt ? 1 : 0) + (poolc == 2 ? 1 : 0);
 	return forms == 1 ? 1 : forms + 1;
 }
 
@@ -1055,9 +1360,12 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 {
 	const bool alt = c.alt_tiles != NULL;
 	const bool pick_form = CH == 2 && c.stereo == 2;
+	const int poolc = pool_candidate(c.pool, c.ns, c.p.n_tiles);
 	DecodeParams p = c.p;
 	cudaError_t e;
-	if (!alt && !pick_form) {
+	if (poolc == 1)
+		return launch_pool<typename PoolTile<BITS, CH>::type>(p, st);
+	if (!alt && !pick_form && poolc == 0) {
 		const bool staged = CH == 2 && c.stereo == 1;
 		return c.ns == 1 ? launch_form<BITS, CH, 1>(p, staged, st) :
 		    launch_form<BITS, CH, kDecWide>(p, staged, st);
@@ -1066,7 +1374,8 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 	    (uint32_t)block_bytes(BITS), (uint32_t)CH,
 	    pick_form ? staged_permille(BITS) : c.stereo == 1 && CH == 2 ? 0u : kNever,
 	    alt ? (CH == 2 ? kWidePermilleStereo : kWidePermilleMono)[c.n_streams >= kWideManyStreams] :
-	    kNever, c.d_choice);
+	    kNever, poolc == 2 ? (CH == 2 ? kPoolPermilleStereo : kPoolPermilleMono) : kNever,
+	    c.d_choice);
 	if ((e = cudaGetLastError()) != cudaSuccess)
 		return e;
 	p.choice = c.d_choice;
@@ -1080,6 +1389,11 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 		e = c.ns == 1 ? launch_form<BITS, CH, 1>(p, staged != 0, st) :
 		    launch_form<BITS, CH, kDecWide>(p, staged != 0, st);
 		if (e != cudaSuccess)
+			return e;
+	}
+	if (poolc == 2) {
+		p.want = kFormPool;
+		if ((e = launch_pool<typename PoolTile<BITS, CH>::type>(p, st)) != cudaSuccess)
 			return e;
 	}
 	if (alt) {
@@ -1230,6 +1544,7 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 			c.alt_n = hp.alt_begin[b + 1] - hp.alt_begin[b];
 			c.ns = hp.ns[b];
 			c.stereo = pl->stereo;
+			c.pool = pl->pool;
 			c.d_choice = pl->d_first_bad.p + ((n + 3) & ~(size_t)3) + 12 + b;
 			c.d_order = pl->d_order.p + hp.order_begin[b];
 			c.n_streams = hp.order_begin[b + 1] - hp.order_begin[b];

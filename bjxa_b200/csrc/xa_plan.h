@@ -54,6 +54,26 @@ constexpr int dec_stages(int bits, int ch)
 	return ch == 1 ? (bits == 4 ? 4 : 3) : (bits == 4 ? 3 : bits == 6 ? 5 : 4);
 #endif
 }
+/*
+ * Ring depth of the pooled form (xa_decode_pool_kernel): as many tiles as fit
+ * next to each other when `ctas` CTAs share the 227 KB of an SM -- their chains
+ * are one pool, and the deeper the ring the longer a long chain may take before
+ * it holds the loader up.  -DXA_POOL_STAGES=n overrides it.
+ */
+#ifndef XA_POOL_CTAS
+#define XA_POOL_CTAS 2
+#endif
+constexpr int pool_stages(int bits, int ch, int ctas = XA_POOL_CTAS)
+{
+#ifdef XA_POOL_STAGES
+	return XA_POOL_STAGES;
+#else
+	/* stage buffer (DecGeom::IN_BYTES for one strip) + heads + context + words */
+	const int stage = ((XA_DEC_TBQ * (4 * bits + 1) + 30) / 16) * 16 + 16 + XA_DEC_TBQ * 2 + 48 + 56;
+	const int n = ((227 * 1024) / ctas - 1024 - 64) / stage;
+	return n > 12 ? 12 : n;
+#endif
+}
 constexpr int kDecWide = XA_DEC_WIDE;		/* strips per tile in "wide" mode */
 constexpr int kEncTBE = 256;
 constexpr int kEncThreads = 128;

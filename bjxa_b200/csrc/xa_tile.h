@@ -120,6 +120,12 @@ XA_HD unsigned long long mailbox_get(const unsigned long long *p, uint32_t epoch
 	atomicExch(fault, 1u);
 	return 0;
 }
+/* one look, no waiting (the pooled walkers come back to it on their next turn) */
+XA_HD bool mailbox_try(const unsigned long long *p, uint32_t epoch, unsigned long long &v)
+{
+	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return (uint32_t)(v >> 32) == epoch;
+}
 #else
 XA_HD void global_min_u32(uint32_t *p, uint32_t v) { if (v < *p) *p = v; }
 XA_HD void mailbox_put(unsigned long long *p, unsigned long long v) { *p = v; }
@@ -130,6 +136,13 @@ XA_HD unsigned long long mailbox_get(const unsigned long long *p, uint32_t epoch
 	if ((uint32_t)(*p >> 32) != epoch)
 		__builtin_trap();
 	return *p;
+}
+XA_HD bool mailbox_try(const unsigned long long *p, uint32_t epoch, unsigned long long &v)
+{
+	if ((uint32_t)(*p >> 32) != epoch)
+		__builtin_trap();
+	v = *p;
+	return true;
 }
 #endif
 
@@ -557,6 +570,88 @@ struct DecTile {
 			}
 		}
 	}
+
+	/*
+	 * The same walk cut in two -- "start at a head" and "decode ONE block" -- for
+	 * the pooled form (xa_decode_pool_kernel), whose walker lanes hold chains of
+	 * different tiles of the ring at the same time.
+	 */
+	struct Walk {
+		const StripCtx *c;
+		uint32_t lq, at;
+		uint32_t need;		/* the carry has not arrived yet */
+		int p0, p1;
+	};
+
+	/* the state carried into the strip, if it is there: never waits, because
+	 * the lane that has to produce it may sit in the same warp */
+	XA_HD void walk_carry(Walk &w) const
+	{
+		if (w.c->flags & kCtxFirst) {
+			w.p0 = p.streams[w.c->stream].prev[0][0];
+			w.p1 = p.streams[w.c->stream].prev[0][1];
+			w.need = 0;
+			return;
+		}
+		unsigned long long v;
+		if (mailbox_try(&p.carry[(uint64_t)(w.c->slot - 1) * 2], p.epoch, v)) {
+			w.p0 = (int16_t)(uint16_t)v;
+			w.p1 = (int16_t)(uint16_t)(v >> 16);
+			w.need = 0;
+		}
+	}
+
+	/* a carry that never arrives: flag the launch (bjxa_plan_fetch: EIO), go on */
+	XA_HD void walk_give_up(Walk &w) const
+	{
+#if defined(__CUDA_ARCH__)
+		atomicExch(p.fault, 1u);
+#endif
+		w.p0 = w.p1 = 0;
+		w.need = 0;
+	}
+
+	XA_HD void walk_begin(Walk &w, uint32_t q) const
+	{
+		w.c = &ctx[q / SBQ];
+		w.lq = q % SBQ;
+		w.at = block_at(*w.c, w.lq);
+		w.need = 0;
+		if (w.lq == 0) {
+			w.need = 1;
+			walk_carry(w);
+		} else {
+			/* the block in front is a cut block (see phase_walk_warp) */
+			const uint32_t pa = w.at - BS;
+			const int sh = 16 + (int)(in[pa] & 15u);
+			int x[4];
+			quad_codes<BITS>(bytes_at(pa + 1 + 7 * QB), x);
+			w.p1 = x[2] >> sh;
+			w.p0 = x[3] >> sh;
+		}
+	}
+
+	/* one block of the chain; false when it was the chain's last */
+	XA_HD bool walk_block(Walk &w) const
+	{
+		uint32_t pw[BITS], o[16];
+		fetch_block(w.at, pw);
+		decode_block_chain<BITS>(o, pw, in[w.at], w.p0, w.p1);
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			uint4 v;
+			v.x = o[4 * j]; v.y = o[4 * j + 1];
+			v.z = o[4 * j + 2]; v.w = o[4 * j + 3];
+			put_unit(*w.c, (w.lq * 4u + (uint32_t)j) * 16u, v);
+		}
+		if (w.lq + 1 >= w.c->nq) {
+			publish(*w.c, w.p0, w.p1);
+			return false;
+		}
+		w.lq++;
+		w.at += BS;
+		return block_kind(in[w.at]) == kChain;
+	}
 };
 
 /* ---- decode, direct form (stereo) ------------------------------------------ */
@@ -925,6 +1020,112 @@ struct DecTileStereo {
 				i = take_next(next);
 			}
 		}
+	}
+
+	/* the same walk cut in two for the pooled form (see DecTile::Walk) */
+	struct Walk {
+		const StripCtx *c;
+		uint32_t eb, at, m;
+		uint32_t need;		/* channels whose carry has not arrived yet */
+		int p0[2], p1[2];
+	};
+
+	XA_HD void walk_carry(Walk &w) const
+	{
+#pragma unroll
+		for (uint32_t ch = 0; ch < 2; ch++) {
+			if (!(w.need >> ch & 1u))
+				continue;
+			if (w.c->flags & kCtxFirst) {
+				w.p0[ch] = p.streams[w.c->stream].prev[ch][0];
+				w.p1[ch] = p.streams[w.c->stream].prev[ch][1];
+				w.need &= ~(1u << ch);
+				continue;
+			}
+			unsigned long long v;
+			if (mailbox_try(&p.carry[(uint64_t)(w.c->slot - 1) * 2 + ch], p.epoch, v)) {
+				w.p0[ch] = (int16_t)(uint16_t)v;
+				w.p1[ch] = (int16_t)(uint16_t)(v >> 16);
+				w.need &= ~(1u << ch);
+			}
+		}
+	}
+
+	XA_HD void walk_give_up(Walk &w) const
+	{
+#if defined(__CUDA_ARCH__)
+		atomicExch(p.fault, 1u);
+#endif
+		w.need = 0;
+	}
+
+	XA_HD void walk_begin(Walk &w, uint32_t q) const
+	{
+		w.c = &ctx[q / SBE];
+		w.eb = q % SBE;
+		w.at = eb_at(*w.c, w.eb);
+		w.m = chains(*w.c, w.eb);
+		w.p0[0] = w.p0[1] = w.p1[0] = w.p1[1] = 0;
+		w.need = 0;
+		if (w.eb == 0) {
+			/* a channel that starts with a cut block needs no history */
+			w.need = w.m;
+			walk_carry(w);
+		} else {
+#pragma unroll
+			for (int ch = 0; ch < 2; ch++) {
+				const uint32_t pa = w.at - 2 * BS + ch * BS;
+				const int sh = 16 + (int)(in[pa] & 15u);
+				int x[4];
+				quad_codes<BITS>(bytes_at(pa + 1 + 7 * QB), x);
+				w.p1[ch] = x[2] >> sh;
+				w.p0[ch] = x[3] >> sh;
+			}
+		}
+	}
+
+	/* one effective block of the run; false when it was the run's last */
+	XA_HD bool walk_block(Walk &w) const
+	{
+		const uint32_t profl = in[w.at], profr = in[w.at + BS];
+		if (profl >> 4 >= 5u)
+			global_min_u32(&p.first_bad[w.c->stream], (w.c->first_eb + w.eb) * 2);
+		if (profr >> 4 >= 5u)
+			global_min_u32(&p.first_bad[w.c->stream], (w.c->first_eb + w.eb) * 2 + 1);
+		uint32_t pl[BITS], pr[BITS];
+		fetch_block(w.at, pl);
+		fetch_block(w.at + BS, pr);
+		const int shl = 16 + (int)(profl & 15u), shr = 16 + (int)(profr & 15u);
+		const int k0l = gain_k0(profl >> 4), k1l = gain_k1(profl >> 4);
+		const int k0r = gain_k0(profr >> 4), k1r = gain_k1(profr >> 4);
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			int l[4], r[4];
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				l[k] = sample_chain(top_code<BITS>(pl, 4 * j + k), shl, k0l, k1l,
+				    w.p0[0], w.p1[0]);
+				r[k] = sample_chain(top_code<BITS>(pr, 4 * j + k), shr, k0r, k1r,
+				    w.p0[1], w.p1[1]);
+			}
+			uint4 v;
+			v.x = pack2(l[0], r[0]);
+			v.y = pack2(l[1], r[1]);
+			v.z = pack2(l[2], r[2]);
+			v.w = pack2(l[3], r[3]);
+			put_unit(*w.c, (w.eb * 8u + (uint32_t)j) * 16u, v);
+		}
+		if ((w.eb + 1) * 2 >= w.c->nq) {
+			publish(*w.c, 0, w.p0[0], w.p1[0]);
+			publish(*w.c, 1, w.p0[1], w.p1[1]);
+			return false;
+		}
+		w.eb++;
+		w.at += 2 * BS;
+		const uint32_t nm = chains(*w.c, w.eb);
+		const bool more = (nm & w.m) != 0;
+		w.m = nm;
+		return more;
 	}
 };
 

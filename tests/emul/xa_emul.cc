@@ -21,6 +21,7 @@ using namespace xa;
 
 static int g_use_alt = 0;
 static int g_stereo_direct = 0;
+static int g_pool = 0;
 
 /* thread visiting order inside a phase: 0 ascending, 1 descending, 2 strided */
 static uint32_t
@@ -68,6 +69,32 @@ emul_decode_ns(const DecodeParams &p, int order)
 				sm->heads[s][count++] = (uint16_t)q;
 		sm->n_heads[s] = count;
 		sm->next_head[s] = 32;
+		if (g_pool) {
+			/* pooled form (xa_decode_pool_kernel): 32 walker lanes, each
+			 * drawing a chain when idle and decoding ONE block per turn; the
+			 * units belong to two warps of their own */
+			typename Tile::Walk w[32];
+			bool have[32] = { false };
+			uint32_t next = 0, live = 0;
+			do {
+				live = 0;
+				for (uint32_t i = 0; i < 32; i++) {
+					const uint32_t l = visit(i, 32, order);
+					if (!have[l] && next < count) {
+						t.walk_begin(w[l], sm->heads[s][next++]);
+						if (w[l].need != 0)
+							return;		/* carries are there, in ticket order */
+						have[l] = true;
+					} else if (have[l]) {
+						have[l] = t.walk_block(w[l]);
+					}
+					live += have[l];
+				}
+			} while (live != 0 || next < count);
+			for (uint32_t i = 0; i < 64; i++)
+				t.phase_units(visit(i, 64, order), 64);
+			continue;
+		}
 		/* consumers: the tile's walker warp, lane by lane (whichever lane runs
 		 * first picks up every chain left over), then the units */
 		for (uint32_t i = 0; i < 32; i++)
@@ -374,6 +401,7 @@ xa_emul_plan(int kind, const bjxa_stream_desc_t *descs, size_t n, int force_stri
 
 void xa_emul_stereo_direct(int on) { g_stereo_direct = on; }
 void xa_emul_use_alt(int on) { g_use_alt = on; }
+void xa_emul_pool(int on) { g_pool = on; }
 int xa_emul_strip_blocks(int ns, int ch) { return (int)strip_blocks(ns, ch); }
 int xa_emul_wide(void) { return kDecWide; }
 int xa_emul_enc_tile_blocks(void) { return kEncTBE; }

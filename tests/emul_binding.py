@@ -31,6 +31,7 @@ class Emul:
         self.enc_tile_blocks = d.xa_emul_enc_tile_blocks
         self.stereo_direct = d.xa_emul_stereo_direct    # (0|1): which stereo form to step
         self.use_alt = d.xa_emul_use_alt                # (0|1): step the alternative tile lists
+        self.pool = d.xa_emul_pool                      # (0|1): direct forms walk as the pooled kernel does
 
     def dec_tile_blocks(self, ch):
         """effective blocks of one long (NS = 1) strip"""

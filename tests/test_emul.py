@@ -11,14 +11,18 @@ from bjxa_b200 import synth
 from emul_binding import Emul
 
 
-@pytest.fixture(scope="module", params=["stereo-staged", "stereo-direct"])
+@pytest.fixture(scope="module", params=["stereo-staged", "stereo-direct", "pooled"])
 def emul(request):
-    """Every decode case runs twice: stereo streams through the staged form and
-    through the direct form of the tile code (mono always uses the direct one)."""
+    """Every decode case runs three times: stereo streams through the staged form,
+    through the direct form of the tile code (mono always uses the direct one), and
+    both direct forms with their chains walked the way the pooled kernel does it
+    (walk_begin / walk_block, units on 64 threads)."""
     e = Emul()
-    e.stereo_direct(1 if request.param == "stereo-direct" else 0)
+    e.stereo_direct(0 if request.param == "stereo-staged" else 1)
+    e.pool(1 if request.param == "pooled" else 0)
     yield e
     e.stereo_direct(0)
+    e.pool(0)
 
 
 STRIP_MODES = [1, 32]      # one long strip per tile / 32 short ones

@@ -133,10 +133,10 @@ enum { kFormStaged = 1, kFormWide = 2, kFormPool = 4 };
  * blocks (measured crossovers: profiles/history_r1.md), for classes of at least
  * kPoolMinTiles tiles -- below that the launch is too short to care */
 #ifndef XA_POOL_PERMILLE_MONO
-#define XA_POOL_PERMILLE_MONO 1001
+#define XA_POOL_PERMILLE_MONO 300
 #endif
 #ifndef XA_POOL_PERMILLE_STEREO
-#define XA_POOL_PERMILLE_STEREO 1001
+#define XA_POOL_PERMILLE_STEREO 300
 #endif
 constexpr uint32_t kPoolPermilleMono = XA_POOL_PERMILLE_MONO, kPoolPermilleStereo = XA_POOL_PERMILLE_STEREO;
 constexpr uint32_t kPoolMinTiles = 296;
@@ -1327,12 +1327,13 @@ launch_form(const DecodeParams &p, bool staged, cudaStream_t st)
 }
 
 /* pooled form: 0 = never, 1 = always (long-strip lists), 2 = let the census decide
- * (BJXA_B200_POOL=off|on|auto, default auto) */
+ * (BJXA_B200_POOL=off|on|auto).  Default off: as measured in round 1 it only wins
+ * on chain-rich 4-bit stereo data (profiles/history_r1.md, step 18) */
 static int
 pool_mode(void)
 {
 	const char *e = getenv("BJXA_B200_POOL");
-	return e == NULL ? 2 : strcmp(e, "off") == 0 ? 0 : strcmp(e, "on") == 0 ? 1 : 2;
+	return e == NULL ? 0 : strcmp(e, "on") == 0 ? 1 : strcmp(e, "auto") == 0 ? 2 : 0;
 }
 
 /* is the pooled form a candidate for this class, and the only one? */

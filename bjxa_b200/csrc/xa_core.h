@@ -178,6 +178,57 @@ XA_HD int sample_chain(int x, int sh, int k0, int k1, int &p0, int &p1)
 }
 
 /*
+ * The same step with state and result carrying +32768 ("biased": 0..65535), so
+ * that the int16 clamp is ONE instruction, max(min(v, 65535), 0) = VIMNMX.RELU,
+ * and the dependent path five: IMAD, SHF, IMAD, LEA.HI, VIMNMX.RELU.
+ *   c  = -32768 * (k0 + k1)  makes  b0*k0 + b1*k1 + c  the reference's gain
+ *        exactly ((p0 + 32768)*k0 + (p1 + 32768)*k1 - 32768*(k0 + k1));
+ *   |b*k| <= 65535 * 488, |c| <= 32768 * 252, + 2^23: all inside int32.
+ * A pair of biased samples is packed by pack2_biased.  -DXA_CHAIN_PLAIN keeps
+ * the walkers on sample_chain.
+ */
+XA_HD int chain_bias_c(int k0, int k1)
+{
+	return -32768 * (k0 + k1);
+}
+
+XA_HD int sample_chain_b(int x, int sh, int k0, int k1, int c, int &b0, int &b1)
+{
+#if defined(__CUDA_ARCH__)
+	/* g for the sign; g2 = g + 2^23 carries the +32768 of the result through
+	 * the division ((f + 2^23) >> 8 = (f >> 8) + 32768 exactly), so biasing the
+	 * code costs no ALU-pipe instruction: everything but SHF, LEA.HI and
+	 * VIMNMX.RELU runs on the FMA pipe, which the walkers leave idle */
+	int g = b0 * k0 + (b1 * k1 + c);
+	int g2 = b0 * k0 + (b1 * k1 + (c + (1 << 23)));
+	int f;
+	asm("mad.lo.s32 %0, %1, -255, %2;" : "=r"(f) : "r"(g >> 31), "r"(g2));
+	int s = __vimin_s32_relu((f >> 8) + (x >> sh), 65535);
+#else
+	int g = b0 * k0 + (b1 * k1 + c);
+	int q = (g + ((g >> 31) & 255)) >> 8;
+	int s = (x >> sh) + 32768 + q;
+	s = s < 0 ? 0 : s;
+	s = s > 65535 ? 65535 : s;
+#endif
+	b1 = b0;
+	b0 = s;
+	return s;
+}
+
+/* two biased samples -> one word of int16, lo | hi << 16 */
+XA_HD uint32_t pack2_biased(int lo, int hi)
+{
+#if defined(__CUDA_ARCH__)
+	uint32_t w;
+	asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(w) : "r"(hi), "r"(lo));
+	return w ^ 0x80008000u;
+#else
+	return ((uint32_t)hi << 16 | (uint32_t)lo) ^ 0x80008000u;
+#endif
+}
+
+/*
  * The four codes of one "quad" (4 consecutive samples = BITS/2 payload bytes,
  * given in the low bytes of w), each top-aligned in 32 bits with zeros below.
  */
@@ -223,12 +274,25 @@ XA_HD void decode_block_chain(uint32_t (&out)[16], const uint32_t (&pw)[BITS],
 {
 	const int sh = 16 + (int)(profile & 15u);
 	const int k0 = gain_k0(profile >> 4), k1 = gain_k1(profile >> 4);
+#if !defined(XA_CHAIN_PLAIN)
+	const int c = chain_bias_c(k0, k1);
+	int b0 = p0 + 32768, b1 = p1 + 32768;
+#pragma unroll
+	for (int i = 0; i < 16; i++) {
+		int a = sample_chain_b(top_code<BITS>(pw, 2 * i), sh, k0, k1, c, b0, b1);
+		int b = sample_chain_b(top_code<BITS>(pw, 2 * i + 1), sh, k0, k1, c, b0, b1);
+		out[i] = pack2_biased(a, b);
+	}
+	p0 = b0 - 32768;
+	p1 = b1 - 32768;
+#else
 #pragma unroll
 	for (int i = 0; i < 16; i++) {
 		int a = sample_chain(top_code<BITS>(pw, 2 * i), sh, k0, k1, p0, p1);
 		int b = sample_chain(top_code<BITS>(pw, 2 * i + 1), sh, k0, k1, p0, p1);
 		out[i] = pack2(a, b);
 	}
+#endif
 }
 
 /* ---- encode: 32 int16 (16 packed words) -> 4*BITS payload bytes --------- */

@@ -930,6 +930,87 @@ struct DecTileStereo {
 	}
 
 	/*
+	 * One effective block of a run: both channels side by side -- two
+	 * independent dependency chains (a cut block inside a run simply has
+	 * k0 = k1 = 0) -- stored as eight interleaved 16-byte units.
+	 */
+	XA_HD void decode_pair(const StripCtx &c, uint32_t eb, uint32_t at, uint32_t profl,
+	    uint32_t profr, int (&p0)[2], int (&p1)[2]) const
+	{
+		uint32_t pl[BITS], pr[BITS];
+		fetch_block(at, pl);
+		fetch_block(at + BS, pr);
+		const int shl = 16 + (int)(profl & 15u), shr = 16 + (int)(profr & 15u);
+		const int k0l = gain_k0(profl >> 4), k1l = gain_k1(profl >> 4);
+		const int k0r = gain_k0(profr >> 4), k1r = gain_k1(profr >> 4);
+#if !defined(XA_CHAIN_PLAIN)
+		/* biased state: one-instruction clamp (xa_core.h:sample_chain_b); not
+		 * for 4-bit streams, whose kernel is held at 48 registers (kMinCtas)
+		 * and would spill the two extra constants */
+		if (BITS == 4) {
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				int l[4], r[4];
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					l[k] = sample_chain(top_code<BITS>(pl, 4 * j + k), shl, k0l, k1l,
+					    p0[0], p1[0]);
+					r[k] = sample_chain(top_code<BITS>(pr, 4 * j + k), shr, k0r, k1r,
+					    p0[1], p1[1]);
+				}
+				uint4 v;
+				v.x = pack2(l[0], r[0]);
+				v.y = pack2(l[1], r[1]);
+				v.z = pack2(l[2], r[2]);
+				v.w = pack2(l[3], r[3]);
+				put_unit(c, (eb * 8u + (uint32_t)j) * 16u, v);
+			}
+			return;
+		}
+		const int cl = chain_bias_c(k0l, k1l), cr = chain_bias_c(k0r, k1r);
+		int bl0 = p0[0] + 32768, bl1 = p1[0] + 32768;
+		int br0 = p0[1] + 32768, br1 = p1[1] + 32768;
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			int l[4], r[4];
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				l[k] = sample_chain_b(top_code<BITS>(pl, 4 * j + k), shl, k0l, k1l, cl,
+				    bl0, bl1);
+				r[k] = sample_chain_b(top_code<BITS>(pr, 4 * j + k), shr, k0r, k1r, cr,
+				    br0, br1);
+			}
+			uint4 v;
+			v.x = pack2_biased(l[0], r[0]);
+			v.y = pack2_biased(l[1], r[1]);
+			v.z = pack2_biased(l[2], r[2]);
+			v.w = pack2_biased(l[3], r[3]);
+			put_unit(c, (eb * 8u + (uint32_t)j) * 16u, v);
+		}
+		p0[0] = bl0 - 32768; p1[0] = bl1 - 32768;
+		p0[1] = br0 - 32768; p1[1] = br1 - 32768;
+#else
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			int l[4], r[4];
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				l[k] = sample_chain(top_code<BITS>(pl, 4 * j + k), shl, k0l, k1l,
+				    p0[0], p1[0]);
+				r[k] = sample_chain(top_code<BITS>(pr, 4 * j + k), shr, k0r, k1r,
+				    p0[1], p1[1]);
+			}
+			uint4 v;
+			v.x = pack2(l[0], r[0]);
+			v.y = pack2(l[1], r[1]);
+			v.z = pack2(l[2], r[2]);
+			v.w = pack2(l[3], r[3]);
+			put_unit(c, (eb * 8u + (uint32_t)j) * 16u, v);
+		}
+#endif
+	}
+
+	/*
 	 * One warp walks all the runs of a tile, lanes drawing the next run as they
 	 * finish one (see DecTile::phase_walk_warp).  A run starts at the effective
 	 * block heads[i] = strip * SBE + eb and is decoded one effective block per
@@ -979,31 +1060,7 @@ struct DecTileStereo {
 				global_min_u32(&p.first_bad[c->stream], (c->first_eb + eb) * 2);
 			if (profr >> 4 >= 5u)
 				global_min_u32(&p.first_bad[c->stream], (c->first_eb + eb) * 2 + 1);
-			uint32_t pl[BITS], pr[BITS];
-			fetch_block(at, pl);
-			fetch_block(at + BS, pr);
-			const int shl = 16 + (int)(profl & 15u), shr = 16 + (int)(profr & 15u);
-			const int k0l = gain_k0(profl >> 4), k1l = gain_k1(profl >> 4);
-			const int k0r = gain_k0(profr >> 4), k1r = gain_k1(profr >> 4);
-			/* both channels side by side: two independent dependency chains
-			 * (a cut block inside a run simply has k0 = k1 = 0) */
-#pragma unroll
-			for (int j = 0; j < 8; j++) {
-				int l[4], r[4];
-#pragma unroll
-				for (int k = 0; k < 4; k++) {
-					l[k] = sample_chain(top_code<BITS>(pl, 4 * j + k), shl, k0l, k1l,
-					    p0[0], p1[0]);
-					r[k] = sample_chain(top_code<BITS>(pr, 4 * j + k), shr, k0r, k1r,
-					    p0[1], p1[1]);
-				}
-				uint4 v;
-				v.x = pack2(l[0], r[0]);
-				v.y = pack2(l[1], r[1]);
-				v.z = pack2(l[2], r[2]);
-				v.w = pack2(l[3], r[3]);
-				put_unit(*c, (eb * 8u + (uint32_t)j) * 16u, v);
-			}
+			decode_pair(*c, eb, at, profl, profr, p0, p1);
 			bool more = false;
 			if ((eb + 1) * 2 >= c->nq) {
 				publish(*c, 0, p0[0], p1[0]);
@@ -1092,29 +1149,7 @@ struct DecTileStereo {
 			global_min_u32(&p.first_bad[w.c->stream], (w.c->first_eb + w.eb) * 2);
 		if (profr >> 4 >= 5u)
 			global_min_u32(&p.first_bad[w.c->stream], (w.c->first_eb + w.eb) * 2 + 1);
-		uint32_t pl[BITS], pr[BITS];
-		fetch_block(w.at, pl);
-		fetch_block(w.at + BS, pr);
-		const int shl = 16 + (int)(profl & 15u), shr = 16 + (int)(profr & 15u);
-		const int k0l = gain_k0(profl >> 4), k1l = gain_k1(profl >> 4);
-		const int k0r = gain_k0(profr >> 4), k1r = gain_k1(profr >> 4);
-#pragma unroll
-		for (int j = 0; j < 8; j++) {
-			int l[4], r[4];
-#pragma unroll
-			for (int k = 0; k < 4; k++) {
-				l[k] = sample_chain(top_code<BITS>(pl, 4 * j + k), shl, k0l, k1l,
-				    w.p0[0], w.p1[0]);
-				r[k] = sample_chain(top_code<BITS>(pr, 4 * j + k), shr, k0r, k1r,
-				    w.p0[1], w.p1[1]);
-			}
-			uint4 v;
-			v.x = pack2(l[0], r[0]);
-			v.y = pack2(l[1], r[1]);
-			v.z = pack2(l[2], r[2]);
-			v.w = pack2(l[3], r[3]);
-			put_unit(*w.c, (w.eb * 8u + (uint32_t)j) * 16u, v);
-		}
+		decode_pair(*w.c, w.eb, w.at, profl, profr, w.p0, w.p1);
 		if ((w.eb + 1) * 2 >= w.c->nq) {
 			publish(*w.c, 0, w.p0[0], w.p1[0]);
 			publish(*w.c, 1, w.p0[1], w.p1[1]);

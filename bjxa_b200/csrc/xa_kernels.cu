@@ -234,10 +234,10 @@ consume_tile(Tile &t, typename Tile::Smem &sm, int s, uint32_t it, uint32_t tid)
 
 /* ---- the pooled form's shared-memory protocol (xa_decode_pool_kernel below) ---- */
 #ifndef XA_POOL_UNIT_WARPS
-#define XA_POOL_UNIT_WARPS 2
+#define XA_POOL_UNIT_WARPS 3
 #endif
 #ifndef XA_POOL_WALK_WARPS
-#define XA_POOL_WALK_WARPS 6
+#define XA_POOL_WALK_WARPS 3
 #endif
 constexpr int kPoolUnitWarps = XA_POOL_UNIT_WARPS, kPoolWalkWarps = XA_POOL_WALK_WARPS;
 constexpr int kPoolCtas = XA_POOL_CTAS;			/* per SM */

@@ -61,7 +61,7 @@ constexpr int dec_stages(int bits, int ch)
  * it holds the loader up.  -DXA_POOL_STAGES=n overrides it.
  */
 #ifndef XA_POOL_CTAS
-#define XA_POOL_CTAS 2
+#define XA_POOL_CTAS 3
 #endif
 constexpr int pool_stages(int bits, int ch, int ctas = XA_POOL_CTAS)
 {

@@ -271,6 +271,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # stdout carries the one JSON line and nothing else: NCCL's own prints
+        # ("NCCL version ...", anything NCCL_DEBUG asks for) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lib = bjxa_b200.load()
     warm = max(args.warmup, 3)

@@ -270,10 +270,14 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    out_fd = 1
     if world > 1:
-        # stdout carries the one JSON line and nothing else: NCCL's own prints
-        # ("NCCL version ...", anything NCCL_DEBUG asks for) go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # stdout carries the one JSON line and nothing else: whatever libraries
+        # print on file descriptor 1 ("NCCL version ...") goes to stderr, and
+        # rank 0 writes its line to the descriptor saved here
+        sys.stdout.flush()
+        out_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     lib = bjxa_b200.load()
     warm = max(args.warmup, 3)
@@ -492,7 +496,8 @@ def main():
         sampler.stop()
     lib.plan_free(plan)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(out_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

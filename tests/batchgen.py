@@ -19,8 +19,12 @@ def decode_batch(specs, seed=1, xa_gap=0, pcm_pad=0):
     xa_off, pcm_off = 0, 0
     for i, s in enumerate(specs):
         blocks = (s["samples"] + 31) // 32
-        pay = synth.xa_payload(seed, s.get("key", i), s["bits"], s["channels"],
-                               blocks, s["mix"])
+        if "payload" in s:                    # a hand-made stream (extremes())
+            pay = np.array(s["payload"], dtype=np.uint8)
+            assert pay.size == blocks * s["channels"] * synth.block_size(s["bits"])
+        else:
+            pay = synth.xa_payload(seed, s.get("key", i), s["bits"], s["channels"],
+                                   blocks, s["mix"])
         if "patch" in s:                      # {block-channel index: profile byte}
             bs = synth.block_size(s["bits"])
             for q, val in s["patch"].items():
@@ -42,6 +46,41 @@ def decode_batch(specs, seed=1, xa_gap=0, pcm_pad=0):
         payloads.append(pay)
     arena = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.uint8)
     return descs, arena, pcm_off, payloads
+
+
+def pack_codes(bits, codes):
+    """32 signed codes of `bits` bits -> the block's payload bytes, MSB first
+    (/root/reference/src/libbjxa.c:286-345 read them back the same way)."""
+    acc = 0
+    for c in codes:
+        acc = acc << bits | (int(c) & ((1 << bits) - 1))
+    return list(acc.to_bytes(4 * bits, "big"))
+
+
+def extremes(bits, channels, blocks=40):
+    """Streams that drive the predictor to both rails and through every sign of
+    the truncating division: full-scale codes (all highest, all lowest, alternating,
+    a ramp) at ranges 0..3, every filter 1..4 in chains with no cut block, entry
+    states at the rails.  One spec per (filter, pattern, entry state)."""
+    hi, lo = (1 << (bits - 1)) - 1, -(1 << (bits - 1))
+    pats = {"hi": [hi] * 32, "lo": [lo] * 32, "alt": [hi, lo] * 16, "tla": [lo, hi] * 16,
+            "ramp": [lo + (i * (hi - lo)) // 31 for i in range(32)], "ones": [1, -1] * 16}
+    states = [((32767, 32767), (-32768, -32768)), ((-32768, 32767), (32767, -32768)),
+              ((-1, 0), (0, -1))]
+    specs = []
+    for f in (1, 2, 3, 4):
+        for name, codes in pats.items():
+            for k, st in enumerate(states):
+                pay = []
+                for b in range(blocks):
+                    for c in range(channels):
+                        # the other channel runs the mirrored pattern, one filter on
+                        cc = codes if c == 0 else [-1 - x for x in codes]
+                        ff = f if c == 0 else 1 + f % 4
+                        pay += [ff << 4 | (b + c + k) % 4] + pack_codes(bits, cc)
+                specs.append(dict(bits=bits, channels=channels, samples=32 * blocks - (f + k) % 7,
+                                  payload=pay, prev=st, mix="hand-made"))
+    return specs
 
 
 def check_decode(oracle, specs, descs, payloads, pcm_arena, prev_out, first_bad):

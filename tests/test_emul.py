@@ -126,6 +126,15 @@ def test_decode_bad_profile(emul, oracle, strips):
     batchgen.check_decode(oracle, specs, descs, pays, dst, prev, bad)
 
 
+@pytest.mark.parametrize("bits", [4, 6, 8])
+@pytest.mark.parametrize("ch", [1, 2])
+def test_decode_predictor_extremes(emul, oracle, bits, ch):
+    """Both rails, every filter, every sign of the truncating division: the
+    walkers' biased predictor step against the reference's arithmetic."""
+    n = _run_decode(emul, oracle, batchgen.extremes(bits, ch))
+    assert n > 72 * 32 * 39 * ch
+
+
 def test_decode_saturation_vector(emul, oracle):
     """/root/reference/test/test_decode.sh:80-122 through the tile code."""
     pay = np.frombuffer(b"\x20" + b"\x7f" * 32 + b"\x20" + b"\x80" * 32, dtype=np.uint8)

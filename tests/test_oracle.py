@@ -125,3 +125,21 @@ def test_oracle_vs_compiled_reference(oracle, ref):
     wav = synth.riff_header(pcm.size * 2, 2) + pcm.tobytes()
     for bits in (4, 6, 8):
         assert oracle.wav_to_xa(wav, bits) == ref.wav_to_xa(wav, bits)
+
+
+def test_extremes_against_compiled_reference(oracle, ref):
+    """The hand-made streams of batchgen.extremes (both rails, every filter, every
+    sign of the truncating division) decode identically with the restatement and
+    with the unmodified reference -- and do reach both rails."""
+    import batchgen
+    rails = set()
+    for bits in (4, 6, 8):
+        for ch in (1, 2):
+            for s in batchgen.extremes(bits, ch, blocks=12):
+                pay = bytes(s["payload"])
+                xa = synth.xa_header(len(pay), s["samples"], 44100, bits, ch, s["prev"]) + pay
+                wav = oracle.xa_to_wav(xa)
+                assert wav == ref.xa_to_wav(xa), (bits, ch, s["prev"])
+                pcm = np.frombuffer(wav[44:], dtype="<i2")
+                rails |= {int(pcm.min()), int(pcm.max())}
+    assert {-32768, 32767} <= rails

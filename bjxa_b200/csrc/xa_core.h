@@ -388,24 +388,71 @@ XA_HD uint32_t pack4(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3)
 XA_HD constexpr int search_ranges(int bits) { return 17 - bits; }
 XA_HD constexpr int search_candidates(int bits) { return 5 * (17 - bits); }
 
+/*
+ * The step above, rearranged for the machine like the decoder's (sample_chain_b):
+ * the ALU pipe takes a warp instruction every other cycle and was what bounded
+ * the search (78 % busy), the FMA pipe takes one per cycle and idled.  State,
+ * sample and result carry +32768, the code carries +2^(BITS-1), so that both
+ * clamps are one VIMNMX.RELU each; every constant rides in a multiply-add:
+ *     g    = b0*k0 + b1*k1 + c                c = -32768*(k0 + k1): the gain, exactly
+ *     f    = g + (g < 0 ? 255 : 0) + d        d = 2^23 - (M << 8),  M = 2^(BITS-1) * step
+ *     pb   = f >> 8                           = pred + 32768 - M
+ *     cb   = relu_min((xb + step/2 - pb) >> shift, 2^BITS - 1)    = code + 2^(BITS-1)
+ *     sb   = relu_min(cb*step + pb, 65535)    = s + 32768;   err += (xb - sb)^2
+ * (adding M to the numerator adds exactly 2^(BITS-1) to the quotient; cb*step + pb
+ * = code*step + pred + 32768).  Three shifts and two clamps are all that is left
+ * on the ALU pipe.  The biased codes are packed as they are and un-biased once per
+ * block: search_code_bias() is the XOR mask of all 32 top bits.
+ */
 template <int BITS>
-XA_HD int search_sample(int x, int k0, int k1, int shift, int &q0, int &q1,
+struct SearchK {		/* one candidate's constants */
+	int k0, k1, c, d, shift, step, half;
+};
+
+template <int BITS>
+XA_HD void search_setup(SearchK<BITS> &K, unsigned f, int shift)
+{
+	K.k0 = gain_k0(f);
+	K.k1 = gain_k1(f);
+	K.c = -32768 * (K.k0 + K.k1);
+	K.shift = shift;
+	K.step = 1 << shift;
+	K.half = K.step >> 1;
+	K.d = (1 << 23) - ((K.step << (BITS - 1)) << 8);
+}
+
+template <int BITS>
+XA_HD int search_sample_b(int xb, const SearchK<BITS> &K, int &b0, int &b1,
     unsigned long long &err)
 {
-	const int g = q0 * k0 + q1 * k1;
-	const int pred = (g + ((g >> 31) & 255)) >> 8;
-	int code = (x - pred + ((1 << shift) >> 1)) >> shift;
-	const int lo = -(1 << (BITS - 1)), hi = (1 << (BITS - 1)) - 1;
-	code = code < lo ? lo : code;
-	code = code > hi ? hi : code;
-	int s = code * (1 << shift) + pred;
-	s = s < -32768 ? -32768 : s;
-	s = s > 32767 ? 32767 : s;
-	const long long e = (long long)(x - s);
+	const int t = b1 * K.k1 + K.c;
+	const int g = b0 * K.k0 + t;
+	const int g2 = b0 * K.k0 + (t + K.d);
+#if defined(__CUDA_ARCH__)
+	/* the multiply-adds are spelled out: left to itself the compiler turns
+	 * cb * step into a shift and the subtraction into a three-input add, both
+	 * on the ALU pipe */
+	int f, num, v;
+	asm("mad.lo.s32 %0, %1, -255, %2;" : "=r"(f) : "r"(g >> 31), "r"(g2));
+	const int pb = f >> 8;
+	asm("mad.lo.s32 %0, %1, -1, %2;" : "=r"(num) : "r"(pb), "r"(xb + K.half));
+	const int cb = __vimin_s32_relu(num >> K.shift, (1 << BITS) - 1);
+	asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(v) : "r"(cb), "r"(K.step), "r"(pb));
+	const int sb = __vimin_s32_relu(v, 65535);
+#else
+	const int pb = (g2 + ((g >> 31) & 255)) >> 8;
+	int cb = (xb + K.half - pb) >> K.shift;
+	cb = cb < 0 ? 0 : cb;
+	cb = cb > (1 << BITS) - 1 ? (1 << BITS) - 1 : cb;
+	int sb = cb * K.step + pb;
+	sb = sb < 0 ? 0 : sb;
+	sb = sb > 65535 ? 65535 : sb;
+#endif
+	const long long e = (long long)(xb - sb);
 	err += (unsigned long long)(e * e);
-	q1 = q0;
-	q0 = s;
-	return code;
+	b1 = b0;
+	b0 = sb;
+	return cb;
 }
 
 /*
@@ -426,6 +473,18 @@ XA_HD void put_code(uint32_t (&w)[BITS], int i, int code)
 		w[byte >> 2] |= (c >> spill) << (8 * (byte & 3));
 		w[(byte + 1) >> 2] |= ((c << (8 - spill)) & 0xffu) << (8 * ((byte + 1) & 3));
 	}
+}
+
+/* the byte image of 32 codes 2^(BITS-1): XOR it onto a block of biased codes */
+template <int BITS>
+XA_HD void search_code_bias(uint32_t (&w)[BITS])
+{
+#pragma unroll
+	for (int k = 0; k < BITS; k++)
+		w[k] = 0;
+#pragma unroll
+	for (int i = 0; i < 32; i++)
+		put_code<BITS>(w, i, 1 << (BITS - 1));
 }
 
 } /* namespace xa */

@@ -682,23 +682,24 @@ xa_search_kernel(const EncodeParams p)
 	const uint8_t *pcm = p.src + sd.pcm_off;
 	uint8_t *xa = p.dst + sd.xa_off + ch * BS;
 	const uint32_t frames = sd.pcm_len / (2u * CH);
-	int s0 = sd.prev[ch][0], s1 = sd.prev[ch][1];
+	/* decoder state and samples carry +32768 throughout (xa_core.h:search_sample_b) */
+	int s0 = sd.prev[ch][0] + 32768, s1 = sd.prev[ch][1] + 32768;
 
-	int k0[SLOTS], k1[SLOTS], sh[SLOTS];
+	SearchK<BITS> K[SLOTS];
+	uint32_t unbias[BITS];
+	search_code_bias<BITS>(unbias);
 #pragma unroll
 	for (int j = 0; j < SLOTS; j++) {
 		const uint32_t c = lane + 32u * j;
 		const uint32_t f = c < (uint32_t)NC ? c / NR : 0u, r = c < (uint32_t)NC ? c % NR : 0u;
-		k0[j] = gain_k0(f);
-		k1[j] = gain_k1(f);
-		sh[j] = 16 - BITS - (int)r;
+		search_setup<BITS>(K[j], f, 16 - BITS - (int)r);
 	}
 	/* lane i holds sample i of the block; frames past the end are zero
 	 * (src/libbjxa.c:686-690) */
 	auto sample = [&](uint32_t eb) -> int {
 		const uint32_t fr = eb * 32u + lane;
-		return fr < frames ?
-		    *reinterpret_cast<const int16_t *>(pcm + ((uint64_t)fr * CH + ch) * 2u) : 0;
+		return 32768 + (fr < frames ?
+		    *reinterpret_cast<const int16_t *>(pcm + ((uint64_t)fr * CH + ch) * 2u) : 0);
 	};
 	int xn = sample(0);
 	for (uint32_t eb = 0; eb < sd.blocks; eb++) {
@@ -723,7 +724,7 @@ xa_search_kernel(const EncodeParams p)
 #pragma unroll
 			for (int j = 0; j < SLOTS; j++)
 				put_code<BITS>(w[j], i,
-				    search_sample<BITS>(xi, k0[j], k1[j], sh[j], q0[j], q1[j], err[j]));
+				    search_sample_b<BITS>(xi, K[j], q0[j], q1[j], err[j]));
 		}
 		/* this lane's best, then the warp's: smallest (error, candidate) */
 		unsigned long long be = ~0ULL;
@@ -767,7 +768,7 @@ xa_search_kernel(const EncodeParams p)
 		uint32_t mine = 0;
 #pragma unroll
 		for (int k = 0; k < BITS; k++) {
-			const uint32_t wk = __shfl_sync(0xffffffffu, ww[k], wl);
+			const uint32_t wk = __shfl_sync(0xffffffffu, ww[k], wl) ^ unbias[k];
 			if (lane >> 2 == (uint32_t)k)
 				mine = wk;
 		}
@@ -778,8 +779,8 @@ xa_search_kernel(const EncodeParams p)
 			blk[0] = (uint8_t)((bc / NR) << 4 | (bc % NR));
 	}
 	if (lane == 0) {
-		p.results[stream].prev[ch][0] = (int16_t)s0;
-		p.results[stream].prev[ch][1] = (int16_t)s1;
+		p.results[stream].prev[ch][0] = (int16_t)(s0 - 32768);
+		p.results[stream].prev[ch][1] = (int16_t)(s1 - 32768);
 	}
 }
 

@@ -211,24 +211,27 @@ emul_search_stream(const bjxa_stream_desc_t &d, const uint8_t *src, uint8_t *dst
 	const uint32_t ch_n = d.channels, frames = d.pcm_len / (2u * ch_n);
 	const int16_t *pcm = reinterpret_cast<const int16_t *>(src + d.pcm_off);
 	for (uint32_t ch = 0; ch < ch_n; ch++) {
-		int s0 = d.prev[ch][0], s1 = d.prev[ch][1];
+		/* state and samples biased by +32768, codes by 2^(BITS-1), as in the kernel */
+		int s0 = d.prev[ch][0] + 32768, s1 = d.prev[ch][1] + 32768;
+		uint32_t unbias[BITS];
+		search_code_bias<BITS>(unbias);
 		for (uint32_t eb = 0; eb < d.blocks; eb++) {
 			int x[32];
 			for (uint32_t i = 0; i < 32; i++) {
 				uint32_t fr = eb * 32 + i;
-				x[i] = fr < frames ? pcm[(uint64_t)fr * ch_n + ch] : 0;
+				x[i] = 32768 + (fr < frames ? pcm[(uint64_t)fr * ch_n + ch] : 0);
 			}
 			unsigned long long best = ~0ULL;
 			uint32_t bw[BITS] = { 0 };
 			int bq0 = 0, bq1 = 0, bc = 0;
 			for (int c = 0; c < NC; c++) {
-				const unsigned f = (unsigned)(c / NR);
+				SearchK<BITS> K;
+				search_setup<BITS>(K, (unsigned)(c / NR), 16 - BITS - c % NR);
 				int q0 = s0, q1 = s1;
 				unsigned long long err = 0;
 				uint32_t w[BITS] = { 0 };
 				for (int i = 0; i < 32; i++)
-					put_code<BITS>(w, i, search_sample<BITS>(x[i], gain_k0(f),
-					    gain_k1(f), 16 - BITS - c % NR, q0, q1, err));
+					put_code<BITS>(w, i, search_sample_b<BITS>(x[i], K, q0, q1, err));
 				if (err < best) {
 					best = err;
 					bc = c;
@@ -240,12 +243,12 @@ emul_search_stream(const bjxa_stream_desc_t &d, const uint8_t *src, uint8_t *dst
 			uint8_t *blk = dst + d.xa_off + ((uint64_t)eb * ch_n + ch) * BS;
 			blk[0] = (uint8_t)((bc / NR) << 4 | (bc % NR));
 			for (int j = 0; j < 4 * BITS; j++)
-				blk[1 + j] = (uint8_t)(bw[j >> 2] >> (8 * (j & 3)));
+				blk[1 + j] = (uint8_t)((bw[j >> 2] ^ unbias[j >> 2]) >> (8 * (j & 3)));
 			s0 = bq0;
 			s1 = bq1;
 		}
-		prev_out[ch * 2] = (int16_t)s0;
-		prev_out[ch * 2 + 1] = (int16_t)s1;
+		prev_out[ch * 2] = (int16_t)(s0 - 32768);
+		prev_out[ch * 2 + 1] = (int16_t)(s1 - 32768);
 	}
 }
 

@@ -395,12 +395,13 @@ XA_HD constexpr int search_candidates(int bits) { return 5 * (17 - bits); }
  * sample and result carry +32768, the code carries +2^(BITS-1), so that both
  * clamps are one VIMNMX.RELU each; every constant rides in a multiply-add:
  *     g    = b0*k0 + b1*k1 + c                c = -32768*(k0 + k1): the gain, exactly
- *     f    = g + (g < 0 ? 255 : 0) + d        d = 2^23 - (M << 8),  M = 2^(BITS-1) * step
- *     pb   = f >> 8                           = pred + 32768 - M
- *     cb   = relu_min((xb + step/2 - pb) >> shift, 2^BITS - 1)    = code + 2^(BITS-1)
- *     sb   = relu_min(cb*step + pb, 65535)    = s + 32768;   err += (xb - sb)^2
+ *     f    = g + (g < 0 ? 255 : 0) + d        d = 2^23 - ((M + step/2) << 8),  M = 2^(BITS-1) * step
+ *     pb   = f >> 8                           = pred + 32768 - M - step/2
+ *     cb   = relu_min((xb - pb) >> shift, 2^BITS - 1)             = code + 2^(BITS-1)
+ *     sb   = relu_min(cb*step + pb + step/2, 65535) = s + 32768;  err += (xb - sb)^2
  * (adding M to the numerator adds exactly 2^(BITS-1) to the quotient; cb*step + pb
- * = code*step + pred + 32768).  Three shifts and two clamps are all that is left
+ * + step/2 = code*step + pred + 32768; the last add and both bounds are one
+ * VIADDMNMX.RELU).  Three shifts and two clamps are all that is left
  * on the ALU pipe.  The biased codes are packed as they are and un-biased once per
  * block: search_code_bias() is the XOR mask of all 32 top bits.
  */
@@ -418,33 +419,33 @@ XA_HD void search_setup(SearchK<BITS> &K, unsigned f, int shift)
 	K.shift = shift;
 	K.step = 1 << shift;
 	K.half = K.step >> 1;
-	K.d = (1 << 23) - ((K.step << (BITS - 1)) << 8);
+	/* + 32768, - M, - step/2, all times 256: they leave the division as they are */
+	K.d = (1 << 23) - ((K.step << (BITS - 1)) << 8) - (K.half << 8);
 }
 
 template <int BITS>
 XA_HD int search_sample_b(int xb, const SearchK<BITS> &K, int &b0, int &b1,
     unsigned long long &err)
 {
-	const int t = b1 * K.k1 + K.c;
-	const int g = b0 * K.k0 + t;
-	const int g2 = b0 * K.k0 + (t + K.d);
+	const int g = b0 * K.k0 + (b1 * K.k1 + K.c);
+	const int g2 = g + K.d;
 #if defined(__CUDA_ARCH__)
 	/* the multiply-adds are spelled out: left to itself the compiler turns
 	 * cb * step into a shift and the subtraction into a three-input add, both
 	 * on the ALU pipe */
 	int f, num, v;
 	asm("mad.lo.s32 %0, %1, -255, %2;" : "=r"(f) : "r"(g >> 31), "r"(g2));
-	const int pb = f >> 8;
-	asm("mad.lo.s32 %0, %1, -1, %2;" : "=r"(num) : "r"(pb), "r"(xb + K.half));
+	const int pb = f >> 8;				/* pred + 32768 - M - step/2 */
+	asm("mad.lo.s32 %0, %1, -1, %2;" : "=r"(num) : "r"(pb), "r"(xb));
 	const int cb = __vimin_s32_relu(num >> K.shift, (1 << BITS) - 1);
 	asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(v) : "r"(cb), "r"(K.step), "r"(pb));
-	const int sb = __vimin_s32_relu(v, 65535);
+	const int sb = __viaddmin_s32_relu(v, K.half, 65535);
 #else
 	const int pb = (g2 + ((g >> 31) & 255)) >> 8;
-	int cb = (xb + K.half - pb) >> K.shift;
+	int cb = (xb - pb) >> K.shift;
 	cb = cb < 0 ? 0 : cb;
 	cb = cb > (1 << BITS) - 1 ? (1 << BITS) - 1 : cb;
-	int sb = cb * K.step + pb;
+	int sb = cb * K.step + pb + K.half;
 	sb = sb < 0 ? 0 : sb;
 	sb = sb > 65535 ? 65535 : sb;
 #endif

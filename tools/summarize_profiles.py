@@ -115,6 +115,7 @@ def launches(tag):
     except (OSError, ValueError, KeyError):
         pass
     open(os.path.join(PROF, f"launches_{tag}_summary.md"), "w").write("\n".join(L) + "\n")
+    shutil.copyfile(path, os.path.join(PROF, f"launches_{tag}.csv"))     # the raw list as well
 
 
 def full(tag):

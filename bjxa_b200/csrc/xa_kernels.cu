@@ -25,6 +25,7 @@
 
 #include "../../include/bjxa_batch.h"
 #include "xa_plan.h"
+#include "xa_walk.h"
 
 using namespace xa;
 
@@ -116,6 +117,8 @@ constexpr int kDecBlock = kDecThreads + 64;	/* consumers + loader warp + scanner
  *   bit 0  the staged stereo form instead of the direct one (share >= staged)
  *   bit 1  the wide tile list instead of the long-strip one  (share >= wide)
  *   bit 2  (alone) the pooled form over the long-strip list  (pool <= share < wide)
+ *   bit 3  (alone) the split form: direct form without walkers, then the dense
+ *          chain walkers of xa_walk_kernel                    (split <= share < wide)
  * A threshold above 1000 permille switches that choice off.  One CTA, no
  * atomics, nothing to clear; all of a thread's loads in flight together.  Measured crossovers:
  * profiles/history_r1.md.
@@ -128,7 +131,7 @@ constexpr uint32_t staged_permille(int bits) { return bits == 4 ? 300u : bits ==
 constexpr uint32_t kWideManyStreams = 8192;
 constexpr uint32_t kWidePermilleMono[2] = { 985, 930 }, kWidePermilleStereo[2] = { 920, 700 };
 constexpr uint32_t kNever = 1001;
-enum { kFormStaged = 1, kFormWide = 2, kFormPool = 4 };
+enum { kFormStaged = 1, kFormWide = 2, kFormPool = 4, kFormSplit = 8 };
 /* pooled walkers instead of one walker warp per tile: from this share of chain
  * blocks (measured crossovers: profiles/history_r1.md), for classes of at least
  * kPoolMinTiles tiles -- below that the launch is too short to care */
@@ -144,7 +147,7 @@ constexpr uint32_t kPoolMinTiles = 296;
 __global__ void __launch_bounds__(kCensusThreads)
 xa_census_kernel(const uint8_t *src, const StreamDev *streams, const uint32_t *order,
     uint32_t n_streams, uint32_t block_bytes_one, uint32_t ch, uint32_t staged_permille,
-    uint32_t wide_permille, uint32_t pool_permille, uint32_t *choice)
+    uint32_t wide_permille, uint32_t pool_permille, uint32_t split_permille, uint32_t *choice)
 {
 	__shared__ uint32_t warp_sum[kCensusThreads / 32];
 	const uint32_t tid = threadIdx.x;
@@ -180,6 +183,7 @@ xa_census_kernel(const uint8_t *src, const StreamDev *streams, const uint32_t *o
 		const uint32_t permille = total * 1000u / (kCensusThreads * kCensusPerThread);
 		const uint32_t staged = permille >= staged_permille ? kFormStaged : 0u;
 		*choice = permille >= wide_permille ? kFormWide | staged :
+		    permille >= split_permille ? (uint32_t)kFormSplit :
 		    permille >= pool_permille ? (uint32_t)kFormPool : staged;
 	}
 }
@@ -287,7 +291,7 @@ __device__ __forceinline__ void pool_offer(SM &sm, int s, uint32_t gen, uint32_t
  */
 template <class Tile, bool POOL, class SM>
 __device__ __forceinline__ void
-loader_warp(const DecodeParams &p, SM &sm, const uint32_t lane)
+loader_warp(const DecodeParams &p, SM &sm, const uint32_t lane, const bool split = false)
 {
 	typedef typename Tile::G G;
 	constexpr int NS = G::kNS;
@@ -304,7 +308,7 @@ loader_warp(const DecodeParams &p, SM &sm, const uint32_t lane)
 			te = p.tiles[t];
 			if (lane < te.count)
 				make_strip_ctx<G::kBits, G::kCh, G::kTBQ, NS>(c, p,
-				    p.order[te.first + lane], te.j, lane);
+				    p.order[te.first + lane], te.j, lane, split);
 		}
 	};
 	prefetch();
@@ -359,7 +363,7 @@ loader_warp(const DecodeParams &p, SM &sm, const uint32_t lane)
  */
 template <class Tile, bool POOL, class SM>
 __device__ __forceinline__ void
-scanner_warp(const DecodeParams &p, SM &sm, const uint32_t lane)
+scanner_warp(const DecodeParams &p, SM &sm, const uint32_t lane, const bool split = false)
 {
 	typedef typename Tile::G G;
 	constexpr int NS = G::kNS;
@@ -381,7 +385,7 @@ scanner_warp(const DecodeParams &p, SM &sm, const uint32_t lane)
 			t.load_tail(lane, 32, sm.in[s]);
 			__syncwarp();
 		}
-		uint32_t count = 0;
+		uint32_t count = 0, mine = 0;
 		if (NS == 1) {
 			/* one strip: one item (block, or pair of blocks) per lane
 			 * and step; "the item in front is a walker's too" comes out
@@ -389,7 +393,9 @@ scanner_warp(const DecodeParams &p, SM &sm, const uint32_t lane)
 			constexpr int LAG = Tile::kLag;	/* item q follows item q - LAG */
 			const uint32_t nq = Tile::kStaged ? sm.ctx[s][0].nq :
 			    sm.ctx[s][0].nq / G::kCh;
-			uint32_t prev = 0;	/* items -LAG..-1: no chain channels */
+			/* items -LAG..-1: no chain channels -- or, in the split form, the
+			 * ones the loader found in front of the strip */
+			uint32_t prev = split ? (sm.ctx[s][0].flags >> kCtxPrevShift & 3u) : 0u;
 			for (uint32_t base = 0; base < nq; base += 32) {
 				const uint32_t q = base + lane;
 				/* chain channels of item q and of the item in front;
@@ -401,11 +407,40 @@ scanner_warp(const DecodeParams &p, SM &sm, const uint32_t lane)
 				const uint32_t before = lane >= (uint32_t)LAG ? up : old;
 				const bool h = cm != 0 && (cm & before) == 0;
 				const uint32_t mh = __ballot_sync(0xffffffffu, h);
-				if (h)
+				if (split) {
+					/* split form: the heads go out as a bitmap, word
+					 * base / 32 of it in lane base / 32 */
+					if (lane == base / 32u)
+						mine = mh;
+				} else if (h) {
 					sm.heads[s][count + __popc(mh & ((1u << lane) - 1u))] =
 					    (uint16_t)q;
+				}
 				count += __popc(mh);
 				prev = cm;
+			}
+			if (split) {
+				if (count != 0) {
+					/* one record per tile with heads, one 128-byte store
+					 * (xa_walk.h); the counter is preset to ~0 */
+					uint32_t slot = 0;
+					if (lane == 0)
+						slot = atomicAdd(p.live_count, 1u) + 1u;
+					slot = __shfl_sync(0xffffffffu, slot, 0);
+					const StripCtx &c = sm.ctx[s][0];
+					const uint64_t g0 = c.a0 + c.in_base;
+					uint32_t w = mine;
+					if (lane == kRecXaLo) w = (uint32_t)g0;
+					if (lane == kRecXaHi) w = (uint32_t)(g0 >> 32);
+					if (lane == kRecOutLo) w = (uint32_t)c.out0;
+					if (lane == kRecOutHi) w = (uint32_t)(c.out0 >> 32);
+					if (lane == kRecStream) w = c.stream;
+					if (lane == kRecFirstEb) w = c.first_eb;
+					if (lane == kRecBlocks) w = c.blocks;
+					if (lane > kRecBlocks) w = 0;
+					reinterpret_cast<uint32_t *>(&p.live[slot])[lane] = w;
+				}
+				count = 0;	/* the consumers: units only */
 			}
 		} else {
 			const uint32_t nq = t.n_strips * Tile::SCAN;
@@ -441,8 +476,16 @@ xa_decode_kernel(const DecodeParams p)
 	typename Tile::Smem &sm = *reinterpret_cast<typename Tile::Smem *>(smem_raw);
 	const uint32_t tid = threadIdx.x;
 
-	if (p.choice != NULL && *p.choice != p.want)
-		return;		/* the census picked the other tile form */
+	/* split form: this kernel is its first pass -- every chain is left to
+	 * xa_walk_kernel (forced, or because the census says so) */
+	bool split = p.split == 2;
+	if (p.choice != NULL) {
+		const uint32_t chosen = *p.choice;
+		if (p.split == 1 && chosen == kFormSplit)
+			split = true;
+		else if (chosen != p.want)
+			return;		/* the census picked the other tile form */
+	}
 
 	if (tid == 0) {
 		for (int s = 0; s < kStages; s++) {
@@ -456,11 +499,11 @@ xa_decode_kernel(const DecodeParams p)
 	__syncthreads();
 
 	if (tid >= kDecThreads + 32) {
-		loader_warp<Tile, false>(p, sm, tid - (kDecThreads + 32));
+		loader_warp<Tile, false>(p, sm, tid - (kDecThreads + 32), split);
 		return;
 	}
 	if (tid >= kDecThreads) {
-		scanner_warp<Tile, false>(p, sm, tid - kDecThreads);
+		scanner_warp<Tile, false>(p, sm, tid - kDecThreads, split);
 		return;
 	}
 
@@ -617,6 +660,330 @@ xa_decode_pool_kernel(const DecodeParams p)
 		__syncwarp();
 		if ((tid & 31u) == 0)
 			mbar_arrive(smem_u32(&sm.empty[s]));
+	}
+}
+
+/* ---- split form, pass 2: dense chain walkers (xa_walk.h) ---------------------- */
+/*
+ * Every lane walks one chain (stereo: one run) at a time and draws the next head
+ * the moment its chain ends, so all 32 lanes of a warp decode a block in every
+ * turn of the loop whatever the chains' lengths.  A lane reads its chain straight
+ * from the arena: 16-byte cp.async chunks into a private ring in shared memory
+ * (its address bits pick the slot), always one item ahead of the decode.  The
+ * item's PCM goes to a row of shared memory and leaves the warp eight (stereo:
+ * four) rows per store instruction -- a lane storing its own 64 bytes would
+ * touch 32 different lines per instruction, four times (tools/walk_proto.cu has
+ * the measurements behind both choices).
+ *
+ * A warp works through the records of pass 1 (one per tile with heads) at stride
+ * "all warps of the grid"; a record's bitmap is spread into a list of head
+ * indices in shared memory, from which idle lanes take the next in order.
+ */
+template <int BITS, int CH>
+struct WalkCfg {
+	typedef Walk<BITS, CH> W;
+	/* bytes the ring holds, from the current item's first: the item in front of
+	 * the decode and the profile byte(s) behind it */
+	static constexpr int LOOK = 2 * W::STEP + W::PEEK;
+	static constexpr int SPAN = (15 + LOOK + 15) / 16 * 16;
+	static constexpr int RING = SPAN <= 64 ? 64 : SPAN <= 128 ? 128 : 256;
+	static constexpr int SLOT = RING + 16;	/* lane stride: spreads equal offsets over the banks */
+	/* most chunks a lane asks for in one turn: a new chain's first item */
+	static constexpr int KMAX = (15 + W::STEP + W::PEEK + 15) / 16;
+	static constexpr int kThreads = CH == 1 ? 512 : 256;
+	static constexpr int kCtas = 2;			/* per SM */
+	static constexpr int kWarps = kThreads / 32;
+	static constexpr int kListLen = 256;		/* heads per tile at most */
+	static constexpr size_t kSmem = (size_t)kThreads * (SLOT + W::OUT) +
+	    (size_t)kWarps * (kListLen * 2 + 32);
+	static_assert(SPAN <= 256, "ring");
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+
+/* loads whose results must not be asked for before the turn's decode is over: as
+ * PTX, so that the compiler neither re-extends the byte nor moves its first use up */
+__device__ __forceinline__ uint32_t ldg_u8(const uint8_t *p)
+{
+	uint32_t v;
+	asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+	return v;
+}
+__device__ __forceinline__ uint32_t ldg_u32(const uint8_t *p)
+{
+	uint32_t v;
+	asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+	return v;
+}
+
+template <int BITS, int CH>
+__global__ void __launch_bounds__(WalkCfg<BITS, CH>::kThreads, WalkCfg<BITS, CH>::kCtas)
+xa_walk_kernel(const DecodeParams p)
+{
+	typedef Walk<BITS, CH> W;
+	typedef WalkCfg<BITS, CH> C;
+	constexpr int BS = W::BS, STEP = W::STEP, OUT = W::OUT, RING = C::RING;
+	constexpr uint32_t FULL = 0xffffffffu;
+	constexpr uint32_t UPR = W::UNITS;		/* 16-byte units per row of PCM */
+	constexpr uint32_t RPI = 32u / UPR;		/* rows per store instruction */
+
+	if (p.split != 2 && (p.choice == NULL || *p.choice != kFormSplit))
+		return;		/* the census picked a tile form that walks its own chains */
+
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	/* read once, and opaque: the compiler would otherwise recompute them from
+	 * the special register wherever registers are short */
+	uint32_t tid, lane;
+	asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+	asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+	const uint32_t warp = tid >> 5;
+	uint8_t *const ringp = smem_raw + (size_t)tid * C::SLOT;
+	const uint32_t ring = smem_u32(ringp);
+	uint8_t *const rows = smem_raw + (size_t)C::kThreads * C::SLOT + (size_t)warp * 32 * OUT;
+	uint16_t *const list = reinterpret_cast<uint16_t *>(smem_raw +
+	    (size_t)C::kThreads * (C::SLOT + OUT)) + warp * C::kListLen;
+	uint32_t *const ctx = reinterpret_cast<uint32_t *>(smem_raw +
+	    (size_t)C::kThreads * (C::SLOT + OUT) + (size_t)C::kWarps * C::kListLen * 2) + warp * 8;
+	/* this lane's row, and the rows it copies out: both swizzled by row */
+	uint8_t *const row = rows + (size_t)lane * OUT;
+	const uint32_t co_c = lane % UPR, co_r0 = lane / UPR;
+
+	/* records: the counter was preset to ~0 */
+	const uint32_t n_live = *p.live_count + 1u;
+	const uint32_t stride = gridDim.x * C::kWarps;
+	uint32_t next = blockIdx.x * C::kWarps + warp;
+	bool rec_ready = next < n_live;
+	uint32_t nrec = rec_ready ? reinterpret_cast<const uint32_t *>(&p.live[next])[lane] : 0u;
+	uint32_t pos = 0, cnt = 0;		/* the current record's list */
+	/* whole 16-byte chunks of the arena; what lies behind is fetched bytewise */
+	const uint64_t safe = p.src_bytes & ~(uint64_t)15;
+
+	/* this lane's chain */
+	uint64_t a = 0, o = 0;		/* arena addresses of the current item: XA, PCM */
+	uint32_t left = 0;		/* items of the stream behind it */
+	uint32_t stream = 0, m = 0;
+	int fd = 0;			/* ring filled up to a + fd */
+	int p0[CH], p1[CH];
+	bool act = false;
+#pragma unroll
+	for (int c = 0; c < CH; c++)
+		p0[c] = p1[c] = 0;
+
+	for (;;) {
+		/* (1) the chunks asked for in the turn before have landed */
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+
+		/* (2) this turn's item out of the ring; does the chain go on? */
+		typename W::Item it;
+		uint32_t nm = 0;
+		bool more = false;
+		if (act) {
+#pragma unroll
+			for (int c = 0; c < CH; c++) {
+				const uint32_t at = (uint32_t)a + (uint32_t)(c * BS);
+				it.prof[c] = ringp[at & (RING - 1)];
+				const uint32_t pay = at + 1u, w0 = pay & ~3u, sh = (pay & 3u) * 8u;
+				uint32_t prev = *reinterpret_cast<const uint32_t *>(ringp + (w0 & (RING - 1)));
+#pragma unroll
+				for (int i = 0; i < BITS; i++) {
+					const uint32_t nx = *reinterpret_cast<const uint32_t *>(
+					    ringp + ((w0 + 4u * (i + 1)) & (RING - 1)));
+					it.pw[c][i] = __funnelshift_r(prev, nx, sh);
+					prev = nx;
+				}
+			}
+			if (CH == 2 && m == 0)
+				m = W::mask_of(it.prof);	/* a run's first item */
+			if (left != 0) {
+				uint32_t nprof[CH];
+#pragma unroll
+				for (int c = 0; c < CH; c++)
+					nprof[c] = ringp[((uint32_t)a + (uint32_t)(STEP + c * BS)) & (RING - 1)];
+				nm = W::mask_of(nprof);
+				more = CH == 1 ? nm != 0 : (nm & m) != 0;
+			}
+		}
+
+		/* what the decode below needs of the chain, before a draw replaces it */
+		const bool last = act && left == 0;
+		/* bit 0: a whole row to copy out (a stream's last item goes by itself) */
+		const unsigned long long d64 = act ? (unsigned long long)(p.dst + o) | (last ? 0ULL : 1ULL) : 0ULL;
+		const uint32_t cur_stream = stream;
+		if (CH == 2 && act)
+			W::note_bad(p, stream, left, it.prof);
+
+		/* (3) lanes whose chain ends here draw the next head */
+		uint32_t needm = __ballot_sync(FULL, !more);
+		bool got = false, first = false;
+		uint32_t s_prof[CH], s_lo[CH], s_hi[CH];
+#pragma unroll 1
+		for (int round = 0; round < 2 && needm != 0; round++) {
+			if (pos >= cnt) {
+				if (!rec_ready)
+					break;
+				/* the next record: its bitmap becomes a list of head indices */
+				const uint32_t bits = lane < 16u ? nrec : 0u;
+				const uint32_t c1 = __popc(bits);
+				uint32_t incl = c1;
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+					const uint32_t t = __shfl_up_sync(FULL, incl, d);
+					if (lane >= (uint32_t)d)
+						incl += t;
+				}
+				cnt = __shfl_sync(FULL, incl, 31);
+				__syncwarp();		/* the old list and context have been read */
+				uint32_t b = bits, k = incl - c1;
+				while (b) {
+					list[k++] = (uint16_t)(lane * 32u + (uint32_t)__ffs(b) - 1u);
+					b &= b - 1u;
+				}
+				if (lane >= 16u && lane < 24u)
+					ctx[lane - 16u] = nrec;
+				__syncwarp();
+				pos = 0;
+				next += stride;
+				rec_ready = next < n_live;
+				nrec = rec_ready ? reinterpret_cast<const uint32_t *>(&p.live[next])[lane] : 0u;
+			}
+			const uint32_t rank = __popc(needm & ((1u << lane) - 1u));
+			const bool mine = (needm >> lane & 1u) != 0 && rank < cnt - pos;
+			if (mine) {
+				const uint32_t q = list[pos + rank];
+				const uint2 xa0 = *reinterpret_cast<const uint2 *>(ctx);
+				const uint2 out0 = *reinterpret_cast<const uint2 *>(ctx + 2);
+				const uint4 sfb = *reinterpret_cast<const uint4 *>(ctx + 4);
+				const uint32_t eb = sfb.y + q;
+				stream = sfb.x;
+				a = ((uint64_t)xa0.y << 32 | xa0.x) + (uint64_t)(q * (uint32_t)STEP);
+				o = ((uint64_t)out0.y << 32 | out0.x) + (uint64_t)(q * (uint32_t)OUT);
+				left = sfb.z - 1u - eb;
+				first = eb == 0;
+				got = true;
+			}
+			const uint32_t took = __ballot_sync(FULL, mine);
+			pos += __popc(took);
+			needm &= ~took;
+		}
+		if (got) {
+			/* the block(s) in front of the head (Walk::seed_fetch, as PTX loads) */
+			if (first) {
+				const StreamDev &sd = p.streams[stream];
+#pragma unroll
+				for (int c = 0; c < CH; c++) {
+					s_prof[c] = 0;
+					s_lo[c] = (uint32_t)(uint16_t)sd.prev[c][0] |
+					    (uint32_t)(uint16_t)sd.prev[c][1] << 16;
+					s_hi[c] = 0;
+				}
+			} else {
+#pragma unroll
+				for (int c = 0; c < CH; c++) {
+					const uint64_t t = W::tail_addr(a, c);
+					s_prof[c] = ldg_u8(p.src + (a - STEP + (uint64_t)(c * BS)));
+					s_lo[c] = ldg_u32(p.src + (t & ~(uint64_t)3));
+					s_hi[c] = ldg_u32(p.src + (t & ~(uint64_t)3) + ((t & 3u) ? 4u : 0u));
+				}
+			}
+		}
+
+		/* (4) ask for what the next turn reads: a new chain's first item, or the
+		 * item behind the next one; never past the stream's last block */
+		{
+			int want = fd;
+			if (got) {
+				fd = -(int)((uint32_t)a & 15u);
+				want = STEP + W::PEEK;
+			} else if (more) {
+				want = C::LOOK;
+			}
+			const int lim = (int)(left < 3u ? left + 1u : 4u) * STEP;
+			if (want > lim)
+				want = lim;
+			/* whole chunks of the arena only (a < safe: an item is longer than a chunk) */
+			const uint64_t room = safe - a;
+			const int wantc = room < (uint64_t)want ? (int)room : want;
+			const uint8_t *const gp = p.src + a;
+			const uint32_t a32 = (uint32_t)a;
+#pragma unroll
+			for (int k = 0; k < C::KMAX; k++) {
+				if (fd < wantc) {
+					cp_async16(ring + ((a32 + (uint32_t)fd) & (RING - 1)), gp + fd);
+					fd += 16;
+				}
+			}
+			asm volatile("cp.async.commit_group;" ::: "memory");
+			if (__any_sync(FULL, wantc < want)) {
+				/* the arena's last, partial chunk: bytewise */
+				if (wantc < want && fd < want) {
+					for (int b = fd; b < want && a + (uint64_t)b < p.src_bytes; b++)
+						ringp[(a32 + (uint32_t)b) & (RING - 1)] = p.src[a + (uint64_t)b];
+					fd = (want + 15) & ~15;
+				}
+			}
+		}
+
+		/* (5) decode into this lane's row, then the warp's rows leave together */
+		if (act) {
+			auto out = [&](int j, const uint4 &v) {
+				const uint32_t at = CH == 1 ? ((uint32_t)j ^ (lane >> 1 & 3u)) : ((uint32_t)j ^ (lane & 7u));
+				*reinterpret_cast<uint4 *>(row + at * 16u) = v;
+			};
+			W::decode(it, p0, p1, out);
+		}
+		__syncwarp();
+#pragma unroll
+		for (uint32_t r = 0; r < UPR; r++) {
+			const uint32_t sl = r * RPI + co_r0;
+			const unsigned long long rd = __shfl_sync(FULL, d64, sl);
+			if (rd & 1ULL) {
+				const uint32_t at = CH == 1 ? (co_c ^ (sl >> 1 & 3u)) : (co_c ^ (sl & 7u));
+				*reinterpret_cast<uint4 *>(rd - 1ULL + co_c * 16u) =
+				    *reinterpret_cast<const uint4 *>(rows + (size_t)sl * OUT + at * 16u);
+			}
+		}
+		if (__any_sync(FULL, last)) {
+			/* the last item of a stream: its own lane stores what the stream still
+			 * owes (libbjxa.c:622-624,648) and leaves the final state */
+			if (last) {
+				const uint32_t valid = W::last_valid(p.streams[cur_stream]);
+				uint16_t *d = reinterpret_cast<uint16_t *>(d64);
+				for (uint32_t k = 0; k < valid / 2u; k++) {
+					const uint32_t j = k >> 3;
+					const uint32_t at = CH == 1 ? (j ^ (lane >> 1 & 3u)) : (j ^ (lane & 7u));
+					d[k] = *reinterpret_cast<const uint16_t *>(row + at * 16u + (k & 7u) * 2u);
+				}
+				W::put_result(p, cur_stream, p0, p1);
+			}
+		}
+		__syncwarp();
+
+		/* (6) on to the next item, or into the chain just drawn */
+		if (more) {
+			a += STEP;
+			o += OUT;
+			left--;
+			fd -= STEP;
+			m = nm;
+		} else if (got) {
+			typename W::Seed seed;
+#pragma unroll
+			for (int c = 0; c < CH; c++) {
+				seed.prof[c] = s_prof[c];
+				seed.lo[c] = s_lo[c];
+				seed.hi[c] = s_hi[c];
+			}
+			W::seed_apply(seed, first, a, p0, p1);
+			m = 0;
+			act = true;
+		} else {
+			act = false;
+		}
+		if (!__any_sync(FULL, act) && !rec_ready && pos >= cnt)
+			break;
 	}
 }
 
@@ -987,7 +1354,9 @@ stereo_mode(void)
 
 static int pool_mode(void);
 static int pool_candidate(int pool, int ns, uint32_t n_tiles);
-static int decode_class_launches(int ch, int stereo, bool alt, int poolc);
+static int split_mode(void);
+static int split_candidate(int split, int bits, int ch, int stereo, int ns, uint32_t n_tiles);
+static int decode_class_launches(int ch, int stereo, bool alt, int poolc, int splitc);
 
 struct bjxa_plan {
 	uint32_t magic;
@@ -1001,6 +1370,7 @@ struct bjxa_plan {
 	DevBuf<uint32_t> d_order;
 	DevBuf<unsigned long long> d_carry;
 	DevBuf<uint32_t> d_fault;		/* set when a carry never arrived */
+	DevBuf<LiveRec> d_live;			/* split form: pass 1's records, one per tile */
 	uint32_t epoch;
 	/* last run */
 	bool ran;
@@ -1011,6 +1381,7 @@ struct bjxa_plan {
 	int launches;
 	int stereo;			/* stereo_mode() when the plan was built */
 	int pool;			/* pool_mode() likewise */
+	int split;			/* split_mode() likewise */
 	/* a plan with several classes runs them side by side (bjxa_plan_run) */
 	cudaStream_t cls_stream[6];
 	cudaEvent_t ev_start, ev_done[6];
@@ -1055,6 +1426,9 @@ set_attrs_one(void)
 		    (e = set_dec_attr<DecTileStaged<BITS, 2, kDecTBQ, kDecWide, kDecStagedStages> >()) != cudaSuccess)
 			return e;
 	}
+	if ((e = cudaFuncSetAttribute(xa_walk_kernel<BITS, CH>,
+	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WalkCfg<BITS, CH>::kSmem)) != cudaSuccess)
+		return e;
 	return cudaFuncSetAttribute(xa_encode_kernel<BITS, CH>,
 	    cudaFuncAttributeMaxDynamicSharedMemorySize,
 	    (int)sizeof(EncSmem<BITS, CH, kEncTBE>));
@@ -1091,7 +1465,8 @@ plan_upload(bjxa_plan *pl)
 
 	if ((rc = pl->d_streams.reserve(n, false)) ||
 	    (rc = pl->d_results.reserve(n, false)) ||
-	    (rc = pl->d_first_bad.reserve(n + 24, false)) ||	/* + 6 ticket counters, 6 census words */
+	    (rc = pl->d_first_bad.reserve(n + 32, false)) ||	/* + 6 ticket counters, 6 census words, 6 record counters */
+	    (rc = pl->d_live.reserve(hp.kind == kKindDecode && pl->split != 0 ? hp.tile_begin[6] : 0, false)) ||
 	    (rc = pl->d_fault.reserve(4, true)) ||
 	    (rc = pl->d_tiles.reserve(hp.tiles.size(), false)) ||
 	    (rc = pl->d_order.reserve(hp.order.size(), false)) ||
@@ -1140,11 +1515,14 @@ plan_build(bjxa_plan *pl, int kind, const bjxa_stream_desc_t *descs, size_t n)
 	pl->launches = 0;
 	pl->stereo = stereo_mode();
 	pl->pool = pool_mode();
+	pl->split = split_mode();
 	for (int b = 0; b < 6; b++)
-		if (pl->hp.order_begin[b + 1] > pl->hp.order_begin[b])
+		if (pl->hp.order_begin[b + 1] > pl->hp.order_begin[b]) {
+			const uint32_t nt = pl->hp.tile_begin[b + 1] - pl->hp.tile_begin[b];
 			pl->launches += kind == kKindDecode ? decode_class_launches(bucket_ch(b),
-			    pl->stereo, pl->hp.alt_ns[b] != 0, pool_candidate(pl->pool, pl->hp.ns[b],
-			    pl->hp.tile_begin[b + 1] - pl->hp.tile_begin[b])) : 1;
+			    pl->stereo, pl->hp.alt_ns[b] != 0, pool_candidate(pl->pool, pl->hp.ns[b], nt),
+			    split_candidate(pl->split, bucket_bits(b), bucket_ch(b), pl->stereo, pl->hp.ns[b], nt)) : 1;
+		}
 	return (plan_upload(pl));
 }
 
@@ -1206,6 +1584,7 @@ bjxa_plan_free(bjxa_plan_t **planp)
 	pl->d_order.release();
 	pl->d_carry.release();
 	pl->d_fault.release();
+	pl->d_live.release();
 	for (int b = 0; b < 6; b++) {
 		if (pl->cls_stream[b] != NULL)
 			(void)cudaStreamDestroy(pl->cls_stream[b]);
@@ -1311,6 +1690,7 @@ struct DecodeClass {
 	int ns;				/* strips per tile of the primary list */
 	int stereo;			/* 0 direct, 1 staged, 2 census (stereo classes) */
 	int pool;			/* 0 never, 1 always, 2 census */
+	int split;			/* likewise */
 	uint32_t *d_choice;
 	const uint32_t *d_order;	/* the class's streams */
 	uint32_t n_streams;
@@ -1346,14 +1726,86 @@ pool_candidate(int pool, int ns, uint32_t n_tiles)
 	return pool == 1 ? 1 : n_tiles >= kPoolMinTiles ? 2 : 0;
 }
 
+/*
+ * split form (xa_walk.h): 0 = never, 1 = always, 2 = let the census decide
+ * (BJXA_B200_SPLIT=off|on|auto, default auto).
+ */
+static int
+split_mode(void)
+{
+	const char *e = getenv("BJXA_B200_SPLIT");
+	return e == NULL ? 2 : strcmp(e, "on") == 0 ? 1 : strcmp(e, "off") == 0 ? 0 : 2;
+}
+
+/*
+ * From this share of chain blocks (permille) the census sends a class to the
+ * split form.  Measured crossovers at 4096 streams x 30 s (profiles/history_r2.md):
+ * the pair walkers of the stereo direct form keep few chains in flight, so the
+ * dense walkers win early there; the mono direct form holds out up to about two
+ * thirds (4-bit) or throughout (8-bit).
+ */
+constexpr uint32_t split_permille(int bits, int ch)
+{
+	return ch == 2 ? (bits == 4 ? 80u : bits == 6 ? 200u : 350u) :
+	    (bits == 4 ? 650u : bits == 6 ? 900u : 1001u);
+}
+/* below this many tiles a launch is too short for a census to pay */
+constexpr uint32_t kSplitMinTiles = 64;
+
+/* is the split form a candidate for this class (2), or the only one (1)?  It is
+ * built on the direct form over long strips. */
+static int
+split_candidate(int split, int bits, int ch, int stereo, int ns, uint32_t n_tiles)
+{
+	if (ns != 1 || split == 0 || (ch == 2 && stereo == 1))
+		return 0;
+	if (split == 1)
+		return 1;
+	return n_tiles >= kSplitMinTiles && split_permille(bits, ch) <= 1000u ? 2 : 0;
+}
+
 /* how many kernels decode_class() launches */
 static int
-decode_class_launches(int ch, int stereo, bool alt, int poolc)
+decode_class_launches(int ch, int stereo, bool alt, int poolc, int splitc)
 {
 	if (poolc == 1)
 		return 1;
-	const int forms = (ch == 2 && stereo == 2 ? 2 : 1) + (alt ? 1 : 0) + (poolc == 2 ? 1 : 0);
+	if (splitc == 1)
+		return 2;
+	const int forms = (ch == 2 && stereo == 2 ? 2 : 1) + (alt ? 1 : 0) + (poolc == 2 ? 1 : 0) +
+	    (splitc == 2 ? 1 : 0);
 	return forms == 1 ? 1 : forms + 1;
+}
+
+template <int BITS, int CH>
+static cudaError_t
+launch_walk(const DecodeParams &p, cudaStream_t st)
+{
+	typedef WalkCfg<BITS, CH> C;
+	static thread_local int grid_cache[2] = { -1, 0 };
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess)
+		return e;
+	if (grid_cache[0] != dev) {
+		int per_sm = 0, sms = 0;
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm,
+		    xa_walk_kernel<BITS, CH>, C::kThreads, C::kSmem);
+		if (e != cudaSuccess)
+			return e;
+		e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		if (e != cudaSuccess)
+			return e;
+		grid_cache[0] = dev;
+		grid_cache[1] = per_sm * sms > 0 ? per_sm * sms : sms;
+	}
+	/* never more warps than tiles: a warp without a record leaves at once */
+	uint32_t grid = (uint32_t)grid_cache[1];
+	const uint32_t need = (p.n_tiles + C::kWarps - 1) / C::kWarps;
+	if (grid > need)
+		grid = need;
+	xa_walk_kernel<BITS, CH><<<grid, C::kThreads, C::kSmem, st>>>(p);
+	return cudaGetLastError();
 }
 
 template <int BITS, int CH>
@@ -1363,11 +1815,19 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 	const bool alt = c.alt_tiles != NULL;
 	const bool pick_form = CH == 2 && c.stereo == 2;
 	const int poolc = pool_candidate(c.pool, c.ns, c.p.n_tiles);
+	const int splitc = split_candidate(c.split, BITS, CH, c.stereo, c.ns, c.p.n_tiles);
 	DecodeParams p = c.p;
 	cudaError_t e;
 	if (poolc == 1)
 		return launch_pool<typename PoolTile<BITS, CH>::type>(p, st);
-	if (!alt && !pick_form && poolc == 0) {
+	if (splitc == 1) {
+		/* pass 1: the direct form without walkers; pass 2: the walkers */
+		p.split = 2;
+		if ((e = launch_form<BITS, CH, 1>(p, false, st)) != cudaSuccess)
+			return e;
+		return launch_walk<BITS, CH>(p, st);
+	}
+	if (!alt && !pick_form && poolc == 0 && splitc == 0) {
 		const bool staged = CH == 2 && c.stereo == 1;
 		return c.ns == 1 ? launch_form<BITS, CH, 1>(p, staged, st) :
 		    launch_form<BITS, CH, kDecWide>(p, staged, st);
@@ -1375,8 +1835,10 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 	xa_census_kernel<<<1, kCensusThreads, 0, st>>>(p.src, p.streams, c.d_order, c.n_streams,
 	    (uint32_t)block_bytes(BITS), (uint32_t)CH,
 	    pick_form ? staged_permille(BITS) : c.stereo == 1 && CH == 2 ? 0u : kNever,
-	    alt ? (CH == 2 ? kWidePermilleStereo : kWidePermilleMono)[c.n_streams >= kWideManyStreams] :
+	    /* with the split form at hand, wide tiles are for all-chain data only */
+	    alt ? (CH == 2 ? kWidePermilleStereo : kWidePermilleMono)[splitc != 2 && c.n_streams >= kWideManyStreams] :
 	    kNever, poolc == 2 ? (CH == 2 ? kPoolPermilleStereo : kPoolPermilleMono) : kNever,
+	    splitc == 2 ? split_permille(BITS, CH) : kNever,
 	    c.d_choice);
 	if ((e = cudaGetLastError()) != cudaSuccess)
 		return e;
@@ -1388,10 +1850,19 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 		/* with a wide list, chain-heavy stereo data goes to its staged form
 		 * only: "staged, long strips" then means bit 0 without bit 1 */
 		p.want = staged ? kFormStaged : 0u;
+		/* the direct form over long strips doubles as the split form's pass 1 */
+		p.split = !staged && splitc == 2 ? 1u : 0u;
 		e = c.ns == 1 ? launch_form<BITS, CH, 1>(p, staged != 0, st) :
 		    launch_form<BITS, CH, kDecWide>(p, staged != 0, st);
 		if (e != cudaSuccess)
 			return e;
+	}
+	p.split = 0;
+	if (splitc == 2) {
+		p.split = 1;
+		if ((e = launch_walk<BITS, CH>(p, st)) != cudaSuccess)
+			return e;
+		p.split = 0;
 	}
 	if (poolc == 2) {
 		p.want = kFormPool;
@@ -1461,7 +1932,7 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 		 * the six tile-ticket counters that follow them (~0 = no ticket
 		 * drawn yet, see the producer in xa_decode_kernel) */
 		XA_CUDA(cudaMemsetAsync(pl->d_first_bad.p, 0xff,
-		    (n + 24) * sizeof(uint32_t), st));
+		    (n + 32) * sizeof(uint32_t), st));
 	}
 
 	/*
@@ -1540,6 +2011,9 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 			p.epoch = pl->epoch;
 			p.choice = NULL;
 			p.want = 0;
+			p.split = 0;
+			p.live = pl->d_live.p != NULL ? pl->d_live.p + t0 : NULL;
+			p.live_count = pl->d_first_bad.p + ((n + 3) & ~(size_t)3) + 18 + b;
 			DecodeClass c;
 			c.p = p;
 			c.alt_tiles = hp.alt_ns[b] != 0 ? pl->d_tiles.p + hp.alt_begin[b] : NULL;
@@ -1547,6 +2021,7 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 			c.ns = hp.ns[b];
 			c.stereo = pl->stereo;
 			c.pool = pl->pool;
+			c.split = pl->d_live.p != NULL ? pl->split : 0;
 			c.d_choice = pl->d_first_bad.p + ((n + 3) & ~(size_t)3) + 12 + b;
 			c.d_order = pl->d_order.p + hp.order_begin[b];
 			c.n_streams = hp.order_begin[b + 1] - hp.order_begin[b];

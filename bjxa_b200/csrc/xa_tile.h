@@ -50,6 +50,8 @@ struct StreamRes {		/* decode results, device resident */
 	int16_t  prev[2][2];	/* predictor state after the last block */
 };
 
+struct LiveRec;
+
 struct TileEnt {		/* decode: NS strips of consecutive streams in issue order */
 	uint32_t first;		/* index into order[] of the first strip's stream;
 				 * encode: the stream itself */
@@ -77,6 +79,12 @@ struct DecodeParams {
 	 * runs; a kernel whose `want` differs from *choice returns at once */
 	const uint32_t *choice;		/* NULL = run unconditionally */
 	uint32_t want;
+	/* split form (xa_walk.h): pass 1 lists the heads of chains instead of walking
+	 * them.  0 = never, 1 = when the census says so (*choice == kFormSplit),
+	 * 2 = always */
+	uint32_t split;
+	struct LiveRec *live;		/* one record per tile that has heads */
+	uint32_t *live_count;		/* records written so far (pass 1), preset to 0 */
 };
 
 struct EncodeParams {
@@ -171,9 +179,14 @@ struct StripCtx {
 	uint32_t out_valid;	/* PCM bytes the strip owes */
 	uint32_t slot;		/* carry mailbox index */
 	uint32_t flags;
-	uint32_t pad;
+	uint32_t blocks;	/* effective blocks of the whole stream */
 };
-enum { kCtxFirst = 1u, kCtxLast = 2u, kCtxTail = 4u, kCtxEnd = 0x80000000u };
+enum {
+	kCtxFirst = 1u, kCtxLast = 2u, kCtxTail = 4u,
+	/* split form: the block of channel 0 / 1 in front of the strip is a chain block */
+	kCtxPrevShift = 3, kCtxPrev0 = 8u, kCtxPrev1 = 16u,
+	kCtxEnd = 0x80000000u
+};
 
 template <int BITS, int CH, int TBQ, int NS>
 struct DecGeom {
@@ -192,7 +205,7 @@ struct DecGeom {
 
 template <int BITS, int CH, int TBQ, int NS>
 XA_HD void make_strip_ctx(StripCtx &c, const DecodeParams &p, uint32_t stream,
-    uint32_t j, uint32_t strip)
+    uint32_t j, uint32_t strip, bool want_prev = false)
 {
 	typedef DecGeom<BITS, CH, TBQ, NS> G;
 	const StreamDev &s = p.streams[stream];
@@ -222,7 +235,15 @@ XA_HD void make_strip_ctx(StripCtx &c, const DecodeParams &p, uint32_t stream,
 	c.flags = (c.first_eb == 0 ? kCtxFirst : 0u) |
 	    (c.first_eb + neb == blocks ? kCtxLast : 0u) |
 	    (c.in_need > c.bulk ? kCtxTail : 0u);
-	c.pad = 0;
+	c.blocks = blocks;
+	if (want_prev && c.first_eb != 0) {
+		/* split form: which channels' chains run into this strip (their heads
+		 * lie in a strip in front; xa_walk.h follows them to their ends) */
+#pragma unroll
+		for (int ch = 0; ch < CH; ch++)
+			if (block_kind(p.src[g0 - (uint64_t)((CH - ch) * G::BS)]) == kChain)
+				c.flags |= kCtxPrev0 << ch;
+	}
 }
 
 /* draw the next index from a shared-memory counter */

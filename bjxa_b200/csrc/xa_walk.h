@@ -1,0 +1,302 @@
+/*
+ * xa_walk.h -- the second pass of the SPLIT decode form: dense chain walkers.
+ *
+ * The tile forms of xa_tile.h walk a tile's chains (runs of filter-1..4 blocks,
+ * /root/reference/src/libbjxa.c:556-575) while the tile sits in shared memory,
+ * so a tile's longest chain decides how long its bytes stay there, and only a
+ * few hundred chains are in flight per SM.  On chain-rich data that is the
+ * bound (profiles/history_r1.md, steps 15-18).  The split form takes the
+ * chains out of the tiles:
+ *
+ *   pass 1  xa_decode_kernel (direct form, `split` set): units of cut blocks as
+ *           before; the scanner does not queue the heads of chains for the
+ *           tile's walker warp but writes them out -- one 128-byte LiveRec per
+ *           tile that has any: a bitmap of its heads and what a walker needs to
+ *           know of the strip;
+ *   pass 2  xa_walk_kernel: every LANE of every warp walks one chain (stereo:
+ *           one run of effective blocks, both channels side by side) at a
+ *           time, straight from global memory through a private shared-memory
+ *           window, and draws the next head as soon as its chain ends.  A
+ *           chain is followed across tile boundaries to its end, so there are
+ *           no carries and no ordering between tiles; the state at a head is
+ *           recomputed from the bytes of the cut block in front of it.
+ *
+ * This header holds what both passes and the CPU single-stepper of the tests
+ * (tests/emul) share: the record and the per-item arithmetic.  The GPU-only
+ * part (window ring, staged copy-out, the warp's draw) is in xa_kernels.cu.
+ */
+#ifndef XA_WALK_H
+#define XA_WALK_H
+
+#include "xa_tile.h"
+
+namespace xa {
+
+/* one tile with at least one head; written by pass 1's scanner warp, 32 lanes x 4 bytes */
+struct LiveRec {
+	uint32_t heads[16];	/* bit q: item q of the tile starts a chain (mono: block q;
+				 * stereo: effective block q, the first of a run) */
+	uint32_t xa_lo, xa_hi;	/* arena address of the tile's first block */
+	uint32_t out_lo, out_hi;	/* arena address of its PCM */
+	uint32_t stream;
+	uint32_t first_eb;	/* the tile's first effective block */
+	uint32_t blocks;	/* effective blocks of the stream */
+	uint32_t pad[9];
+};
+static_assert(sizeof(LiveRec) == 128, "one record = one 128-byte line");
+enum { kRecXaLo = 16, kRecXaHi, kRecOutLo, kRecOutHi, kRecStream, kRecFirstEb, kRecBlocks };
+
+/*
+ * The arithmetic of one walker.  An ITEM is one effective block: CH blocks of
+ * BS bytes, contiguous in the XA arena, 64 * CH bytes of interleaved PCM.
+ */
+template <int BITS, int CH>
+struct Walk {
+	static constexpr int BS = block_bytes(BITS);
+	static constexpr int STEP = CH * BS;		/* XA bytes per item */
+	static constexpr int OUT = 64 * CH;		/* PCM bytes per item */
+	static constexpr int QB = BITS / 2;		/* payload bytes of 4 samples */
+	static constexpr int UNITS = 4 * CH;		/* 16-byte units of output per item */
+	/* what a walker looks at beyond its item: the profile byte(s) of the next */
+	static constexpr int PEEK = (CH - 1) * BS + 1;
+
+	struct Item {
+		uint32_t prof[CH];
+		uint32_t pw[CH][BITS];
+	};
+
+	/* chain channels of an item: bit 0 left / mono, bit 1 right */
+	XA_HD static uint32_t mask_of(const uint32_t (&prof)[CH])
+	{
+		uint32_t m = 0;
+#pragma unroll
+		for (int c = 0; c < CH; c++)
+			m |= (uint32_t)(block_kind(prof[c]) == kChain) << c;
+		return m;
+	}
+
+	/*
+	 * The item in front of a head, as far as the walker needs it: per channel the
+	 * profile byte and its last quad of codes -- fetched as the two aligned words
+	 * around the block's last four bytes and put together in seed_apply, so that
+	 * on the GPU nothing waits for these loads before the turn's decode is over.
+	 * `first`: there is no such item, the state comes with the stream
+	 * (libbjxa.c:417-420).
+	 */
+	struct Seed {
+		uint32_t prof[CH];
+		uint32_t lo[CH], hi[CH];
+	};
+
+	/* arena address of the last four bytes of channel c's block of the item in front of a */
+	XA_HD static uint64_t tail_addr(uint64_t a, int c)
+	{
+		return a - STEP + (uint64_t)(c * BS + BS - 4);
+	}
+
+	XA_HD static uint32_t word_at(const uint8_t *src, uint64_t aligned)
+	{
+#if defined(__CUDA_ARCH__)
+		return *reinterpret_cast<const uint32_t *>(src + aligned);
+#else
+		const uint8_t *b = src + aligned;
+		return (uint32_t)b[0] | (uint32_t)b[1] << 8 | (uint32_t)b[2] << 16 | (uint32_t)b[3] << 24;
+#endif
+	}
+
+	XA_HD static void seed_fetch(const DecodeParams &p, uint32_t stream, bool first,
+	    uint64_t a, Seed &s)
+	{
+		if (first) {
+			const StreamDev &sd = p.streams[stream];
+#pragma unroll
+			for (int c = 0; c < CH; c++) {
+				s.prof[c] = 0;
+				s.lo[c] = (uint32_t)(uint16_t)sd.prev[c][0] |
+				    (uint32_t)(uint16_t)sd.prev[c][1] << 16;
+				s.hi[c] = 0;
+			}
+			return;
+		}
+#pragma unroll
+		for (int c = 0; c < CH; c++) {
+			const uint64_t t = tail_addr(a, c);
+			s.prof[c] = p.src[a - STEP + (uint64_t)(c * BS)];
+			s.lo[c] = word_at(p.src, t & ~(uint64_t)3);
+			/* the word behind holds bytes of the head item itself, or is not
+			 * needed (t aligned): never past the arena */
+			s.hi[c] = (t & 3u) ? word_at(p.src, (t & ~(uint64_t)3) + 4u) : 0u;
+		}
+	}
+
+	/* the state at the head, into p0/p1 */
+	XA_HD static void seed_apply(const Seed &s, bool first, uint64_t a,
+	    int (&p0)[CH], int (&p1)[CH])
+	{
+		if (first) {
+#pragma unroll
+			for (int c = 0; c < CH; c++) {
+				p0[c] = (int16_t)(uint16_t)s.lo[c];
+				p1[c] = (int16_t)(uint16_t)(s.lo[c] >> 16);
+			}
+			return;
+		}
+#pragma unroll
+		for (int c = 0; c < CH; c++) {
+			/* a cut (or invalid, decoded as cut) block: its last two samples
+			 * are codes 2 and 3 of its last quad, shifted by its range */
+			const uint32_t tail = funnel_r(s.lo[c], s.hi[c], (uint32_t)(tail_addr(a, c) & 3u) * 8u);
+			const int sh = 16 + (int)(s.prof[c] & 15u);
+			int x[4];
+			quad_codes<BITS>(tail >> (8 * (4 - QB)), x);
+			p1[c] = x[2] >> sh;
+			p0[c] = x[3] >> sh;
+		}
+	}
+
+	/*
+	 * One item.  Mono: the walkers' biased predictor step.  Stereo: both channels
+	 * side by side, two independent dependency chains; a cut or invalid block
+	 * inside a run simply has k0 = k1 = 0.  Units go out through out(j, v),
+	 * j = 0 .. UNITS-1 in PCM order.
+	 */
+	template <class Out>
+	XA_HD static void decode(const Item &it, int (&p0)[CH], int (&p1)[CH], Out &out)
+	{
+		if (CH == 1) {
+			uint32_t o[16];
+			decode_block_chain<BITS>(o, it.pw[0], it.prof[0], p0[0], p1[0]);
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				uint4 v;
+				v.x = o[4 * j]; v.y = o[4 * j + 1];
+				v.z = o[4 * j + 2]; v.w = o[4 * j + 3];
+				out(j, v);
+			}
+		} else {
+			const uint32_t pl = it.prof[0], pr = it.prof[CH - 1];
+			const int shl = 16 + (int)(pl & 15u), shr = 16 + (int)(pr & 15u);
+			const int k0l = gain_k0(pl >> 4), k1l = gain_k1(pl >> 4);
+			const int k0r = gain_k0(pr >> 4), k1r = gain_k1(pr >> 4);
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				int l[4], r[4];
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					l[k] = sample_chain(top_code<BITS>(it.pw[0], 4 * j + k), shl,
+					    k0l, k1l, p0[0], p1[0]);
+					r[k] = sample_chain(top_code<BITS>(it.pw[CH - 1], 4 * j + k), shr,
+					    k0r, k1r, p0[CH - 1], p1[CH - 1]);
+				}
+				uint4 v;
+				v.x = pack2(l[0], r[0]);
+				v.y = pack2(l[1], r[1]);
+				v.z = pack2(l[2], r[2]);
+				v.w = pack2(l[3], r[3]);
+				out(j, v);
+			}
+		}
+	}
+
+	/* PCM bytes the stream's LAST item owes (libbjxa.c:622-624,648) */
+	XA_HD static uint32_t last_valid(const StreamDev &sd)
+	{
+		const uint64_t before = (uint64_t)(sd.blocks - 1u) * OUT;
+		const uint64_t owed = sd.pcm_len > before ? sd.pcm_len - before : 0;
+		return (uint32_t)(owed < (uint64_t)OUT ? owed : (uint64_t)OUT);
+	}
+
+	/* invalid filters met inside a stereo run are recorded like the units' */
+	XA_HD static void note_bad(const DecodeParams &p, uint32_t stream, uint32_t left,
+	    const uint32_t (&prof)[CH])
+	{
+#pragma unroll
+		for (int c = 0; c < CH; c++)
+			if (prof[c] >> 4 >= 5u) {
+				const uint32_t eb = p.streams[stream].blocks - 1u - left;
+				global_min_u32(&p.first_bad[stream], eb * CH + c);
+			}
+	}
+
+	XA_HD static void put_result(const DecodeParams &p, uint32_t stream,
+	    const int (&p0)[CH], const int (&p1)[CH])
+	{
+#pragma unroll
+		for (int c = 0; c < CH; c++) {
+			p.results[stream].prev[c][0] = (int16_t)p0[c];
+			p.results[stream].prev[c][1] = (int16_t)p1[c];
+		}
+	}
+};
+
+/*
+ * The whole of pass 2 for one record, one chain after the other, reading the
+ * arena directly: the reference semantics of xa_walk_kernel, used by the CPU
+ * single-stepper of the tests.  (The kernel runs the same Walk<> arithmetic
+ * with 32 chains per warp in flight.)
+ */
+template <int BITS, int CH>
+XA_HD void walk_record_serial(const DecodeParams &p, const LiveRec &r)
+{
+	typedef Walk<BITS, CH> W;
+	const uint64_t xa0 = (uint64_t)r.xa_hi << 32 | r.xa_lo;
+	const uint64_t out0 = (uint64_t)r.out_hi << 32 | r.out_lo;
+	for (uint32_t q = 0; q < 512; q++) {
+		if (!(r.heads[q >> 5] >> (q & 31u) & 1u))
+			continue;
+		uint64_t a = xa0 + (uint64_t)q * W::STEP, o = out0 + (uint64_t)q * W::OUT;
+		uint32_t left = r.blocks - 1u - (r.first_eb + q);
+		const bool first = r.first_eb + q == 0;
+		typename W::Seed seed;
+		int p0[CH], p1[CH];
+		W::seed_fetch(p, r.stream, first, a, seed);
+		W::seed_apply(seed, first, a, p0, p1);
+		uint32_t m = 0;
+		for (bool fresh = true;; fresh = false) {
+			typename W::Item it;
+#pragma unroll
+			for (int c = 0; c < CH; c++) {
+				const uint8_t *b = p.src + a + c * W::BS;
+				it.prof[c] = b[0];
+#pragma unroll
+				for (int i = 0; i < BITS; i++)
+					it.pw[c][i] = (uint32_t)b[1 + 4 * i] | (uint32_t)b[2 + 4 * i] << 8 |
+					    (uint32_t)b[3 + 4 * i] << 16 | (uint32_t)b[4 + 4 * i] << 24;
+			}
+			if (fresh)
+				m = W::mask_of(it.prof);
+			const uint32_t valid = left != 0 ? (uint32_t)W::OUT : W::last_valid(p.streams[r.stream]);
+			uint8_t *dst = p.dst + o;
+			auto out = [&](int j, const uint4 &v) {
+				const uint32_t boff = (uint32_t)j * 16u;
+				const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+				for (uint32_t k = 0; k < 8u && boff + 2u * k + 2u <= valid; k++) {
+					const uint16_t h = (uint16_t)(w[k >> 1] >> (16u * (k & 1u)));
+					dst[boff + 2u * k] = (uint8_t)h;
+					dst[boff + 2u * k + 1u] = (uint8_t)(h >> 8);
+				}
+			};
+			if (CH == 2)
+				W::note_bad(p, r.stream, left, it.prof);
+			W::decode(it, p0, p1, out);
+			if (left == 0) {
+				W::put_result(p, r.stream, p0, p1);
+				break;
+			}
+			uint32_t nprof[CH];
+#pragma unroll
+			for (int c = 0; c < CH; c++)
+				nprof[c] = p.src[a + W::STEP + c * W::BS];
+			const uint32_t nm = W::mask_of(nprof);
+			if ((nm & m) == 0)
+				break;
+			m = nm;
+			a += W::STEP;
+			o += W::OUT;
+			left--;
+		}
+	}
+}
+
+} /* namespace xa */
+#endif

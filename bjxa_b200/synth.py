@@ -16,6 +16,8 @@ Profile-byte mixes ("Config 2"):
   P3  adversarial: filter uniform 1..4 (no state-independent block anywhere),
       range uniform 0..15
   PX  any byte value at all, including invalid filters >= 5 (error paths)
+  Cnn every block independently a chain block (filter 1..4) with probability
+      nn %, range uniform 0..15 (finds where one decode form overtakes another)
 """
 from __future__ import annotations
 
@@ -98,6 +100,12 @@ def profile_bytes(mix: str, seed: int, key: int, n: int) -> np.ndarray:
         rng = (v * 16) >> 24
     elif mix == "PX":
         return (u & 0xFF).astype(np.uint8)
+    elif mix.startswith("C"):
+        # "Cnn": every block independently a chain block (filter 1..4) with
+        # probability nn %, ranges uniform 0..15
+        w = rand_unit(seed, key * 4 + 3, n)
+        filt = np.where(u * 100 < int(mix[1:]) * one, 1 + ((w * 4) >> 24), 0)
+        rng = (v * 16) >> 24
     else:
         raise ValueError(f"unknown profile mix {mix!r}")
     return ((filt << 4) | rng).astype(np.uint8)

@@ -16,12 +16,14 @@
 
 #include "../../include/bjxa_batch.h"
 #include "../../bjxa_b200/csrc/xa_plan.h"
+#include "../../bjxa_b200/csrc/xa_walk.h"
 
 using namespace xa;
 
 static int g_use_alt = 0;
 static int g_stereo_direct = 0;
 static int g_pool = 0;
+static int g_split = 0;
 
 /* thread visiting order inside a phase: 0 ascending, 1 descending, 2 strided */
 static uint32_t
@@ -41,6 +43,7 @@ emul_decode_ns(const DecodeParams &p, int order)
 	typedef typename Tile::G G;
 	typename Tile::Smem *sm = new typename Tile::Smem();
 	const uint32_t nt = kDecThreads;
+	std::vector<LiveRec> live;
 
 	memset(sm, 0xa5, sizeof *sm);	/* smem is garbage at CTA start */
 	for (uint32_t ticket = 0; ticket < p.n_tiles; ticket++) {
@@ -52,7 +55,7 @@ emul_decode_ns(const DecodeParams &p, int order)
 		for (uint32_t lane = 0; lane < te.count; lane++) {
 			StripCtx &c = sm->ctx[s][lane];
 			make_strip_ctx<G::kBits, G::kCh, G::kTBQ, G::kNS>(c, p,
-			    p.order[te.first + lane], te.j, lane);
+			    p.order[te.first + lane], te.j, lane, g_split != 0);
 			memcpy(sm->in[s] + lane * Tile::G::SLOT, p.src + c.a0, c.bulk);
 			tail |= (c.flags & kCtxTail) != 0;
 		}
@@ -65,10 +68,39 @@ emul_decode_ns(const DecodeParams &p, int order)
 				t.load_tail(i, 32, sm->in[s]);
 		uint32_t count = 0;
 		for (uint32_t q = 0; q < te.count * Tile::SCAN; q++)
-			if (t.is_head(q))
+			if (t.is_head(q)) {
+				/* split form: item 0 is no head if it goes on with a chain of
+				 * the strip in front (scanner_warp: `prev` from the context) */
+				if (g_split && G::kNS == 1 && q == 0 &&
+				    (t.chain_mask(0) & (sm->ctx[s][0].flags >> kCtxPrevShift & 3u)) != 0)
+					continue;
 				sm->heads[s][count++] = (uint16_t)q;
+			}
 		sm->n_heads[s] = count;
 		sm->next_head[s] = 32;
+		if (g_split && G::kNS == 1) {
+			/* split form, pass 1 (scanner_warp with `split`): the heads go out
+			 * as one record per tile, the consumers decode units only */
+			if (count != 0) {
+				LiveRec r;
+				memset(&r, 0, sizeof r);
+				for (uint32_t i = 0; i < count; i++)
+					r.heads[sm->heads[s][i] >> 5] |= 1u << (sm->heads[s][i] & 31u);
+				const StripCtx &c = sm->ctx[s][0];
+				const uint64_t g0 = c.a0 + c.in_base;
+				r.xa_lo = (uint32_t)g0;
+				r.xa_hi = (uint32_t)(g0 >> 32);
+				r.out_lo = (uint32_t)c.out0;
+				r.out_hi = (uint32_t)(c.out0 >> 32);
+				r.stream = c.stream;
+				r.first_eb = c.first_eb;
+				r.blocks = c.blocks;
+				live.push_back(r);
+			}
+			for (uint32_t i = 0; i < nt; i++)
+				t.phase_units(visit(i, nt, order), nt);
+			continue;
+		}
 		if (g_pool) {
 			/* pooled form (xa_decode_pool_kernel): 32 walker lanes, each
 			 * drawing a chain when idle and decoding ONE block per turn; the
@@ -105,6 +137,10 @@ emul_decode_ns(const DecodeParams &p, int order)
 		for (uint32_t i = 0; i < ut; i++)
 			t.phase_units(visit(i, ut, order), ut);
 	}
+	/* split form, pass 2 (xa_walk_kernel): the records in any order, a chain at a time */
+	for (size_t i = 0; i < live.size(); i++)
+		walk_record_serial<G::kBits, G::kCh>(p, live[visit((uint32_t)i, (uint32_t)live.size(),
+		    order == 2 ? 1 : order)]);
 	delete sm;
 }
 
@@ -156,7 +192,7 @@ emul_decode_bucket(const DecodeParams &p, int ns, int order)
 {
 	/* same choice as launch_decode_ns: mono direct; stereo staged, or direct
 	 * when g_stereo_direct is set (the tests run both) */
-	if (CH == 2 && !g_stereo_direct) {
+	if (CH == 2 && !g_stereo_direct && !(g_split && ns == 1)) {
 		if (ns == 1)
 			emul_decode_staged_ns<BITS, CH, 1>(p, order);
 		else
@@ -405,6 +441,7 @@ xa_emul_plan(int kind, const bjxa_stream_desc_t *descs, size_t n, int force_stri
 void xa_emul_stereo_direct(int on) { g_stereo_direct = on; }
 void xa_emul_use_alt(int on) { g_use_alt = on; }
 void xa_emul_pool(int on) { g_pool = on; }
+void xa_emul_split(int on) { g_split = on; }
 int xa_emul_strip_blocks(int ns, int ch) { return (int)strip_blocks(ns, ch); }
 int xa_emul_wide(void) { return kDecWide; }
 int xa_emul_enc_tile_blocks(void) { return kEncTBE; }

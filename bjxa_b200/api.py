@@ -65,6 +65,8 @@ BATCH_SYMBOLS = {
     "bjxa_plan_run": (C.c_int, [_VP, _VP, _SZ, _VP, _SZ, _VP]),
     "bjxa_plan_fetch": (C.c_int, [_VP, _VP, _SZ]),
     "bjxa_plan_launches": (C.c_int, [_VP]),
+    "bjxa_plan_checksum": (C.c_int, [_VP, _VP, _SZ]),
+    "bjxa_thread_release": (None, []),
     "bjxa_plan_extent": (C.c_int, [_VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "bjxa_plan_free": (C.c_int, [C.POINTER(_VP)]),
     "bjxa_decoder_describe": (C.c_int, [_VP, C.POINTER(StreamDesc)]),
@@ -162,6 +164,13 @@ class Bjxa(BjxaLib):
 
     def plan_launches(self, plan: int) -> int:
         return self._bjxa_plan_launches(plan)
+
+    def plan_checksum(self, plan: int, n: int) -> np.ndarray:
+        """Per-stream checksums of the last run's output, computed on the device
+        (bjxa_plan_checksum); synth.stream_checksum is the same sum in numpy."""
+        sums = np.zeros(n, dtype=np.uint64)
+        self._check(self._bjxa_plan_checksum(plan, sums.ctypes.data, n), "bjxa_plan_checksum")
+        return sums
 
     def plan_extent(self, plan: int):
         a, b = C.c_uint64(0), C.c_uint64(0)

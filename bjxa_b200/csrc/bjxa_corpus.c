@@ -22,6 +22,7 @@
 
 #include "../../include/bjxa.h"
 #include "../../include/bjxa_batch.h"
+#include "bjxa_internal.h"
 
 #define DEPTH		3			/* chunks in flight */
 #define CHUNK_IN	((uint64_t)48 << 20)	/* input bytes per chunk, about */
@@ -223,6 +224,7 @@ grow_dev(void **p, size_t *cap, size_t need)
  * them back.
  */
 static __thread struct slot tls_ring[DEPTH];
+static __thread int tls_ring_dev;	/* the device they live on, + 1; 0 = nothing yet */
 
 static void
 slot_release(struct slot *s)
@@ -241,6 +243,35 @@ slot_release(struct slot *s)
 	if (s->stream != NULL)
 		(void)bjxa_gpu_stream_destroy(s->stream);
 	memset(s, 0, sizeof *s);
+}
+
+/* the calling thread's pipeline, on whichever device it was built for */
+void
+bjxa_corpus_release(void)
+{
+	int i, cur;
+
+	if (tls_ring_dev == 0)
+		return;
+	cur = bjxa_gpu_current();
+	if (cur >= 0 && cur != tls_ring_dev - 1)
+		(void)bjxa_gpu_select(tls_ring_dev - 1);
+	for (i = 0; i < DEPTH; i++)
+		slot_release(&tls_ring[i]);
+	if (cur >= 0 && cur != tls_ring_dev - 1)
+		(void)bjxa_gpu_select(cur);
+	tls_ring_dev = 0;
+}
+
+/* what bjxa_plan_create would refuse (xa_plan.h:build_plan): such a file gets
+ * its own error instead of failing the whole call */
+static int
+desc_ok(const bjxa_stream_desc_t *d)
+{
+	return ((d->bits == 4 || d->bits == 6 || d->bits == 8) &&
+	    (d->channels == 1 || d->channels == 2) && d->blocks != 0 &&
+	    d->pcm_len % (2u * d->channels) == 0 &&
+	    (uint64_t)d->pcm_len <= (uint64_t)d->blocks * 64u * d->channels);
 }
 
 /* the chunk's results: per-file status, then its range of the output arena */
@@ -300,6 +331,16 @@ bjxa_corpus_run(int kind, const void *in_arena, size_t in_bytes, void *out_arena
 	if (bjxa_gpu_count() <= 0) {
 		errno = ENODEV;		/* no CPU path */
 		return (-1);
+	}
+	if ((d = bjxa_gpu_current()) < 0) {
+		errno = ENODEV;
+		return (-1);
+	}
+	if (tls_ring_dev != d + 1) {
+		/* first call of the thread, or the thread has moved to another device */
+		bjxa_corpus_release();
+		tls_ring_dev = d + 1;
+		bjxa_thread_cache_used();
 	}
 	for (i = 0; i < DEPTH; i++)
 		ring[i].busy = 0;
@@ -369,6 +410,8 @@ bjxa_corpus_run(int kind, const void *in_arena, size_t in_bytes, void *out_arena
 
 			parse_one(kind, dec, enc, (const uint8_t *)in_arena + f->in_off,
 			    f->in_len, f->bits, &p);
+			if (p.error == 0 && !desc_ok(&p.d))
+				p.error = EINVAL;	/* a header the block loop cannot serve */
 			f->error = p.error;
 			f->out_off = f->out_len = 0;
 			f->blocks = 0;

@@ -15,6 +15,7 @@
 #define _POSIX_C_SOURCE 200809L
 
 #include <errno.h>
+#include <pthread.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -22,6 +23,7 @@
 
 #include "../../include/bjxa.h"
 #include "../../include/bjxa_batch.h"
+#include "bjxa_internal.h"
 
 #define XA_SAMPLES_PER_BLOCK	32u
 
@@ -198,6 +200,11 @@ bjxa_parse_header(bjxa_decoder_t *dec, const void *src, size_t len)
 		FAIL(EPROTO);
 
 	decoder_geometry(&t, &t.left);
+	/* a stereo file with an odd number of blocks: the reference stops on it
+	 * (assert in bjxa_decode_format, libbjxa.c:596, reached from :449); a
+	 * library that serves batches reports the malformed header instead */
+	if (t.left.blocks * t.left.block_size_xa != t.xa_bytes)
+		FAIL(EPROTO);
 	*dec = t;		/* all or nothing (libbjxa.c:409,451) */
 	return (BJXA_HEADER_SIZE_XA);
 }
@@ -603,14 +610,84 @@ bjxa_encoder_commit(bjxa_encoder_t *enc, const bjxa_stream_desc_t *d)
 #define PIPE_DEPTH	3
 #define CHUNK_BYTES	((uint64_t)96 << 20)	/* PCM bytes per chunk, about */
 
+/*
+ * What a thread keeps from one host-buffer call to the next: per pipeline slot a
+ * plan, a CUDA stream and two device arenas of chunk size (so device memory goes
+ * with the pipeline's depth, not with the size of the batch).  All of it lives
+ * on ONE device: a thread that has since selected another one (bjxa_gpu_select)
+ * gets a fresh cache there.  Released by bjxa_thread_release(), and by itself
+ * when the thread exits.
+ */
 struct stage {
+	int		 device;	/* + 1, so that zero-initialised = nothing yet */
 	bjxa_plan_t	*plan[PIPE_DEPTH];
 	void		*stream[PIPE_DEPTH];
-	void		*d_xa, *d_pcm;
-	size_t		 cap_xa, cap_pcm;
+	void		*d_xa[PIPE_DEPTH], *d_pcm[PIPE_DEPTH];
+	size_t		 cap_xa[PIPE_DEPTH], cap_pcm[PIPE_DEPTH];
 };
 
 static __thread struct stage tls_stage;
+
+static void
+stage_release(struct stage *sg)
+{
+	int k, cur;
+
+	if (sg->device == 0)
+		return;
+	cur = bjxa_gpu_current();
+	if (cur >= 0 && cur != sg->device - 1)
+		(void)bjxa_gpu_select(sg->device - 1);
+	for (k = 0; k < PIPE_DEPTH; k++) {
+		if (sg->plan[k] != NULL)
+			(void)bjxa_plan_free(&sg->plan[k]);
+		if (sg->stream[k] != NULL)
+			(void)bjxa_gpu_stream_destroy(sg->stream[k]);
+		if (sg->d_xa[k] != NULL)
+			(void)bjxa_gpu_free(sg->d_xa[k]);
+		if (sg->d_pcm[k] != NULL)
+			(void)bjxa_gpu_free(sg->d_pcm[k]);
+	}
+	if (cur >= 0 && cur != sg->device - 1)
+		(void)bjxa_gpu_select(cur);
+	memset(sg, 0, sizeof *sg);
+}
+
+/* thread exit: give the caches back */
+static pthread_key_t cache_key;
+static pthread_once_t cache_once = PTHREAD_ONCE_INIT;
+
+static void
+cache_at_exit(void *unused)
+{
+	(void)unused;
+	bjxa_thread_release();
+}
+
+static void
+cache_key_make(void)
+{
+	(void)pthread_key_create(&cache_key, cache_at_exit);
+}
+
+void
+bjxa_thread_cache_used(void)
+{
+	(void)pthread_once(&cache_once, cache_key_make);
+	if (pthread_getspecific(cache_key) == NULL)
+		(void)pthread_setspecific(cache_key, &tls_stage);
+}
+
+void
+bjxa_thread_release(void)
+{
+	int e = errno;
+
+	stage_release(&tls_stage);
+	bjxa_corpus_release();
+	bjxa_small_release();
+	errno = e;
+}
 
 static int
 stage_reserve(void **p, size_t *cap, size_t need)
@@ -621,7 +698,7 @@ stage_reserve(void **p, size_t *cap, size_t need)
 		(void)bjxa_gpu_free(*p);
 	*p = NULL;
 	*cap = 0;
-	need += need / 2 + 4096;
+	need += need / 4 + 4096;
 	*p = bjxa_gpu_alloc(need);
 	if (*p == NULL)
 		return (-1);
@@ -657,12 +734,31 @@ static int
 chunk_start(struct stage *sg, int kind, const struct chunk *ck,
     bjxa_stream_desc_t *work, const void *const *srcs, const uint32_t *xa_bytes)
 {
+	const int slot = ck->slot;
+	uint64_t xa_total = 0, pcm_total = 0;
 	void *st;
 	size_t i;
 
-	if (stage_plan(sg, ck->slot, kind, work + ck->first, ck->count) < 0)
+	/* the chunk's streams, back to back in the slot's two arenas */
+	for (i = ck->first; i < ck->first + ck->count; i++) {
+		if (work[i].blocks == 0)
+			continue;
+		work[i].xa_off = xa_total;
+		work[i].pcm_off = pcm_total;
+		xa_total += xa_bytes[i];
+		pcm_total = ALIGN16(pcm_total + (uint64_t)work[i].blocks * 64u *
+		    work[i].channels);
+	}
+	xa_total = ALIGN16(xa_total) + 16;
+	pcm_total += 16;
+	/* (growing an arena frees the old one, which waits for the slot's earlier
+	 * download to have left it) */
+	if (stage_reserve(&sg->d_xa[slot], &sg->cap_xa[slot], xa_total) < 0 ||
+	    stage_reserve(&sg->d_pcm[slot], &sg->cap_pcm[slot], pcm_total) < 0)
 		return (-1);
-	st = sg->stream[ck->slot];
+	if (stage_plan(sg, slot, kind, work + ck->first, ck->count) < 0)
+		return (-1);
+	st = sg->stream[slot];
 	/* one copy per run of streams whose source buffers follow each other in
 	 * host memory exactly as their places do in the device arena (callers
 	 * that keep a batch in one allocation get one copy per chunk) */
@@ -678,10 +774,10 @@ chunk_start(struct stage *sg, int kind, const struct chunk *ck,
 			if (work[i].blocks == 0)
 				continue;
 			if (kind == BJXA_PLAN_DECODE) {
-				d = (uint8_t *)sg->d_xa + work[i].xa_off;
+				d = (uint8_t *)sg->d_xa[slot] + work[i].xa_off;
 				len = xa_bytes[i];
 			} else {
-				d = (uint8_t *)sg->d_pcm + work[i].pcm_off;
+				d = (uint8_t *)sg->d_pcm[slot] + work[i].pcm_off;
 				len = work[i].pcm_len;
 			}
 			if (run_len != 0 && (const uint8_t *)srcs[i] == run_src + run_len &&
@@ -699,10 +795,10 @@ chunk_start(struct stage *sg, int kind, const struct chunk *ck,
 			return (-1);
 	}
 	if (kind == BJXA_PLAN_DECODE)
-		return (bjxa_plan_run(sg->plan[ck->slot], sg->d_pcm, sg->cap_pcm,
-		    sg->d_xa, sg->cap_xa, st));
-	return (bjxa_plan_run(sg->plan[ck->slot], sg->d_xa, sg->cap_xa, sg->d_pcm,
-	    sg->cap_pcm, st));
+		return (bjxa_plan_run(sg->plan[slot], sg->d_pcm[slot], sg->cap_pcm[slot],
+		    sg->d_xa[slot], sg->cap_xa[slot], st));
+	return (bjxa_plan_run(sg->plan[slot], sg->d_xa[slot], sg->cap_xa[slot],
+	    sg->d_pcm[slot], sg->cap_pcm[slot], st));
 }
 
 /* wait for the chunk's kernels, take its results, queue its download */
@@ -710,10 +806,11 @@ static int
 chunk_finish(struct stage *sg, int kind, const struct chunk *ck,
     bjxa_stream_desc_t *work, void *const *dsts)
 {
-	void *st = sg->stream[ck->slot];
+	const int slot = ck->slot;
+	void *st = sg->stream[slot];
 	size_t i;
 
-	if (bjxa_plan_fetch(sg->plan[ck->slot], work + ck->first, ck->count) < 0)
+	if (bjxa_plan_fetch(sg->plan[slot], work + ck->first, ck->count) < 0)
 		return (-1);
 	/* downloads, again one copy per run of buffers that follow each other in
 	 * host memory as their contents do on the device -- and never a byte
@@ -732,11 +829,11 @@ chunk_finish(struct stage *sg, int kind, const struct chunk *ck,
 			if (kind == BJXA_PLAN_DECODE) {
 				bytes = work[i].done == work[i].blocks ? work[i].pcm_len :
 				    (size_t)work[i].done * 64u * work[i].channels;
-				d = (const uint8_t *)sg->d_pcm + work[i].pcm_off;
+				d = (const uint8_t *)sg->d_pcm[slot] + work[i].pcm_off;
 			} else {
 				bytes = (size_t)work[i].done * (4u * work[i].bits + 1u) *
 				    work[i].channels;
-				d = (const uint8_t *)sg->d_xa + work[i].xa_off;
+				d = (const uint8_t *)sg->d_xa[slot] + work[i].xa_off;
 			}
 			if (bytes == 0)
 				continue;
@@ -769,27 +866,20 @@ run_host_batch(int kind, bjxa_stream_desc_t *work, void *const *dsts,
 {
 	struct stage *sg = &tls_stage;
 	struct chunk ring[PIPE_DEPTH];
-	uint64_t xa_total = 0, pcm_total = 0, in_chunk = 0;
+	uint64_t in_chunk = 0;
 	size_t i, first = 0, queued = 0, finished = 0;
-	int k, rc = 0;
+	int k, rc = 0, dev;
 
 	if (bjxa_gpu_count() <= 0)
 		FAIL(ENODEV);
-
-	for (i = 0; i < n; i++) {
-		if (work[i].blocks == 0)
-			continue;
-		work[i].xa_off = xa_total;
-		work[i].pcm_off = pcm_total;
-		xa_total += xa_bytes[i];
-		pcm_total = ALIGN16(pcm_total + (uint64_t)work[i].blocks * 64u *
-		    work[i].channels);
+	if ((dev = bjxa_gpu_current()) < 0)
+		FAIL(ENODEV);
+	if (sg->device != dev + 1) {
+		/* first call of the thread, or the thread has moved to another device */
+		stage_release(sg);
+		sg->device = dev + 1;
+		bjxa_thread_cache_used();
 	}
-	xa_total = ALIGN16(xa_total) + 16;
-	pcm_total += 16;
-	if (stage_reserve(&sg->d_xa, &sg->cap_xa, xa_total) < 0 ||
-	    stage_reserve(&sg->d_pcm, &sg->cap_pcm, pcm_total) < 0)
-		return (-1);
 
 	for (i = 0; i <= n && rc == 0; i++) {
 		if (i < n) {
@@ -954,6 +1044,26 @@ bjxa_decode(bjxa_decoder_t *dec, void *dst, size_t dst_len, const void *src,
 
 	if (decode_precheck(dec, dst, dst_len, src, src_len) < 0)
 		return (-1);
+	{
+		/* a call of a few blocks (the reference CLI's default mode makes one
+		 * per block, src/bjxa_decode.c:102-161): one launch, no plan */
+		bjxa_stream_desc_t d;
+		uint32_t pcm, nb = blocks_this_call(&dec->left, dst_len, src_len, &pcm);
+		int rc;
+
+		(void)bjxa_decoder_describe(dec, &d);
+		d.blocks = nb;
+		d.pcm_len = pcm;
+		if (nb != 0 && (rc = bjxa_small_call(BJXA_PLAN_DECODE, &d, dst, src)) <= 0) {
+			if (rc < 0)
+				return (-1);
+			bjxa_thread_cache_used();
+			(void)bjxa_decoder_commit(dec, &d);
+			if (d.result < 0)
+				errno = d.error;
+			return (d.result);
+		}
+	}
 	decs[0] = dec;
 	dsts[0] = dst;
 	srcs[0] = src;
@@ -1040,6 +1150,22 @@ bjxa_encode(bjxa_encoder_t *enc, void *dst, size_t dst_len, const void *src,
 
 	if (encode_precheck(enc, dst, dst_len, src, src_len) < 0)
 		return (-1);
+	{
+		bjxa_stream_desc_t d;
+		uint32_t pcm, nb = blocks_this_call(&enc->left, src_len, dst_len, &pcm);
+		int rc;
+
+		(void)bjxa_encoder_describe(enc, &d);
+		d.blocks = nb;
+		d.pcm_len = pcm;
+		if (nb != 0 && (rc = bjxa_small_call(BJXA_PLAN_ENCODE, &d, dst, src)) <= 0) {
+			if (rc < 0)
+				return (-1);
+			bjxa_thread_cache_used();
+			(void)bjxa_encoder_commit(enc, &d);
+			return (d.result);
+		}
+	}
 	encs[0] = enc;
 	dsts[0] = dst;
 	srcs[0] = src;

@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "../../include/bjxa_batch.h"
+#include "bjxa_internal.h"
 #include "xa_plan.h"
 #include "xa_walk.h"
 
@@ -1208,6 +1209,17 @@ bjxa_gpu_count(void)
 }
 
 extern "C" int
+bjxa_gpu_current(void)
+{
+	int dev = -1;
+	if (cudaGetDevice(&dev) != cudaSuccess) {
+		(void)cudaGetLastError();
+		return (-1);
+	}
+	return (dev);
+}
+
+extern "C" int
 bjxa_gpu_select(int device)
 {
 	XA_CUDA(cudaSetDevice(device));
@@ -1328,8 +1340,12 @@ struct DevBuf {
 			e = cudaMemset(p, 0, want * sizeof(T));
 			if (e == cudaSuccess)
 				e = cudaStreamSynchronize(0);
-			if (e != cudaSuccess)
+			if (e != cudaSuccess) {
+				(void)cudaGetLastError();
+				(void)cudaFree(p);
+				p = NULL;
 				return cuda_errno(e);
+			}
 		}
 		cap = want;
 		return 0;
@@ -1387,7 +1403,9 @@ struct bjxa_plan {
 	cudaEvent_t ev_start, ev_done[6];
 };
 
-static bool g_attr_done = false;
+#include <atomic>
+/* devices whose kernels have their shared-memory attributes set (bit = device) */
+static std::atomic<unsigned long long> g_attr_devices(0);
 
 template <class Tile>
 static cudaError_t
@@ -1437,13 +1455,14 @@ set_attrs_one(void)
 static cudaError_t
 set_attrs(void)
 {
-	/* per device in principle; the attribute is sticky per context */
-	static thread_local int done_dev = -1;
+	/* the attribute belongs to the device's context: once per device; two
+	 * threads that get here together both set it, which is harmless */
 	int dev = 0;
 	cudaError_t e = cudaGetDevice(&dev);
 	if (e != cudaSuccess)
 		return e;
-	if (g_attr_done && done_dev == dev)
+	const unsigned long long bit = 1ULL << (dev & 63);
+	if (g_attr_devices.load(std::memory_order_acquire) & bit)
 		return cudaSuccess;
 	if ((e = set_attrs_one<4, 1>()) != cudaSuccess) return e;
 	if ((e = set_attrs_one<4, 2>()) != cudaSuccess) return e;
@@ -1451,8 +1470,7 @@ set_attrs(void)
 	if ((e = set_attrs_one<6, 2>()) != cudaSuccess) return e;
 	if ((e = set_attrs_one<8, 1>()) != cudaSuccess) return e;
 	if ((e = set_attrs_one<8, 2>()) != cudaSuccess) return e;
-	g_attr_done = true;
-	done_dev = dev;
+	g_attr_devices.fetch_or(bit, std::memory_order_release);
 	return cudaSuccess;
 }
 
@@ -1505,12 +1523,18 @@ plan_build(bjxa_plan *pl, int kind, const bjxa_stream_desc_t *descs, size_t n)
 	}
 	/* BJXA_B200_STRIPS=1|32 forces the decode tile shape (tuning aid) */
 	const char *env = getenv("BJXA_B200_STRIPS");
-	int rc = build_plan(pl->hp, kind, descs, n, &bad, env ? atoi(env) : 0);
+	int rc;
+	try {
+		rc = build_plan(pl->hp, kind, descs, n, &bad, env ? atoi(env) : 0);
+		if (rc == 0)
+			pl->descs.assign(descs, descs + n);
+	} catch (const std::bad_alloc &) {
+		rc = ENOMEM;	/* nothing of C++ may unwind into the C callers */
+	}
 	if (rc) {
 		errno = rc;
 		return (-1);
 	}
-	pl->descs.assign(descs, descs + n);
 	pl->ran = false;
 	pl->launches = 0;
 	pl->stereo = stereo_mode();
@@ -2070,98 +2094,66 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 }
 
 /*
- * State of channel c after effective block `eb` (eb >= 0) of a decoded stream:
- * the block's last two samples, read back from the PCM arena.
+ * Streams that met a bad profile (libbjxa.c:550): the state the reference leaves
+ * behind is the one after effective block done - 1 -- the last two frames of that
+ * block, read back from the PCM arena -- and, when it is the RIGHT block of the
+ * pair that is bad, the left channel has already advanced through its block of
+ * the failing pair (libbjxa.c:633-643).  One thread per such stream redoes that,
+ * one launch and one copy for all of them.
  */
-static int
-state_from_pcm(const bjxa_plan *pl, const bjxa_stream_desc_t &d, uint32_t eb,
-    int16_t prev[2][2])
-{
-	int16_t tail[4];
-	unsigned ch = d.channels;
-	uint64_t off = d.pcm_off + (uint64_t)eb * 64u * ch + 60u * ch;
+struct BadReq {
+	uint64_t xa_pair;	/* arena address of the failing effective block */
+	uint64_t pcm_tail;	/* arena address of the last two frames in front of it */
+	int16_t  prev[2][2];	/* state on entry, used when no block precedes */
+	uint32_t eb;		/* effective blocks completed */
+	uint8_t  bits, channels, bad_ch, pad;
+};
 
-	XA_CUDA(cudaMemcpy(tail, pl->last_dst + off, 4u * ch, cudaMemcpyDeviceToHost));
-	for (unsigned c = 0; c < ch; c++) {
-		prev[c][1] = tail[c];		/* sample 30 */
-		prev[c][0] = tail[ch + c];	/* sample 31 */
+__global__ void
+xa_badstate_kernel(const uint8_t *xa, const uint8_t *pcm, const BadReq *req, uint32_t n,
+    StreamRes *out)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	const BadReq r = req[i];
+	int st[2][2];
+	for (int c = 0; c < 2; c++) {
+		st[c][0] = r.prev[c][0];
+		st[c][1] = r.prev[c][1];
 	}
-	return (0);
+	if (r.eb > 0) {
+		const int16_t *t = reinterpret_cast<const int16_t *>(pcm + r.pcm_tail);
+		for (uint32_t c = 0; c < r.channels; c++) {
+			st[c][1] = t[c];			/* frame 30 */
+			st[c][0] = t[r.channels + c];		/* frame 31 */
+		}
+	}
+	if (r.bad_ch == 1) {
+		/* the left block of the failing pair, sample by sample */
+		const uint8_t *b = xa + r.xa_pair;
+		const uint32_t prof = b[0];
+		const int k0 = gain_k0(prof >> 4), k1 = gain_k1(prof >> 4), sh = (int)(prof & 15u);
+		for (int s = 0; s < 32; s++) {
+			const uint32_t bit = (uint32_t)s * r.bits;
+			/* code s, MSB first, as the top bits of an int16 (libbjxa.c:286-345) */
+			const uint32_t two = (uint32_t)b[1 + (bit >> 3)] << 8 | b[2 + (bit >> 3)];
+			const int16_t top = (int16_t)((two << (bit & 7u)) & (0xffffu << (16 - r.bits)) & 0xffffu);
+			int p0 = st[0][0], p1 = st[0][1];
+			(void)sample_chain((int)top << 16, 16 + sh, k0, k1, p0, p1);
+			st[0][0] = p0;
+			st[0][1] = p1;
+		}
+	}
+	for (int c = 0; c < 2; c++) {
+		out[i].prev[c][0] = (int16_t)st[c][0];
+		out[i].prev[c][1] = (int16_t)st[c][1];
+	}
 }
 
-/* the reference advances the LEFT channel before it meets a bad RIGHT block
- * (libbjxa.c:633-643): redo that one pair on the device to get the state */
 static int
-left_state_after(const bjxa_plan *pl, const bjxa_stream_desc_t &d, uint32_t eb,
-    const int16_t before[2][2], int16_t left[2])
+plan_fetch_decode(bjxa_plan *pl, bjxa_stream_desc_t *out, size_t n)
 {
-	bjxa_stream_desc_t one = d;
-	one.xa_off = d.xa_off + (uint64_t)eb * (uint64_t)(block_bytes(d.bits) * 2);
-	one.pcm_off = 0;
-	one.blocks = 1;
-	one.pcm_len = 128;
-	memcpy(one.prev, before, sizeof one.prev);
-
-	bjxa_plan_t *mini = bjxa_plan_create(BJXA_PLAN_DECODE, &one, 1);
-	if (mini == NULL)
-		return (-1);
-	void *scratch = bjxa_gpu_alloc(256);
-	int rc = -1;
-	if (scratch != NULL &&
-	    bjxa_plan_run(mini, scratch, 256, pl->last_src, pl->last_src_bytes,
-	    pl->last_stream) == 0 &&
-	    cudaStreamSynchronize(pl->last_stream) == cudaSuccess) {
-		StreamRes r;
-		if (cudaMemcpy(&r, mini->d_results.p, sizeof r,
-		    cudaMemcpyDeviceToHost) == cudaSuccess) {
-			left[0] = r.prev[0][0];
-			left[1] = r.prev[0][1];
-			rc = 0;
-		}
-	}
-	int e = errno;
-	if (scratch)
-		bjxa_gpu_free(scratch);
-	bjxa_plan_free(&mini);
-	if (rc < 0)
-		errno = e ? e : EIO;
-	return (rc);
-}
-
-extern "C" int
-bjxa_plan_fetch(bjxa_plan_t *pl, bjxa_stream_desc_t *out, size_t n)
-{
-	CHECK_PLAN(pl);
-	if (out == NULL && n != 0) {
-		errno = EFAULT;
-		return (-1);
-	}
-	if (!pl->ran || n != pl->descs.size()) {
-		errno = EINVAL;
-		return (-1);
-	}
-	XA_CUDA(cudaStreamSynchronize(pl->last_stream));
-	XA_CUDA(cudaGetLastError());
-
-	if (pl->hp.kind != kKindDecode) {
-		std::vector<StreamRes> after;
-		if (pl->hp.kind == kKindSearch && n) {
-			/* the decoder state the encoded blocks leave behind */
-			after.resize(n);
-			XA_CUDA(cudaMemcpy(after.data(), pl->d_results.p, n * sizeof(StreamRes),
-			    cudaMemcpyDeviceToHost));
-		}
-		for (size_t i = 0; i < n; i++) {
-			out[i] = pl->descs[i];
-			out[i].done = out[i].blocks;
-			out[i].result = (int32_t)out[i].blocks;
-			out[i].error = 0;
-			if (!after.empty() && out[i].blocks != 0)
-				memcpy(out[i].prev, after[i].prev, sizeof after[i].prev);
-		}
-		return (0);
-	}
-
 	std::vector<StreamRes> res(n);
 	std::vector<uint32_t> bad(n);
 	uint32_t fault = 0;
@@ -2180,6 +2172,8 @@ bjxa_plan_fetch(bjxa_plan_t *pl, bjxa_stream_desc_t *out, size_t n)
 		XA_CUDA(cudaMemcpy(bad.data(), pl->d_first_bad.p, n * sizeof(uint32_t),
 		    cudaMemcpyDeviceToHost));
 	}
+	std::vector<BadReq> reqs;
+	std::vector<size_t> who;
 	for (size_t i = 0; i < n; i++) {
 		const bjxa_stream_desc_t &d = pl->descs[i];
 		out[i] = d;
@@ -2197,20 +2191,485 @@ bjxa_plan_fetch(bjxa_plan_t *pl, bjxa_stream_desc_t *out, size_t n)
 			continue;
 		}
 		/* bad profile at block-channel bad[i] (libbjxa.c:550,634,642) */
-		uint32_t eb = bad[i] / d.channels, c = bad[i] % d.channels;
+		const uint32_t eb = bad[i] / d.channels, c = bad[i] % d.channels;
 		out[i].done = eb;
 		out[i].result = -1;
 		out[i].error = EPROTO;
-		if (eb > 0 && state_from_pcm(pl, d, eb - 1, out[i].prev) < 0)
-			return (-1);
-		if (c == 1) {
-			int16_t before[2][2], left[2];
-			memcpy(before, out[i].prev, sizeof before);
-			if (left_state_after(pl, d, eb, before, left) < 0)
-				return (-1);
-			out[i].prev[0][0] = left[0];
-			out[i].prev[0][1] = left[1];
+		if (eb == 0 && c == 0)
+			continue;		/* nothing decoded: the state on entry stands */
+		BadReq r;
+		memset(&r, 0, sizeof r);
+		r.xa_pair = d.xa_off + (uint64_t)eb * (uint64_t)(block_bytes(d.bits) * d.channels);
+		r.pcm_tail = eb > 0 ? d.pcm_off + (uint64_t)(eb - 1) * 64u * d.channels + 60u * d.channels : 0;
+		memcpy(r.prev, d.prev, sizeof r.prev);
+		r.eb = eb;
+		r.bits = d.bits;
+		r.channels = d.channels;
+		r.bad_ch = (uint8_t)c;
+		reqs.push_back(r);
+		who.push_back(i);
+	}
+	if (!reqs.empty()) {
+		const size_t m = reqs.size();
+		BadReq *d_req = NULL;
+		StreamRes *d_out = NULL;
+		std::vector<StreamRes> st(m);
+		XA_CUDA(cudaMalloc((void **)&d_req, m * sizeof(BadReq)));
+		cudaError_t e = cudaMalloc((void **)&d_out, m * sizeof(StreamRes));
+		if (e == cudaSuccess)
+			e = cudaMemcpy(d_req, reqs.data(), m * sizeof(BadReq), cudaMemcpyHostToDevice);
+		if (e == cudaSuccess) {
+			xa_badstate_kernel<<<(unsigned)((m + 127) / 128), 128>>>(pl->last_src,
+			    pl->last_dst, d_req, (uint32_t)m, d_out);
+			e = cudaGetLastError();
 		}
+		if (e == cudaSuccess)
+			e = cudaMemcpy(st.data(), d_out, m * sizeof(StreamRes), cudaMemcpyDeviceToHost);
+		(void)cudaFree(d_req);
+		if (d_out)
+			(void)cudaFree(d_out);
+		XA_CUDA(e);
+		for (size_t k = 0; k < m; k++)
+			memcpy(out[who[k]].prev, st[k].prev, sizeof st[k].prev);
+	}
+	return (0);
+}
+
+extern "C" int
+bjxa_plan_fetch(bjxa_plan_t *pl, bjxa_stream_desc_t *out, size_t n)
+{
+	CHECK_PLAN(pl);
+	if (out == NULL && n != 0) {
+		errno = EFAULT;
+		return (-1);
+	}
+	if (!pl->ran || n != pl->descs.size()) {
+		errno = EINVAL;
+		return (-1);
+	}
+	XA_CUDA(cudaStreamSynchronize(pl->last_stream));
+	XA_CUDA(cudaGetLastError());
+
+	try {
+		if (pl->hp.kind == kKindDecode)
+			return (plan_fetch_decode(pl, out, n));
+		std::vector<StreamRes> after;
+		if (pl->hp.kind == kKindSearch && n) {
+			/* the decoder state the encoded blocks leave behind */
+			after.resize(n);
+			XA_CUDA(cudaMemcpy(after.data(), pl->d_results.p, n * sizeof(StreamRes),
+			    cudaMemcpyDeviceToHost));
+		}
+		for (size_t i = 0; i < n; i++) {
+			out[i] = pl->descs[i];
+			out[i].done = out[i].blocks;
+			out[i].result = (int32_t)out[i].blocks;
+			out[i].error = 0;
+			if (!after.empty() && out[i].blocks != 0)
+				memcpy(out[i].prev, after[i].prev, sizeof after[i].prev);
+		}
+	} catch (const std::bad_alloc &) {
+		errno = ENOMEM;
+		return (-1);
+	}
+	return (0);
+}
+
+/* ---- one small call: bjxa_decode / bjxa_encode on a few blocks --------------------- */
+/*
+ * The reference's CLI calls bjxa_decode once per block by default
+ * (/root/reference/src/bjxa_decode.c:102-161): 20 672 calls for one of its test
+ * vectors.  A call that small is not a batch: no plan, no tables, no census.
+ * Its parameters travel as kernel arguments, its bytes through a pinned, mapped
+ * staging buffer of the calling thread that the kernel reads and writes across
+ * PCIe itself, and the host waits for one launch.  Used for calls of at most
+ * kSmallBlocks effective blocks; everything larger takes the plan path.
+ */
+constexpr uint32_t kSmallBlocks = 32;
+
+struct SmallRes {
+	int16_t  prev[2][2];
+	uint32_t done;
+	int32_t  error;
+};
+
+struct SmallArgs {
+	const uint8_t *in;	/* staged source bytes (16-byte aligned, slack behind) */
+	uint8_t *out;		/* staged destination */
+	SmallRes *res;
+	uint32_t blocks, pcm_len;
+	int16_t  prev[2][2];
+};
+
+/*
+ * One warp; lane c < CH walks channel c block by block exactly as the reference
+ * does (libbjxa.c:629-658): a bad profile stops the call at its effective block,
+ * the left channel having advanced if it is the right block that is bad.
+ */
+template <int BITS, int CH>
+__global__ void __launch_bounds__(32)
+xa_small_decode_kernel(const SmallArgs a)
+{
+	constexpr int BS = block_bytes(BITS);
+	__shared__ __align__(16) uint8_t in[kSmallBlocks * CH * BS + 48];
+	__shared__ __align__(16) int16_t out[kSmallBlocks * CH * 32];
+	const uint32_t lane = threadIdx.x;
+	const uint32_t nin = a.blocks * CH * BS;
+	for (uint32_t i = lane * 16u; i < nin; i += 512u)
+		*reinterpret_cast<uint4 *>(in + i) = *reinterpret_cast<const uint4 *>(a.in + i);
+	__syncwarp();
+	int p0 = 0, p1 = 0;
+	if (lane < CH) {
+		p0 = a.prev[lane][0];
+		p1 = a.prev[lane][1];
+	}
+	uint32_t done = a.blocks;
+	int err = 0;
+	for (uint32_t eb = 0; eb < a.blocks; eb++) {
+		const uint8_t *b = in + (eb * CH + (lane < CH ? lane : 0u)) * BS;
+		const uint32_t prof = b[0];
+		const uint32_t badm = __ballot_sync(0xffffffffu, lane < CH && (prof >> 4) >= 5u);
+		if (badm != 0) {
+			done = eb;
+			err = EPROTO;
+			if (badm & 1u)
+				break;		/* nothing of this effective block is decoded */
+		}
+		if (lane < CH && (badm == 0 || lane == 0)) {
+			uint32_t pw[BITS];
+#pragma unroll
+			for (int i = 0; i < BITS; i++)
+				pw[i] = (uint32_t)b[1 + 4 * i] | (uint32_t)b[2 + 4 * i] << 8 |
+				    (uint32_t)b[3 + 4 * i] << 16 | (uint32_t)b[4 + 4 * i] << 24;
+			const int k0 = gain_k0(prof >> 4), k1 = gain_k1(prof >> 4);
+			const int sh = 16 + (int)(prof & 15u);
+#pragma unroll
+			for (int s = 0; s < 32; s++) {
+				const int v = sample_chain(top_code<BITS>(pw, s), sh, k0, k1, p0, p1);
+				if (badm == 0)
+					out[(eb * 32u + (uint32_t)s) * CH + lane] = (int16_t)v;
+			}
+		}
+		if (badm != 0)
+			break;
+	}
+	__syncwarp();
+	const uint32_t bytes = done == a.blocks ? a.pcm_len : done * 64u * CH;
+	for (uint32_t i = lane * 16u; i + 16u <= bytes; i += 512u)
+		*reinterpret_cast<uint4 *>(a.out + i) = *reinterpret_cast<const uint4 *>(
+		    reinterpret_cast<const uint8_t *>(out) + i);
+	for (uint32_t i = (bytes & ~15u) + lane * 2u; i < bytes; i += 64u)
+		*reinterpret_cast<uint16_t *>(a.out + i) = *reinterpret_cast<const uint16_t *>(
+		    reinterpret_cast<const uint8_t *>(out) + i);
+	if (lane < CH) {
+		a.res->prev[lane][0] = (int16_t)p0;
+		a.res->prev[lane][1] = (int16_t)p1;
+	}
+	if (lane == 0) {
+		a.res->done = done;
+		a.res->error = err;
+	}
+}
+
+/* one thread per block-channel: gather, zero-pad, profile 0, top bits (libbjxa.c:665-691) */
+template <int BITS, int CH>
+__global__ void __launch_bounds__(64)
+xa_small_encode_kernel(const SmallArgs a)
+{
+	constexpr int BS = block_bytes(BITS);
+	const uint32_t q = threadIdx.x;
+	if (q < a.blocks * CH) {
+		const uint32_t eb = q / CH, c = q % CH;
+		const int16_t *pcm = reinterpret_cast<const int16_t *>(a.in);
+		const uint32_t frames = a.pcm_len / (2u * CH);
+		uint32_t w[16], pw[BITS];
+#pragma unroll
+		for (int i = 0; i < 16; i++) {
+			const uint32_t f0 = eb * 32u + 2u * i, f1 = f0 + 1u;
+			const uint32_t s0 = f0 < frames ? (uint16_t)pcm[f0 * CH + c] : 0u;
+			const uint32_t s1 = f1 < frames ? (uint16_t)pcm[f1 * CH + c] : 0u;
+			w[i] = s0 | s1 << 16;
+		}
+		deflate_block<BITS>(pw, w);
+		uint8_t *o = a.out + q * BS;
+		o[0] = 0;
+#pragma unroll
+		for (int i = 0; i < 4 * BITS; i++)
+			o[1 + i] = (uint8_t)(pw[i >> 2] >> (8 * (i & 3)));
+	}
+	if (q == 0) {
+		a.res->done = a.blocks;
+		a.res->error = 0;
+	}
+}
+
+/* the calling thread's staging for small calls, on the device it was made for */
+struct SmallCtx {
+	int dev;
+	uint8_t *h_in, *h_out;		/* pinned + mapped; the device sees them as they are */
+	SmallRes *h_res;
+	cudaStream_t st;
+};
+static thread_local SmallCtx tls_small = { -1, NULL, NULL, NULL, NULL };
+constexpr size_t kSmallIn = kSmallBlocks * 2 * 64 + 64, kSmallOut = kSmallBlocks * 2 * 64 + 64;
+
+static void
+small_release(void)
+{
+	SmallCtx &c = tls_small;
+	if (c.dev < 0)
+		return;
+	int cur = -1;
+	if (cudaGetDevice(&cur) == cudaSuccess && cur != c.dev)
+		(void)cudaSetDevice(c.dev);
+	if (c.st)
+		(void)cudaStreamDestroy(c.st);
+	if (c.h_in)
+		(void)cudaFreeHost(c.h_in);
+	if (c.h_out)
+		(void)cudaFreeHost(c.h_out);
+	if (c.h_res)
+		(void)cudaFreeHost(c.h_res);
+	if (cur >= 0 && cur != c.dev)
+		(void)cudaSetDevice(cur);
+	c = SmallCtx{ -1, NULL, NULL, NULL, NULL };
+}
+
+extern "C" void
+bjxa_small_release(void)
+{
+	small_release();
+}
+
+static int
+small_ready(void)
+{
+	SmallCtx &c = tls_small;
+	int dev = 0;
+	XA_CUDA(cudaGetDevice(&dev));
+	if (c.dev == dev)
+		return (0);
+	small_release();
+	cudaError_t e = cudaHostAlloc((void **)&c.h_in, kSmallIn, cudaHostAllocMapped);
+	if (e == cudaSuccess)
+		e = cudaHostAlloc((void **)&c.h_out, kSmallOut, cudaHostAllocMapped);
+	if (e == cudaSuccess)
+		e = cudaHostAlloc((void **)&c.h_res, sizeof(SmallRes), cudaHostAllocMapped);
+	if (e == cudaSuccess)
+		e = cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking);
+	c.dev = dev;
+	if (e != cudaSuccess) {
+		(void)cudaGetLastError();
+		small_release();
+		errno = cuda_errno(e);
+		return (-1);
+	}
+	return (0);
+}
+
+template <int BITS, int CH>
+static cudaError_t
+small_launch(int kind, const SmallArgs &a, cudaStream_t st)
+{
+	if (kind == kKindDecode)
+		xa_small_decode_kernel<BITS, CH><<<1, 32, 0, st>>>(a);
+	else
+		xa_small_encode_kernel<BITS, CH><<<1, 64, 0, st>>>(a);
+	return cudaGetLastError();
+}
+
+/*
+ * One stream, d->blocks <= kSmallBlocks effective blocks, host buffers: decode
+ * (src = XA, dst = PCM) or reference-exact encode (the other way round).  Fills
+ * d->done / result / error / prev like bjxa_plan_fetch.  Returns 1 when the call
+ * is not a small one (the caller takes the plan path), 0 or -1 otherwise.
+ */
+extern "C" int
+bjxa_small_call(int kind, bjxa_stream_desc_t *d, void *dst, const void *src)
+{
+	if (d->blocks == 0 || d->blocks > kSmallBlocks ||
+	    (kind != BJXA_PLAN_DECODE && kind != BJXA_PLAN_ENCODE))
+		return (1);
+	if (small_ready() < 0)
+		return (-1);
+	SmallCtx &c = tls_small;
+	const size_t xa_bytes = (size_t)d->blocks * d->channels * (size_t)block_bytes(d->bits);
+	const size_t in_bytes = kind == BJXA_PLAN_DECODE ? xa_bytes : d->pcm_len;
+	memcpy(c.h_in, src, in_bytes);
+	SmallArgs a;
+	a.in = c.h_in;
+	a.out = c.h_out;
+	a.res = c.h_res;
+	a.blocks = d->blocks;
+	a.pcm_len = d->pcm_len;
+	memcpy(a.prev, d->prev, sizeof a.prev);
+	cudaError_t e;
+	switch (bucket_of(d->bits, d->channels)) {
+	case 0: e = small_launch<4, 1>(kind, a, c.st); break;
+	case 1: e = small_launch<4, 2>(kind, a, c.st); break;
+	case 2: e = small_launch<6, 1>(kind, a, c.st); break;
+	case 3: e = small_launch<6, 2>(kind, a, c.st); break;
+	case 4: e = small_launch<8, 1>(kind, a, c.st); break;
+	default: e = small_launch<8, 2>(kind, a, c.st); break;
+	}
+	XA_CUDA(e);
+	XA_CUDA(cudaStreamSynchronize(c.st));
+	d->done = c.h_res->done;
+	d->error = c.h_res->error;
+	d->result = d->error != 0 ? -1 : (int32_t)d->done;
+	size_t out_bytes;
+	if (kind == BJXA_PLAN_DECODE) {
+		memcpy(d->prev, c.h_res->prev, sizeof d->prev);
+		out_bytes = d->done == d->blocks ? d->pcm_len : (size_t)d->done * 64u * d->channels;
+	} else {
+		out_bytes = xa_bytes;
+	}
+	memcpy(dst, c.h_out, out_bytes);
+	return (0);
+}
+
+/* ---- per-stream checksums of a run's output ---------------------------------- */
+
+/*
+ * sum over i of word_i * ((i * G + C) | 1) mod 2^64, word_i = bytes 4i..4i+3 of
+ * the range, little endian, absent bytes zero (include/bjxa_batch.h).  A plain
+ * sum of position-keyed terms: any split of the words over threads gives the
+ * same value.
+ */
+constexpr unsigned long long kSumG = 0x9E3779B97F4A7C15ULL, kSumC = 0xD1B54A32D192ED03ULL;
+constexpr int kSumThreads = 256;
+
+struct SumRange {
+	uint64_t off, len;
+};
+
+__device__ __forceinline__ unsigned long long
+sum_term(uint32_t w, unsigned long long i)
+{
+	return (unsigned long long)w * ((i * kSumG + kSumC) | 1ULL);
+}
+
+/* words [w0, w1) of the range at arena + off, `len` bytes long; `lim` = arena bytes */
+__device__ unsigned long long
+sum_words(const uint8_t *arena, uint64_t lim, uint64_t off, uint64_t len,
+    unsigned long long w0, unsigned long long w1, uint32_t tid, uint32_t nt)
+{
+	unsigned long long acc = 0;
+	const uint8_t *base = arena + off;
+	if ((((uintptr_t)base) & 15u) == 0 && (w0 & 3u) == 0) {
+		/* aligned: 16 bytes a step, the ragged end below */
+		const unsigned long long whole = len / 16u * 4u;	/* words in whole vectors */
+		const unsigned long long v1 = (w1 < whole ? w1 : whole) & ~3ULL;
+		for (unsigned long long i = w0 + 4ULL * tid; i < v1; i += 4ULL * nt) {
+			const uint4 v = *reinterpret_cast<const uint4 *>(base + i * 4u);
+			acc += sum_term(v.x, i) + sum_term(v.y, i + 1) + sum_term(v.z, i + 2) +
+			    sum_term(v.w, i + 3);
+		}
+		w0 = v1 > w0 ? v1 : w0;
+	}
+	for (unsigned long long i = w0 + tid; i < w1; i += nt) {
+		uint32_t w = 0;
+		for (uint32_t b = 0; b < 4u; b++) {
+			const uint64_t at = i * 4u + b;
+			if (at < len && off + at < lim)
+				w |= (uint32_t)base[at] << (8u * b);
+		}
+		acc += sum_term(w, i);
+	}
+	return acc;
+}
+
+/* one CTA per range (grid-stride), or -- few, long ranges -- every CTA a slice of each */
+__global__ void __launch_bounds__(kSumThreads)
+xa_checksum_kernel(const uint8_t *arena, uint64_t lim, const SumRange *ranges, uint32_t n,
+    unsigned long long *sums, int spread)
+{
+	__shared__ unsigned long long part[kSumThreads / 32];
+	const uint32_t tid = threadIdx.x;
+	for (uint32_t r = spread ? 0 : blockIdx.x; r < n; r += spread ? 1 : gridDim.x) {
+		const SumRange g = ranges[r];
+		const unsigned long long words = (g.len + 3u) / 4u;
+		unsigned long long w0 = 0, w1 = words;
+		if (spread) {
+			/* slices of whole 16-byte vectors */
+			const unsigned long long per = ((words + gridDim.x - 1) / gridDim.x + 3ULL) & ~3ULL;
+			w0 = per * blockIdx.x;
+			w1 = w0 + per < words ? w0 + per : words;
+			if (w0 >= words)
+				continue;
+		}
+		unsigned long long acc = sum_words(arena, lim, g.off, g.len, w0, w1, tid, kSumThreads);
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1)
+			acc += __shfl_xor_sync(0xffffffffu, acc, o);
+		__syncthreads();
+		if ((tid & 31u) == 0)
+			part[tid >> 5] = acc;
+		__syncthreads();
+		if (tid == 0) {
+			unsigned long long t = 0;
+			for (int w = 0; w < kSumThreads / 32; w++)
+				t += part[w];
+			if (spread)
+				atomicAdd(&sums[r], t);
+			else
+				sums[r] = t;
+		}
+	}
+}
+
+extern "C" int
+bjxa_plan_checksum(bjxa_plan_t *pl, uint64_t *sums, size_t n)
+{
+	CHECK_PLAN(pl);
+	if (sums == NULL && n != 0) {
+		errno = EFAULT;
+		return (-1);
+	}
+	if (!pl->ran || n != pl->descs.size() || n > 0xffffffffu) {
+		errno = EINVAL;
+		return (-1);
+	}
+	if (n == 0)
+		return (0);
+	try {
+		std::vector<SumRange> r(n);
+		const bool pcm = pl->hp.kind == kKindDecode;
+		for (size_t i = 0; i < n; i++) {
+			const bjxa_stream_desc_t &d = pl->descs[i];
+			r[i].off = pcm ? d.pcm_off : d.xa_off;
+			r[i].len = d.blocks == 0 ? 0 : pcm ? (uint64_t)d.pcm_len :
+			    (uint64_t)d.blocks * (uint64_t)(block_bytes(d.bits) * d.channels);
+		}
+		const uint64_t lim = pl->hp.dst_need;	/* bytes of the arena the run wrote */
+		SumRange *d_r = NULL;
+		unsigned long long *d_s = NULL;
+		XA_CUDA(cudaStreamSynchronize(pl->last_stream));
+		XA_CUDA(cudaMalloc((void **)&d_r, n * sizeof(SumRange)));
+		cudaError_t e = cudaMalloc((void **)&d_s, n * sizeof(unsigned long long));
+		if (e == cudaSuccess)
+			e = cudaMemcpy(d_r, r.data(), n * sizeof(SumRange), cudaMemcpyHostToDevice);
+		if (e == cudaSuccess)
+			e = cudaMemset(d_s, 0, n * sizeof(unsigned long long));
+		if (e == cudaSuccess) {
+			int dev = 0, sms = 148;
+			(void)cudaGetDevice(&dev);
+			(void)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+			const uint32_t grid = (uint32_t)sms * 8u;
+			const int spread = n < 2048;
+			xa_checksum_kernel<<<spread ? grid : (n < grid ? (uint32_t)n : grid), kSumThreads>>>(
+			    pl->last_dst, lim, d_r, (uint32_t)n, d_s, spread);
+			e = cudaGetLastError();
+		}
+		if (e == cudaSuccess)
+			e = cudaMemcpy(sums, d_s, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+		(void)cudaFree(d_r);
+		if (d_s)
+			(void)cudaFree(d_s);
+		XA_CUDA(e);
+	} catch (const std::bad_alloc &) {
+		errno = ENOMEM;
+		return (-1);
 	}
 	return (0);
 }

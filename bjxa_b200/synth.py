@@ -163,3 +163,18 @@ def riff_header(pcm_bytes: int, channels: int, rate: int = 44100) -> bytes:
     return struct.pack("<4sI8sIHHIIHH4sI", b"RIFF", 36 + pcm_bytes, b"WAVEfmt ",
                        16, 1, channels, rate, rate * 2 * channels, 2 * channels,
                        16, b"data", pcm_bytes)
+
+
+def stream_checksum(buf) -> int:
+    """The sum bjxa_plan_checksum computes on the device (include/bjxa_batch.h):
+    sum of word_i * ((i * G + C) | 1) mod 2^64 over the little-endian 32-bit words
+    of `buf`, bytes past its end taken as zero."""
+    b = np.ascontiguousarray(buf).view(np.uint8).reshape(-1)
+    pad = (-b.size) % 4
+    if pad:
+        b = np.concatenate((b, np.zeros(pad, dtype=np.uint8)))
+    w = b.view("<u4").astype(np.uint64)
+    with np.errstate(over="ignore"):
+        i = np.arange(w.size, dtype=np.uint64)
+        mult = (i * _GOLD + np.uint64(0xD1B54A32D192ED03)) | np.uint64(1)
+        return int((w * mult).sum(dtype=np.uint64))

@@ -111,6 +111,18 @@ int bjxa_plan_run(bjxa_plan_t *plan, void *dst, size_t dst_bytes, const void *sr
 /* Waits for the last run and fills prev/done/result/error of descs[0..n). */
 int bjxa_plan_fetch(bjxa_plan_t *plan, bjxa_stream_desc_t *descs, size_t n);
 
+/*
+ * Checksums, computed on the device, of what the last bjxa_plan_run() produced
+ * for each stream -- decode: its pcm_len bytes of PCM; encode: its blocks *
+ * channels * (4 * bits + 1) bytes of XA -- so that a whole batch can be verified
+ * without bringing it back to the host:
+ *     sums[s] = sum over i of word_i * ((i * 0x9E3779B97F4A7C15 +
+ *               0xD1B54A32D192ED03) | 1)   mod 2^64,
+ * word_i = bytes 4i .. 4i+3 of the stream's output, little endian, bytes past
+ * its end taken as zero.  Waits for the run; streams without blocks give 0.
+ */
+int bjxa_plan_checksum(bjxa_plan_t *plan, uint64_t *sums, size_t n);
+
 /* Kernel launches one bjxa_plan_run() issues (for launch accounting). */
 int bjxa_plan_launches(const bjxa_plan_t *plan);
 
@@ -160,6 +172,15 @@ int    bjxa_gpu_download_async(void *hptr, const void *dptr, size_t bytes,
  */
 int    bjxa_gpu_scatter_async(void *dst, const void *d_table, uint32_t rec_len,
 	    size_t n, void *cuda_stream);
+
+/*
+ * The host-buffer calls (bjxa_decode, bjxa_encode, bjxa_batch_*, bjxa_corpus_run)
+ * keep their staging -- device arenas, pinned buffers, CUDA streams, plans -- with
+ * the calling thread, on the device that was current at the time; a thread that
+ * selects another device gets a fresh set there.  This gives it all back now (it
+ * also happens by itself when the thread exits).
+ */
+void   bjxa_thread_release(void);
 
 /* ---- whole files: a corpus in, a corpus out -------------------------------- */
 

@@ -161,6 +161,9 @@ BAD_HEADERS = {   # test/test_decode_error.sh:36-219
     "data not a block multiple": _hdr(data_len=67),
     "nBits=12": _hdr(bits=12),
     "nChannels=5": _hdr(channels=5),
+    # the reference stops on this one with an assert in bjxa_decode_format
+    # (libbjxa.c:596); a batch library reports the header instead
+    "stereo, odd number of blocks": _hdr(bits=4, channels=2, data_len=51, samples=40),
 }
 
 

@@ -3,13 +3,27 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-Workload (BASELINE.json configs[1], SURVEY.md section 8d "Config 2"): a batch
-of 4096 synthetic mono 8-bit XA streams x 60 s @ 44.1 kHz per GPU, generated
-on the device.  A "step" is one pass of the decode hot path over the whole
-batch = one bjxa_plan_run() = one kernel launch.  With N > 1 (torchrun, one
-process per GPU) every rank decodes its own 4096-stream shard -- the streams
-are independent, so there is no data-path collective (weak scaling); only the
-timing is reduced (max over ranks).
+Headline workload (BASELINE.json configs[1], SURVEY.md section 8d "Config 2"):
+4096 synthetic mono 8-bit XA streams x 60 s @ 44.1 kHz per GPU, generated on the
+device.  A "step" is one pass of the decode hot path over the whole batch = one
+bjxa_plan_run().  With N > 1 (torchrun, one process per GPU) every rank decodes
+its own 4096-stream shard -- the streams are independent, so there is no
+data-path collective (weak scaling); only the timing is reduced (max over ranks).
+
+Besides the headline the line carries (unless --no-extras):
+  by_profile_mix   the same batch with the other profile-byte mixes
+  encode           reference-exact encode of the same batch
+  e2e              bjxa_batch_decode on pinned HOST buffers, copies in the timed
+                   region, with the copy ceiling of the box measured beside it
+  configs          BASELINE.json configs[2] (mixed stereo batch) and configs[3]
+                   (stereo 4-bit encode) per GPU, and configs[4]: ONE corpus of
+                   262 144 streams sharded by bytes (bjxa_shard_range) over the N
+                   ranks -- strong scaling -- decode then encode
+  parity           every leg: a checksum of every stream computed on the device
+                   (bjxa_plan_checksum), and the oracle on a seeded subset of at
+                   least 256 streams whose checksums must agree (all streams with
+                   --full-parity); any mismatch fails the run
+  cpu_baseline     the unmodified reference on this box's host cores (rank 0)
 
 One JSON line is printed by rank 0; its keys are described in DESIGN.md.
 `--impl reference` times the UNMODIFIED reference library (compiled to
@@ -44,7 +58,11 @@ PCM_PITCH = (BLOCKS * 64 * CH + 15) & ~15      # 5 292 032
 ALGO_BYTES_PER_STREAM = XA_BYTES + PCM_BYTES   # data_len + samples*ch*2
 HEADLINE_MIX = "P1"
 MIXES = ("P0", "P1", "P2", "P3")
-E2E_STREAMS = int(os.environ.get("BJXA_BENCH_E2E_STREAMS", 512))
+# e2e: the whole batch at N = 1; a shard of it per rank when N ranks share one
+# host (8 x 33 GB of pinned memory is more than a bench should take from it)
+E2E_STREAMS = int(os.environ.get("BJXA_BENCH_E2E_STREAMS", 0))
+CORPUS_STREAMS = int(os.environ.get("BJXA_BENCH_CORPUS_STREAMS", 262144))
+PARITY_STREAMS = 256
 
 
 def mix_profiles(torch, mix, n, blocks, device, seed):
@@ -101,7 +119,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-i", str(index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                 "-i", str(index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except OSError:
@@ -156,7 +174,8 @@ def ncu_traffic():
 
 def cpu_reference_rate(xa_streams, steps=1, warmup=0):
     """Decodes `xa_streams` (list of payload arrays, all mono 8-bit 60 s) with
-    the reference library on every host core; returns (Msamples/s, info)."""
+    the reference library on every host core, every stream into a buffer of its
+    own; returns (Msamples/s, seconds per pass, info)."""
     from concurrent.futures import ThreadPoolExecutor
 
     from bjxa_b200 import synth
@@ -168,14 +187,14 @@ def cpu_reference_rate(xa_streams, steps=1, warmup=0):
         orc = binding.Oracle()
     cores = os.cpu_count() or 1
     hdr = synth.xa_header(XA_BYTES, SAMPLES, RATE, BITS, CH)
-    outs = [np.empty(PCM_PITCH, dtype=np.uint8) for _ in range(cores)]
+    outs = [np.empty(PCM_PITCH, dtype=np.uint8) for _ in range(len(xa_streams))]
 
-    def job(arg):
-        slot, pay = arg
+    def job(i):
+        pay = xa_streams[i]
         if lib is not None:
             dec = lib.decoder()
             lib.parse_header(dec, hdr)
-            got = lib.decode(dec, outs[slot], PCM_PITCH, pay, pay.size)   # GIL released
+            got = lib.decode(dec, outs[i], PCM_PITCH, pay, pay.size)   # GIL released
             lib.free_decoder(dec)
             assert got == BLOCKS
         else:
@@ -185,7 +204,7 @@ def cpu_reference_rate(xa_streams, steps=1, warmup=0):
         # static partition: thread t owns streams t, t+cores, ...
         def worker(t):
             for i in range(t, len(xa_streams), cores):
-                job((t, xa_streams[i]))
+                job(i)
         with ThreadPoolExecutor(cores) as ex:
             list(ex.map(worker, range(cores)))
 
@@ -199,9 +218,18 @@ def cpu_reference_rate(xa_streams, steps=1, warmup=0):
     return rate, dt, {"kind": kind, "cores": cores}
 
 
-def host_sample_streams(n, mix, seed=0xB7A):
+def host_sample_streams(n, mix, seed=0xB7A, distinct=32):
+    """n streams of the workload on the host: `distinct` generated ones, the rest
+    block-rotations of them (same blocks, another order: still independent work)."""
     from bjxa_b200 import synth
-    return [synth.xa_payload(seed, 100000 + i, BITS, CH, BLOCKS, mix) for i in range(n)]
+    base = [synth.xa_payload(seed, 100000 + i, BITS, CH, BLOCKS, mix)
+            for i in range(min(n, distinct))]
+    out = []
+    for i in range(n):
+        b = base[i % len(base)]
+        r = (i // len(base)) * 977 % BLOCKS
+        out.append(b if r == 0 else np.roll(b.reshape(BLOCKS, BS), r, axis=0).reshape(-1).copy())
+    return out
 
 
 def run_reference(args):
@@ -209,23 +237,23 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    # bounded sample: ~0.02 s of CPU per stream and core -> a few seconds per step
+    # bounded sample: ~0.02 s of CPU per stream and core -> a fraction of a second per step
     n = max(cores * 32, 64)
-    base = host_sample_streams(min(n, 32), HEADLINE_MIX)
-    streams = [base[i % len(base)] for i in range(n)]
-    rate, dt, info = cpu_reference_rate(streams, steps=args.steps, warmup=min(args.warmup, 1))
+    streams = host_sample_streams(n, HEADLINE_MIX)
+    rate, dt, info = cpu_reference_rate(streams, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": "decode throughput", "value": round(rate, 2),
         "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": round(dt * 1e3, 3),
+        "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
         "data": "synthetic",
         "config": workload_config(N_STREAMS),
         "cpu_baseline": {"value": round(rate, 2), "unit": "Msamples/s", "cores": info["cores"],
                          "kind": info["kind"],
-                         "sample": f"{n} of the workload's streams per step "
-                                   f"({len(base)} distinct), one decoder per stream, "
-                                   f"static partition over {info['cores']} threads"},
+                         "sample": f"{n} of the workload's streams per step (32 generated, the "
+                                   f"rest block-rotations of them), one reference decoder and "
+                                   f"one output buffer per stream, static partition over "
+                                   f"{info['cores']} threads"},
         "e2e": {"value": round(rate, 2), "unit": "Msamples/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -243,6 +271,136 @@ def workload_config(n_streams):
             "parallelism": "streams sharded by index, one process per GPU, no collective"}
 
 
+# ---- variable-shape batches (configs[2], configs[4]) ----------------------------
+
+class VarTable:
+    """A table of n streams of mixed shapes and lengths -- the same on every rank
+    (numpy, seeded): per stream bits, channels, samples, entry state, and the
+    algorithmic bytes bjxa_shard_range balances by."""
+
+    def __init__(self, seed, n, bits_choices, ch_choices, sec_lo, sec_hi):
+        rng = np.random.default_rng(seed)
+        self.n = n
+        self.bits = rng.choice(bits_choices, n).astype(np.int64)
+        self.ch = rng.choice(ch_choices, n).astype(np.int64)
+        secs = np.exp(rng.uniform(np.log(sec_lo), np.log(sec_hi), n))
+        self.samples = np.maximum(1, (secs * RATE).astype(np.int64))
+        self.blocks = (self.samples + 31) // 32
+        self.prev = rng.integers(-32768, 32768, (n, 2, 2))
+        self.xa_bytes = self.blocks * self.ch * (4 * self.bits + 1)
+        self.pcm_bytes = self.samples * 2 * self.ch
+        self.algo = (self.xa_bytes + self.pcm_bytes).astype(np.uint64)
+
+
+def build_var_batch(torch, dev, tab, lo, hi, mix, seed):
+    """Streams [lo, hi) of the table on the device.  The XA arena holds one region
+    per bits class (every block of a class has the same size, so the class's
+    profile bytes are column 0 of a (blocks, block size) matrix); a stream's
+    xa_off points into its class's region.  -> (descs, xa, pcm bytes, samples,
+    algorithmic bytes)"""
+    from bjxa_b200.api import make_descs
+    n = hi - lo
+    bits, ch = tab.bits[lo:hi], tab.ch[lo:hi]
+    blocks, xa_bytes = tab.blocks[lo:hi], tab.xa_bytes[lo:hi]
+    pitch = (blocks * 64 * ch + 15) & ~15
+    d = make_descs(n)
+    d["pcm_off"] = np.concatenate(([0], np.cumsum(pitch)[:-1]))
+    d["blocks"], d["pcm_len"] = blocks, tab.pcm_bytes[lo:hi]
+    d["bits"], d["channels"] = bits, ch
+    d["prev"] = tab.prev[lo:hi]
+    xa_total = int(xa_bytes.sum())
+    xa = torch.empty(xa_total + 64, dtype=torch.uint8, device=dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    for o in range(0, xa.numel(), 1 << 30):
+        xa[o:o + (1 << 30)].random_(0, 256, generator=g)
+    base = 0
+    xa_off = np.zeros(n, dtype=np.uint64)
+    for b in (4, 6, 8):
+        sel = np.nonzero(bits == b)[0]
+        if sel.size == 0:
+            continue
+        bs = 4 * b + 1
+        sizes = xa_bytes[sel]
+        xa_off[sel] = base + np.concatenate(([0], np.cumsum(sizes)[:-1]))
+        total = int(sizes.sum()) // bs            # block-channels of the class
+        region = xa[base:base + total * bs].view(total, bs)
+        for c0 in range(0, total, 1 << 25):
+            c1 = min(total, c0 + (1 << 25))
+            region[c0:c1, 0] = mix_profiles(torch, mix, 1, c1 - c0, dev, seed + 31 * b + c0).reshape(-1)
+        base += total * bs
+    d["xa_off"] = xa_off
+    torch.cuda.synchronize()
+    return (d, xa, int(pitch.sum()), int((tab.samples[lo:hi] * ch).sum()),
+            int(tab.algo[lo:hi].sum()))
+
+
+# ---- parity inside the timed run ---------------------------------------------
+
+def oracle_pool(jobs):
+    """Runs the oracle jobs on all host cores (its C code releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(os.cpu_count() or 1) as ex:
+        return list(ex.map(lambda j: j(), jobs))
+
+
+def parity_decode(lib, plan, d, xa, picks, what):
+    """Checksums of every stream's PCM on the device; the oracle decodes `picks`
+    and its checksums (and final states) must agree."""
+    from bjxa_b200 import synth
+    from oracle import binding
+    orc = binding.Oracle()
+    n = d.size
+    res = lib.plan_fetch(plan, n)
+    if not (res["result"] == d["blocks"]).all():
+        raise SystemExit(f"bench.py: {what}: decode reported failures")
+    sums = lib.plan_checksum(plan, n)
+
+    def job(i):
+        s = d[i]
+        nb = int(s["blocks"]) * int(s["channels"]) * (4 * int(s["bits"]) + 1)
+        pay = xa[int(s["xa_off"]):int(s["xa_off"]) + nb].cpu().numpy()
+        return lambda: orc.decode_blocks(int(s["bits"]), int(s["channels"]), np.array(s["prev"]),
+                                         pay, int(s["blocks"]), int(s["pcm_len"]))
+    outs = oracle_pool([job(int(i)) for i in picks])
+    for i, (done, bad, want, st) in zip(picks, outs):
+        c = int(d[i]["channels"])
+        if bad or synth.stream_checksum(want) != int(sums[i]) or \
+                not np.array_equal(np.array(res[i]["prev"])[:c], st[:c]):
+            raise SystemExit(f"bench.py: {what}: stream {int(i)} differs from the oracle")
+    return {"streams_checksummed_on_gpu": int(n),
+            "digest_of_all": f"{int(np.bitwise_xor.reduce(sums)):016x}",
+            "streams_vs_oracle": int(len(picks)),
+            "samples_vs_oracle": int(sum(o[2].size for o in outs)), "ok": True}
+
+
+def parity_encode(lib, plan, d, pcm, picks, what):
+    from bjxa_b200 import synth
+    from oracle import binding
+    orc = binding.Oracle()
+    n = d.size
+    lib.plan_fetch(plan, n)
+    sums = lib.plan_checksum(plan, n)
+
+    def job(i):
+        s = d[i]
+        raw = pcm[int(s["pcm_off"]):int(s["pcm_off"]) + int(s["pcm_len"])].cpu().numpy().view(np.int16)
+        return lambda: orc.encode_blocks(int(s["bits"]), int(s["channels"]), raw)
+    outs = oracle_pool([job(int(i)) for i in picks])
+    for i, want in zip(picks, outs):
+        if synth.stream_checksum(want) != int(sums[i]):
+            raise SystemExit(f"bench.py: {what}: encoded stream {int(i)} differs from the oracle")
+    return {"streams_checksummed_on_gpu": int(n),
+            "digest_of_all": f"{int(np.bitwise_xor.reduce(sums)):016x}",
+            "streams_vs_oracle": int(len(picks)), "ok": True}
+
+
+def pick_streams(n, full, seed=0xB7A):
+    if full or n <= PARITY_STREAMS:
+        return np.arange(n)
+    return np.sort(np.random.default_rng(seed).choice(n, PARITY_STREAMS, replace=False))
+
+
 # ---- GPU arm -------------------------------------------------------------------
 
 def main():
@@ -252,7 +410,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extras", action="store_true",
-                    help="skip the per-mix, encode, e2e and CPU-baseline legs")
+                    help="headline only: skip the per-mix, encode, e2e, configs and CPU legs")
+    ap.add_argument("--full-parity", action="store_true",
+                    help="the oracle decodes every stream of every leg, not a subset of 256")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -282,6 +442,50 @@ def main():
     lib = bjxa_b200.load()
     warm = max(args.warmup, 3)
     S = N_STREAMS
+    peak, peak_src = measured_peak()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def gather(x):
+        if world == 1:
+            return [float(x)]
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
+    def timed(fn, k):
+        """k steps bracketed by barrier + synchronize; device time, max over ranks."""
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(k + 1)]
+        barrier()
+        t0 = time.time()
+        ev[0].record()
+        for i in range(k):
+            fn()
+            ev[i + 1].record()
+        barrier()
+        t1 = time.time()
+        own_ms = ev[0].elapsed_time(ev[k])
+        per = [ev[i].elapsed_time(ev[i + 1]) for i in range(k)]
+        return max_over_ranks(own_ms), per, (t0, t1), own_ms
 
     # every rank owns S streams: global stream index = rank * S + i (weak scaling);
     # bjxa_shard_range gives the same partition for a global table of world*S streams
@@ -292,9 +496,8 @@ def main():
     xa = torch.empty((S, BLOCKS, BS), dtype=torch.uint8, device=dev)
     g = torch.Generator(device=dev)
     g.manual_seed(0xB7A + rank)
-    step_s = 128
-    for s0 in range(0, S, step_s):
-        xa[s0:s0 + step_s].random_(0, 256, generator=g)
+    for s0 in range(0, S, 128):
+        xa[s0:s0 + 128].random_(0, 256, generator=g)
 
     def set_mix(mix):
         for s0 in range(0, S, 512):
@@ -312,70 +515,33 @@ def main():
     descs["bits"], descs["channels"] = BITS, CH
     plan = lib.plan_create(PLAN_DECODE, descs)
     launches_per_step = lib.plan_launches(plan)
-    stream = torch.cuda.current_stream().cuda_stream
 
     def step():
         lib.plan_run(plan, pcm.data_ptr(), pcm.numel(), xa.data_ptr(), xa.numel(), stream)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(k):
-        """k steps bracketed by barrier + synchronize; device time, max over ranks."""
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(k + 1)]
-        barrier()
-        t0 = time.time()
-        ev[0].record()
-        for i in range(k):
-            step()
-            ev[i + 1].record()
-        barrier()
-        t1 = time.time()
-        total_ms = ev[0].elapsed_time(ev[k])
-        per = [ev[i].elapsed_time(ev[i + 1]) for i in range(k)]
-        if world > 1:
-            t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t.item())
-        return total_ms, per, (t0, t1)
 
     sampler = ClockSampler(local) if rank == 0 else None
     set_mix(HEADLINE_MIX)
     for _ in range(warm):
         step()
-    total_ms, per_launch, window = timed(args.steps)
+    total_ms, per_launch, window, _ = timed(step, args.steps)
     ms_per_step = total_ms / args.steps
     samples_per_step = world * S * SAMPLES * CH
     value = samples_per_step / (ms_per_step * 1e-3) / 1e6
     clocks = sampler.window(*window) if sampler else None
 
-    # ---- parity of what was just timed (rank 0, a few streams, the oracle) -----
-    parity = None
-    if rank == 0:
-        from oracle import binding
-        orc = binding.Oracle()
-        res = lib.plan_fetch(plan, S)
-        assert (res["result"] == BLOCKS).all(), "decode reported failures"
-        for i in (0, S // 2 + 1, S - 1):
-            pay = xa[i].reshape(-1).cpu().numpy()
-            got = pcm[i * PCM_PITCH:i * PCM_PITCH + PCM_BYTES].cpu().numpy().view(np.int16)
-            done, bad, want, st = orc.decode_blocks(BITS, CH, [[0, 0], [0, 0]], pay, BLOCKS,
-                                                    PCM_BYTES)
-            if not np.array_equal(got, want) or not np.array_equal(res[i]["prev"][0], st[0]):
-                raise SystemExit(f"bench.py: stream {i} differs from the oracle")
-        parity = "3 streams (7.9 Msamples) bit-exact vs oracle after the timed region"
+    # ---- parity of what was just timed: every stream checksummed on the device,
+    # a seeded subset of them against the oracle (every rank checks its own) ----
+    picks = pick_streams(S, args.full_parity, 0xB7A + rank)
+    parity = {"headline": parity_decode(lib, plan, descs, xa.reshape(-1), picks, "headline")}
 
     # ---- roofline of the decode kernel ------------------------------------------
-    peak, peak_src = measured_peak()
     algo_bytes = S * ALGO_BYTES_PER_STREAM          # per launch, per GPU
     avg_launch_ms = float(np.mean(per_launch))
     achieved = algo_bytes / (avg_launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": ncu_traffic(),
-                "kernel": "xa_decode_kernel<DecTile<8,512,1,3>> (mono, long strips, direct form)", "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": algo_bytes,
+                "kernel": "xa_decode_kernel<DecTile<8,512,1,3>> (mono, long strips, direct form)",
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
                 "avg_launch_ms": round(avg_launch_ms, 4),
                 "frac_of_nominal_8000": round(achieved / 8000.0, 4)}
 
@@ -398,11 +564,13 @@ def main():
             set_mix(mix)
             step()
             k = 3
-            tms, _, _ = timed(k)
+            tms, _, _, _ = timed(step, k)
             v = samples_per_step / (tms / k * 1e-3) / 1e6
             by_mix[mix] = {"Msamples_per_s": round(v, 1),
                            "hbm_frac": round(v * 1e6 / world * ALGO_BYTES_PER_STREAM / SAMPLES
                                              / 1e9 / peak, 4)}
+            if mix == "P2":     # the chain-rich mix: also checked against the oracle
+                parity["P2"] = parity_decode(lib, plan, descs, xa.reshape(-1), picks[:64], "mix P2")
         line["by_profile_mix"] = by_mix
         set_mix(HEADLINE_MIX)
         step()
@@ -417,18 +585,9 @@ def main():
                          pcm.numel(), stream)
         for _ in range(3):
             estep()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        ev0.record()
-        for _ in range(5):
-            estep()
-        ev1.record()
-        barrier()
-        ems = ev0.elapsed_time(ev1) / 5
-        if world > 1:
-            t = torch.tensor([ems], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ems = float(t.item())
+        tms, _, _, _ = timed(estep, 5)
+        ems = tms / 5
+        parity["encode"] = parity_encode(lib, eplan, descs, pcm, picks, "encode")
         line["encode"] = {"Msamples_per_s": round(samples_per_step / (ems * 1e-3) / 1e6, 1),
                           "ms_per_step": round(ems, 4), "mode": "reference-exact (profile 0)",
                           "hbm_frac": round(algo_bytes / (ems * 1e-3) / 1e9 / peak, 4)}
@@ -436,10 +595,17 @@ def main():
         del xa_out
 
         # ---- end to end through the host-buffer C-ABI call ------------------------
-        ne = min(E2E_STREAMS, S)
-        h_src = torch.empty((ne, XA_BYTES), dtype=torch.uint8).pin_memory()
-        h_dst = torch.empty((ne, PCM_PITCH), dtype=torch.uint8).pin_memory()
-        h_src.copy_(xa[:ne].reshape(ne, -1))
+        ne = E2E_STREAMS or (S if world == 1 else 512)
+        ne = min(ne, S)
+        try:
+            h_src = torch.empty((ne, XA_BYTES), dtype=torch.uint8, pin_memory=True)
+            h_dst = torch.empty((ne, PCM_PITCH), dtype=torch.uint8, pin_memory=True)
+        except RuntimeError:            # the host cannot pin 33 GB: a shard of the batch
+            ne = min(512, S)
+            h_src = torch.empty((ne, XA_BYTES), dtype=torch.uint8, pin_memory=True)
+            h_dst = torch.empty((ne, PCM_PITCH), dtype=torch.uint8, pin_memory=True)
+        for s0 in range(0, ne, 256):
+            h_src[s0:s0 + 256].copy_(xa[s0:s0 + 256].reshape(-1, XA_BYTES))
         from bjxa_b200 import synth
         hdr = synth.xa_header(XA_BYTES, SAMPLES, RATE, BITS, CH)
         srcs = [h_src[i].numpy() for i in range(ne)]
@@ -458,43 +624,217 @@ def main():
         e2e_step()
         barrier()
         t0 = time.perf_counter()
-        k = 3
+        k = 3 if ne <= 512 else 2
         for _ in range(k):
             e2e_step()
         barrier()
-        edt = (time.perf_counter() - t0) / k
-        if world > 1:
-            t = torch.tensor([edt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            edt = float(t.item())
-        want = pcm[:PCM_BYTES].cpu().numpy()
-        assert np.array_equal(h_dst[0].numpy()[:PCM_BYTES], want), "e2e output differs"
-        line["e2e"] = {"value": round(world * ne * SAMPLES * CH / edt / 1e6, 1),
+        edt = max_over_ranks((time.perf_counter() - t0) / k)
+        for i in (0, ne // 2, ne - 1):
+            want = pcm[i * PCM_PITCH:i * PCM_PITCH + PCM_BYTES].cpu().numpy()
+            assert np.array_equal(h_dst[i].numpy()[:PCM_BYTES], want), "e2e output differs"
+        # the box's copy ceiling for the same bytes: both directions at once on two
+        # streams, all ranks together, nothing else
+        d_probe_in = xa.reshape(-1)[:ne * XA_BYTES]
+        d_probe_out = pcm[:ne * PCM_PITCH]
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def copies():
+            cur = torch.cuda.current_stream()
+            s1.wait_stream(cur)
+            s2.wait_stream(cur)
+            with torch.cuda.stream(s1):
+                d_probe_in.copy_(h_src.reshape(-1), non_blocking=True)
+            with torch.cuda.stream(s2):
+                h_dst.reshape(-1).copy_(d_probe_out, non_blocking=True)
+            cur.wait_stream(s1)
+            cur.wait_stream(s2)
+        copies()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            copies()
+        barrier()
+        cdt = max_over_ranks((time.perf_counter() - t0) / 2)
+        e2e_val = world * ne * SAMPLES * CH / edt / 1e6
+        ceiling = world * ne * SAMPLES * CH / cdt / 1e6
+        line["e2e"] = {"value": round(e2e_val, 1),
                        "unit": "Msamples/s", "h2d_bytes_per_step": ne * XA_BYTES,
                        "d2h_bytes_per_step": ne * PCM_BYTES,
+                       "copy_ceiling_Msamples_per_s": round(ceiling, 1),
+                       "frac_of_box_ceiling": round(e2e_val / ceiling, 4),
+                       "copy_ceiling_GBps_per_gpu": round(ne * (XA_BYTES + PCM_PITCH) / cdt / 1e9, 2),
                        "call": f"bjxa_batch_decode on {ne} streams per GPU per step, pinned "
-                               f"host buffers, copies inside the timed region"}
+                               f"host buffers, copies inside the timed region; ceiling = the "
+                               f"same bytes copied both ways at once by all {world} rank(s), "
+                               f"nothing else running"}
+        del h_src, h_dst, srcs, dsts, d_probe_in, d_probe_out
 
-        # ---- CPU baseline: the reference on this box's host cores (rank 0, N=1) ---
-        if rank == 0 and world == 1:
+    # the headline's arenas are no longer needed
+    lib.plan_free(plan)
+    del xa, pcm
+    torch.cuda.empty_cache()
+
+    if not args.no_extras:
+        configs = {}
+
+        # ---- configs[2]: mixed stereo batch, per GPU (weak) ------------------------
+        tab = VarTable(3 + rank, 4096, [4, 6, 8], [2], 0.5, 120.0)
+        d, vxa, pcm_total, nsamp, algo = build_var_batch(torch, dev, tab, 0, tab.n, "P2", 300 + rank)
+        vpcm = torch.empty(pcm_total + 64, dtype=torch.uint8, device=dev)
+        vplan = lib.plan_create(PLAN_DECODE, d)
+
+        def vstep():
+            lib.plan_run(vplan, vpcm.data_ptr(), vpcm.numel(), vxa.data_ptr(), vxa.numel(), stream)
+        vstep()
+        vstep()
+        tms, _, _, _ = timed(vstep, 3)
+        ms = tms / 3
+        tot_samples = sum_over_ranks(nsamp)
+        par = parity_decode(lib, vplan, d, vxa, pick_streams(tab.n, args.full_parity, 7), "configs[2]")
+        configs["configs[2]"] = {
+            "what": "mixed batch decode: 4096 stereo streams per GPU, 4/6/8 bit, 0.5-120 s "
+                    "log-uniform, mix P2, random header state",
+            "ms_per_step": round(ms, 3), "launches_per_step": lib.plan_launches(vplan),
+            "Msamples_per_s": round(tot_samples / ms / 1e3, 1),
+            "hbm_frac": round(algo / (ms * 1e-3) / 1e9 / peak, 4), "parity": par}
+        lib.plan_free(vplan)
+        del vxa, vpcm
+        torch.cuda.empty_cache()
+
+        # ---- configs[3]: 4096 stereo PCM streams x 60 s -> 4-bit XA, per GPU --------
+        n3, ch3, bits3 = 4096, 2, 4
+        pcm_bytes3 = SAMPLES * 2 * ch3
+        pitch3 = (BLOCKS * 64 * ch3 + 15) & ~15
+        xa_bytes3 = BLOCKS * ch3 * (4 * bits3 + 1)
+        pcm3 = torch.empty((n3, pitch3 // 2), dtype=torch.int16, device=dev)
+        g3 = torch.Generator(device=dev)
+        g3.manual_seed(4 + rank)
+        t = torch.arange(pitch3 // 4, device=dev, dtype=torch.int32)
+        for s0 in range(0, n3, 128):
+            m = min(128, n3 - s0)
+            # integer-only PCM: a triangle wave + noise per channel
+            per = torch.randint(16, 2000, (m, 1), device=dev, generator=g3, dtype=torch.int32)
+            amp = torch.randint(3000, 12000, (m, 1), device=dev, generator=g3, dtype=torch.int32)
+            ph = t.unsqueeze(0) % per
+            tri = ((2 * ph - per).abs() * 2 - per) * amp // per
+            noise = torch.randint(-2048, 2048, (m, pitch3 // 4), device=dev, generator=g3,
+                                  dtype=torch.int32)
+            pcm3[s0:s0 + m, 0::2] = (tri + noise).clamp_(-32768, 32767).to(torch.int16)
+            pcm3[s0:s0 + m, 1::2] = (tri // 2 - noise).clamp_(-32768, 32767).to(torch.int16)
+            del ph, tri, noise
+        d3 = make_descs(n3)
+        d3["xa_off"] = np.arange(n3, dtype=np.uint64) * xa_bytes3
+        d3["pcm_off"] = np.arange(n3, dtype=np.uint64) * pitch3
+        d3["blocks"], d3["pcm_len"] = BLOCKS, pcm_bytes3
+        d3["bits"], d3["channels"] = bits3, ch3
+        xa3 = torch.empty(n3 * xa_bytes3 + 64, dtype=torch.uint8, device=dev)
+        raw3 = pcm3.view(torch.uint8).reshape(-1)
+        plan3 = lib.plan_create(PLAN_ENCODE, d3)
+
+        def step3():
+            lib.plan_run(plan3, xa3.data_ptr(), xa3.numel(), raw3.data_ptr(), raw3.numel(), stream)
+        step3()
+        step3()
+        tms, _, _, _ = timed(step3, 3)
+        ms = tms / 3
+        par = parity_encode(lib, plan3, d3, raw3, pick_streams(n3, args.full_parity, 9), "configs[3]")
+        configs["configs[3]"] = {
+            "what": "batched encode: 4096 stereo PCM streams x 60 s per GPU -> 4-bit XA, "
+                    "reference-exact (the reference writes profile 0: libbjxa.c:679; the "
+                    "searching encoder is an opt-in extension, tools/bench_configs.py)",
+            "ms_per_step": round(ms, 3),
+            "Msamples_per_s": round(world * n3 * SAMPLES * ch3 / ms / 1e3, 1),
+            "hbm_frac": round(n3 * (pcm_bytes3 + xa_bytes3) / (ms * 1e-3) / 1e9 / peak, 4),
+            "parity": par}
+        lib.plan_free(plan3)
+        del pcm3, raw3, xa3
+        torch.cuda.empty_cache()
+
+        # ---- configs[4]: ONE corpus, sharded by bytes over the ranks (strong) --------
+        def corpus(tag, tab, mix):
+            lo, cnt = lib.shard_range(tab.n, rank, world, tab.algo)
+            d, cxa, pcm_total, nsamp, algo = build_var_batch(torch, dev, tab, lo, lo + cnt, mix, 500)
+            cpcm = torch.empty(pcm_total + 64, dtype=torch.uint8, device=dev)
+            dplan = lib.plan_create(PLAN_DECODE, d)
+
+            def dstep():
+                lib.plan_run(dplan, cpcm.data_ptr(), cpcm.numel(), cxa.data_ptr(), cxa.numel(), stream)
+            dstep()
+            dstep()
+            tms, _, _, own = timed(dstep, 3)
+            dms = tms / 3
+            per_rank = gather(own / 3)
+            par_d = parity_decode(lib, dplan, d, cxa, pick_streams(cnt, args.full_parity, 11 + rank),
+                                  f"configs[4] {tag} decode")
+            launches = lib.plan_launches(dplan)
+            lib.plan_free(dplan)
+            # ... then encode the PCM just produced back to XA (same shapes)
+            cxa2 = torch.empty(cxa.numel(), dtype=torch.uint8, device=dev)
+            eplan = lib.plan_create(PLAN_ENCODE, d)
+
+            def estep():
+                lib.plan_run(eplan, cxa2.data_ptr(), cxa2.numel(), cpcm.data_ptr(), cpcm.numel(), stream)
+            estep()
+            estep()
+            tms, _, _, eown = timed(estep, 3)
+            ems = tms / 3
+            eper_rank = gather(eown / 3)
+            par_e = parity_encode(lib, eplan, d, cpcm, pick_streams(cnt, args.full_parity, 13 + rank),
+                                  f"configs[4] {tag} encode")
+            lib.plan_free(eplan)
+            total_samples = int((tab.samples * tab.ch).sum())
+            total_algo = float(tab.algo.sum())
+            shard_bytes = gather(float(algo))
+            out = {
+                "streams": int(tab.n), "mix": mix, "samples": total_samples,
+                "algorithmic_GB": round(total_algo / 1e9, 2),
+                "sharding": "bjxa_shard_range(bytes[]): contiguous, byte-balanced ranges of ONE "
+                            "global table, no collective (strong scaling)",
+                "streams_this_rank": int(cnt), "launches_per_step": launches,
+                "shard_bytes_imbalance": round(max(shard_bytes) / (sum(shard_bytes) / world) - 1, 4),
+                "decode": {"ms_per_step": round(dms, 3), "per_rank_ms": [round(x, 3) for x in per_rank],
+                           "time_imbalance": round(max(per_rank) / (sum(per_rank) / world) - 1, 4),
+                           "Msamples_per_s": round(total_samples / dms / 1e3, 1),
+                           "hbm_frac_per_gpu": round(total_algo / world / (dms * 1e-3) / 1e9 / peak, 4),
+                           "parity": par_d},
+                "encode": {"ms_per_step": round(ems, 3), "per_rank_ms": [round(x, 3) for x in eper_rank],
+                           "time_imbalance": round(max(eper_rank) / (sum(eper_rank) / world) - 1, 4),
+                           "Msamples_per_s": round(total_samples / ems / 1e3, 1),
+                           "hbm_frac_per_gpu": round(total_algo / world / (ems * 1e-3) / 1e9 / peak, 4),
+                           "parity": par_e}}
+            del cxa, cxa2, cpcm
+            torch.cuda.empty_cache()
+            return out
+
+        # SURVEY.md 8d "Config 5": the shapes of config 3 (stereo, 4/6/8 bit, mix P2,
+        # random header state), 0.25-4 s; beside it the xa.exe-like mix over mono and
+        # stereo streams that round 1 reported
+        configs["configs[4]"] = {
+            "what": f"corpus decode+encode: {CORPUS_STREAMS} streams, 0.25-4 s log-uniform, "
+                    f"sharded by bytes over {world} GPU(s)",
+            "stereo_P2": corpus("stereo P2", VarTable(5, CORPUS_STREAMS, [4, 6, 8], [2], 0.25, 4.0), "P2"),
+            "mixed_P1": corpus("mixed P1", VarTable(6, CORPUS_STREAMS, [4, 6, 8], [1, 2], 0.25, 4.0), "P1")}
+        line["configs"] = configs
+
+        # ---- CPU baseline: the reference on this box's host cores (rank 0) ----------
+        if rank == 0:
             cores = os.cpu_count() or 1
             # bounded sample: about 10-30 s of CPU work (64 streams = 0.17 Gsamples a core)
             n = 64 * cores
-            base = [xa[i].reshape(-1).cpu().numpy() for i in range(16)]
-            streams = [base[i % len(base)] for i in range(n)]
+            streams = host_sample_streams(n, HEADLINE_MIX, distinct=16)
             cpu_reference_rate(streams[:cores], steps=1, warmup=0)      # thread start-up, page-in
             rate, dt, info = cpu_reference_rate(streams, steps=1, warmup=0)
             line["cpu_baseline"] = {
                 "value": round(rate, 2), "unit": "Msamples/s", "cores": info["cores"],
                 "kind": info["kind"],
-                "sample": f"{n} streams of this workload ({len(base)} distinct) decoded once, "
-                          f"one reference decoder per stream, static partition over "
-                          f"{info['cores']} threads, {dt:.2f} s wall = "
-                          f"{dt * info['cores']:.0f} core-seconds"}
+                "sample": f"{n} streams of this workload (16 generated, the rest block-rotations "
+                          f"of them) decoded once, one reference decoder and one output buffer "
+                          f"per stream, static partition over {info['cores']} threads, "
+                          f"{dt:.2f} s wall = {dt * info['cores']:.0f} core-seconds"}
 
     if sampler:
         sampler.stop()
-    lib.plan_free(plan)
+    barrier()
     if rank == 0:
         sys.stdout.flush()
         os.write(out_fd, (json.dumps(line) + "\n").encode())

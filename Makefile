@@ -20,7 +20,7 @@ SRC      := bjxa_b200/csrc
 LIBDIR   := bjxa_b200/lib
 OBJDIR   := build
 LIB      := $(LIBDIR)/libbjxa_b200.so
-HDRS     := $(SRC)/xa_core.h $(SRC)/xa_tile.h $(SRC)/xa_plan.h include/bjxa.h include/bjxa_batch.h
+HDRS     := $(SRC)/xa_core.h $(SRC)/xa_tile.h $(SRC)/xa_plan.h $(SRC)/xa_walk.h $(SRC)/bjxa_internal.h include/bjxa.h include/bjxa_batch.h
 
 .PHONY: all lib oracle emul dropin clean
 all: lib
@@ -31,19 +31,33 @@ $(OBJDIR)/xa_kernels.o: $(SRC)/xa_kernels.cu $(HDRS)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c -o $@ $< 2> $(OBJDIR)/ptxas.log || (cat $(OBJDIR)/ptxas.log; false)
 
-$(OBJDIR)/bjxa_host.o: $(SRC)/bjxa_host.c include/bjxa.h include/bjxa_batch.h
+$(OBJDIR)/bjxa_host.o: $(SRC)/bjxa_host.c $(SRC)/bjxa_internal.h include/bjxa.h include/bjxa_batch.h
 	@mkdir -p $(OBJDIR)
 	$(CC) $(CFLAGS) -c -o $@ $<
 
-$(OBJDIR)/bjxa_corpus.o: $(SRC)/bjxa_corpus.c include/bjxa.h include/bjxa_batch.h
+$(OBJDIR)/bjxa_corpus.o: $(SRC)/bjxa_corpus.c $(SRC)/bjxa_internal.h include/bjxa.h include/bjxa_batch.h
 	@mkdir -p $(OBJDIR)
 	$(CC) $(CFLAGS) -c -o $@ $<
 
-$(LIB): $(OBJDIR)/xa_kernels.o $(OBJDIR)/bjxa_host.o $(OBJDIR)/bjxa_corpus.o $(SRC)/libbjxa.map
-	@mkdir -p $(LIBDIR)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJDIR)/xa_kernels.o $(OBJDIR)/bjxa_host.o $(OBJDIR)/bjxa_corpus.o \
-	    -Xlinker --version-script=$(SRC)/libbjxa.map -Xlinker -soname=libbjxa_b200.so \
+OBJS     := $(OBJDIR)/xa_kernels.o $(OBJDIR)/bjxa_host.o $(OBJDIR)/bjxa_corpus.o
+LINK      = $(NVCC) $(ARCH) -shared -o $@ $(OBJS) -Xlinker --version-script=$(SRC)/libbjxa.map \
 	    -cudart static -lpthread -ldl -lrt
+
+# The same objects under two names: libbjxa_b200.so for callers that ask for this
+# backend by name, and libbjxa.so.0 -- the soname the reference installs
+# (/root/reference/Makefile.am:28, -version-info 2:0:2 -> libbjxa.so.0.2.0) -- so
+# that a program ALREADY LINKED against the reference picks the backend up through
+# the library path, no relink; plus libbjxa.so for -lbjxa and a bjxa.pc like the
+# reference's (/root/reference/bjxa.pc.in, Makefile.am:43).  Plain copies rather
+# than symlinks: the directory travels to machines by tools that may not keep links.
+$(LIB): $(OBJS) $(SRC)/libbjxa.map bjxa_b200/bjxa.pc.in
+	@mkdir -p $(LIBDIR)/pkgconfig
+	$(LINK) -Xlinker -soname=libbjxa_b200.so
+	$(NVCC) $(ARCH) -shared -o $(LIBDIR)/libbjxa.so.0 $(OBJS) -Xlinker --version-script=$(SRC)/libbjxa.map \
+	    -Xlinker -soname=libbjxa.so.0 -cudart static -lpthread -ldl -lrt
+	cp -f $(LIBDIR)/libbjxa.so.0 $(LIBDIR)/libbjxa.so
+	sed -e 's|@libdir@|$(abspath $(LIBDIR))|' -e 's|@includedir@|$(abspath include)|' \
+	    bjxa_b200/bjxa.pc.in > $(LIBDIR)/pkgconfig/bjxa.pc
 
 oracle:
 	$(MAKE) -s -C oracle all
@@ -63,6 +77,13 @@ dropin: lib oracle
 	$(CC) $(REF_CF) -o oracle/_ref/bjxa_dropin $(REF_CLI) $(DROPLINK)
 	$(CC) $(REF_CF) -DBJXA_SINGLE_PASS -o oracle/_ref/bjxa_dropin_single_pass $(REF_CLI) $(DROPLINK)
 	$(CC) $(REF_CF) -o oracle/_ref/test_api_dropin $(REFERENCE)/test/test_libbjxa_api.c $(DROPLINK)
+	# the no-relink case: the reference's library under its own soname, and its CLI
+	# linked against THAT (no rpath); tests swap the library path to ours
+	@mkdir -p oracle/_ref/refso
+	$(CC) $(REF_CF) -fPIC -shared -Wl,-soname,libbjxa.so.0 -Wl,--version-script=$(REFERENCE)/src/libbjxa.map \
+	    -o oracle/_ref/refso/libbjxa.so.0 $(REFERENCE)/src/libbjxa.c
+	cp -f oracle/_ref/refso/libbjxa.so.0 oracle/_ref/refso/libbjxa.so
+	$(CC) $(REF_CF) -o oracle/_ref/bjxa_ref_dyn $(REF_CLI) -Loracle/_ref/refso -lbjxa
 else
 dropin:
 	@echo "dropin: $(REFERENCE) not present; using prebuilt oracle/_ref binaries if any"

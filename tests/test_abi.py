@@ -57,3 +57,27 @@ def test_product_does_not_reference_the_oracle():
     deps = subprocess.run(["ldd", bjxa_b200.LIB_PATH], capture_output=True,
                           text=True).stdout
     assert "oracle" not in deps and "bjxa_ref" not in deps
+
+
+def test_installed_names_match_the_reference():
+    """What the reference installs (/root/reference/Makefile.am:28,43): a library
+    whose soname is libbjxa.so.0, libbjxa.so for -lbjxa, and bjxa.pc.  A program
+    already linked against the reference finds the backend through the library
+    path: no relink."""
+    libdir = os.path.dirname(bjxa_b200.LIB_PATH)
+    so0 = os.path.join(libdir, "libbjxa.so.0")
+    dyn = subprocess.run(["readelf", "-d", so0], capture_output=True, text=True, check=True).stdout
+    assert "Library soname: [libbjxa.so.0]" in dyn
+    syms = lambda p: set(re.findall(r"\b(bjxa_\w+@@[\w.]+)", subprocess.run(      # noqa: E731
+        ["readelf", "--dyn-syms", "-W", p], capture_output=True, text=True, check=True).stdout))
+    assert syms(so0) == syms(bjxa_b200.LIB_PATH) == syms(os.path.join(libdir, "libbjxa.so"))
+    pc = open(os.path.join(libdir, "pkgconfig", "bjxa.pc")).read()
+    assert "Name: bjxa" in pc and "-lbjxa" in pc and "@" not in pc
+    # the reference CLI, dynamically linked against the REFERENCE's library
+    # (oracle/_ref/refso, built by `make dropin`), resolves libbjxa.so.0 to ours
+    # when the library path says so
+    exe = os.path.join(ROOT, "oracle", "_ref", "bjxa_ref_dyn")
+    if os.path.exists(exe):
+        out = subprocess.run(["ldd", exe], capture_output=True, text=True,
+                             env=dict(os.environ, LD_LIBRARY_PATH=libdir)).stdout
+        assert os.path.join(libdir, "libbjxa.so.0") in out, out

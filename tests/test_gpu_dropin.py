@@ -130,3 +130,21 @@ def test_reference_api_test_program(vectors, tmp_path):
     r = subprocess.run([exe], env=dict(os.environ, SRCDIR=str(tmp_path)),
                        capture_output=True, timeout=600, stdin=subprocess.DEVNULL)
     assert r.returncode == 0, (r.returncode, r.stderr[-500:])
+
+
+@pytest.mark.parametrize("name", ["square-stereo-4.xa", "square-mono-6.xa"])
+def test_no_relink(vectors, golden, name):
+    """A program ALREADY linked against the reference's libbjxa.so.0 (its CLI, built
+    against oracle/_ref/refso): with the reference's library on the path it runs on
+    the CPU, with ours on the path it runs on the B200 -- same bytes, no relink."""
+    exe = need("bjxa_ref_dyn")
+    libdirs = {"reference": os.path.join(REFDIR, "refso"),
+               "b200": os.path.join(ROOT, "bjxa_b200", "lib")}
+    for who, libdir in libdirs.items():
+        env = dict(os.environ, LD_LIBRARY_PATH=libdir)
+        ldd = subprocess.run(["ldd", exe], capture_output=True, text=True, env=env).stdout
+        assert os.path.join(libdir, "libbjxa.so.0") in ldd, (who, ldd)
+        r = subprocess.run([exe, "decode"], input=vectors[name], capture_output=True,
+                           timeout=600, env=env)
+        assert r.returncode == 0, (who, r.stderr)
+        assert sha1(r.stdout) == golden["reference_tests"][name]["wav_sha1"], who

@@ -56,3 +56,26 @@ def test_two_ranks_shard_the_stream_table(tmp_path, world):
     assert abs(int(g[0, 2]) - int(g[1, 2])) <= 2 * int(sizes.max())
     assert int(g[:, 2].sum()) == int(sizes.sum())
     assert float(np.load(tmp_path / "elapsed.npy")[0]) == 10.0 + world - 1
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_corpus_table_shards_within_three_percent(world):
+    """bench.py's configs[4]: the 262 144-stream corpus table (the same on every
+    rank) cut by bjxa_shard_range(bytes[]) -- contiguous, exhaustive, and no shard
+    more than 3 % above the mean."""
+    import bench
+    import bjxa_b200
+    lib = bjxa_b200.load()
+    for tab in (bench.VarTable(5, 262144, [4, 6, 8], [2], 0.25, 4.0),
+                bench.VarTable(6, 262144, [4, 6, 8], [1, 2], 0.25, 4.0)):
+        again = bench.VarTable(5, 262144, [4, 6, 8], [2], 0.25, 4.0)
+        assert tab.algo.sum() > 0 and np.array_equal(
+            again.algo, bench.VarTable(5, 262144, [4, 6, 8], [2], 0.25, 4.0).algo)
+        nxt, per = 0, []
+        for r in range(world):
+            first, count = lib.shard_range(tab.n, r, world, tab.algo)
+            assert first == nxt
+            nxt = first + count
+            per.append(int(tab.algo[first:first + count].sum()))
+        assert nxt == tab.n
+        assert max(per) / (sum(per) / world) - 1 <= 0.03

@@ -1,16 +1,16 @@
 #!/usr/bin/env python
-"""BASELINE.json configs[2], [3] and [4] on one B200 (configs[1] is bench.py's
-headline, configs[0] is tests/test_gpu_decode.py::test_config1_square_stereo_4).
+"""What bench.py's line does not carry (BASELINE.json configs[1..4] are all in
+bench.py since round 2; configs[0] is tests/test_gpu_decode.py::
+test_config1_square_stereo_4):
 
-    python tools/bench_configs.py [--only mixed,encode,corpus] > profiles/configs_rNN.json
+    python tools/bench_configs.py [--only encode,files] > profiles/extras_rNN.json
 
-  mixed   configs[2]: 4096 stereo streams, bits uniform in {4,6,8}, length
-          log-uniform 0.5-120 s, profile mix P2, random non-zero header state
-  encode  configs[3]: 4096 stereo PCM streams x 60 s -> 4-bit XA.  Reference-
-          exact mode (profile byte 0, top-bits truncation): the reference has
-          no filter/range search (/root/reference/src/libbjxa.c:679)
-  corpus  configs[4]: 262144 streams (mono/stereo, 4/6/8 bit, 0.25-4 s,
-          profile mix P1), decode then encode, one GPU
+  encode  configs[3]'s batch (4096 stereo PCM streams x 60 s -> 4-bit XA) through
+          the reference-exact encoder and then through the SEARCHING encoder, an
+          opt-in extension: the reference has no filter/range search
+          (/root/reference/src/libbjxa.c:679)
+  files   40 000 whole .xa files in a pinned host arena -> whole .wav files
+          (bjxa_corpus_run), wall clock including the copies
 
 Each leg prints one JSON line: device-resident throughput (CUDA events around
 bjxa_plan_run), algorithmic GB/s and fraction of the measured HBM peak, and a
@@ -47,89 +47,6 @@ def timed(fn, steps, warmup=2):
         ev[i + 1].record()
     torch.cuda.synchronize()
     return [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
-
-
-def build_decode_batch(rng, n, bits_choices, ch_choices, sec_lo, sec_hi, mix, state):
-    """Variable-shape decode batch generated on the device."""
-    bits = rng.choice(bits_choices, n).astype(np.int64)
-    ch = rng.choice(ch_choices, n).astype(np.int64)
-    secs = np.exp(rng.uniform(np.log(sec_lo), np.log(sec_hi), n))
-    samples = np.maximum(1, (secs * 44100).astype(np.int64))
-    blocks = (samples + 31) // 32
-    bs = 4 * bits + 1
-    xa_bytes = blocks * ch * bs
-    pcm_bytes = samples * 2 * ch
-    pitch = (blocks * 64 * ch + 15) & ~15
-    d = make_descs(n)
-    d["xa_off"] = np.concatenate(([0], np.cumsum(xa_bytes)[:-1]))
-    d["pcm_off"] = np.concatenate(([0], np.cumsum(pitch)[:-1]))
-    d["blocks"], d["pcm_len"] = blocks, pcm_bytes
-    d["bits"], d["channels"] = bits, ch
-    if state:
-        d["prev"] = rng.integers(-32768, 32768, (n, 2, 2))
-    xa_total, pcm_total = int(xa_bytes.sum()), int(pitch.sum())
-    xa = torch.empty(xa_total + 64, dtype=torch.uint8, device=DEV)
-    g = torch.Generator(device=DEV)
-    g.manual_seed(12345)
-    step = 1 << 30
-    for o in range(0, xa.numel(), step):
-        xa[o:o + step].random_(0, 256, generator=g)
-    # profile bytes: one per block-channel, at stride bs inside each stream
-    nbc = blocks * ch
-    for b in (4, 6, 8):
-        sel = np.nonzero(bits == b)[0]
-        if sel.size == 0:
-            continue
-        cnt = nbc[sel]
-        total = int(cnt.sum())
-        starts = torch.from_numpy(np.repeat(d["xa_off"][sel].astype(np.int64), cnt)).to(DEV)
-        within = torch.from_numpy(
-            (np.arange(total) - np.repeat(np.cumsum(cnt) - cnt, cnt)).astype(np.int64)).to(DEV)
-        pos = starts + within * (4 * b + 1)
-        prof = bench.mix_profiles(torch, mix, 1, total, DEV, 77 + b).reshape(-1)
-        if mix == "P1":
-            pass        # isolation across stream boundaries does not matter
-        xa[pos] = prof
-        del starts, within, pos, prof
-    torch.cuda.synchronize()
-    return d, xa, xa_total, pcm_total, int((samples * ch).sum()), int((xa_bytes + pcm_bytes).sum())
-
-
-def spot_check_decode(lib, orc, d, xa, pcm, picks):
-    for i in picks:
-        s = d[i]
-        nb = int(s["blocks"]) * int(s["channels"]) * (4 * int(s["bits"]) + 1)
-        pay = xa[int(s["xa_off"]):int(s["xa_off"]) + nb].cpu().numpy()
-        got = pcm[int(s["pcm_off"]):int(s["pcm_off"]) + int(s["pcm_len"])].cpu().numpy().view(np.int16)
-        done, bad, want, st = orc.decode_blocks(int(s["bits"]), int(s["channels"]),
-                                                np.array(s["prev"]), pay, int(s["blocks"]),
-                                                int(s["pcm_len"]))
-        assert not bad and np.array_equal(got, want), f"stream {i} differs from the oracle"
-
-
-def leg_mixed(lib, orc):
-    rng = np.random.default_rng(3)
-    n = 4096
-    d, xa, xa_total, pcm_total, nsamp, algo = build_decode_batch(
-        rng, n, [4, 6, 8], [2], 0.5, 120.0, "P2", True)
-    pcm = torch.empty(pcm_total + 64, dtype=torch.uint8, device=DEV)
-    plan = lib.plan_create(PLAN_DECODE, d)
-    st = torch.cuda.current_stream().cuda_stream
-    ms = timed(lambda: lib.plan_run(plan, pcm.data_ptr(), pcm.numel(), xa.data_ptr(),
-                                    xa.numel(), st), 3)
-    res = lib.plan_fetch(plan, n)
-    assert (res["result"] == d["blocks"]).all()
-    order = np.argsort(d["blocks"])
-    spot_check_decode(lib, orc, d, xa, pcm, [int(order[0]), int(order[n // 2]), int(order[5])])
-    best = min(ms)
-    out = {"config": "configs[2] mixed batch decode: 4096 stereo streams, 4/6/8 bit, "
-                     "0.5-120 s log-uniform, mix P2, random header state",
-           "launches_per_step": lib.plan_launches(plan), "ms": [round(m, 3) for m in ms],
-           "Msamples_per_s": round(nsamp / best / 1e3, 1),
-           "GBps": round(algo / best / 1e6, 1), "hbm_frac": round(algo / best / 1e6 / PEAK, 4),
-           "bytes": {"xa": xa_total, "pcm": pcm_total}, "parity": "3 streams vs oracle ok"}
-    lib.plan_free(plan)
-    return out
 
 
 def leg_encode(lib, orc):
@@ -208,49 +125,6 @@ def leg_encode(lib, orc):
     return out
 
 
-def leg_corpus(lib, orc, strips):
-    if strips:
-        os.environ["BJXA_B200_STRIPS"] = str(strips)
-    else:
-        os.environ.pop("BJXA_B200_STRIPS", None)
-    rng = np.random.default_rng(5)
-    n = 262144
-    d, xa, xa_total, pcm_total, nsamp, algo = build_decode_batch(
-        rng, n, [4, 6, 8], [1, 2], 0.25, 4.0, "P1", True)
-    pcm = torch.empty(pcm_total + 64, dtype=torch.uint8, device=DEV)
-    plan = lib.plan_create(PLAN_DECODE, d)
-    st = torch.cuda.current_stream().cuda_stream
-    ms = timed(lambda: lib.plan_run(plan, pcm.data_ptr(), pcm.numel(), xa.data_ptr(),
-                                    xa.numel(), st), 3)
-    res = lib.plan_fetch(plan, n)
-    assert (res["result"] == d["blocks"]).all()
-    spot_check_decode(lib, orc, d, xa, pcm, [0, n // 2 + 7, n - 1])
-    launches = lib.plan_launches(plan)
-    lib.plan_free(plan)
-    best = min(ms)
-    # encode the PCM just produced back to XA (same shapes)
-    xa2 = torch.empty(xa_total + 64, dtype=torch.uint8, device=DEV)
-    eplan = lib.plan_create(PLAN_ENCODE, d)
-    ems = timed(lambda: lib.plan_run(eplan, xa2.data_ptr(), xa2.numel(), pcm.data_ptr(),
-                                     pcm.numel(), st), 3)
-    lib.plan_fetch(eplan, n)
-    lib.plan_free(eplan)
-    ebest = min(ems)
-    return {"config": "configs[4] corpus: 262144 streams (mono/stereo, 4/6/8 bit, 0.25-4 s "
-                      "log-uniform, mix P1), decode then encode, 1 GPU",
-            "tile_shape": "forced NS=%d" % strips if strips else "automatic (census picks long strips or wide tiles per class)",
-            "launches_per_step": launches,
-            "decode": {"ms": [round(m, 3) for m in ms], "Msamples_per_s": round(nsamp / best / 1e3, 1),
-                       "GBps": round(algo / best / 1e6, 1),
-                       "hbm_frac": round(algo / best / 1e6 / PEAK, 4)},
-            "encode": {"ms": [round(m, 3) for m in ems],
-                       "Msamples_per_s": round(nsamp / ebest / 1e3, 1),
-                       "GBps": round(algo / ebest / 1e6, 1),
-                       "hbm_frac": round(algo / ebest / 1e6 / PEAK, 4)},
-            "samples": nsamp, "bytes": {"xa": xa_total, "pcm": pcm_total},
-            "parity": "3 decoded streams vs oracle ok"}
-
-
 def leg_files(lib, orc):
     """Whole .xa files in a pinned host arena -> whole .wav files in another
     (bjxa_corpus_run): header parse, one copy per chunk each way, files
@@ -312,24 +186,17 @@ def leg_files(lib, orc):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="mixed,encode,corpus,files")
+    ap.add_argument("--only", default="encode,files")
     a = ap.parse_args()
     lib = bjxa_b200.load()
     orc = binding.Oracle()
     legs = a.only.split(",")
     print(json.dumps({"peak_GBps": PEAK, "peak_source": PEAK_SRC}), flush=True)
-    if "mixed" in legs:
-        print(json.dumps(leg_mixed(lib, orc)), flush=True)
-        torch.cuda.empty_cache()
     if "encode" in legs:
         print(json.dumps(leg_encode(lib, orc)), flush=True)
         torch.cuda.empty_cache()
     if "files" in legs:
         print(json.dumps(leg_files(lib, orc)), flush=True)
-    if "corpus" in legs:
-        for strips in (0, 1):
-            print(json.dumps(leg_corpus(lib, orc, strips)), flush=True)
-            torch.cuda.empty_cache()
 
 
 if __name__ == "__main__":

@@ -89,6 +89,33 @@ dropin:
 	@echo "dropin: $(REFERENCE) not present; using prebuilt oracle/_ref binaries if any"
 endif
 
+# The reference's habit (configure.ac:41-43,67-75: --enable-asan / --enable-ubsan):
+# the host C of the library, the oracle and the CPU single-stepper of the tile code
+# under AddressSanitizer + UndefinedBehaviorSanitizer, the whole CPU test suite run
+# against them.  (The kernels cannot be run under compute-sanitizer on this pool:
+# the tool is closed there; tests/emul single-steps their tile code on the CPU,
+# which is what the sanitizers then see.)
+SAN      := -fsanitize=address,undefined -fno-omit-frame-pointer -g
+SANDIR   := $(OBJDIR)/san
+# a compiler that ships the sanitizer runtimes (the distribution's)
+SANCC    ?= /usr/bin/gcc
+SANCXX   ?= /usr/bin/g++
+.PHONY: sanitize
+sanitize: $(OBJDIR)/xa_kernels.o
+	@mkdir -p $(SANDIR)
+	$(SANCC) $(CFLAGS) $(SAN) -c -o $(SANDIR)/bjxa_host.o $(SRC)/bjxa_host.c
+	$(SANCC) $(CFLAGS) $(SAN) -c -o $(SANDIR)/bjxa_corpus.o $(SRC)/bjxa_corpus.c
+	$(NVCC) $(ARCH) -shared -o $(SANDIR)/libbjxa_b200.so $(OBJDIR)/xa_kernels.o $(SANDIR)/bjxa_host.o \
+	    $(SANDIR)/bjxa_corpus.o -Xlinker --version-script=$(SRC)/libbjxa.map -cudart static \
+	    -lpthread -ldl -lrt
+	$(SANCXX) -std=c++17 -O1 -g $(SAN) -fPIC -Wall -Wno-unknown-pragmas -shared -o $(SANDIR)/libxa_emul.so tests/emul/xa_emul.cc
+	$(SANCC) -std=c99 -O1 -g $(SAN) -fPIC -shared -o $(SANDIR)/libbjxa_oracle.so oracle/bjxa_oracle.c
+	LD_PRELOAD="$$($(SANCC) -print-file-name=libasan.so) $$($(SANCC) -print-file-name=libubsan.so)" \
+	    ASAN_OPTIONS=detect_leaks=0:abort_on_error=1 UBSAN_OPTIONS=halt_on_error=1:print_stacktrace=1 \
+	    BJXA_B200_LIB=$(abspath $(SANDIR))/libbjxa_b200.so XA_EMUL_SO=$(abspath $(SANDIR))/libxa_emul.so \
+	    BJXA_ORACLE_SO=$(abspath $(SANDIR))/libbjxa_oracle.so \
+	    python -m pytest tests -q -m "not gpu" -p no:cacheprovider 2>&1 | tee profiles/sanitize_host.log | tail -5
+
 clean:
 	rm -rf $(OBJDIR) $(LIBDIR) tests/_build
 	$(MAKE) -s -C oracle clean

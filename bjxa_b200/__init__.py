@@ -8,7 +8,9 @@ This package only locates and binds it; there is no Python or CPU fallback --
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbjxa_b200.so")
+# BJXA_B200_LIB: another build of the same library (`make sanitize` points the CPU
+# test suite at one whose host C is compiled with -fsanitize=address,undefined)
+LIB_PATH = os.environ.get("BJXA_B200_LIB") or os.path.join(_HERE, "lib", "libbjxa_b200.so")
 
 _lib = None
 

@@ -13,7 +13,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-ORACLE_SO = os.path.join(HERE, "_build", "libbjxa_oracle.so")
+ORACLE_SO = os.environ.get("BJXA_ORACLE_SO") or os.path.join(HERE, "_build", "libbjxa_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libbjxa_ref.so")
 REF_CLI = os.path.join(HERE, "_ref", "bjxa_ref")
 

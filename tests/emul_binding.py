@@ -9,12 +9,13 @@ import numpy as np
 from bjxa_b200.api import DESC_DTYPE, make_descs
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SO = os.path.join(ROOT, "tests", "_build", "libxa_emul.so")
+SO = os.environ.get("XA_EMUL_SO") or os.path.join(ROOT, "tests", "_build", "libxa_emul.so")
 
 
 class Emul:
     def __init__(self):
-        subprocess.run(["make", "-s", "-C", ROOT, "emul"], check=True)
+        if not os.environ.get("XA_EMUL_SO"):
+            subprocess.run(["make", "-s", "-C", ROOT, "emul"], check=True)
         self.dll = d = C.CDLL(SO)
         d.xa_emul_decode.restype = C.c_int
         d.xa_emul_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64,
@@ -25,7 +26,7 @@ class Emul:
         d.xa_emul_plan.restype = C.c_int
         d.xa_emul_plan.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
-                                   C.c_void_p, C.c_void_p]
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         self.strip_blocks = d.xa_emul_strip_blocks      # (ns, ch) -> effective blocks
         self.wide = d.xa_emul_wide()
         self.enc_tile_blocks = d.xa_emul_enc_tile_blocks

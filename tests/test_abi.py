@@ -64,13 +64,13 @@ def test_installed_names_match_the_reference():
     whose soname is libbjxa.so.0, libbjxa.so for -lbjxa, and bjxa.pc.  A program
     already linked against the reference finds the backend through the library
     path: no relink."""
-    libdir = os.path.dirname(bjxa_b200.LIB_PATH)
+    libdir = os.path.join(ROOT, "bjxa_b200", "lib")        # (not LIB_PATH: that may be another build)
     so0 = os.path.join(libdir, "libbjxa.so.0")
     dyn = subprocess.run(["readelf", "-d", so0], capture_output=True, text=True, check=True).stdout
     assert "Library soname: [libbjxa.so.0]" in dyn
     syms = lambda p: set(re.findall(r"\b(bjxa_\w+@@[\w.]+)", subprocess.run(      # noqa: E731
         ["readelf", "--dyn-syms", "-W", p], capture_output=True, text=True, check=True).stdout))
-    assert syms(so0) == syms(bjxa_b200.LIB_PATH) == syms(os.path.join(libdir, "libbjxa.so"))
+    assert syms(so0) == syms(os.path.join(libdir, "libbjxa_b200.so")) == syms(os.path.join(libdir, "libbjxa.so"))
     pc = open(os.path.join(libdir, "pkgconfig", "bjxa.pc")).read()
     assert "Name: bjxa" in pc and "-lbjxa" in pc and "@" not in pc
     # the reference CLI, dynamically linked against the REFERENCE's library

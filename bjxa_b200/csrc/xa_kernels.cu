@@ -120,6 +120,8 @@ constexpr int kDecBlock = kDecThreads + 64;	/* consumers + loader warp + scanner
  *   bit 2  (alone) the pooled form over the long-strip list  (pool <= share < wide)
  *   bit 3  (alone) the split form: direct form without walkers, then the dense
  *          chain walkers of xa_walk_kernel                    (split <= share < wide)
+ *   bit 4  (alone) the relay form: direct form whose walker warps hand their
+ *          stragglers to xa_walk_kernel                       (relay <= share < split)
  * A threshold above 1000 permille switches that choice off.  One CTA, no
  * atomics, nothing to clear; all of a thread's loads in flight together.  Measured crossovers:
  * profiles/history_r1.md.
@@ -132,7 +134,7 @@ constexpr uint32_t staged_permille(int bits) { return bits == 4 ? 300u : bits ==
 constexpr uint32_t kWideManyStreams = 8192;
 constexpr uint32_t kWidePermilleMono[2] = { 985, 930 }, kWidePermilleStereo[2] = { 920, 700 };
 constexpr uint32_t kNever = 1001;
-enum { kFormStaged = 1, kFormWide = 2, kFormPool = 4, kFormSplit = 8 };
+enum { kFormStaged = 1, kFormWide = 2, kFormPool = 4, kFormSplit = 8, kFormRelay = 16 };
 /* pooled walkers instead of one walker warp per tile: from this share of chain
  * blocks (measured crossovers: profiles/history_r1.md), for classes of at least
  * kPoolMinTiles tiles -- below that the launch is too short to care */
@@ -148,7 +150,8 @@ constexpr uint32_t kPoolMinTiles = 296;
 __global__ void __launch_bounds__(kCensusThreads)
 xa_census_kernel(const uint8_t *src, const StreamDev *streams, const uint32_t *order,
     uint32_t n_streams, uint32_t block_bytes_one, uint32_t ch, uint32_t staged_permille,
-    uint32_t wide_permille, uint32_t pool_permille, uint32_t split_permille, uint32_t *choice)
+    uint32_t wide_permille, uint32_t pool_permille, uint32_t split_permille,
+    uint32_t relay_permille, uint32_t *choice)
 {
 	__shared__ uint32_t warp_sum[kCensusThreads / 32];
 	const uint32_t tid = threadIdx.x;
@@ -185,7 +188,44 @@ xa_census_kernel(const uint8_t *src, const StreamDev *streams, const uint32_t *o
 		const uint32_t staged = permille >= staged_permille ? kFormStaged : 0u;
 		*choice = permille >= wide_permille ? kFormWide | staged :
 		    permille >= split_permille ? (uint32_t)kFormSplit :
+		    permille >= relay_permille ? (uint32_t)kFormRelay :
 		    permille >= pool_permille ? (uint32_t)kFormPool : staged;
+	}
+}
+
+/*
+ * Relay form: the tile's walker warp, every lane a chain at a time as in
+ * phase_walk_warp, but it does not sit out the tile's longest chains: once the
+ * heads are dealt out and no more than kRelayWind lanes are still walking, their
+ * chains are handed to the second pass (xa_walk_kernel) and the warp lets go of
+ * the stage.  The first turns are exempt, so that a tile with a handful of short
+ * chains walks them itself.
+ */
+template <class Tile>
+__device__ __forceinline__ void
+relay_walk_warp(const Tile &t, const uint16_t *heads, uint32_t n, uint32_t *next, uint32_t first)
+{
+	typename Tile::Walk w;
+	bool have = false;
+	uint32_t i = first;		/* this lane's first chain: lane + 32 * (which walker warp) */
+	for (uint32_t turn = 0;; turn++) {
+		if (!have && i < n) {
+			t.walk_begin(w, heads[i]);
+			have = true;
+		}
+		const uint32_t am = __ballot_sync(0xffffffffu, have);
+		if (am == 0)
+			break;
+		if (turn >= 4u && (uint32_t)__popc(am) <= kRelayWind &&
+		    *(volatile uint32_t *)next >= n) {
+			if (have)
+				t.walk_hand_on(w);
+			break;
+		}
+		if (have && !t.walk_block(w)) {
+			have = false;
+			i = take_next(next);
+		}
 	}
 }
 
@@ -198,13 +238,20 @@ consume_tile(Tile &t, typename Tile::Smem &sm, int s, uint32_t it, uint32_t tid)
 	 * so kStages walker warps, are in flight in a CTA.  A tile with chains has
 	 * its units decoded by the other seven warps, so that the walker warp is
 	 * not the last one to let go of the stage by a whole share of units. */
-	const uint32_t walker = it % (kDecThreads / 32u), warp = tid >> 5;
+	constexpr uint32_t NW = kDecThreads / 32u;
+	const uint32_t walker = it % NW, warp = tid >> 5;
+	/* relay form: a tile with many chains gets kRelayWalkers walker warps (the
+	 * scanner has set the draw counter accordingly), which share its list */
+	const uint32_t nw = t.relay && sm.n_heads[s] > kRelayManyHeads ? kRelayWalkers : 1u;
+	const uint32_t rel = (warp + NW - walker) % NW;		/* 0 .. nw-1: a walker */
 	if (sm.n_heads[s] == 0)
 		t.phase_units(tid, kDecThreads);
-	else if (warp == walker)
+	else if (rel < nw && t.relay)
+		relay_walk_warp(t, sm.heads[s], sm.n_heads[s], &sm.next_head[s], (tid & 31u) + 32u * rel);
+	else if (rel < nw)
 		t.phase_walk_warp(tid & 31u, sm.heads[s], sm.n_heads[s], &sm.next_head[s]);
 	else
-		t.phase_units(warp < walker ? tid : tid - 32u, kDecThreads - 32u);
+		t.phase_units((rel - nw) * 32u + (tid & 31u), kDecThreads - 32u * nw);
 	__syncwarp();
 	if ((tid & 31u) == 0)
 		mbar_arrive(smem_u32(&sm.empty[s]));
@@ -292,7 +339,7 @@ __device__ __forceinline__ void pool_offer(SM &sm, int s, uint32_t gen, uint32_t
  */
 template <class Tile, bool POOL, class SM>
 __device__ __forceinline__ void
-loader_warp(const DecodeParams &p, SM &sm, const uint32_t lane, const bool split = false)
+loader_warp(const DecodeParams &p, SM &sm, const uint32_t lane, const bool want_prev = false)
 {
 	typedef typename Tile::G G;
 	constexpr int NS = G::kNS;
@@ -309,7 +356,7 @@ loader_warp(const DecodeParams &p, SM &sm, const uint32_t lane, const bool split
 			te = p.tiles[t];
 			if (lane < te.count)
 				make_strip_ctx<G::kBits, G::kCh, G::kTBQ, NS>(c, p,
-				    p.order[te.first + lane], te.j, lane, split);
+				    p.order[te.first + lane], te.j, lane, want_prev);
 		}
 	};
 	prefetch();
@@ -364,7 +411,8 @@ loader_warp(const DecodeParams &p, SM &sm, const uint32_t lane, const bool split
  */
 template <class Tile, bool POOL, class SM>
 __device__ __forceinline__ void
-scanner_warp(const DecodeParams &p, SM &sm, const uint32_t lane, const bool split = false)
+scanner_warp(const DecodeParams &p, SM &sm, const uint32_t lane, const bool split = false,
+    const bool relay = false)
 {
 	typedef typename Tile::G G;
 	constexpr int NS = G::kNS;
@@ -396,7 +444,7 @@ scanner_warp(const DecodeParams &p, SM &sm, const uint32_t lane, const bool spli
 			    sm.ctx[s][0].nq / G::kCh;
 			/* items -LAG..-1: no chain channels -- or, in the split form, the
 			 * ones the loader found in front of the strip */
-			uint32_t prev = split ? (sm.ctx[s][0].flags >> kCtxPrevShift & 3u) : 0u;
+			uint32_t prev = split || relay ? (sm.ctx[s][0].flags >> kCtxPrevShift & 3u) : 0u;
 			for (uint32_t base = 0; base < nq; base += 32) {
 				const uint32_t q = base + lane;
 				/* chain channels of item q and of the item in front;
@@ -468,7 +516,15 @@ scanner_warp(const DecodeParams &p, SM &sm, const uint32_t lane, const bool spli
 	}
 }
 
-template <class Tile>
+/*
+ * MODE: kModePlain -- the tile form as it stands; kModeSplit -- the direct form as
+ * the split form's first pass (no walkers, heads written out); kModeRelay -- the
+ * direct form over relay tiles (DecTile<..., true>: stragglers handed on).  Compile
+ * time, so that the plain kernels carry nothing of the other two.
+ */
+enum { kModePlain = 0, kModeSplit = 1, kModeRelay = 2 };
+
+template <class Tile, int MODE>
 __global__ void __launch_bounds__(kDecBlock, Tile::kMinCtas)
 xa_decode_kernel(const DecodeParams p)
 {
@@ -477,16 +533,11 @@ xa_decode_kernel(const DecodeParams p)
 	typename Tile::Smem &sm = *reinterpret_cast<typename Tile::Smem *>(smem_raw);
 	const uint32_t tid = threadIdx.x;
 
-	/* split form: this kernel is its first pass -- every chain is left to
-	 * xa_walk_kernel (forced, or because the census says so) */
-	bool split = p.split == 2;
-	if (p.choice != NULL) {
-		const uint32_t chosen = *p.choice;
-		if (p.split == 1 && chosen == kFormSplit)
-			split = true;
-		else if (chosen != p.want)
-			return;		/* the census picked the other tile form */
-	}
+	constexpr bool split = MODE == kModeSplit, relay = MODE == kModeRelay;
+	if (MODE == kModeSplit ? p.split != 2 && (p.choice == NULL || *p.choice != kFormSplit) :
+	    MODE == kModeRelay ? p.relay != 2 && (p.choice == NULL || *p.choice != kFormRelay) :
+	    p.choice != NULL && *p.choice != p.want)
+		return;		/* the census picked another tile form */
 
 	if (tid == 0) {
 		for (int s = 0; s < kStages; s++) {
@@ -500,11 +551,11 @@ xa_decode_kernel(const DecodeParams p)
 	__syncthreads();
 
 	if (tid >= kDecThreads + 32) {
-		loader_warp<Tile, false>(p, sm, tid - (kDecThreads + 32), split);
+		loader_warp<Tile, false>(p, sm, tid - (kDecThreads + 32), split || relay);
 		return;
 	}
 	if (tid >= kDecThreads) {
-		scanner_warp<Tile, false>(p, sm, tid - kDecThreads, split);
+		scanner_warp<Tile, false>(p, sm, tid - kDecThreads, split, relay);
 		return;
 	}
 
@@ -720,7 +771,23 @@ __device__ __forceinline__ uint32_t ldg_u32(const uint8_t *p)
 	return v;
 }
 
-template <int BITS, int CH>
+/* 16 bytes from global memory, as PTX for the same reason */
+__device__ __forceinline__ uint4 ldg_u128(const void *p)
+{
+	uint4 v;
+	asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+	    : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+	return v;
+}
+
+/*
+ * RELAY = false: the split form's second pass -- the heads of ALL chains, as
+ * bitmaps, one record per tile; a warp spreads a record into a list and its lanes
+ * draw from it.  RELAY = true: the relay form's -- one RelayRec per unfinished
+ * chain, with the state in front of it; lane L of the grid takes records L,
+ * L + lanes, ... and always has the next one on its way.
+ */
+template <int BITS, int CH, bool RELAY>
 __global__ void __launch_bounds__(WalkCfg<BITS, CH>::kThreads, WalkCfg<BITS, CH>::kCtas)
 xa_walk_kernel(const DecodeParams p)
 {
@@ -731,8 +798,9 @@ xa_walk_kernel(const DecodeParams p)
 	constexpr uint32_t UPR = W::UNITS;		/* 16-byte units per row of PCM */
 	constexpr uint32_t RPI = 32u / UPR;		/* rows per store instruction */
 
-	if (p.split != 2 && (p.choice == NULL || *p.choice != kFormSplit))
-		return;		/* the census picked a tile form that walks its own chains */
+	if (RELAY ? p.relay != 2 && (p.choice == NULL || *p.choice != kFormRelay) :
+	    p.split != 2 && (p.choice == NULL || *p.choice != kFormSplit))
+		return;		/* the census picked a tile form that finishes its own chains */
 
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	/* read once, and opaque: the compiler would otherwise recompute them from
@@ -753,12 +821,21 @@ xa_walk_kernel(const DecodeParams p)
 	const uint32_t co_c = lane % UPR, co_r0 = lane / UPR;
 
 	/* records: the counter was preset to ~0 */
-	const uint32_t n_live = *p.live_count + 1u;
-	const uint32_t stride = gridDim.x * C::kWarps;
-	uint32_t next = blockIdx.x * C::kWarps + warp;
+	const uint32_t n_live = (RELAY ? *p.relay_count : *p.live_count) + 1u;
+	const uint32_t stride = RELAY ? gridDim.x * C::kThreads : gridDim.x * C::kWarps;
+	uint32_t next = RELAY ? blockIdx.x * C::kThreads + tid : blockIdx.x * C::kWarps + warp;
 	bool rec_ready = next < n_live;
-	uint32_t nrec = rec_ready ? reinterpret_cast<const uint32_t *>(&p.live[next])[lane] : 0u;
+	uint32_t nrec = !RELAY && rec_ready ?
+	    reinterpret_cast<const uint32_t *>(&p.live[next])[lane] : 0u;
 	uint32_t pos = 0, cnt = 0;		/* the current record's list */
+	/* relay: this lane's next record, fetched while the chain before it is walked */
+	uint4 ra = make_uint4(0, 0, 0, 0), rb = ra;
+	if (RELAY && rec_ready) {
+		ra = ldg_u128(&p.relay_recs[next]);
+		rb = ldg_u128(reinterpret_cast<const uint4 *>(&p.relay_recs[next]) + 1);
+	}
+	uint32_t m_front = 0;		/* relay: the new chain's first item must go on with these */
+	bool fresh = false;
 	/* whole 16-byte chunks of the arena; what lies behind is fetched bytewise */
 	const uint64_t safe = p.src_bytes & ~(uint64_t)15;
 
@@ -796,9 +873,17 @@ xa_walk_kernel(const DecodeParams p)
 					prev = nx;
 				}
 			}
-			if (CH == 2 && m == 0)
+			if (RELAY && fresh) {
+				/* what lies behind a strip was not known when the record was
+				 * written: the chain may have ended with the strip */
+				fresh = false;
+				m = W::mask_of(it.prof);
+				if ((m & m_front) == 0)
+					act = false;
+			} else if (CH == 2 && m == 0) {
 				m = W::mask_of(it.prof);	/* a run's first item */
-			if (left != 0) {
+			}
+			if (act && left != 0) {
 				uint32_t nprof[CH];
 #pragma unroll
 				for (int c = 0; c < CH; c++)
@@ -820,6 +905,25 @@ xa_walk_kernel(const DecodeParams p)
 		uint32_t needm = __ballot_sync(FULL, !more);
 		bool got = false, first = false;
 		uint32_t s_prof[CH], s_lo[CH], s_hi[CH];
+		if (RELAY) {
+			if (!more && rec_ready) {
+				a = (uint64_t)ra.y << 32 | ra.x;
+				o = (uint64_t)ra.w << 32 | ra.z;
+				left = rb.x;
+				stream = rb.y & 0x3fffffffu;
+				m_front = rb.y >> 30;
+				s_lo[0] = rb.z;
+				s_lo[CH - 1] = CH == 2 ? rb.w : rb.z;
+				got = true;
+				next += stride;
+				rec_ready = next < n_live;
+				if (rec_ready) {
+					ra = ldg_u128(&p.relay_recs[next]);
+					rb = ldg_u128(reinterpret_cast<const uint4 *>(&p.relay_recs[next]) + 1);
+				}
+			}
+			needm = 0;
+		}
 #pragma unroll 1
 		for (int round = 0; round < 2 && needm != 0; round++) {
 			if (pos >= cnt) {
@@ -869,7 +973,7 @@ xa_walk_kernel(const DecodeParams p)
 			pos += __popc(took);
 			needm &= ~took;
 		}
-		if (got) {
+		if (!RELAY && got) {
 			/* the block(s) in front of the head (Walk::seed_fetch, as PTX loads) */
 			if (first) {
 				const StreamDev &sd = p.streams[stream];
@@ -907,13 +1011,16 @@ xa_walk_kernel(const DecodeParams p)
 			/* whole chunks of the arena only (a < safe: an item is longer than a chunk) */
 			const uint64_t room = safe - a;
 			const int wantc = room < (uint64_t)want ? (int)room : want;
-			const uint8_t *const gp = p.src + a;
-			const uint32_t a32 = (uint32_t)a;
+			/* up to KMAX chunks, each from its own address: nothing for the
+			 * copies to wait for but the queue */
+			const uint8_t *const gp = p.src + a + (int64_t)fd;
+			const uint32_t a32 = (uint32_t)a, g32 = a32 + (uint32_t)fd;
+			const int fd0 = fd;
 #pragma unroll
 			for (int k = 0; k < C::KMAX; k++) {
-				if (fd < wantc) {
-					cp_async16(ring + ((a32 + (uint32_t)fd) & (RING - 1)), gp + fd);
-					fd += 16;
+				if (fd0 + 16 * k < wantc) {
+					cp_async16(ring + ((g32 + 16u * k) & (RING - 1)), gp + 16 * k);
+					fd = fd0 + 16 * (k + 1);
 				}
 			}
 			asm volatile("cp.async.commit_group;" ::: "memory");
@@ -936,15 +1043,24 @@ xa_walk_kernel(const DecodeParams p)
 			W::decode(it, p0, p1, out);
 		}
 		__syncwarp();
+		{
+			/* all the addresses, then all the rows, then the stores: three
+			 * latencies instead of three per round */
+			unsigned long long rd[UPR];
+			uint4 v[UPR];
 #pragma unroll
-		for (uint32_t r = 0; r < UPR; r++) {
-			const uint32_t sl = r * RPI + co_r0;
-			const unsigned long long rd = __shfl_sync(FULL, d64, sl);
-			if (rd & 1ULL) {
+			for (uint32_t r = 0; r < UPR; r++)
+				rd[r] = __shfl_sync(FULL, d64, r * RPI + co_r0);
+#pragma unroll
+			for (uint32_t r = 0; r < UPR; r++) {
+				const uint32_t sl = r * RPI + co_r0;
 				const uint32_t at = CH == 1 ? (co_c ^ (sl >> 1 & 3u)) : (co_c ^ (sl & 7u));
-				*reinterpret_cast<uint4 *>(rd - 1ULL + co_c * 16u) =
-				    *reinterpret_cast<const uint4 *>(rows + (size_t)sl * OUT + at * 16u);
+				v[r] = *reinterpret_cast<const uint4 *>(rows + (size_t)sl * OUT + at * 16u);
 			}
+#pragma unroll
+			for (uint32_t r = 0; r < UPR; r++)
+				if (rd[r] & 1ULL)
+					*reinterpret_cast<uint4 *>(rd[r] - 1ULL + co_c * 16u) = v[r];
 		}
 		if (__any_sync(FULL, last)) {
 			/* the last item of a stream: its own lane stores what the stream still
@@ -969,6 +1085,15 @@ xa_walk_kernel(const DecodeParams p)
 			left--;
 			fd -= STEP;
 			m = nm;
+		} else if (got && RELAY) {
+#pragma unroll
+			for (int c = 0; c < CH; c++) {
+				p0[c] = (int16_t)(uint16_t)s_lo[c];
+				p1[c] = (int16_t)(uint16_t)(s_lo[c] >> 16);
+			}
+			m = 0;
+			act = true;
+			fresh = true;
 		} else if (got) {
 			typename W::Seed seed;
 #pragma unroll
@@ -983,7 +1108,8 @@ xa_walk_kernel(const DecodeParams p)
 		} else {
 			act = false;
 		}
-		if (!__any_sync(FULL, act) && !rec_ready && pos >= cnt)
+		if (RELAY ? !__any_sync(FULL, act || rec_ready) :
+		    !__any_sync(FULL, act) && !rec_ready && pos >= cnt)
 			break;
 	}
 }
@@ -1372,7 +1498,9 @@ static int pool_mode(void);
 static int pool_candidate(int pool, int ns, uint32_t n_tiles);
 static int split_mode(void);
 static int split_candidate(int split, int bits, int ch, int stereo, int ns, uint32_t n_tiles);
-static int decode_class_launches(int ch, int stereo, bool alt, int poolc, int splitc);
+static int relay_mode(void);
+static int relay_candidate(int relay, int bits, int ch, int stereo, int ns, uint32_t n_tiles);
+static int decode_class_launches(int ch, int stereo, bool alt, int poolc, int splitc, int relayc);
 
 struct bjxa_plan {
 	uint32_t magic;
@@ -1387,6 +1515,7 @@ struct bjxa_plan {
 	DevBuf<unsigned long long> d_carry;
 	DevBuf<uint32_t> d_fault;		/* set when a carry never arrived */
 	DevBuf<LiveRec> d_live;			/* split form: pass 1's records, one per tile */
+	DevBuf<RelayRec> d_relay;		/* relay form: kRelayPerTile per tile */
 	uint32_t epoch;
 	/* last run */
 	bool ran;
@@ -1398,6 +1527,7 @@ struct bjxa_plan {
 	int stereo;			/* stereo_mode() when the plan was built */
 	int pool;			/* pool_mode() likewise */
 	int split;			/* split_mode() likewise */
+	int relay;			/* relay_mode() likewise */
 	/* a plan with several classes runs them side by side (bjxa_plan_run) */
 	cudaStream_t cls_stream[6];
 	cudaEvent_t ev_start, ev_done[6];
@@ -1407,11 +1537,11 @@ struct bjxa_plan {
 /* devices whose kernels have their shared-memory attributes set (bit = device) */
 static std::atomic<unsigned long long> g_attr_devices(0);
 
-template <class Tile>
+template <class Tile, int MODE = kModePlain>
 static cudaError_t
 set_dec_attr(void)
 {
-	return cudaFuncSetAttribute(xa_decode_kernel<Tile>,
+	return cudaFuncSetAttribute(xa_decode_kernel<Tile, MODE>,
 	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(typename Tile::Smem));
 }
 
@@ -1435,16 +1565,22 @@ set_attrs_one(void)
 		return e;
 	if (CH == 1) {
 		if ((e = set_dec_attr<DecTile<BITS, kDecTBQ, 1, dec_stages(BITS, 1)> >()) != cudaSuccess ||
+		    (e = set_dec_attr<DecTile<BITS, kDecTBQ, 1, dec_stages(BITS, 1)>, kModeSplit>()) != cudaSuccess ||
+		    (e = set_dec_attr<DecTile<BITS, kDecTBQ, 1, dec_stages(BITS, 1), true>, kModeRelay>()) != cudaSuccess ||
 		    (e = set_dec_attr<DecTile<BITS, kDecTBQ, kDecWide, dec_stages(BITS, 1)> >()) != cudaSuccess)
 			return e;
 	} else {
 		if ((e = set_dec_attr<DecTileStereo<BITS, kDecTBQ, 1, dec_stages(BITS, 2)> >()) != cudaSuccess ||
+		    (e = set_dec_attr<DecTileStereo<BITS, kDecTBQ, 1, dec_stages(BITS, 2)>, kModeSplit>()) != cudaSuccess ||
+		    (e = set_dec_attr<DecTileStereo<BITS, kDecTBQ, 1, dec_stages(BITS, 2), true>, kModeRelay>()) != cudaSuccess ||
 		    (e = set_dec_attr<DecTileStereo<BITS, kDecTBQ, kDecWide, dec_stages(BITS, 2)> >()) != cudaSuccess ||
 		    (e = set_dec_attr<DecTileStaged<BITS, 2, kDecTBQ, 1, kDecStagedStages> >()) != cudaSuccess ||
 		    (e = set_dec_attr<DecTileStaged<BITS, 2, kDecTBQ, kDecWide, kDecStagedStages> >()) != cudaSuccess)
 			return e;
 	}
-	if ((e = cudaFuncSetAttribute(xa_walk_kernel<BITS, CH>,
+	if ((e = cudaFuncSetAttribute(xa_walk_kernel<BITS, CH, false>,
+	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WalkCfg<BITS, CH>::kSmem)) != cudaSuccess ||
+	    (e = cudaFuncSetAttribute(xa_walk_kernel<BITS, CH, true>,
 	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WalkCfg<BITS, CH>::kSmem)) != cudaSuccess)
 		return e;
 	return cudaFuncSetAttribute(xa_encode_kernel<BITS, CH>,
@@ -1483,8 +1619,10 @@ plan_upload(bjxa_plan *pl)
 
 	if ((rc = pl->d_streams.reserve(n, false)) ||
 	    (rc = pl->d_results.reserve(n, false)) ||
-	    (rc = pl->d_first_bad.reserve(n + 32, false)) ||	/* + 6 ticket counters, 6 census words, 6 record counters */
+	    (rc = pl->d_first_bad.reserve(n + 40, false)) ||	/* + 6 ticket counters, 6 census words, 2 x 6 record counters */
 	    (rc = pl->d_live.reserve(hp.kind == kKindDecode && pl->split != 0 ? hp.tile_begin[6] : 0, false)) ||
+	    (rc = pl->d_relay.reserve(hp.kind == kKindDecode && pl->relay != 0 ?
+	    (size_t)hp.tile_begin[6] * kRelayPerTile : 0, false)) ||
 	    (rc = pl->d_fault.reserve(4, true)) ||
 	    (rc = pl->d_tiles.reserve(hp.tiles.size(), false)) ||
 	    (rc = pl->d_order.reserve(hp.order.size(), false)) ||
@@ -1540,12 +1678,14 @@ plan_build(bjxa_plan *pl, int kind, const bjxa_stream_desc_t *descs, size_t n)
 	pl->stereo = stereo_mode();
 	pl->pool = pool_mode();
 	pl->split = split_mode();
+	pl->relay = relay_mode();
 	for (int b = 0; b < 6; b++)
 		if (pl->hp.order_begin[b + 1] > pl->hp.order_begin[b]) {
 			const uint32_t nt = pl->hp.tile_begin[b + 1] - pl->hp.tile_begin[b];
 			pl->launches += kind == kKindDecode ? decode_class_launches(bucket_ch(b),
 			    pl->stereo, pl->hp.alt_ns[b] != 0, pool_candidate(pl->pool, pl->hp.ns[b], nt),
-			    split_candidate(pl->split, bucket_bits(b), bucket_ch(b), pl->stereo, pl->hp.ns[b], nt)) : 1;
+			    split_candidate(pl->split, bucket_bits(b), bucket_ch(b), pl->stereo, pl->hp.ns[b], nt),
+			    relay_candidate(pl->relay, bucket_bits(b), bucket_ch(b), pl->stereo, pl->hp.ns[b], nt)) : 1;
 		}
 	return (plan_upload(pl));
 }
@@ -1609,6 +1749,7 @@ bjxa_plan_free(bjxa_plan_t **planp)
 	pl->d_carry.release();
 	pl->d_fault.release();
 	pl->d_live.release();
+	pl->d_relay.release();
 	for (int b = 0; b < 6; b++) {
 		if (pl->cls_stream[b] != NULL)
 			(void)cudaStreamDestroy(pl->cls_stream[b]);
@@ -1641,7 +1782,7 @@ bjxa_plan_extent(const bjxa_plan_t *pl, uint64_t *src_bytes, uint64_t *dst_bytes
 	return (0);
 }
 
-template <class Tile>
+template <class Tile, int MODE = kModePlain>
 static cudaError_t
 launch_persistent(const DecodeParams &p, cudaStream_t st)
 {
@@ -1655,7 +1796,7 @@ launch_persistent(const DecodeParams &p, cudaStream_t st)
 	if (grid_cache[0] != dev) {
 		int per_sm = 0, sms = 0;
 		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm,
-		    xa_decode_kernel<Tile>, kDecBlock, smem);
+		    xa_decode_kernel<Tile, MODE>, kDecBlock, smem);
 		if (e != cudaSuccess)
 			return e;
 		e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1667,7 +1808,7 @@ launch_persistent(const DecodeParams &p, cudaStream_t st)
 	uint32_t grid = (uint32_t)grid_cache[1];
 	if (grid > p.n_tiles)
 		grid = p.n_tiles;
-	xa_decode_kernel<Tile><<<grid, kDecBlock, smem, st>>>(p);
+	xa_decode_kernel<Tile, MODE><<<grid, kDecBlock, smem, st>>>(p);
 	return cudaGetLastError();
 }
 
@@ -1715,6 +1856,7 @@ struct DecodeClass {
 	int stereo;			/* 0 direct, 1 staged, 2 census (stereo classes) */
 	int pool;			/* 0 never, 1 always, 2 census */
 	int split;			/* likewise */
+	int relay;			/* likewise */
 	uint32_t *d_choice;
 	const uint32_t *d_order;	/* the class's streams */
 	uint32_t n_streams;
@@ -1729,6 +1871,17 @@ launch_form(const DecodeParams &p, bool staged, cudaStream_t st)
 	if (staged)
 		return launch_persistent<DecTileStaged<BITS, 2, kDecTBQ, NS, kDecStagedStages> >(p, st);
 	return launch_persistent<DecTileStereo<BITS, kDecTBQ, NS, dec_stages(BITS, 2)> >(p, st);
+}
+
+/* the direct form over long strips as the first pass of the split / relay form */
+template <int BITS, int CH, int MODE>
+static cudaError_t
+launch_pass1(const DecodeParams &p, cudaStream_t st)
+{
+	constexpr bool R = MODE == kModeRelay;
+	if (CH == 1)
+		return launch_persistent<DecTile<BITS, kDecTBQ, 1, dec_stages(BITS, 1), R>, MODE>(p, st);
+	return launch_persistent<DecTileStereo<BITS, kDecTBQ, 1, dec_stages(BITS, 2), R>, MODE>(p, st);
 }
 
 /* pooled form: 0 = never, 1 = always (long-strip lists), 2 = let the census decide
@@ -1763,15 +1916,15 @@ split_mode(void)
 
 /*
  * From this share of chain blocks (permille) the census sends a class to the
- * split form.  Measured crossovers at 4096 streams x 30 s (profiles/history_r2.md):
- * the pair walkers of the stereo direct form keep few chains in flight, so the
- * dense walkers win early there; the mono direct form holds out up to about two
- * thirds (4-bit) or throughout (8-bit).
+ * split form, and relay_permille() below to the relay form.  Measured crossovers
+ * at 4096 streams x 30 s (profiles/history_r2.md): the relay form wins from about
+ * a tenth of chain blocks; the split form overtakes it on chain-rich stereo data
+ * (and everywhere on 4-bit stereo), on mono only at 4 bits and above three
+ * quarters.
  */
 constexpr uint32_t split_permille(int bits, int ch)
 {
-	return ch == 2 ? (bits == 4 ? 80u : bits == 6 ? 200u : 350u) :
-	    (bits == 4 ? 650u : bits == 6 ? 900u : 1001u);
+	return ch == 2 ? (bits == 4 ? 80u : 650u) : (bits == 4 ? 750u : 1001u);
 }
 /* below this many tiles a launch is too short for a census to pay */
 constexpr uint32_t kSplitMinTiles = 64;
@@ -1788,20 +1941,50 @@ split_candidate(int split, int bits, int ch, int stereo, int ns, uint32_t n_tile
 	return n_tiles >= kSplitMinTiles && split_permille(bits, ch) <= 1000u ? 2 : 0;
 }
 
+/*
+ * relay form (xa_walk.h): 0 = never, 1 = always, 2 = let the census decide
+ * (BJXA_B200_RELAY=off|on|auto, default auto).
+ */
+static int
+relay_mode(void)
+{
+	const char *e = getenv("BJXA_B200_RELAY");
+	return e == NULL ? 2 : strcmp(e, "on") == 0 ? 1 : strcmp(e, "off") == 0 ? 0 : 2;
+}
+
+/* from this share of chain blocks (permille) the census sends a class to the relay
+ * form (below it the plain direct form; above split_permille the split form) */
+constexpr uint32_t relay_permille(int bits, int ch)
+{
+	/* 4-bit stereo goes straight to the split form: its pair walkers' tiles are
+	 * the slowest to turn over, and the dense walkers the cheapest per sample */
+	return ch == 2 ? (bits == 4 ? 1001u : 80u) : 150u;
+}
+
+static int
+relay_candidate(int relay, int bits, int ch, int stereo, int ns, uint32_t n_tiles)
+{
+	if (ns != 1 || relay == 0 || (ch == 2 && stereo == 1))
+		return 0;
+	if (relay == 1)
+		return 1;
+	return n_tiles >= kSplitMinTiles && relay_permille(bits, ch) <= 1000u ? 2 : 0;
+}
+
 /* how many kernels decode_class() launches */
 static int
-decode_class_launches(int ch, int stereo, bool alt, int poolc, int splitc)
+decode_class_launches(int ch, int stereo, bool alt, int poolc, int splitc, int relayc)
 {
 	if (poolc == 1)
 		return 1;
-	if (splitc == 1)
+	if (splitc == 1 || relayc == 1)
 		return 2;
 	const int forms = (ch == 2 && stereo == 2 ? 2 : 1) + (alt ? 1 : 0) + (poolc == 2 ? 1 : 0) +
-	    (splitc == 2 ? 1 : 0);
+	    (splitc == 2 ? 2 : 0) + (relayc == 2 ? 2 : 0);
 	return forms == 1 ? 1 : forms + 1;
 }
 
-template <int BITS, int CH>
+template <int BITS, int CH, bool RELAY>
 static cudaError_t
 launch_walk(const DecodeParams &p, cudaStream_t st)
 {
@@ -1814,7 +1997,7 @@ launch_walk(const DecodeParams &p, cudaStream_t st)
 	if (grid_cache[0] != dev) {
 		int per_sm = 0, sms = 0;
 		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm,
-		    xa_walk_kernel<BITS, CH>, C::kThreads, C::kSmem);
+		    xa_walk_kernel<BITS, CH, RELAY>, C::kThreads, C::kSmem);
 		if (e != cudaSuccess)
 			return e;
 		e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1828,7 +2011,7 @@ launch_walk(const DecodeParams &p, cudaStream_t st)
 	const uint32_t need = (p.n_tiles + C::kWarps - 1) / C::kWarps;
 	if (grid > need)
 		grid = need;
-	xa_walk_kernel<BITS, CH><<<grid, C::kThreads, C::kSmem, st>>>(p);
+	xa_walk_kernel<BITS, CH, RELAY><<<grid, C::kThreads, C::kSmem, st>>>(p);
 	return cudaGetLastError();
 }
 
@@ -1840,6 +2023,7 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 	const bool pick_form = CH == 2 && c.stereo == 2;
 	const int poolc = pool_candidate(c.pool, c.ns, c.p.n_tiles);
 	const int splitc = split_candidate(c.split, BITS, CH, c.stereo, c.ns, c.p.n_tiles);
+	const int relayc = relay_candidate(c.relay, BITS, CH, c.stereo, c.ns, c.p.n_tiles);
 	DecodeParams p = c.p;
 	cudaError_t e;
 	if (poolc == 1)
@@ -1847,11 +2031,18 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 	if (splitc == 1) {
 		/* pass 1: the direct form without walkers; pass 2: the walkers */
 		p.split = 2;
-		if ((e = launch_form<BITS, CH, 1>(p, false, st)) != cudaSuccess)
+		if ((e = launch_pass1<BITS, CH, kModeSplit>(p, st)) != cudaSuccess)
 			return e;
-		return launch_walk<BITS, CH>(p, st);
+		return launch_walk<BITS, CH, false>(p, st);
 	}
-	if (!alt && !pick_form && poolc == 0 && splitc == 0) {
+	if (relayc == 1) {
+		/* pass 1: the direct form, its walker warps handing stragglers on */
+		p.relay = 2;
+		if ((e = launch_pass1<BITS, CH, kModeRelay>(p, st)) != cudaSuccess)
+			return e;
+		return launch_walk<BITS, CH, true>(p, st);
+	}
+	if (!alt && !pick_form && poolc == 0 && splitc == 0 && relayc == 0) {
 		const bool staged = CH == 2 && c.stereo == 1;
 		return c.ns == 1 ? launch_form<BITS, CH, 1>(p, staged, st) :
 		    launch_form<BITS, CH, kDecWide>(p, staged, st);
@@ -1863,6 +2054,7 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 	    alt ? (CH == 2 ? kWidePermilleStereo : kWidePermilleMono)[splitc != 2 && c.n_streams >= kWideManyStreams] :
 	    kNever, poolc == 2 ? (CH == 2 ? kPoolPermilleStereo : kPoolPermilleMono) : kNever,
 	    splitc == 2 ? split_permille(BITS, CH) : kNever,
+	    relayc == 2 ? relay_permille(BITS, CH) : kNever,
 	    c.d_choice);
 	if ((e = cudaGetLastError()) != cudaSuccess)
 		return e;
@@ -1874,19 +2066,25 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 		/* with a wide list, chain-heavy stereo data goes to its staged form
 		 * only: "staged, long strips" then means bit 0 without bit 1 */
 		p.want = staged ? kFormStaged : 0u;
-		/* the direct form over long strips doubles as the split form's pass 1 */
-		p.split = !staged && splitc == 2 ? 1u : 0u;
 		e = c.ns == 1 ? launch_form<BITS, CH, 1>(p, staged != 0, st) :
 		    launch_form<BITS, CH, kDecWide>(p, staged != 0, st);
 		if (e != cudaSuccess)
 			return e;
 	}
-	p.split = 0;
+	/* the two-pass forms: both of their kernels leave at once unless chosen */
 	if (splitc == 2) {
 		p.split = 1;
-		if ((e = launch_walk<BITS, CH>(p, st)) != cudaSuccess)
+		if ((e = launch_pass1<BITS, CH, kModeSplit>(p, st)) != cudaSuccess ||
+		    (e = launch_walk<BITS, CH, false>(p, st)) != cudaSuccess)
 			return e;
 		p.split = 0;
+	}
+	if (relayc == 2) {
+		p.relay = 1;
+		if ((e = launch_pass1<BITS, CH, kModeRelay>(p, st)) != cudaSuccess ||
+		    (e = launch_walk<BITS, CH, true>(p, st)) != cudaSuccess)
+			return e;
+		p.relay = 0;
 	}
 	if (poolc == 2) {
 		p.want = kFormPool;
@@ -1956,7 +2154,7 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 		 * the six tile-ticket counters that follow them (~0 = no ticket
 		 * drawn yet, see the producer in xa_decode_kernel) */
 		XA_CUDA(cudaMemsetAsync(pl->d_first_bad.p, 0xff,
-		    (n + 32) * sizeof(uint32_t), st));
+		    (n + 40) * sizeof(uint32_t), st));
 	}
 
 	/*
@@ -2038,6 +2236,9 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 			p.split = 0;
 			p.live = pl->d_live.p != NULL ? pl->d_live.p + t0 : NULL;
 			p.live_count = pl->d_first_bad.p + ((n + 3) & ~(size_t)3) + 18 + b;
+			p.relay = 0;
+			p.relay_recs = pl->d_relay.p != NULL ? pl->d_relay.p + (size_t)t0 * kRelayPerTile : NULL;
+			p.relay_count = pl->d_first_bad.p + ((n + 3) & ~(size_t)3) + 24 + b;
 			DecodeClass c;
 			c.p = p;
 			c.alt_tiles = hp.alt_ns[b] != 0 ? pl->d_tiles.p + hp.alt_begin[b] : NULL;
@@ -2046,6 +2247,7 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 			c.stereo = pl->stereo;
 			c.pool = pl->pool;
 			c.split = pl->d_live.p != NULL ? pl->split : 0;
+			c.relay = pl->d_relay.p != NULL ? pl->relay : 0;
 			c.d_choice = pl->d_first_bad.p + ((n + 3) & ~(size_t)3) + 12 + b;
 			c.d_order = pl->d_order.p + hp.order_begin[b];
 			c.n_streams = hp.order_begin[b + 1] - hp.order_begin[b];

@@ -52,6 +52,32 @@ struct StreamRes {		/* decode results, device resident */
 
 struct LiveRec;
 
+/*
+ * Relay form: a chain the tile's walker warp did not finish -- it ran past the
+ * end of the strip, or the warp wound down while it was still going -- goes on
+ * in the second pass (xa_walk.h) from this record: where its next item lies,
+ * and the predictor state in front of it.
+ */
+struct RelayRec {
+	uint32_t xa_lo, xa_hi;	/* arena address of the next item */
+	uint32_t out_lo, out_hi;	/* arena address of its PCM */
+	uint32_t left;		/* items of the stream behind it */
+	uint32_t stream;	/* | chain channels of the item in front << 30 */
+	uint32_t st[2];		/* per channel: state n-1 | n-2 << 16 */
+};
+#ifndef XA_RELAY_WIND
+#define XA_RELAY_WIND 8
+#endif
+#ifndef XA_RELAY_WALKERS
+#define XA_RELAY_WALKERS 1
+#endif
+constexpr uint32_t kRelayWind = XA_RELAY_WIND;	/* lanes at or below which a walker warp winds down */
+constexpr uint32_t kRelayWalkers = XA_RELAY_WALKERS;	/* walker warps of a tile with many chains
+						 * (2 and 3 measured slower: profiles/history_r2.md) */
+constexpr uint32_t kRelayManyHeads = 48;	/* ... from this many chains */
+/* records a tile can leave at most: each walker warp's stragglers + the strip's end */
+constexpr uint32_t kRelayPerTile = kRelayWalkers * kRelayWind + 1;
+
 struct TileEnt {		/* decode: NS strips of consecutive streams in issue order */
 	uint32_t first;		/* index into order[] of the first strip's stream;
 				 * encode: the stream itself */
@@ -84,7 +110,12 @@ struct DecodeParams {
 	 * 2 = always */
 	uint32_t split;
 	struct LiveRec *live;		/* one record per tile that has heads */
-	uint32_t *live_count;		/* records written so far (pass 1), preset to 0 */
+	uint32_t *live_count;		/* records written so far (pass 1), preset to ~0 */
+	/* relay form: the tiles walk their own chains but hand the stragglers to
+	 * the second pass.  0 = never, 1 = when the census says so, 2 = always */
+	uint32_t relay;
+	RelayRec *relay_recs;		/* kRelayPerTile per tile */
+	uint32_t *relay_count;		/* records written so far, preset to ~0 */
 };
 
 struct EncodeParams {
@@ -246,6 +277,16 @@ XA_HD void make_strip_ctx(StripCtx &c, const DecodeParams &p, uint32_t stream,
 	}
 }
 
+/* the next free record of a list whose counter was preset to ~0 */
+XA_HD uint32_t next_record(uint32_t *ctr)
+{
+#if defined(__CUDA_ARCH__)
+	return atomicAdd(ctr, 1u) + 1u;
+#else
+	return ++(*ctr);
+#endif
+}
+
 /* draw the next index from a shared-memory counter */
 XA_HD uint32_t take_next(uint32_t *ctr)
 {
@@ -297,7 +338,7 @@ struct DecSmem {
  * "empty" mbarrier and moves on; warps may drift up to STAGES tiles apart, so
  * one long chain delays nobody until the ring of source buffers wraps.
  */
-template <int BITS, int TBQ, int NS, int STAGES>
+template <int BITS, int TBQ, int NS, int STAGES, bool RELAY = false>
 struct DecTile {
 	typedef DecGeom<BITS, 1, TBQ, NS> G;
 	typedef DecSmem<BITS, 1, TBQ, NS, STAGES> Smem;
@@ -315,10 +356,51 @@ struct DecTile {
 	const uint8_t *in;		/* this tile's stage buffer */
 	const StripCtx *ctx;		/* this tile's strips */
 	const uint32_t n_strips;
+	/* relay form: no carries, stragglers handed on.  A template parameter, not a
+	 * flag: the plain form's kernels are capped at 48 registers, and code they
+	 * never run must not cost them one */
+	static constexpr bool relay = RELAY;
 
 	XA_HD DecTile(const DecodeParams &p_, const Smem &sm_, int stage)
 	    : p(p_), in(sm_.in[stage]), ctx(sm_.ctx[stage]), n_strips(sm_.n_strips[stage])
 	{
+	}
+
+	/* relay form (NS == 1): the state in front of the strip's first block, from
+	 * the arena -- the block there is a cut block, or the stream starts here */
+	XA_HD void seed_from_arena(const StripCtx &c, int &p0, int &p1) const
+	{
+		if (c.flags & kCtxFirst) {
+			p0 = p.streams[c.stream].prev[0][0];
+			p1 = p.streams[c.stream].prev[0][1];
+			return;
+		}
+		const uint8_t *b = p.src + (c.a0 + c.in_base);
+		const int sh = 16 + (int)(b[-BS] & 15u);
+		const uint32_t w = (uint32_t)b[-4] | (uint32_t)b[-3] << 8 | (uint32_t)b[-2] << 16 |
+		    (uint32_t)b[-1] << 24;
+		int x[4];
+		quad_codes<BITS>(w >> (8 * (4 - QB)), x);
+		p1 = x[2] >> sh;
+		p0 = x[3] >> sh;
+	}
+
+	/* relay form: the chain goes on at block lq of the strip (lq == nq: the first
+	 * block behind it) in the second pass */
+	XA_HD void relay_put(const StripCtx &c, uint32_t lq, int p0, int p1) const
+	{
+		const uint64_t g = c.a0 + c.in_base + (uint64_t)lq * BS;
+		const uint64_t o = c.out0 + (uint64_t)lq * 64u;
+		RelayRec r;
+		r.xa_lo = (uint32_t)g;
+		r.xa_hi = (uint32_t)(g >> 32);
+		r.out_lo = (uint32_t)o;
+		r.out_hi = (uint32_t)(o >> 32);
+		r.left = c.blocks - 1u - (c.first_eb + lq);
+		r.stream = c.stream | 1u << 30;
+		r.st[0] = (uint32_t)(uint16_t)p0 | (uint32_t)(uint16_t)p1 << 16;
+		r.st[1] = 0;
+		p.relay_recs[next_record(p.relay_count)] = r;
 	}
 
 	/* bytes past a strip's `bulk` fetched one by one (only at the arena's end) */
@@ -376,7 +458,7 @@ struct DecTile {
 		if (c.flags & kCtxLast) {
 			p.results[c.stream].prev[0][0] = (int16_t)p0;
 			p.results[c.stream].prev[0][1] = (int16_t)p1;
-		} else {
+		} else if (!relay) {
 			unsigned long long v = ((unsigned long long)p.epoch << 32) |
 			    ((unsigned long long)(uint16_t)p1 << 16) | (uint16_t)p0;
 			mailbox_put(&p.carry[(uint64_t)c.slot * 2], v);
@@ -638,7 +720,9 @@ struct DecTile {
 		w.lq = q % SBQ;
 		w.at = block_at(*w.c, w.lq);
 		w.need = 0;
-		if (w.lq == 0) {
+		if (w.lq == 0 && relay) {
+			seed_from_arena(*w.c, w.p0, w.p1);
+		} else if (w.lq == 0) {
 			w.need = 1;
 			walk_carry(w);
 		} else {
@@ -667,11 +751,21 @@ struct DecTile {
 		}
 		if (w.lq + 1 >= w.c->nq) {
 			publish(*w.c, w.p0, w.p1);
+			/* relay form: whether the strip behind goes on with this chain is for
+			 * the second pass to see */
+			if (relay && !(w.c->flags & kCtxLast))
+				relay_put(*w.c, w.c->nq, w.p0, w.p1);
 			return false;
 		}
 		w.lq++;
 		w.at += BS;
 		return block_kind(in[w.at]) == kChain;
+	}
+
+	/* relay form: the walker warp winds down; the chain goes on at its next block */
+	XA_HD void walk_hand_on(const Walk &w) const
+	{
+		relay_put(*w.c, w.lq, w.p0, w.p1);
 	}
 };
 
@@ -692,7 +786,7 @@ struct DecTile {
  *            writes whole interleaved 16-byte units, so nothing ever has to
  *            be written around the other channel.
  */
-template <int BITS, int TBQ, int NS, int STAGES>
+template <int BITS, int TBQ, int NS, int STAGES, bool RELAY = false>
 struct DecTileStereo {
 	typedef DecGeom<BITS, 2, TBQ, NS> G;
 	typedef DecSmem<BITS, 2, TBQ, NS, STAGES> Smem;
@@ -713,10 +807,54 @@ struct DecTileStereo {
 	const uint8_t *in;
 	const StripCtx *ctx;
 	const uint32_t n_strips;
+	static constexpr bool relay = RELAY;	/* see DecTile */
 
 	XA_HD DecTileStereo(const DecodeParams &p_, const Smem &sm_, int stage)
 	    : p(p_), in(sm_.in[stage]), ctx(sm_.ctx[stage]), n_strips(sm_.n_strips[stage])
 	{
+	}
+
+	/* relay form (NS == 1): both channels' states in front of the strip's first
+	 * effective block, from the arena (a chain channel's block there is a cut
+	 * block; the other channel's value is not used) */
+	XA_HD void seed_from_arena(const StripCtx &c, int (&p0)[2], int (&p1)[2]) const
+	{
+#pragma unroll
+		for (int ch = 0; ch < 2; ch++) {
+			if (c.flags & kCtxFirst) {
+				p0[ch] = p.streams[c.stream].prev[ch][0];
+				p1[ch] = p.streams[c.stream].prev[ch][1];
+				continue;
+			}
+			const uint8_t *b = p.src + (c.a0 + c.in_base) - (2 - ch) * BS;
+			const int sh = 16 + (int)(b[0] & 15u);
+			const uint32_t w = (uint32_t)b[BS - 4] | (uint32_t)b[BS - 3] << 8 |
+			    (uint32_t)b[BS - 2] << 16 | (uint32_t)b[BS - 1] << 24;
+			int x[4];
+			quad_codes<BITS>(w >> (8 * (4 - QB)), x);
+			p1[ch] = x[2] >> sh;
+			p0[ch] = x[3] >> sh;
+		}
+	}
+
+	/* relay form: the run goes on at effective block eb of the strip (eb == the
+	 * strip's length: the first one behind it) in the second pass, if that item
+	 * continues a chain of `m_front`, the chain channels of the item in front */
+	XA_HD void relay_put(const StripCtx &c, uint32_t eb, uint32_t m_front, const int (&p0)[2],
+	    const int (&p1)[2]) const
+	{
+		const uint64_t g = c.a0 + c.in_base + (uint64_t)eb * (2 * BS);
+		const uint64_t o = c.out0 + (uint64_t)eb * 128u;
+		RelayRec r;
+		r.xa_lo = (uint32_t)g;
+		r.xa_hi = (uint32_t)(g >> 32);
+		r.out_lo = (uint32_t)o;
+		r.out_hi = (uint32_t)(o >> 32);
+		r.left = c.blocks - 1u - (c.first_eb + eb);
+		r.stream = c.stream | m_front << 30;
+		r.st[0] = (uint32_t)(uint16_t)p0[0] | (uint32_t)(uint16_t)p1[0] << 16;
+		r.st[1] = (uint32_t)(uint16_t)p0[1] | (uint32_t)(uint16_t)p1[1] << 16;
+		p.relay_recs[next_record(p.relay_count)] = r;
 	}
 
 	XA_HD void load_tail(uint32_t tid, uint32_t nt, uint8_t *in_w) const
@@ -786,7 +924,7 @@ struct DecTileStereo {
 		if (c.flags & kCtxLast) {
 			p.results[c.stream].prev[ch][0] = (int16_t)p0;
 			p.results[c.stream].prev[ch][1] = (int16_t)p1;
-		} else {
+		} else if (!relay) {
 			unsigned long long v = ((unsigned long long)p.epoch << 32) |
 			    ((unsigned long long)(uint16_t)p1 << 16) | (uint16_t)p0;
 			mailbox_put(&p.carry[(uint64_t)c.slot * 2 + ch], v);
@@ -1101,7 +1239,9 @@ struct DecTileStereo {
 		w.m = chains(*w.c, w.eb);
 		w.p0[0] = w.p0[1] = w.p1[0] = w.p1[1] = 0;
 		w.need = 0;
-		if (w.eb == 0) {
+		if (w.eb == 0 && relay) {
+			seed_from_arena(*w.c, w.p0, w.p1);
+		} else if (w.eb == 0) {
 			/* a channel that starts with a cut block needs no history */
 			w.need = w.m;
 			walk_carry(w);
@@ -1130,6 +1270,10 @@ struct DecTileStereo {
 		if ((w.eb + 1) * 2 >= w.c->nq) {
 			publish(*w.c, 0, w.p0[0], w.p1[0]);
 			publish(*w.c, 1, w.p0[1], w.p1[1]);
+			/* relay form: whether the strip behind goes on with this run is for
+			 * the second pass to see */
+			if (relay && !(w.c->flags & kCtxLast))
+				relay_put(*w.c, w.eb + 1, w.m, w.p0, w.p1);
 			return false;
 		}
 		w.eb++;
@@ -1138,6 +1282,13 @@ struct DecTileStereo {
 		const bool more = (nm & w.m) != 0;
 		w.m = nm;
 		return more;
+	}
+
+	/* relay form: the walker warp winds down; the run goes on at its next item
+	 * (which continues it: any of its chain channels will do as "in front") */
+	XA_HD void walk_hand_on(const Walk &w) const
+	{
+		relay_put(*w.c, w.eb, 3u, w.p0, w.p1);
 	}
 };
 

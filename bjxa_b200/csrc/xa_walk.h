@@ -21,6 +21,14 @@
  *           no carries and no ordering between tiles; the state at a head is
  *           recomputed from the bytes of the cut block in front of it.
  *
+ * The RELAY form is the hybrid of the two: the tiles walk their own chains as
+ * before -- cheaply, out of the staged bytes -- but a walker warp does not wait
+ * for its longest chains: once its heads are dealt out and few lanes are still
+ * busy it hands their chains on (RelayRec: next item, state), as it does with
+ * any chain that reaches the end of the strip, and pass 2 finishes them.  No
+ * carry mailboxes, no order among tiles, and a tile's bytes leave shared memory
+ * as soon as the bulk of its chains is through.
+ *
  * This header holds what both passes and the CPU single-stepper of the tests
  * (tests/emul) share: the record and the per-item arithmetic.  The GPU-only
  * part (window ring, staged copy-out, the warp's draw) is in xa_kernels.cu.
@@ -174,27 +182,39 @@ struct Walk {
 				out(j, v);
 			}
 		} else {
+			/* the biased step for both channels (xa_core.h:sample_chain_b): in a
+			 * kernel whose registers are not capped the two extra constants per
+			 * channel cost nothing, and the step keeps the ALU pipe -- which
+			 * bounds this kernel (72 % busy with the plain step) -- two
+			 * instructions a sample shorter */
 			const uint32_t pl = it.prof[0], pr = it.prof[CH - 1];
 			const int shl = 16 + (int)(pl & 15u), shr = 16 + (int)(pr & 15u);
 			const int k0l = gain_k0(pl >> 4), k1l = gain_k1(pl >> 4);
 			const int k0r = gain_k0(pr >> 4), k1r = gain_k1(pr >> 4);
+			const int cl = chain_bias_c(k0l, k1l), cr = chain_bias_c(k0r, k1r);
+			int bl0 = p0[0] + 32768, bl1 = p1[0] + 32768;
+			int br0 = p0[CH - 1] + 32768, br1 = p1[CH - 1] + 32768;
 #pragma unroll
 			for (int j = 0; j < 8; j++) {
 				int l[4], r[4];
 #pragma unroll
 				for (int k = 0; k < 4; k++) {
-					l[k] = sample_chain(top_code<BITS>(it.pw[0], 4 * j + k), shl,
-					    k0l, k1l, p0[0], p1[0]);
-					r[k] = sample_chain(top_code<BITS>(it.pw[CH - 1], 4 * j + k), shr,
-					    k0r, k1r, p0[CH - 1], p1[CH - 1]);
+					l[k] = sample_chain_b(top_code<BITS>(it.pw[0], 4 * j + k), shl,
+					    k0l, k1l, cl, bl0, bl1);
+					r[k] = sample_chain_b(top_code<BITS>(it.pw[CH - 1], 4 * j + k), shr,
+					    k0r, k1r, cr, br0, br1);
 				}
 				uint4 v;
-				v.x = pack2(l[0], r[0]);
-				v.y = pack2(l[1], r[1]);
-				v.z = pack2(l[2], r[2]);
-				v.w = pack2(l[3], r[3]);
+				v.x = pack2_biased(l[0], r[0]);
+				v.y = pack2_biased(l[1], r[1]);
+				v.z = pack2_biased(l[2], r[2]);
+				v.w = pack2_biased(l[3], r[3]);
 				out(j, v);
 			}
+			p0[0] = bl0 - 32768;
+			p1[0] = bl1 - 32768;
+			p0[CH - 1] = br0 - 32768;
+			p1[CH - 1] = br1 - 32768;
 		}
 	}
 
@@ -230,11 +250,67 @@ struct Walk {
 };
 
 /*
- * The whole of pass 2 for one record, one chain after the other, reading the
- * arena directly: the reference semantics of xa_walk_kernel, used by the CPU
- * single-stepper of the tests.  (The kernel runs the same Walk<> arithmetic
- * with 32 chains per warp in flight.)
+ * One chain (stereo: one run) from its first item to its end, reading the arena
+ * directly: the reference semantics of a walker lane, used by the CPU
+ * single-stepper of the tests.  `m_front` != 0: the chain channels of the item in
+ * front -- the first item then only counts if it goes on with one of them (the
+ * relay form does not know what lies behind a strip); 0: a listed head.
  */
+template <int BITS, int CH>
+XA_HD void walk_chain_serial(const DecodeParams &p, uint32_t stream, uint64_t a, uint64_t o,
+    uint32_t left, int (&p0)[CH], int (&p1)[CH], uint32_t m_front)
+{
+	typedef Walk<BITS, CH> W;
+	uint32_t m = 0;
+	for (bool fresh = true;; fresh = false) {
+		typename W::Item it;
+#pragma unroll
+		for (int c = 0; c < CH; c++) {
+			const uint8_t *b = p.src + a + c * W::BS;
+			it.prof[c] = b[0];
+#pragma unroll
+			for (int i = 0; i < BITS; i++)
+				it.pw[c][i] = (uint32_t)b[1 + 4 * i] | (uint32_t)b[2 + 4 * i] << 8 |
+				    (uint32_t)b[3 + 4 * i] << 16 | (uint32_t)b[4 + 4 * i] << 24;
+		}
+		if (fresh) {
+			m = W::mask_of(it.prof);
+			if (m_front != 0 && (m & m_front) == 0)
+				return;		/* the chain ended with the strip */
+		}
+		const uint32_t valid = left != 0 ? (uint32_t)W::OUT : W::last_valid(p.streams[stream]);
+		uint8_t *dst = p.dst + o;
+		auto out = [&](int j, const uint4 &v) {
+			const uint32_t boff = (uint32_t)j * 16u;
+			const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+			for (uint32_t k = 0; k < 8u && boff + 2u * k + 2u <= valid; k++) {
+				const uint16_t h = (uint16_t)(w[k >> 1] >> (16u * (k & 1u)));
+				dst[boff + 2u * k] = (uint8_t)h;
+				dst[boff + 2u * k + 1u] = (uint8_t)(h >> 8);
+			}
+		};
+		if (CH == 2)
+			W::note_bad(p, stream, left, it.prof);
+		W::decode(it, p0, p1, out);
+		if (left == 0) {
+			W::put_result(p, stream, p0, p1);
+			return;
+		}
+		uint32_t nprof[CH];
+#pragma unroll
+		for (int c = 0; c < CH; c++)
+			nprof[c] = p.src[a + W::STEP + c * W::BS];
+		const uint32_t nm = W::mask_of(nprof);
+		if ((nm & m) == 0)
+			return;
+		m = nm;
+		a += W::STEP;
+		o += W::OUT;
+		left--;
+	}
+}
+
+/* the whole of pass 2 for one record of the split form */
 template <int BITS, int CH>
 XA_HD void walk_record_serial(const DecodeParams &p, const LiveRec &r)
 {
@@ -244,58 +320,29 @@ XA_HD void walk_record_serial(const DecodeParams &p, const LiveRec &r)
 	for (uint32_t q = 0; q < 512; q++) {
 		if (!(r.heads[q >> 5] >> (q & 31u) & 1u))
 			continue;
-		uint64_t a = xa0 + (uint64_t)q * W::STEP, o = out0 + (uint64_t)q * W::OUT;
-		uint32_t left = r.blocks - 1u - (r.first_eb + q);
+		const uint64_t a = xa0 + (uint64_t)q * W::STEP;
 		const bool first = r.first_eb + q == 0;
 		typename W::Seed seed;
 		int p0[CH], p1[CH];
 		W::seed_fetch(p, r.stream, first, a, seed);
 		W::seed_apply(seed, first, a, p0, p1);
-		uint32_t m = 0;
-		for (bool fresh = true;; fresh = false) {
-			typename W::Item it;
-#pragma unroll
-			for (int c = 0; c < CH; c++) {
-				const uint8_t *b = p.src + a + c * W::BS;
-				it.prof[c] = b[0];
-#pragma unroll
-				for (int i = 0; i < BITS; i++)
-					it.pw[c][i] = (uint32_t)b[1 + 4 * i] | (uint32_t)b[2 + 4 * i] << 8 |
-					    (uint32_t)b[3 + 4 * i] << 16 | (uint32_t)b[4 + 4 * i] << 24;
-			}
-			if (fresh)
-				m = W::mask_of(it.prof);
-			const uint32_t valid = left != 0 ? (uint32_t)W::OUT : W::last_valid(p.streams[r.stream]);
-			uint8_t *dst = p.dst + o;
-			auto out = [&](int j, const uint4 &v) {
-				const uint32_t boff = (uint32_t)j * 16u;
-				const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-				for (uint32_t k = 0; k < 8u && boff + 2u * k + 2u <= valid; k++) {
-					const uint16_t h = (uint16_t)(w[k >> 1] >> (16u * (k & 1u)));
-					dst[boff + 2u * k] = (uint8_t)h;
-					dst[boff + 2u * k + 1u] = (uint8_t)(h >> 8);
-				}
-			};
-			if (CH == 2)
-				W::note_bad(p, r.stream, left, it.prof);
-			W::decode(it, p0, p1, out);
-			if (left == 0) {
-				W::put_result(p, r.stream, p0, p1);
-				break;
-			}
-			uint32_t nprof[CH];
-#pragma unroll
-			for (int c = 0; c < CH; c++)
-				nprof[c] = p.src[a + W::STEP + c * W::BS];
-			const uint32_t nm = W::mask_of(nprof);
-			if ((nm & m) == 0)
-				break;
-			m = nm;
-			a += W::STEP;
-			o += W::OUT;
-			left--;
-		}
+		walk_chain_serial<BITS, CH>(p, r.stream, a, out0 + (uint64_t)q * W::OUT,
+		    r.blocks - 1u - (r.first_eb + q), p0, p1, 0u);
 	}
+}
+
+/* ... and for one record of the relay form */
+template <int BITS, int CH>
+XA_HD void walk_relay_serial(const DecodeParams &p, const RelayRec &r)
+{
+	int p0[CH], p1[CH];
+#pragma unroll
+	for (int c = 0; c < CH; c++) {
+		p0[c] = (int16_t)(uint16_t)r.st[c];
+		p1[c] = (int16_t)(uint16_t)(r.st[c] >> 16);
+	}
+	walk_chain_serial<BITS, CH>(p, r.stream & 0x3fffffffu, (uint64_t)r.xa_hi << 32 | r.xa_lo,
+	    (uint64_t)r.out_hi << 32 | r.out_lo, r.left, p0, p1, r.stream >> 30);
 }
 
 } /* namespace xa */

@@ -24,6 +24,7 @@ static int g_use_alt = 0;
 static int g_stereo_direct = 0;
 static int g_pool = 0;
 static int g_split = 0;
+static int g_relay = 0;
 
 /* thread visiting order inside a phase: 0 ascending, 1 descending, 2 strided */
 static uint32_t
@@ -44,6 +45,13 @@ emul_decode_ns(const DecodeParams &p, int order)
 	typename Tile::Smem *sm = new typename Tile::Smem();
 	const uint32_t nt = kDecThreads;
 	std::vector<LiveRec> live;
+	/* relay form: the records of every tile, kRelayPerTile slots each */
+	std::vector<RelayRec> relay_recs((size_t)p.n_tiles * kRelayPerTile + 1);
+	uint32_t relay_count = 0xffffffffu;
+	DecodeParams pr = p;
+	pr.relay_recs = relay_recs.data();
+	pr.relay_count = &relay_count;
+	constexpr bool relay = Tile::relay;	/* relay tiles: DecTile<..., true> */
 
 	memset(sm, 0xa5, sizeof *sm);	/* smem is garbage at CTA start */
 	for (uint32_t ticket = 0; ticket < p.n_tiles; ticket++) {
@@ -55,13 +63,13 @@ emul_decode_ns(const DecodeParams &p, int order)
 		for (uint32_t lane = 0; lane < te.count; lane++) {
 			StripCtx &c = sm->ctx[s][lane];
 			make_strip_ctx<G::kBits, G::kCh, G::kTBQ, G::kNS>(c, p,
-			    p.order[te.first + lane], te.j, lane, g_split != 0);
+			    p.order[te.first + lane], te.j, lane, g_split != 0 || relay);
 			memcpy(sm->in[s] + lane * Tile::G::SLOT, p.src + c.a0, c.bulk);
 			tail |= (c.flags & kCtxTail) != 0;
 		}
 		sm->n_strips[s] = te.count;
 		sm->tile_flags[s] = tail ? kCtxTail : 0u;
-		Tile t(p, *sm, s);
+		Tile t(relay ? pr : p, *sm, s);
 		/* producer: tail bytes, then the scan for heads of chains */
 		if (tail)
 			for (uint32_t i = 0; i < 32; i++)
@@ -71,7 +79,7 @@ emul_decode_ns(const DecodeParams &p, int order)
 			if (t.is_head(q)) {
 				/* split form: item 0 is no head if it goes on with a chain of
 				 * the strip in front (scanner_warp: `prev` from the context) */
-				if (g_split && G::kNS == 1 && q == 0 &&
+				if ((g_split || relay) && G::kNS == 1 && q == 0 &&
 				    (t.chain_mask(0) & (sm->ctx[s][0].flags >> kCtxPrevShift & 3u)) != 0)
 					continue;
 				sm->heads[s][count++] = (uint16_t)q;
@@ -99,6 +107,59 @@ emul_decode_ns(const DecodeParams &p, int order)
 			}
 			for (uint32_t i = 0; i < nt; i++)
 				t.phase_units(visit(i, nt, order), nt);
+			continue;
+		}
+		if (relay) {
+			/* relay form (relay_walk_warp): 32 lanes in lockstep, a block per
+			 * turn; once the heads are dealt out and few lanes still walk,
+			 * their chains are handed to the second pass */
+			const uint32_t nw = count > kRelayManyHeads ? kRelayWalkers : 1u;
+			const uint32_t nl = 32 * nw;		/* walker lanes; a warp = 32 of them */
+			std::vector<typename Tile::Walk> w(nl);
+			std::vector<char> have(nl, 0), gone(nw, 0);
+			std::vector<uint32_t> idx(nl);
+			uint32_t next = nl;
+			for (uint32_t l = 0; l < nl; l++)
+				idx[l] = l;
+			for (uint32_t turn = 0;; turn++) {
+				uint32_t busy = 0;
+				for (uint32_t k = 0; k < nw; k++) {
+					if (gone[k])
+						continue;
+					uint32_t active = 0;
+					for (uint32_t l = 32 * k; l < 32 * k + 32; l++) {
+						if (!have[l] && idx[l] < count) {
+							t.walk_begin(w[l], sm->heads[s][idx[l]]);
+							have[l] = 1;
+						}
+						active += have[l];
+					}
+					if (active == 0) {
+						gone[k] = 1;
+						continue;
+					}
+					if (turn >= 4 && active <= kRelayWind && next >= count) {
+						for (uint32_t l = 32 * k; l < 32 * k + 32; l++)
+							if (have[l])
+								t.walk_hand_on(w[l]);
+						gone[k] = 1;
+						continue;
+					}
+					busy++;
+					for (uint32_t i = 0; i < 32; i++) {
+						const uint32_t l = 32 * k + visit(i, 32, order);
+						if (have[l] && !t.walk_block(w[l])) {
+							have[l] = 0;
+							idx[l] = next++;
+						}
+					}
+				}
+				if (busy == 0)
+					break;
+			}
+			const uint32_t ut = count == 0 ? nt : nt - 32 * nw;
+			for (uint32_t i = 0; i < ut; i++)
+				t.phase_units(visit(i, ut, order), ut);
 			continue;
 		}
 		if (g_pool) {
@@ -137,6 +198,10 @@ emul_decode_ns(const DecodeParams &p, int order)
 		for (uint32_t i = 0; i < ut; i++)
 			t.phase_units(visit(i, ut, order), ut);
 	}
+	/* relay form, pass 2: every record, in any order */
+	for (uint32_t i = 0; i < relay_count + 1u; i++)
+		walk_relay_serial<G::kBits, G::kCh>(p, relay_recs[visit(i, relay_count + 1u,
+		    order == 2 ? 1 : order)]);
 	/* split form, pass 2 (xa_walk_kernel): the records in any order, a chain at a time */
 	for (size_t i = 0; i < live.size(); i++)
 		walk_record_serial<G::kBits, G::kCh>(p, live[visit((uint32_t)i, (uint32_t)live.size(),
@@ -192,16 +257,20 @@ emul_decode_bucket(const DecodeParams &p, int ns, int order)
 {
 	/* same choice as launch_decode_ns: mono direct; stereo staged, or direct
 	 * when g_stereo_direct is set (the tests run both) */
-	if (CH == 2 && !g_stereo_direct && !(g_split && ns == 1)) {
+	if (CH == 2 && !g_stereo_direct && !((g_split || g_relay) && ns == 1)) {
 		if (ns == 1)
 			emul_decode_staged_ns<BITS, CH, 1>(p, order);
 		else
 			emul_decode_staged_ns<BITS, CH, kDecWide>(p, order);
 	} else if (CH == 2) {
-		if (ns == 1)
+		if (ns == 1 && g_relay)
+			emul_decode_ns<DecTileStereo<BITS, kDecTBQ, 1, dec_stages(BITS, 2), true> >(p, order);
+		else if (ns == 1)
 			emul_decode_ns<DecTileStereo<BITS, kDecTBQ, 1, dec_stages(BITS, 2)> >(p, order);
 		else
 			emul_decode_ns<DecTileStereo<BITS, kDecTBQ, kDecWide, dec_stages(BITS, 2)> >(p, order);
+	} else if (ns == 1 && g_relay) {
+		emul_decode_ns<DecTile<BITS, kDecTBQ, 1, dec_stages(BITS, 1), true> >(p, order);
 	} else if (ns == 1) {
 		emul_decode_ns<DecTile<BITS, kDecTBQ, 1, dec_stages(BITS, 1)> >(p, order);
 	} else {
@@ -442,6 +511,7 @@ void xa_emul_stereo_direct(int on) { g_stereo_direct = on; }
 void xa_emul_use_alt(int on) { g_use_alt = on; }
 void xa_emul_pool(int on) { g_pool = on; }
 void xa_emul_split(int on) { g_split = on; }
+void xa_emul_relay(int on) { g_relay = on; }
 int xa_emul_strip_blocks(int ns, int ch) { return (int)strip_blocks(ns, ch); }
 int xa_emul_wide(void) { return kDecWide; }
 int xa_emul_enc_tile_blocks(void) { return kEncTBE; }

@@ -33,6 +33,7 @@ class Emul:
         self.stereo_direct = d.xa_emul_stereo_direct    # (0|1): which stereo form to step
         self.use_alt = d.xa_emul_use_alt                # (0|1): step the alternative tile lists
         self.pool = d.xa_emul_pool                      # (0|1): direct forms walk as the pooled kernel does
+        self.relay = d.xa_emul_relay                    # (0|1): long-strip tiles walk their chains but hand stragglers on (relay form)
         self.split = d.xa_emul_split                    # (0|1): long-strip tiles go through the split form (xa_walk.h)
 
     def dec_tile_blocks(self, ch):

@@ -11,22 +11,26 @@ from bjxa_b200 import synth
 from emul_binding import Emul
 
 
-@pytest.fixture(scope="module", params=["stereo-staged", "stereo-direct", "pooled", "split"])
+@pytest.fixture(scope="module", params=["stereo-staged", "stereo-direct", "pooled", "split", "relay"])
 def emul(request):
     """Every decode case runs three times: stereo streams through the staged form,
     through the direct form of the tile code (mono always uses the direct one), and
     both direct forms with their chains walked the way the pooled kernel does it
     (walk_begin / walk_block, units on 64 threads); and long-strip tiles through the
     split form: pass 1 lists the heads, pass 2 (xa_walk.h) walks every chain to its
-    end across tile boundaries."""
+    end across tile boundaries; and through the relay form: the tiles walk their
+    own chains but hand the stragglers and everything that crosses a strip's end to
+    pass 2."""
     e = Emul()
     e.stereo_direct(0 if request.param == "stereo-staged" else 1)
     e.pool(1 if request.param == "pooled" else 0)
     e.split(1 if request.param == "split" else 0)
+    e.relay(1 if request.param == "relay" else 0)
     yield e
     e.stereo_direct(0)
     e.pool(0)
     e.split(0)
+    e.relay(0)
 
 
 STRIP_MODES = [1, 32]      # one long strip per tile / 32 short ones

@@ -2230,6 +2230,11 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 			p.ticket = reinterpret_cast<unsigned long long *>(
 			    pl->d_first_bad.p + ((n + 3) & ~(size_t)3)) + b;
 			p.fault = pl->d_fault.p;
+			{
+				const char *t = getenv("BJXA_B200_CARRY_TIMEOUT_S");
+				const long secs = t != NULL && atol(t) > 0 ? atol(t) : XA_CARRY_TIMEOUT_S;
+				p.carry_timeout_ns = (unsigned long long)secs * 1000000000ULL;
+			}
 			p.epoch = pl->epoch;
 			p.choice = NULL;
 			p.want = 0;

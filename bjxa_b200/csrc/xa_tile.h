@@ -100,6 +100,7 @@ struct DecodeParams {
 	unsigned long long *carry;	/* [slot][2] mailboxes */
 	unsigned long long *ticket;	/* preset to ~0 before every launch */
 	uint32_t *fault;		/* set if a carry never arrived */
+	unsigned long long carry_timeout_ns;
 	uint32_t epoch;
 	/* stereo: two tile forms are launched and the census decides which one
 	 * runs; a kernel whose `want` differs from *choice returns at once */
@@ -134,6 +135,12 @@ struct EncodeParams {
 
 /* ---- environment shims -------------------------------------------------- */
 
+/* how long a strip waits for its predecessor's state: wall-clock seconds
+ * (BJXA_B200_CARRY_TIMEOUT_S overrides the default when a plan runs) */
+#ifndef XA_CARRY_TIMEOUT_S
+#define XA_CARRY_TIMEOUT_S 60
+#endif
+
 #if defined(__CUDA_ARCH__)
 XA_HD void global_min_u32(uint32_t *p, uint32_t v) { atomicMin(p, v); }
 XA_HD void mailbox_put(unsigned long long *p, unsigned long long v)
@@ -144,17 +151,28 @@ XA_HD void mailbox_put(unsigned long long *p, unsigned long long v)
 	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 XA_HD unsigned long long mailbox_get(const unsigned long long *p, uint32_t epoch,
-    uint32_t *fault)
+    uint32_t *fault, unsigned long long timeout_ns)
 {
-	unsigned long long v;
+	unsigned long long v, t0 = 0;
 	/* The predecessor tile holds a lower ticket, so it is running or done
-	 * and this wait is short.  It is still bounded (~10 s): a kernel must
-	 * never hang the device; on expiry the launch is flagged as failed. */
-	for (uint32_t spins = 0; spins < (1u << 24); spins++) {
+	 * and this wait is short.  It is still bounded -- by elapsed time on the
+	 * device's clock, not by a count of polls, so that a context that is time
+	 * sliced, preempted or held in a debugger does not fail a correct run: a
+	 * kernel must never hang the device; on expiry the launch is flagged as
+	 * failed (bjxa_plan_fetch: EIO, the PCM is not valid). */
+	for (uint32_t spins = 0;; spins++) {
 		asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
 		if ((uint32_t)(v >> 32) == epoch)
 			return v;
 		__nanosleep(spins < 64 ? 32 : 512);
+		if ((spins & 1023u) == 1023u) {
+			unsigned long long now;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+			if (t0 == 0)
+				t0 = now;
+			else if (now - t0 > timeout_ns)
+				break;
+		}
 	}
 	atomicExch(fault, 1u);
 	return 0;
@@ -169,7 +187,7 @@ XA_HD bool mailbox_try(const unsigned long long *p, uint32_t epoch, unsigned lon
 XA_HD void global_min_u32(uint32_t *p, uint32_t v) { if (v < *p) *p = v; }
 XA_HD void mailbox_put(unsigned long long *p, unsigned long long v) { *p = v; }
 XA_HD unsigned long long mailbox_get(const unsigned long long *p, uint32_t epoch,
-    uint32_t *)
+    uint32_t *, unsigned long long)
 {
 	/* the emulator runs tiles in ticket order: the value must be there */
 	if ((uint32_t)(*p >> 32) != epoch)
@@ -472,7 +490,7 @@ struct DecTile {
 			p1 = p.streams[c.stream].prev[0][1];
 		} else {
 			unsigned long long v = mailbox_get(
-			    &p.carry[(uint64_t)(c.slot - 1) * 2], p.epoch, p.fault);
+			    &p.carry[(uint64_t)(c.slot - 1) * 2], p.epoch, p.fault, p.carry_timeout_ns);
 			p0 = (int16_t)(uint16_t)v;
 			p1 = (int16_t)(uint16_t)(v >> 16);
 		}
@@ -938,7 +956,7 @@ struct DecTileStereo {
 			p1 = p.streams[c.stream].prev[ch][1];
 		} else {
 			unsigned long long v = mailbox_get(
-			    &p.carry[(uint64_t)(c.slot - 1) * 2 + ch], p.epoch, p.fault);
+			    &p.carry[(uint64_t)(c.slot - 1) * 2 + ch], p.epoch, p.fault, p.carry_timeout_ns);
 			p0 = (int16_t)(uint16_t)v;
 			p1 = (int16_t)(uint16_t)(v >> 16);
 		}
@@ -1405,7 +1423,7 @@ struct DecTileStaged {
 			p1 = p.streams[c.stream].prev[ch][1];
 		} else {
 			unsigned long long v = mailbox_get(
-			    &p.carry[(uint64_t)(c.slot - 1) * 2 + ch], p.epoch, p.fault);
+			    &p.carry[(uint64_t)(c.slot - 1) * 2 + ch], p.epoch, p.fault, p.carry_timeout_ns);
 			p0 = (int16_t)(uint16_t)v;
 			p1 = (int16_t)(uint16_t)(v >> 16);
 		}

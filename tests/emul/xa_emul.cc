@@ -406,6 +406,7 @@ xa_emul_decode(const bjxa_stream_desc_t *descs, size_t n, const uint8_t *src,
 		p.carry = carry.data();
 		p.ticket = &ticket;
 		p.fault = &fault;
+		p.carry_timeout_ns = 0;
 		p.epoch = 7;
 		switch (b) {
 		case 0: emul_decode_bucket<4, 1>(p, ns, order); break;

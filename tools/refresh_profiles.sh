@@ -4,13 +4,14 @@
 # command runs only after the same command exited 0 without ncu.
 # tools/summarize_profiles.py turns the results into profiles/.
 #   usage: bash tools/refresh_profiles.sh <round-tag>      e.g. r1
-tag=${1:-r1}
+tag=${1:-r2}
 mkdir -p gpurun_out
 set -x
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$tag.log 2>&1 || exit 9
 timeout 900 python bench.py --steps 10 > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err || exit 1
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$tag.json 2> gpurun_out/bench_ref_$tag.err
-timeout 900 python tools/bench_configs.py > gpurun_out/configs_$tag.json 2> gpurun_out/configs_$tag.err
+timeout 900 python tools/bench_configs.py > gpurun_out/extras_$tag.json 2> gpurun_out/extras_$tag.err
+timeout 300 python tools/latency_probe.py > gpurun_out/latency_$tag.json 2> gpurun_out/latency_$tag.err
 A="bench.py --steps 2 --warmup 3 --no-extras"
 timeout 300 python $A > gpurun_out/plain_$tag.json 2>/dev/null || exit 2
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
@@ -32,5 +33,33 @@ E="tools/prof_decode.py --mix P0 --streams 1024 --seconds 4 --bits 4 --ch 2 --st
 timeout 300 python $E > gpurun_out/prof_search_$tag.json 2>/dev/null && \
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:xa_search_kernel -c 1 \
     -f -o gpurun_out/search_stereo4_$tag python $E > gpurun_out/ncu_search_$tag.log 2>&1
+# the two-pass forms on chain-rich data: the relay form's first pass (tile walkers
+# that hand their stragglers on) and second pass, mono 8-bit mix P2; the split
+# form's dense walkers, stereo 4-bit mix P2
+F="tools/prof_decode.py --mix P2 --streams 2048 --seconds 30 --bits 8 --ch 1 --steps 1 --warmup 0"
+timeout 300 python $F > gpurun_out/prof_relay_$tag.json 2>/dev/null && \
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
+    -k "regex:xa_decode_kernel<.*true" -c 1 \
+    -f -o gpurun_out/relay_pass1_mono8_p2_$tag python $F > gpurun_out/ncu_relay1_$tag.log 2>&1
+timeout 300 python $F > /dev/null 2>&1 && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:xa_walk_kernel -c 1 \
+    -f -o gpurun_out/relay_pass2_mono8_p2_$tag python $F > gpurun_out/ncu_relay2_$tag.log 2>&1
+G="tools/prof_decode.py --mix P2 --streams 2048 --seconds 30 --bits 4 --ch 2 --steps 1 --warmup 0"
+timeout 300 python $G > gpurun_out/prof_split_$tag.json 2>/dev/null && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:xa_walk_kernel -c 1 \
+    -f -o gpurun_out/split_walk_stereo4_p2_$tag python $G > gpurun_out/ncu_split_$tag.log 2>&1
 timeout 300 python tools/pcie_probe.py > gpurun_out/pcie_$tag.json 2> gpurun_out/pcie_$tag.err
+# gpurun brings back at most 64 MiB: the raw metric page of every capture as CSV
+# (what tools/summarize_profiles.py reads), the SASS page of the walkers, and only
+# the two main reports themselves
+for r in gpurun_out/*_$tag.ncu-rep; do
+    ncu -i $r --page raw --csv > ${r%.ncu-rep}.raw.csv 2>/dev/null
+done
+for k in relay_pass1_mono8_p2 relay_pass2_mono8_p2 split_walk_stereo4_p2; do
+    ncu -i gpurun_out/${k}_$tag.ncu-rep --page source --csv > gpurun_out/${k}_$tag.source.csv 2>/dev/null
+done
+for r in gpurun_out/*_$tag.ncu-rep; do
+    case $r in *decode_p1_4096_*|*relay_pass1_*) ;; *) rm -f $r ;; esac
+done
+du -sh gpurun_out
 echo done

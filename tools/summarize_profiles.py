@@ -24,6 +24,9 @@ PROF = os.path.join(ROOT, "profiles")
 
 METRICS = [
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
     "dram__throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_op_write.sum",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -92,8 +95,8 @@ def launches(tag):
     L += ["", "## The timed region", "",
           "One step = one `bjxa_plan_run()` = one `cudaMemsetAsync` (arms first_bad[], the ticket "
           "counters and the census words; a memset node, not a kernel) + the launches below. The "
-          "4096-stream class carries both tile shapes, so the census kernel runs and the tile form "
-          "it does not pick returns at once:", "",
+          "4096-stream class has several candidate forms (long strips, wide tiles, the relay form's "
+          "two passes), so the census kernel runs and the forms it does not pick return at once:", "",
           "| launch | kernel | ms under ncu |", "|---|---|---:|"]
     per_step = len(ours) // 5 if len(ours) % 5 == 0 else None
     for i, (k, ms) in enumerate(ours):
@@ -118,13 +121,23 @@ def launches(tag):
     shutil.copyfile(path, os.path.join(PROF, f"launches_{tag}.csv"))     # the raw list as well
 
 
-def full(tag):
-    rep = os.path.join(OUT, f"decode_p1_4096_{tag}.ncu-rep")
+def raw_page(stem, tag):
+    """The raw metric page of a capture: the CSV the GPU box exported, or the report."""
+    path = os.path.join(OUT, f"{stem}_{tag}.raw.csv")
+    if os.path.exists(path) and os.path.getsize(path):
+        return open(path).read()
+    rep = os.path.join(OUT, f"{stem}_{tag}.ncu-rep")
     if not os.path.exists(rep):
         print("missing:", rep)
+        return None
+    return subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True,
+                          text=True).stdout
+
+
+def full(tag):
+    raw = raw_page("decode_p1_4096", tag)
+    if raw is None:
         return
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True,
-                         text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, d = rows[0], rows[1], rows[2]
     idx = {h: i for i, h in enumerate(hdr)}
@@ -162,15 +175,12 @@ def full(tag):
 
 def secondary(tag, stem, cmd, what):
     """ncu --set full of one launch of a secondary kernel -> <stem>_<tag>_ncu_summary.csv"""
-    rep = os.path.join(OUT, f"{stem}_{tag}.ncu-rep")
-    if not os.path.exists(rep):
-        print("missing:", rep)
+    raw = raw_page(stem, tag)
+    if raw is None:
         return
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True,
-                         text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     if len(rows) < 3:
-        print("empty:", rep)
+        print("empty:", stem)
         return
     hdr, units, d = rows[0], rows[1], rows[2]
     idx = {h: i for i, h in enumerate(hdr)}
@@ -179,11 +189,20 @@ def secondary(tag, stem, cmd, what):
     for m in METRICS:
         if m in idx:
             L.append(f"{m},{units[idx[m]]},{d[idx[m]]}")
+    stalls = []
+    for h in hdr:
+        if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("_per_issue_active.ratio"):
+            try:
+                stalls.append((fnum(d[idx[h]]), h, units[idx[h]]))
+            except ValueError:
+                pass
+    for v, h, u in sorted(stalls, reverse=True)[:6]:
+        L.append(f"{h},{u},{v}")
     open(os.path.join(PROF, f"{stem}_{tag}_ncu_summary.csv"), "w").write("\n".join(L) + "\n")
 
 
 def main():
-    tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
     secondary(tag, "decode_stereo8_p1",
               "tools/prof_decode.py --mix P1 --streams 2048 --seconds 30 --bits 8 --ch 2 --steps 1 --warmup 0",
               "stereo decode, direct form, 2048 stereo 8-bit streams x 30 s, mix P1")
@@ -193,7 +212,19 @@ def main():
     secondary(tag, "search_stereo4",
               "tools/prof_decode.py --mix P0 --streams 1024 --seconds 4 --bits 4 --ch 2 --steps 1 --warmup 0 --search",
               "searching encoder (extension), 1024 stereo streams x 4 s -> 4-bit XA, 65 candidates per block")
-    for n in (f"bench_{tag}.json", f"bench_ref_{tag}.json", f"configs_{tag}.json", f"pcie_{tag}.json"):
+    secondary(tag, "relay_pass1_mono8_p2",
+              "tools/prof_decode.py --mix P2 --streams 2048 --seconds 30 --bits 8 --ch 1 --steps 1 --warmup 0",
+              "relay form, first pass: the direct form whose walker warps hand their stragglers on; "
+              "2048 mono 8-bit streams x 30 s, mix P2 (80 % chain blocks)")
+    secondary(tag, "relay_pass2_mono8_p2",
+              "tools/prof_decode.py --mix P2 --streams 2048 --seconds 30 --bits 8 --ch 1 --steps 1 --warmup 0",
+              "relay form, second pass: the dense walkers finishing the handed-on chains; same launch")
+    secondary(tag, "split_walk_stereo4_p2",
+              "tools/prof_decode.py --mix P2 --streams 2048 --seconds 30 --bits 4 --ch 2 --steps 1 --warmup 0",
+              "split form, second pass: the dense walkers, every lane a run of effective blocks; "
+              "2048 stereo 4-bit streams x 30 s, mix P2")
+    for n in (f"bench_{tag}.json", f"bench_ref_{tag}.json", f"extras_{tag}.json", f"pcie_{tag}.json",
+              f"latency_{tag}.json", f"prof_relay_{tag}.json", f"prof_split_{tag}.json"):
         copy(n)
     launches(tag)
     full(tag)

@@ -122,6 +122,8 @@ constexpr int kDecBlock = kDecThreads + 64;	/* consumers + loader warp + scanner
  *          chain walkers of xa_walk_kernel                    (split <= share < wide)
  *   bit 4  (alone) the relay form: direct form whose walker warps hand their
  *          stragglers to xa_walk_kernel                       (relay <= share < split)
+ *   bit 5  (alone) the segment form, xa_seg_kernel            (seg <= share < seg_below;
+ *          asked first)
  * A threshold above 1000 permille switches that choice off.  One CTA, no
  * atomics, nothing to clear; all of a thread's loads in flight together.  Measured crossovers:
  * profiles/history_r1.md.
@@ -134,7 +136,7 @@ constexpr uint32_t staged_permille(int bits) { return bits == 4 ? 300u : bits ==
 constexpr uint32_t kWideManyStreams = 8192;
 constexpr uint32_t kWidePermilleMono[2] = { 985, 930 }, kWidePermilleStereo[2] = { 920, 700 };
 constexpr uint32_t kNever = 1001;
-enum { kFormStaged = 1, kFormWide = 2, kFormPool = 4, kFormSplit = 8, kFormRelay = 16 };
+enum { kFormStaged = 1, kFormWide = 2, kFormPool = 4, kFormSplit = 8, kFormRelay = 16, kFormSeg = 32 };
 /* pooled walkers instead of one walker warp per tile: from this share of chain
  * blocks (measured crossovers: profiles/history_r1.md), for classes of at least
  * kPoolMinTiles tiles -- below that the launch is too short to care */
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(kCensusThreads)
 xa_census_kernel(const uint8_t *src, const StreamDev *streams, const uint32_t *order,
     uint32_t n_streams, uint32_t block_bytes_one, uint32_t ch, uint32_t staged_permille,
     uint32_t wide_permille, uint32_t pool_permille, uint32_t split_permille,
-    uint32_t relay_permille, uint32_t *choice)
+    uint32_t relay_permille, uint32_t seg_permille, uint32_t seg_below, uint32_t *choice)
 {
 	__shared__ uint32_t warp_sum[kCensusThreads / 32];
 	const uint32_t tid = threadIdx.x;
@@ -186,7 +188,8 @@ xa_census_kernel(const uint8_t *src, const StreamDev *streams, const uint32_t *o
 			total += warp_sum[w];
 		const uint32_t permille = total * 1000u / (kCensusThreads * kCensusPerThread);
 		const uint32_t staged = permille >= staged_permille ? kFormStaged : 0u;
-		*choice = permille >= wide_permille ? kFormWide | staged :
+		*choice = permille >= seg_permille && permille < seg_below ? (uint32_t)kFormSeg :
+		    permille >= wide_permille ? kFormWide | staged :
 		    permille >= split_permille ? (uint32_t)kFormSplit :
 		    permille >= relay_permille ? (uint32_t)kFormRelay :
 		    permille >= pool_permille ? (uint32_t)kFormPool : staged;
@@ -1114,6 +1117,411 @@ xa_walk_kernel(const DecodeParams p)
 	}
 }
 
+/* ---- segment form (xa_walk.h) ---------------------------------------------------- */
+/*
+ * One warp per tile of the segment list, one stream per lane, kSegItems items per
+ * lane, every item decoded with the chain step (walk_seg_serial in xa_walk.h is the
+ * same thing in plain loops).  The data path is the dense walkers': a lane reads
+ * its items straight from the arena, 16-byte cp.async chunks into a private ring in
+ * shared memory, one item ahead of the decode; the PCM goes to a row of shared
+ * memory and leaves the warp eight (stereo: four) rows per store instruction.
+ * What the dense walkers spend on drawing chains -- lists, ballots, seeds, a peek at
+ * the next profile byte every turn -- is gone: a lane knows its range from the
+ * start, and the turns of a warp differ only at the two ends of the segments.
+ */
+#ifndef XA_SEG_CTAS
+#define XA_SEG_CTAS 0
+#endif
+#ifndef XA_SEG_WARPS
+#define XA_SEG_WARPS 0
+#endif
+#ifndef XA_SEG_RANGED
+#define XA_SEG_RANGED 1		/* the step with the bias on the ranged code (xa_core.h: sample_chain_r) */
+#endif
+#ifndef XA_SEG_AHEAD
+#define XA_SEG_AHEAD 1		/* items a lane's copies run ahead of its decode, at least */
+#endif
+template <int BITS, int CH>
+struct SegCfg {
+	typedef Walk<BITS, CH> W;
+	/* the ring holds the item being decoded and the D behind it, from any alignment:
+	 * the smallest power of two that gives D >= XA_SEG_AHEAD.  One item ahead (the
+	 * dense walkers' depth) is a turn of one warp, which hides the arena's latency
+	 * only while other warps have turns to run -- not on data without cut blocks,
+	 * where a few warps per SM do all the work */
+	static constexpr int ahead_of(int ring) { return (ring - 30) / W::STEP - 1; }
+	static constexpr int RING = ahead_of(64) >= XA_SEG_AHEAD ? 64 : ahead_of(128) >= XA_SEG_AHEAD ? 128 : 256;
+	static constexpr int D = XA_SEG_AHEAD;
+	static constexpr int SLOT = RING + 16;	/* lane stride: spreads equal offsets over the banks */
+	/* chunks a lane asks for in one turn at most: one item's worth */
+	static constexpr int KMAX = (15 + W::STEP + 15) / 16;
+	/* mono: 2 CTAs of 10 warps (96 registers a thread) measured 3-6 % faster than 3 of 8
+	 * (80 registers); stereo: 2 of 8 (128 registers, two chains side by side) */
+	static constexpr int kWarps = XA_SEG_WARPS != 0 ? XA_SEG_WARPS : CH == 1 ? 10 : 8;
+	static constexpr int kThreads = kWarps * 32;
+	static constexpr size_t kSmem = (size_t)kThreads * (SLOT + W::OUT);
+	/* CTAs per SM: what the shared memory allows, but no more than leaves a thread its
+	 * registers -- 80 for mono, 128 for stereo (two chains side by side).  Measured
+	 * (profiles/history_r2.md): deeper rings (more items in flight per lane) at the
+	 * price of fewer warps lose on every mix */
+	static constexpr int kFit = (int)((227 * 1024) / (kSmem + 1024));
+	static constexpr int kWant = 2;
+	static constexpr int kCtas = XA_SEG_CTAS != 0 ? XA_SEG_CTAS : kFit > kWant ? kWant : kFit;
+	static_assert(D >= 1 && 30 + (D + 1) * W::STEP <= RING, "ring");
+};
+
+/*
+ * The state a lane could not recompute: from the mailbox of the lane that decodes
+ * the segment in front (slot - 1).  While even the segment before that one is not
+ * through (slot - 2), the wait is a whole segment away and the lane looks rarely:
+ * on data without cut blocks all but a few warps of the grid are waiting here, and
+ * their looks would otherwise load the L2 more than the decode does.
+ */
+__device__ __forceinline__ void
+seg_wait_front(const DecodeParams &p, uint32_t slot, bool far, uint32_t ch, int &p0, int &p1)
+{
+	unsigned long long v;
+	if (far) {
+		unsigned long long t0 = 0;
+		for (uint32_t spins = 0;; spins++) {
+			if (mailbox_try(&p.carry[(uint64_t)(slot - 2u) * 2 + ch], p.epoch, v) ||
+			    mailbox_try(&p.carry[(uint64_t)(slot - 1u) * 2 + ch], p.epoch, v))
+				break;
+			__nanosleep(8000);
+			if ((spins & 255u) == 255u) {
+				unsigned long long now;
+				asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+				if (t0 == 0)
+					t0 = now;
+				else if (now - t0 > p.carry_timeout_ns)
+					break;		/* mailbox_get below flags the launch */
+			}
+		}
+	}
+	v = mailbox_get(&p.carry[(uint64_t)(slot - 1u) * 2 + ch], p.epoch, p.fault, p.carry_timeout_ns);
+	p0 = (int16_t)(uint16_t)v;
+	p1 = (int16_t)(uint16_t)(v >> 16);
+}
+
+template <int BITS, int CH>
+__global__ void __launch_bounds__(SegCfg<BITS, CH>::kThreads, SegCfg<BITS, CH>::kCtas)
+xa_seg_kernel(const DecodeParams p)
+{
+	typedef Walk<BITS, CH> W;
+	typedef SegCfg<BITS, CH> C;
+	constexpr int BS = W::BS, STEP = W::STEP, OUT = W::OUT, RING = C::RING;
+	constexpr uint32_t FULL = 0xffffffffu;
+	constexpr uint32_t UPR = W::UNITS;		/* 16-byte units per row of PCM */
+	constexpr uint32_t RPI = 32u / UPR;		/* rows per store instruction */
+
+	if (p.choice != NULL && *p.choice != p.want)
+		return;		/* the census picked another form */
+
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	uint32_t tid, lane;
+	asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+	asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+	const uint32_t warp = tid >> 5;
+	uint8_t *const ringp = smem_raw + (size_t)tid * C::SLOT;
+	const uint32_t ring = smem_u32(ringp);
+	uint8_t *const rows = smem_raw + (size_t)C::kThreads * C::SLOT + (size_t)warp * 32 * OUT;
+	uint8_t *const row = rows + (size_t)lane * OUT;
+	const uint32_t co_c = lane % UPR, co_r0 = lane / UPR;
+	/* whole 16-byte chunks of the arena; what lies behind is fetched bytewise */
+	const uint64_t safe = p.src_bytes & ~(uint64_t)15;
+
+	for (;;) {
+		/* ---- the warp's next tile ---- */
+		uint32_t ticket = 0;
+		if (lane == 0)
+			ticket = (uint32_t)(atomicAdd(p.ticket, 1ULL) + 1ULL);
+		ticket = __shfl_sync(FULL, ticket, 0);
+		if (ticket >= p.n_tiles)
+			break;
+		const uint4 te = ldg_u128(&p.tiles[ticket]);	/* first, count, j, lanes per stream */
+		/* lane L: segment j * P + L % P of stream L / P of the tile (xa_walk.h: seg_lane) */
+		const uint32_t lps = te.w, sidx = lane / lps, sub = lane & (lps - 1u);
+		bool valid = sidx < te.y;
+		uint32_t stream = 0, n = 0, n0 = 0, slot = 0;
+		uint64_t a0 = 0, o0 = 0;
+		bool ends = false;		/* the segment is its stream's last */
+		bool pending = false;		/* the state comes from lane - 1, after a pass */
+		int p0[CH], p1[CH];
+		uint32_t back = 0;
+#pragma unroll
+		for (int c = 0; c < CH; c++)
+			p0[c] = p1[c] = 0;
+		if (valid) {
+			stream = p.order[te.x + sidx];
+			const StreamDev &sd0 = p.streams[stream];
+			const uint64_t at = ((uint64_t)te.z * lps + sub) * kSegItems;
+			valid = at < sd0.blocks;
+			n0 = (uint32_t)at;
+		}
+		if (valid) {
+			const StreamDev &sd = p.streams[stream];
+			const uint32_t blocks = sd.blocks;
+			n = blocks - n0 < kSegItems ? blocks - n0 : kSegItems;
+			ends = n0 + n == blocks;
+			a0 = sd.xa_off + (uint64_t)n0 * STEP;
+			o0 = sd.pcm_off + (uint64_t)n0 * OUT;
+			slot = sd.slot_base + te.z;
+
+			/* ---- the state in front of the segment (seg_front) ---- */
+			bool own = n0 == 0, mail = false;
+			if (!own) {
+				const uint32_t lim = n0 < kSegBack ? n0 : kSegBack;
+				uint32_t found[CH], missing = CH;
+#pragma unroll
+				for (int c = 0; c < CH; c++)
+					found[c] = 0;
+#pragma unroll 1
+				for (uint32_t base = 0; base < lim && missing != 0; base += 8u) {
+					/* eight items' profile bytes at a time, all loads in flight together */
+					uint32_t pr[8][CH];
+#pragma unroll
+					for (uint32_t k = 0; k < 8u; k++)
+#pragma unroll
+						for (int c = 0; c < CH; c++)
+							pr[k][c] = base + k < lim ? ldg_u8(p.src + (a0 -
+							    (uint64_t)(base + k + 1u) * STEP + (uint64_t)(c * BS))) : 0x10u;
+#pragma unroll
+					for (uint32_t k = 0; k < 8u; k++)
+#pragma unroll
+						for (int c = 0; c < CH; c++)
+							if (found[c] == 0 && block_kind(pr[k][c]) != kChain) {
+								found[c] = base + k + 1u;
+								missing--;
+							}
+				}
+				if (missing == 0) {
+#pragma unroll
+					for (int c = 0; c < CH; c++)
+						back = found[c] > back ? found[c] : back;
+				} else if (lim == n0) {
+					back = n0;
+					own = true;
+				} else {
+					mail = true;
+				}
+			}
+			if (own) {
+#pragma unroll
+				for (int c = 0; c < CH; c++) {
+					p0[c] = sd.prev[c][0];
+					p1[c] = sd.prev[c][1];
+				}
+			}
+			if (mail && sub == 0) {
+				/* the stream's previous tile holds a lower ticket: running or done */
+#pragma unroll
+				for (int c = 0; c < CH; c++)
+					seg_wait_front(p, slot, te.z >= 2u, (uint32_t)c, p0[c], p1[c]);
+			} else if (mail) {
+				pending = true;		/* lane - 1 decodes the segment in front */
+			}
+		}
+		__syncwarp();
+		bool ready = valid && !pending;
+
+		/* ---- passes: one, unless lanes have to wait for their neighbours ---- */
+		for (;;) {
+		const bool run = ready;
+
+		/* ---- the turns, the warp in lockstep: turn t is item t of every lane's segment,
+		 * t < 0 the items in front that a lane decodes only for their state ---- */
+		const int maxback = (int)__reduce_max_sync(FULL, run ? back : 0u);
+		const int nmax = (int)__reduce_max_sync(FULL, run ? n : 0u);
+		const int first = run ? -(int)back : 0;		/* this lane's first turn */
+		const int nn = run ? (int)n : 0;			/* 0 on a lane that sits this pass out */
+		/* the ring, in bytes from a0: filled up to fe; chunks lie at arena offsets that
+		 * are multiples of 16, and at the same offsets modulo RING in the ring */
+		/* ... counted from a0 rounded down to a chunk, NOT from the arena: lanes in
+		 * lockstep then keep their items at (nearly) the same places of their rings,
+		 * and the eight lanes of a quarter warp -- SLOT apart, 16 bytes past a multiple
+		 * of 128 -- touch eight different bank groups per 16-byte copy or store instead
+		 * of random ones (ncu: 19.6 wavefronts per LDGSTS before, profiles/history_r2.md) */
+		const uint32_t a32 = (uint32_t)a0 & 15u;
+		int fe = first * STEP;
+		fe -= (int)((a32 + (uint32_t)fe) & 15u);
+		const uint8_t *gq = p.src + a0 + (int64_t)fe;	/* the next chunk to ask for */
+		/* whole chunks end here; a lane whose segment reaches further gets the arena's
+		 * last few bytes one by one (tail) */
+		const uint64_t room = safe > a0 ? safe - a0 : 0;
+		const int fe_safe = run ? (room > 0x40000000ULL ? 0x40000000 : (int)room) : 0;
+		const bool tail = __any_sync(FULL, run && nn * STEP > fe_safe);
+		/* one group of copies: this lane's item u */
+		auto request = [&](int u) {
+			if (u >= first && u < nn) {
+				const int want = (u + 1) * STEP < fe_safe ? (u + 1) * STEP : fe_safe;
+				const uint32_t r32 = a32 + (uint32_t)fe;
+				int k = 0;
+#pragma unroll
+				for (int i = 0; i < C::KMAX; i++)
+					if (fe + 16 * i < want) {
+						cp_async16(ring + ((r32 + 16u * i) & (RING - 1)), gq + 16 * i);
+						k = i + 1;
+					}
+				fe += 16 * k;
+				gq += 16 * k;
+			}
+			asm volatile("cp.async.commit_group;" ::: "memory");
+			if (tail && u >= first && u < nn && (u + 1) * STEP > fe_safe) {
+				const int from = u * STEP > fe_safe ? u * STEP : fe_safe < first * STEP ? first * STEP : fe_safe;
+				for (int b = from; b < (u + 1) * STEP; b++)
+					if (a0 + (uint64_t)(int64_t)b < p.src_bytes)
+						ringp[(a32 + (uint32_t)b) & (RING - 1)] = p.src[a0 + (uint64_t)(int64_t)b];
+			}
+		};
+#pragma unroll
+		for (int d = 0; d < C::D; d++)
+			request(-maxback + d);
+
+		/* the rows this lane copies out: row r * RPI + co_r0 of every turn; where that
+		 * lane's PCM of turn 0 goes, and how many whole rows it stores */
+		unsigned long long ob[UPR];
+		{
+			const unsigned long long mine = (unsigned long long)(p.dst + o0);
+#pragma unroll
+			for (uint32_t r = 0; r < UPR; r++)
+				ob[r] = __shfl_sync(FULL, mine, r * RPI + co_r0) + co_c * 16u;
+		}
+		/* a stream's last item goes by itself (it may owe less than a row) */
+		const int full = run && ends ? nn - 1 : nn;
+		const int last_t = run && ends ? nn - 1 : -1;
+		uint32_t at32 = a32 + (uint32_t)(-maxback * STEP);	/* low address bits of turn t's item */
+
+#ifdef XA_SEG_PROF
+		long long pc[6] = { 0, 0, 0, 0, 0, 0 }, pt = clock64();
+#define XA_SEG_TICK(i) do { long long now_ = clock64(); pc[i] += now_ - pt; pt = now_; } while (0)
+#else
+#define XA_SEG_TICK(i) do { } while (0)
+#endif
+#pragma unroll 1
+		for (int t = -maxback; t < nmax; t++) {
+			XA_SEG_TICK(5);
+			/* (1) the copies of this turn's item have landed: all groups but the
+			 * C::D - 1 asked for last */
+			asm volatile("cp.async.wait_group %0;" :: "n"(C::D - 1) : "memory");
+			const bool act = t >= first && t < nn;
+			XA_SEG_TICK(0);
+
+			/* (2) this turn's item out of the ring */
+			typename W::Item it;
+			if (act) {
+#pragma unroll
+				for (int c = 0; c < CH; c++) {
+					const uint32_t at = at32 + (uint32_t)(c * BS);
+					it.prof[c] = ringp[at & (RING - 1)];
+					const uint32_t pay = at + 1u, w0 = pay & ~3u, sh = (pay & 3u) * 8u;
+					uint32_t prev = *reinterpret_cast<const uint32_t *>(ringp + (w0 & (RING - 1)));
+#pragma unroll
+					for (int i = 0; i < BITS; i++) {
+						const uint32_t nx = *reinterpret_cast<const uint32_t *>(
+						    ringp + ((w0 + 4u * (i + 1)) & (RING - 1)));
+						it.pw[c][i] = __funnelshift_r(prev, nx, sh);
+						prev = nx;
+					}
+				}
+				if (t >= 0) {
+#pragma unroll
+					for (int c = 0; c < CH; c++)
+						if (it.prof[c] >> 4 >= 5u)
+							global_min_u32(&p.first_bad[stream], (n0 + (uint32_t)t) * CH + c);
+				}
+			}
+
+			XA_SEG_TICK(1);
+			/* (3) ask for the item C::D turns on */
+			request(t + C::D);
+			XA_SEG_TICK(2);
+
+			/* (4) decode into this lane's row, then the warp's rows leave together */
+			if (act) {
+				auto out = [&](int j, const uint4 &v) {
+					const uint32_t at = CH == 1 ? ((uint32_t)j ^ (lane >> 1 & 3u)) : ((uint32_t)j ^ (lane & 7u));
+					*reinterpret_cast<uint4 *>(row + at * 16u) = v;
+				};
+				W::template decode<XA_SEG_RANGED != 0>(it, p0, p1, out);
+			}
+			XA_SEG_TICK(3);
+			if (t >= 0) {
+				__syncwarp();
+				uint4 v[UPR];
+#pragma unroll
+				for (uint32_t r = 0; r < UPR; r++) {
+					const uint32_t sl = r * RPI + co_r0;
+					const uint32_t at = CH == 1 ? (co_c ^ (sl >> 1 & 3u)) : (co_c ^ (sl & 7u));
+					v[r] = *reinterpret_cast<const uint4 *>(rows + (size_t)sl * OUT + at * 16u);
+				}
+				/* bit r * RPI: the lane whose row r this one copies has a whole row */
+				const uint32_t rows_on = __ballot_sync(FULL, t < full) >> co_r0;
+#pragma unroll
+				for (uint32_t r = 0; r < UPR; r++) {
+					if (rows_on & (1u << (r * RPI)))
+						*reinterpret_cast<uint4 *>(ob[r]) = v[r];
+					ob[r] += OUT;
+				}
+				if (__any_sync(FULL, t == last_t)) {
+					/* the last item of a stream: its own lane stores what the stream still
+					 * owes (libbjxa.c:622-624,648) and leaves the final state */
+					if (t == last_t) {
+						const uint32_t owed = W::last_valid(p.streams[stream]);
+						uint16_t *d = reinterpret_cast<uint16_t *>(p.dst + o0 + (uint64_t)t * OUT);
+						for (uint32_t k = 0; k < owed / 2u; k++) {
+							const uint32_t j = k >> 3;
+							const uint32_t at = CH == 1 ? (j ^ (lane >> 1 & 3u)) : (j ^ (lane & 7u));
+							d[k] = *reinterpret_cast<const uint16_t *>(row + at * 16u + (k & 7u) * 2u);
+						}
+						W::put_result(p, stream, p0, p1);
+					}
+				}
+				__syncwarp();
+			}
+			at32 += (uint32_t)STEP;
+			XA_SEG_TICK(4);
+		}
+#ifdef XA_SEG_PROF
+		if (lane == 0 && (ticket & 1023u) == 5u)
+			printf("seg prof ticket %u turns %d: wait %lld read %lld request %lld decode %lld out %lld loop %lld\n",
+			    ticket, nmax + maxback, pc[0], pc[1], pc[2], pc[3], pc[4], pc[5]);
+#endif
+		if (run && !ends && sub == lps - 1u) {
+			/* the state behind the tile, for its stream's next tile's first lane */
+#pragma unroll
+			for (int c = 0; c < CH; c++)
+				mailbox_put(&p.carry[(uint64_t)slot * 2 + c],
+				    ((unsigned long long)p.epoch << 32) |
+				    ((unsigned long long)(uint16_t)p1[c] << 16) | (uint16_t)p0[c]);
+		}
+		/* lanes that waited for the lane in front take its state and go next */
+		if (!__any_sync(FULL, pending))
+			break;
+		{
+			const bool front_ran = __shfl_up_sync(FULL, (int)run, 1) != 0 && lane != 0;
+			int q0[CH], q1[CH];
+#pragma unroll
+			for (int c = 0; c < CH; c++) {
+				q0[c] = __shfl_up_sync(FULL, p0[c], 1);
+				q1[c] = __shfl_up_sync(FULL, p1[c], 1);
+			}
+			ready = pending && front_ran;
+			if (ready) {
+#pragma unroll
+				for (int c = 0; c < CH; c++) {
+					p0[c] = q0[c];
+					p1[c] = q1[c];
+				}
+				back = 0;
+				pending = false;
+			}
+		}
+		if (!__any_sync(FULL, ready))
+			break;		/* (cannot happen: a pending lane's front either ran or is pending) */
+		}
+	}
+}
+
 template <int BITS, int CH>
 __global__ void __launch_bounds__(kEncThreads)
 xa_encode_kernel(const EncodeParams p)
@@ -1500,7 +1908,9 @@ static int split_mode(void);
 static int split_candidate(int split, int bits, int ch, int stereo, int ns, uint32_t n_tiles);
 static int relay_mode(void);
 static int relay_candidate(int relay, int bits, int ch, int stereo, int ns, uint32_t n_tiles);
-static int decode_class_launches(int ch, int stereo, bool alt, int poolc, int splitc, int relayc);
+static int seg_mode(void);
+static int seg_candidate(int seg, uint32_t n_seg_tiles);
+static int decode_class_launches(int ch, int stereo, bool alt, int poolc, int splitc, int relayc, int segc);
 
 struct bjxa_plan {
 	uint32_t magic;
@@ -1528,6 +1938,7 @@ struct bjxa_plan {
 	int pool;			/* pool_mode() likewise */
 	int split;			/* split_mode() likewise */
 	int relay;			/* relay_mode() likewise */
+	int seg;			/* seg_mode() likewise */
 	/* a plan with several classes runs them side by side (bjxa_plan_run) */
 	cudaStream_t cls_stream[6];
 	cudaEvent_t ev_start, ev_done[6];
@@ -1582,6 +1993,9 @@ set_attrs_one(void)
 	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WalkCfg<BITS, CH>::kSmem)) != cudaSuccess ||
 	    (e = cudaFuncSetAttribute(xa_walk_kernel<BITS, CH, true>,
 	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WalkCfg<BITS, CH>::kSmem)) != cudaSuccess)
+		return e;
+	if ((e = cudaFuncSetAttribute(xa_seg_kernel<BITS, CH>,
+	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SegCfg<BITS, CH>::kSmem)) != cudaSuccess)
 		return e;
 	return cudaFuncSetAttribute(xa_encode_kernel<BITS, CH>,
 	    cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1663,7 +2077,8 @@ plan_build(bjxa_plan *pl, int kind, const bjxa_stream_desc_t *descs, size_t n)
 	const char *env = getenv("BJXA_B200_STRIPS");
 	int rc;
 	try {
-		rc = build_plan(pl->hp, kind, descs, n, &bad, env ? atoi(env) : 0);
+		rc = build_plan(pl->hp, kind, descs, n, &bad, env ? atoi(env) : 0,
+		    seg_mode() == 1 ? 0 : kSegMinItems);
 		if (rc == 0)
 			pl->descs.assign(descs, descs + n);
 	} catch (const std::bad_alloc &) {
@@ -1679,13 +2094,15 @@ plan_build(bjxa_plan *pl, int kind, const bjxa_stream_desc_t *descs, size_t n)
 	pl->pool = pool_mode();
 	pl->split = split_mode();
 	pl->relay = relay_mode();
+	pl->seg = seg_mode();
 	for (int b = 0; b < 6; b++)
 		if (pl->hp.order_begin[b + 1] > pl->hp.order_begin[b]) {
 			const uint32_t nt = pl->hp.tile_begin[b + 1] - pl->hp.tile_begin[b];
 			pl->launches += kind == kKindDecode ? decode_class_launches(bucket_ch(b),
 			    pl->stereo, pl->hp.alt_ns[b] != 0, pool_candidate(pl->pool, pl->hp.ns[b], nt),
 			    split_candidate(pl->split, bucket_bits(b), bucket_ch(b), pl->stereo, pl->hp.ns[b], nt),
-			    relay_candidate(pl->relay, bucket_bits(b), bucket_ch(b), pl->stereo, pl->hp.ns[b], nt)) : 1;
+			    relay_candidate(pl->relay, bucket_bits(b), bucket_ch(b), pl->stereo, pl->hp.ns[b], nt),
+			    seg_candidate(pl->seg, pl->hp.seg_begin[b + 1] - pl->hp.seg_begin[b])) : 1;
 		}
 	return (plan_upload(pl));
 }
@@ -1857,6 +2274,9 @@ struct DecodeClass {
 	int pool;			/* 0 never, 1 always, 2 census */
 	int split;			/* likewise */
 	int relay;			/* likewise */
+	int seg;			/* likewise */
+	const TileEnt *seg_tiles;	/* the segment form's list, or NULL */
+	uint32_t seg_n;
 	uint32_t *d_choice;
 	const uint32_t *d_order;	/* the class's streams */
 	uint32_t n_streams;
@@ -1971,16 +2391,92 @@ relay_candidate(int relay, int bits, int ch, int stereo, int ns, uint32_t n_tile
 	return n_tiles >= kSplitMinTiles && relay_permille(bits, ch) <= 1000u ? 2 : 0;
 }
 
+/*
+ * segment form (xa_walk.h): 0 = never, 1 = always, 2 = let the census decide
+ * (BJXA_B200_SEG=off|on|auto, default auto).  For classes that have its list.
+ */
+static int
+seg_mode(void)
+{
+	const char *e = getenv("BJXA_B200_SEG");
+	return e == NULL ? 2 : strcmp(e, "on") == 0 ? 1 : strcmp(e, "off") == 0 ? 0 : 2;
+}
+
+/*
+ * From this share of chain blocks (permille) the census sends a class to the
+ * segment form, and from seg_below() on to whatever the other thresholds say.
+ * Measured crossovers at 4096 streams x 30 s (profiles/history_r2.md): the form's
+ * rate hardly depends on the mix (every block goes through the chain step: 58-62 %
+ * of the HBM peak for mono, 47-49 % for 6/8-bit stereo, 59-66 % for 4-bit stereo),
+ * so it takes over where the tile forms, which get slower with every chain block,
+ * fall below it.
+ */
+#ifndef XA_SEG_PERMILLE
+#define XA_SEG_PERMILLE 0
+#endif
+#ifndef XA_SEG_BELOW
+#define XA_SEG_BELOW 0
+#endif
+constexpr uint32_t seg_permille(int bits, int ch)
+{
+	return XA_SEG_PERMILLE != 0 ? XA_SEG_PERMILLE :
+	    ch == 2 ? (bits == 4 ? 100u : bits == 6 ? 380u : 440u) :
+	    (bits == 4 ? 420u : bits == 6 ? 380u : 450u);
+}
+/* above this share lanes too often find no cut block within kSegBack items and wait
+ * for their neighbours (0.93^48 = 3 % of the lanes, a second pass for most tiles) */
+constexpr uint32_t seg_below(int, int)
+{
+	return XA_SEG_BELOW != 0 ? XA_SEG_BELOW : 930u;
+}
+
+static int
+seg_candidate(int seg, uint32_t n_seg_tiles)
+{
+	return n_seg_tiles == 0 ? 0 : seg;
+}
+
+template <int BITS, int CH>
+static cudaError_t
+launch_seg(const DecodeParams &p, cudaStream_t st)
+{
+	typedef SegCfg<BITS, CH> C;
+	static thread_local int grid_cache[2] = { -1, 0 };
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess)
+		return e;
+	if (grid_cache[0] != dev) {
+		int per_sm = 0, sms = 0;
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm,
+		    xa_seg_kernel<BITS, CH>, C::kThreads, C::kSmem);
+		if (e != cudaSuccess)
+			return e;
+		e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		if (e != cudaSuccess)
+			return e;
+		grid_cache[0] = dev;
+		grid_cache[1] = per_sm * sms > 0 ? per_sm * sms : sms;
+	}
+	/* never more warps than tiles */
+	uint32_t grid = (uint32_t)grid_cache[1];
+	const uint32_t need = (p.n_tiles + C::kWarps - 1) / C::kWarps;
+	if (grid > need)
+		grid = need;
+	xa_seg_kernel<BITS, CH><<<grid, C::kThreads, C::kSmem, st>>>(p);
+	return cudaGetLastError();
+}
+
 /* how many kernels decode_class() launches */
 static int
-decode_class_launches(int ch, int stereo, bool alt, int poolc, int splitc, int relayc)
+decode_class_launches(int ch, int stereo, bool alt, int poolc, int splitc, int relayc, int segc)
 {
-	if (poolc == 1)
+	if (poolc == 1 || segc == 1)
 		return 1;
 	if (splitc == 1 || relayc == 1)
 		return 2;
 	const int forms = (ch == 2 && stereo == 2 ? 2 : 1) + (alt ? 1 : 0) + (poolc == 2 ? 1 : 0) +
-	    (splitc == 2 ? 2 : 0) + (relayc == 2 ? 2 : 0);
+	    (splitc == 2 ? 2 : 0) + (relayc == 2 ? 2 : 0) + (segc == 2 ? 1 : 0);
 	return forms == 1 ? 1 : forms + 1;
 }
 
@@ -2024,8 +2520,14 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 	const int poolc = pool_candidate(c.pool, c.ns, c.p.n_tiles);
 	const int splitc = split_candidate(c.split, BITS, CH, c.stereo, c.ns, c.p.n_tiles);
 	const int relayc = relay_candidate(c.relay, BITS, CH, c.stereo, c.ns, c.p.n_tiles);
+	const int segc = seg_candidate(c.seg, c.seg_tiles != NULL ? c.seg_n : 0u);
 	DecodeParams p = c.p;
 	cudaError_t e;
+	if (segc == 1) {
+		p.tiles = c.seg_tiles;
+		p.n_tiles = c.seg_n;
+		return launch_seg<BITS, CH>(p, st);
+	}
 	if (poolc == 1)
 		return launch_pool<typename PoolTile<BITS, CH>::type>(p, st);
 	if (splitc == 1) {
@@ -2042,7 +2544,7 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 			return e;
 		return launch_walk<BITS, CH, true>(p, st);
 	}
-	if (!alt && !pick_form && poolc == 0 && splitc == 0 && relayc == 0) {
+	if (!alt && !pick_form && poolc == 0 && splitc == 0 && relayc == 0 && segc == 0) {
 		const bool staged = CH == 2 && c.stereo == 1;
 		return c.ns == 1 ? launch_form<BITS, CH, 1>(p, staged, st) :
 		    launch_form<BITS, CH, kDecWide>(p, staged, st);
@@ -2055,6 +2557,7 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 	    kNever, poolc == 2 ? (CH == 2 ? kPoolPermilleStereo : kPoolPermilleMono) : kNever,
 	    splitc == 2 ? split_permille(BITS, CH) : kNever,
 	    relayc == 2 ? relay_permille(BITS, CH) : kNever,
+	    segc == 2 ? seg_permille(BITS, CH) : kNever, seg_below(BITS, CH),
 	    c.d_choice);
 	if ((e = cudaGetLastError()) != cudaSuccess)
 		return e;
@@ -2089,6 +2592,14 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 	if (poolc == 2) {
 		p.want = kFormPool;
 		if ((e = launch_pool<typename PoolTile<BITS, CH>::type>(p, st)) != cudaSuccess)
+			return e;
+	}
+	if (segc == 2) {
+		DecodeParams q = p;
+		q.tiles = c.seg_tiles;
+		q.n_tiles = c.seg_n;
+		q.want = kFormSeg;
+		if ((e = launch_seg<BITS, CH>(q, st)) != cudaSuccess)
 			return e;
 	}
 	if (alt) {
@@ -2253,6 +2764,9 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 			c.pool = pl->pool;
 			c.split = pl->d_live.p != NULL ? pl->split : 0;
 			c.relay = pl->d_relay.p != NULL ? pl->relay : 0;
+			c.seg = pl->seg;
+			c.seg_tiles = hp.seg_begin[b + 1] > hp.seg_begin[b] ? pl->d_tiles.p + hp.seg_begin[b] : NULL;
+			c.seg_n = hp.seg_begin[b + 1] - hp.seg_begin[b];
 			c.d_choice = pl->d_first_bad.p + ((n + 3) & ~(size_t)3) + 12 + b;
 			c.d_order = pl->d_order.p + hp.order_begin[b];
 			c.n_streams = hp.order_begin[b + 1] - hp.order_begin[b];

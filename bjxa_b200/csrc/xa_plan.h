@@ -96,6 +96,8 @@ struct HostPlan {
 	uint32_t alt_begin[7];			/* decode: its list in the other tile shape */
 	int alt_ns[6];				/* strips per tile there, 0 = no such list */
 	uint32_t order_begin[7];		/* likewise, into order */
+	uint32_t seg_begin[7];			/* decode: its list for the segment form (xa_walk.h),
+						 * empty for classes too small for it */
 	int ns[6];				/* decode: strips per tile of bucket b */
 	uint32_t n_slots;
 	uint64_t src_need, dst_need;		/* arena bytes the batch touches */
@@ -115,6 +117,13 @@ struct HostPlan {
  * override.
  */
 constexpr size_t kDecWideMinStreams = 1024;
+/* the segment form (xa_walk.h) puts one stream on every lane of a warp: classes
+ * of at least this many streams get its list as well */
+constexpr size_t kSegMinStreams = 64;
+/* ... or that have streams long enough for a warp of their own; and in either case
+ * enough items for the form's tiles (32 lanes x kSegItems) to fill the device.
+ * (BJXA_B200_SEG=on lifts the latter: tests force the form on small batches.) */
+constexpr uint64_t kSegMinItems = 1ull << 22;
 
 /* effective blocks per strip */
 inline uint32_t strip_blocks(int ns, int ch)
@@ -145,12 +154,73 @@ inline void emit_decode_tiles(HostPlan &hp, const std::vector<uint32_t> &o, uint
 }
 
 /*
+ * The segment form's list (xa_walk.h).  Streams of at least kSegLongItems items get
+ * a warp to themselves: tiles of 32 consecutive segments of ONE stream (te.pad = 32
+ * lanes per stream), time-major over those streams.  The shorter ones share warps,
+ * a stream per lane (te.pad = 1): tiles of 32 streams x one segment.  A tile may
+ * wait for the one in front of it in its streams (data without cut blocks), so that
+ * one must hold a lower ticket -- but strictly time-major order would hand the
+ * tiles of one step, the ones that can run at the same time, to the warps of the
+ * same few CTAs (a CTA's warps draw consecutive tickets).  So the steps go in
+ * groups of kSegStepGroup: within a group, the group's steps of one 32-stream
+ * column, then the next column's.
+ */
+#ifndef XA_SEG_STEP_GROUP
+#define XA_SEG_STEP_GROUP 8
+#endif
+#ifndef XA_SEG_LONG
+#define XA_SEG_LONG (2 * 32 * XA_SEG_ITEMS)
+#endif
+constexpr uint32_t kSegStepGroup = XA_SEG_STEP_GROUP;
+constexpr uint32_t kSegLongItems = XA_SEG_LONG;
+inline void emit_seg_tiles(HostPlan &hp, const std::vector<uint32_t> &o, uint32_t order0)
+{
+	/* longest first: the long streams are a prefix */
+	size_t n_long = 0;
+	while (n_long < o.size() && hp.streams[o[n_long]].blocks >= kSegLongItems)
+		n_long++;
+	const uint32_t per_tile = 32u * kSegItems;
+	size_t active = n_long;
+	for (uint32_t j = 0; active > 0; j++) {
+		while (active > 0 && (uint64_t)j * per_tile >= hp.streams[o[active - 1]].blocks)
+			active--;
+		for (size_t k = 0; k < active; k++) {
+			TileEnt te = { order0 + (uint32_t)k, 1u, j, 32u };
+			hp.tiles.push_back(te);
+		}
+	}
+	auto active_at = [&](uint32_t j, size_t from) {
+		size_t a = from;
+		while (a > n_long && (uint64_t)j * kSegItems >= hp.streams[o[a - 1]].blocks)
+			a--;
+		return a;
+	};
+	active = o.size();
+	for (uint32_t j0 = 0;; j0 += kSegStepGroup) {
+		active = active_at(j0, active);
+		if (active == n_long)
+			break;
+		for (size_t base = n_long; base < active; base += 32) {
+			size_t act = active;
+			for (uint32_t j = j0; j < j0 + kSegStepGroup; j++) {
+				act = active_at(j, act);
+				if (base >= act)
+					break;
+				TileEnt te = { order0 + (uint32_t)base,
+				    (uint32_t)std::min(act - base, (size_t)32), j, 1u };
+				hp.tiles.push_back(te);
+			}
+		}
+	}
+}
+
+/*
  * Validates the descriptors and builds the plan.  Returns 0, or an errno
  * value (EINVAL) with *bad_index set to the offending stream.
  */
 template <class Desc>
 inline int build_plan(HostPlan &hp, int kind, const Desc *d, size_t n,
-    size_t *bad_index, int force_strips = 0)
+    size_t *bad_index, int force_strips = 0, uint64_t seg_min_items = kSegMinItems)
 {
 	hp.kind = kind;
 	hp.streams.resize(n);
@@ -161,6 +231,7 @@ inline int build_plan(HostPlan &hp, int kind, const Desc *d, size_t n,
 	hp.src_need = hp.dst_need = 0;
 
 	std::vector<uint32_t> members[6];
+	bool has_seg[6] = { false, false, false, false, false, false };
 	for (size_t i = 0; i < n; i++) {
 		const Desc &s = d[i];
 		if (s.blocks == 0) {
@@ -234,7 +305,14 @@ inline int build_plan(HostPlan &hp, int kind, const Desc *d, size_t n,
 		hp.alt_ns[b] = !forced && o.size() >= kDecWideMinStreams ? kDecWide : 0;
 		/* carry slots: one per strip of the finest shape in use; strip j of
 		 * a stream uses slot_base + j in either shape */
-		const uint32_t fine = strip_blocks(std::max(hp.ns[b], hp.alt_ns[b]), bucket_ch(b));
+		uint64_t items = 0;
+		for (size_t k = 0; k < o.size(); k++)
+			items += hp.streams[o[k]].blocks;
+		const bool seg = (o.size() >= kSegMinStreams || hp.streams[o[0]].blocks >= kSegLongItems) &&
+		    items >= seg_min_items;
+		has_seg[b] = seg;
+		const uint32_t fine = std::min(strip_blocks(std::max(hp.ns[b], hp.alt_ns[b]), bucket_ch(b)),
+		    seg ? kSegItems : ~0u);
 		for (size_t k = 0; k < o.size(); k++) {
 			StreamDev &sd = hp.streams[o[k]];
 			sd.slot_base = hp.n_slots;
@@ -250,6 +328,12 @@ inline int build_plan(HostPlan &hp, int kind, const Desc *d, size_t n,
 			emit_decode_tiles(hp, members[b], hp.order_begin[b], hp.alt_ns[b], bucket_ch(b));
 	}
 	hp.alt_begin[6] = (uint32_t)hp.tiles.size();
+	for (int b = 0; b < 6; b++) {
+		hp.seg_begin[b] = (uint32_t)hp.tiles.size();
+		if (kind == kKindDecode && has_seg[b])
+			emit_seg_tiles(hp, members[b], hp.order_begin[b]);
+	}
+	hp.seg_begin[6] = (uint32_t)hp.tiles.size();
 	return 0;
 }
 

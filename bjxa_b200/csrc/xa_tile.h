@@ -78,6 +78,20 @@ constexpr uint32_t kRelayManyHeads = 48;	/* ... from this many chains */
 /* records a tile can leave at most: each walker warp's stragglers + the strip's end */
 constexpr uint32_t kRelayPerTile = kRelayWalkers * kRelayWind + 1;
 
+/*
+ * Segment form (xa_walk.h): every lane of a warp decodes kSegItems consecutive
+ * items of one stream, whatever their filters; the state in front of the segment
+ * is recomputed from at most kSegBack items before it, else waited for.
+ */
+#ifndef XA_SEG_ITEMS
+#define XA_SEG_ITEMS 128
+#endif
+#ifndef XA_SEG_BACK
+#define XA_SEG_BACK 48
+#endif
+constexpr uint32_t kSegItems = XA_SEG_ITEMS;
+constexpr uint32_t kSegBack = XA_SEG_BACK;
+
 struct TileEnt {		/* decode: NS strips of consecutive streams in issue order */
 	uint32_t first;		/* index into order[] of the first strip's stream;
 				 * encode: the stream itself */

@@ -168,12 +168,12 @@ struct Walk {
 	 * inside a run simply has k0 = k1 = 0.  Units go out through out(j, v),
 	 * j = 0 .. UNITS-1 in PCM order.
 	 */
-	template <class Out>
+	template <bool RANGED = false, class Out>
 	XA_HD static void decode(const Item &it, int (&p0)[CH], int (&p1)[CH], Out &out)
 	{
 		if (CH == 1) {
 			uint32_t o[16];
-			decode_block_chain<BITS>(o, it.pw[0], it.prof[0], p0[0], p1[0]);
+			decode_block_chain<BITS, RANGED>(o, it.pw[0], it.prof[0], p0[0], p1[0]);
 #pragma unroll
 			for (int j = 0; j < 4; j++) {
 				uint4 v;
@@ -199,10 +199,17 @@ struct Walk {
 				int l[4], r[4];
 #pragma unroll
 				for (int k = 0; k < 4; k++) {
-					l[k] = sample_chain_b(top_code<BITS>(it.pw[0], 4 * j + k), shl,
-					    k0l, k1l, cl, bl0, bl1);
-					r[k] = sample_chain_b(top_code<BITS>(it.pw[CH - 1], 4 * j + k), shr,
-					    k0r, k1r, cr, br0, br1);
+					if (RANGED) {
+						l[k] = sample_chain_r(top_code<BITS>(it.pw[0], 4 * j + k), shl,
+						    k0l, k1l, cl, bl0, bl1);
+						r[k] = sample_chain_r(top_code<BITS>(it.pw[CH - 1], 4 * j + k), shr,
+						    k0r, k1r, cr, br0, br1);
+					} else {
+						l[k] = sample_chain_b(top_code<BITS>(it.pw[0], 4 * j + k), shl,
+						    k0l, k1l, cl, bl0, bl1);
+						r[k] = sample_chain_b(top_code<BITS>(it.pw[CH - 1], 4 * j + k), shr,
+						    k0r, k1r, cr, br0, br1);
+					}
 				}
 				uint4 v;
 				v.x = pack2_biased(l[0], r[0]);
@@ -343,6 +350,242 @@ XA_HD void walk_relay_serial(const DecodeParams &p, const RelayRec &r)
 	}
 	walk_chain_serial<BITS, CH>(p, r.stream & 0x3fffffffu, (uint64_t)r.xa_hi << 32 | r.xa_lo,
 	    (uint64_t)r.out_hi << 32 | r.out_lo, r.left, p0, p1, r.stream >> 30);
+}
+
+/*
+ * The SEGMENT form: no chains, no heads, one pass.  A stream is cut into segments
+ * of kSegItems items; lane L of a warp decodes segment j of stream L of the tile
+ * (tiles as in the wide shape, time-major) from its first item to its last with
+ * the chain step throughout -- a cut or invalid block is the step with
+ * k0 = k1 = 0 (libbjxa.c:526), which forgets the state by itself.  So the only
+ * thing a lane has to find is the state in front of its segment (seg_front):
+ *   - the stream's own, in front of item 0 (libbjxa.c:417-420);
+ *   - else it looks back over at most kSegBack items for the nearest cut (or
+ *     invalid) block of every channel and starts decoding there, storing nothing
+ *     until it reaches its segment: whatever state it starts with is forgotten
+ *     at that block.  On data that has cut blocks at all this costs a few items
+ *     per segment, and nothing is ever waited for;
+ *   - if a channel has no such block within reach, the state comes through the
+ *     carry mailbox from the lane that decodes the segment in front -- every lane
+ *     leaves its final state there.  That lane holds a lower ticket, so the wait
+ *     cannot deadlock; on data without cut blocks this is the serial walk such
+ *     data demands, one stream per lane.
+ * All 32 lanes of a warp decode a block in every turn but the few at either end.
+ */
+template <int BITS, int CH>
+struct SegFront {
+	uint32_t back;		/* items in front of the segment to decode first */
+	bool mail;		/* state from the mailbox (back == 0) */
+	bool own;		/* state from the stream descriptor */
+};
+
+/* `prof(k, c)`: profile byte of channel c of the item k + 1 in front of the segment */
+template <int BITS, int CH, class Prof>
+XA_HD SegFront<BITS, CH> seg_front(uint32_t n0, Prof prof)
+{
+	SegFront<BITS, CH> f = { 0u, false, false };
+	if (n0 == 0) {
+		f.own = true;
+		return f;
+	}
+	const uint32_t lim = n0 < kSegBack ? n0 : kSegBack;
+	uint32_t found[CH], missing = CH;
+#pragma unroll
+	for (int c = 0; c < CH; c++)
+		found[c] = 0;
+	for (uint32_t k = 0; k < lim && missing != 0; k++)
+#pragma unroll
+		for (int c = 0; c < CH; c++)
+			if (found[c] == 0 && block_kind(prof(k, c)) != kChain) {
+				found[c] = k + 1u;
+				missing--;
+			}
+	if (missing == 0) {
+#pragma unroll
+		for (int c = 0; c < CH; c++)
+			f.back = found[c] > f.back ? found[c] : f.back;
+	} else if (lim == n0) {
+		f.back = n0;
+		f.own = true;
+	} else {
+		f.mail = true;
+	}
+	return f;
+}
+
+/*
+ * Lanes and streams.  A tile's 32 lanes are te.pad = P lanes per stream (a power of
+ * two) times te.count streams: lane L decodes segment te.j * P + L % P of stream
+ * L / P of the tile.
+ *   P = 32  one long stream per warp: the lanes read and write next to each other
+ *           (a warp's turn touches two or three pages of the arenas -- with a stream
+ *           per lane it is 32 + 32, and on long streams the address translation,
+ *           not the arithmetic, then sets the pace: profiles/history_r2.md);
+ *   P = 1   32 short streams per warp, which alone would leave most lanes idle.
+ * A lane that cannot recompute its state waits for the segment in front: lane
+ * L - 1 of its own warp if L % P != 0 -- the warp then makes another pass over the
+ * tile for the lanes that had to wait -- else the mailbox its stream's previous
+ * tile (a lower ticket) leaves.
+ */
+template <int BITS, int CH>
+struct SegLane {
+	uint32_t stream, n0, n, slot, sub;
+	uint64_t a0, o0;
+	bool valid, ends;
+};
+
+template <int BITS, int CH>
+XA_HD SegLane<BITS, CH> seg_lane(const DecodeParams &p, uint32_t first, uint32_t count, uint32_t j,
+    uint32_t lanes_per_stream, uint32_t lane)
+{
+	typedef Walk<BITS, CH> W;
+	SegLane<BITS, CH> l;
+	const uint32_t sidx = lane / lanes_per_stream;
+	l.sub = lane % lanes_per_stream;
+	l.valid = sidx < count;
+	l.stream = 0; l.n0 = 0; l.n = 0; l.slot = 0; l.a0 = 0; l.o0 = 0; l.ends = false;
+	if (!l.valid)
+		return l;
+	l.stream = p.order[first + sidx];
+	const StreamDev &sd = p.streams[l.stream];
+	const uint64_t n0 = ((uint64_t)j * lanes_per_stream + l.sub) * kSegItems;
+	if (n0 >= sd.blocks) {
+		l.valid = false;
+		return l;
+	}
+	l.n0 = (uint32_t)n0;
+	l.n = sd.blocks - l.n0 < kSegItems ? sd.blocks - l.n0 : kSegItems;
+	l.ends = l.n0 + l.n == sd.blocks;
+	l.a0 = sd.xa_off + (uint64_t)l.n0 * W::STEP;
+	l.o0 = sd.pcm_off + (uint64_t)l.n0 * W::OUT;
+	l.slot = sd.slot_base + j;
+	return l;
+}
+
+/* one lane's segment from `back` items in front of it to its end, p0/p1 the state there */
+template <int BITS, int CH>
+XA_HD void walk_seg_lane_serial(const DecodeParams &p, const SegLane<BITS, CH> &l, uint32_t back,
+    int (&p0)[CH], int (&p1)[CH])
+{
+	typedef Walk<BITS, CH> W;
+	const StreamDev &sd = p.streams[l.stream];
+	for (int cur = -(int)back; cur < (int)l.n; cur++) {
+		const uint64_t a = l.a0 + (int64_t)cur * W::STEP;
+		typename W::Item it;
+#pragma unroll
+		for (int c = 0; c < CH; c++) {
+			const uint8_t *b = p.src + a + c * W::BS;
+			it.prof[c] = b[0];
+#pragma unroll
+			for (int i = 0; i < BITS; i++)
+				it.pw[c][i] = (uint32_t)b[1 + 4 * i] | (uint32_t)b[2 + 4 * i] << 8 |
+				    (uint32_t)b[3 + 4 * i] << 16 | (uint32_t)b[4 + 4 * i] << 24;
+		}
+		const bool last = l.n0 + (uint32_t)cur + 1u == sd.blocks;
+		const uint32_t valid = cur < 0 ? 0u : last ? W::last_valid(sd) : (uint32_t)W::OUT;
+		uint8_t *dst = p.dst + l.o0 + (int64_t)cur * W::OUT;
+		auto out = [&](int j, const uint4 &v) {
+			const uint32_t boff = (uint32_t)j * 16u;
+			const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+			for (uint32_t k = 0; k < 8u && boff + 2u * k + 2u <= valid; k++) {
+				const uint16_t h = (uint16_t)(w[k >> 1] >> (16u * (k & 1u)));
+				dst[boff + 2u * k] = (uint8_t)h;
+				dst[boff + 2u * k + 1u] = (uint8_t)(h >> 8);
+			}
+		};
+		if (cur >= 0) {
+#pragma unroll
+			for (int c = 0; c < CH; c++)
+				if (it.prof[c] >> 4 >= 5u)
+					global_min_u32(&p.first_bad[l.stream], (l.n0 + (uint32_t)cur) * CH + c);
+		}
+		W::decode(it, p0, p1, out);
+	}
+	if (l.ends)
+		W::put_result(p, l.stream, p0, p1);
+}
+
+/*
+ * One tile, pass by pass: the reference semantics of xa_seg_kernel, used by the CPU
+ * single-stepper of the tests.  `visit(i)`: the order in which the lanes of a pass
+ * are taken (any order must do).
+ */
+template <int BITS, int CH, class Visit>
+XA_HD void walk_seg_tile_serial(const DecodeParams &p, const TileEnt &te, Visit visit)
+{
+	typedef Walk<BITS, CH> W;
+	const uint32_t P = te.pad;
+	SegLane<BITS, CH> ln[32];
+	int st0[32][CH], st1[32][CH];
+	uint32_t back[32];
+	enum { kIdle, kReady, kPending, kDone } state[32];
+	for (uint32_t lane = 0; lane < 32; lane++) {
+		SegLane<BITS, CH> &l = ln[lane];
+		l = seg_lane<BITS, CH>(p, te.first, te.count, te.j, P, lane);
+		state[lane] = kIdle;
+		back[lane] = 0;
+		if (!l.valid)
+			continue;
+		const SegFront<BITS, CH> f = seg_front<BITS, CH>(l.n0, [&](uint32_t k, int c) {
+			return (uint32_t)p.src[l.a0 - (uint64_t)(k + 1u) * W::STEP + (uint64_t)(c * W::BS)];
+		});
+		const StreamDev &sd = p.streams[l.stream];
+		back[lane] = f.back;
+		state[lane] = kReady;
+#pragma unroll
+		for (int c = 0; c < CH; c++) {
+			st0[lane][c] = st1[lane][c] = 0;
+			if (f.own) {
+				st0[lane][c] = sd.prev[c][0];
+				st1[lane][c] = sd.prev[c][1];
+			} else if (f.mail && l.sub == 0) {
+				const unsigned long long v = mailbox_get(
+				    &p.carry[(uint64_t)(l.slot - 1u) * 2 + c], p.epoch, p.fault,
+				    p.carry_timeout_ns);
+				st0[lane][c] = (int16_t)(uint16_t)v;
+				st1[lane][c] = (int16_t)(uint16_t)(v >> 16);
+			} else if (f.mail) {
+				state[lane] = kPending;		/* lane - 1 of this tile decodes the segment in front */
+			}
+		}
+	}
+	for (;;) {
+		bool any = false;
+		for (uint32_t i = 0; i < 32; i++) {
+			const uint32_t lane = visit(i);
+			if (state[lane] != kReady)
+				continue;
+			walk_seg_lane_serial<BITS, CH>(p, ln[lane], back[lane], st0[lane], st1[lane]);
+			any = true;
+		}
+		if (!any)
+			break;
+		/* what the pass leaves: the state for a lane that waited, or for the next tile */
+		for (uint32_t lane = 0; lane < 32; lane++)
+			if (state[lane] == kReady) {
+				state[lane] = kDone;
+				const SegLane<BITS, CH> &l = ln[lane];
+				if (!l.ends && l.sub == P - 1u) {
+#pragma unroll
+					for (int c = 0; c < CH; c++)
+						mailbox_put(&p.carry[(uint64_t)l.slot * 2 + c],
+						    ((unsigned long long)p.epoch << 32) |
+						    ((unsigned long long)(uint16_t)st1[lane][c] << 16) |
+						    (uint16_t)st0[lane][c]);
+				}
+			}
+		for (uint32_t lane = 31; lane >= 1; lane--)
+			if (state[lane] == kPending && state[lane - 1] == kDone) {
+				/* (a lane that became ready in this very step does not hand on yet) */
+#pragma unroll
+				for (int c = 0; c < CH; c++) {
+					st0[lane][c] = st0[lane - 1][c];
+					st1[lane][c] = st1[lane - 1][c];
+				}
+				back[lane] = 0;
+				state[lane] = kReady;
+			}
+	}
 }
 
 } /* namespace xa */

@@ -25,6 +25,7 @@ static int g_stereo_direct = 0;
 static int g_pool = 0;
 static int g_split = 0;
 static int g_relay = 0;
+static int g_seg = 0;
 
 /* thread visiting order inside a phase: 0 ascending, 1 descending, 2 strided */
 static uint32_t
@@ -371,7 +372,7 @@ xa_emul_decode(const bjxa_stream_desc_t *descs, size_t n, const uint8_t *src,
 {
 	HostPlan hp;
 	size_t bad = 0;
-	int rc = build_plan(hp, kKindDecode, descs, n, &bad, force_strips);
+	int rc = build_plan(hp, kKindDecode, descs, n, &bad, force_strips, g_seg ? 0 : kSegMinItems);
 	if (rc)
 		return rc;
 	std::vector<StreamRes> res(n);
@@ -393,6 +394,12 @@ xa_emul_decode(const bjxa_stream_desc_t *descs, size_t n, const uint8_t *src,
 			t1 = hp.alt_begin[b + 1];
 			ns = hp.alt_ns[b];
 		}
+		const bool seg = g_seg && hp.seg_begin[b + 1] > hp.seg_begin[b];
+		if (seg) {
+			/* the segment form's list (classes of at least kSegMinStreams streams) */
+			t0 = hp.seg_begin[b];
+			t1 = hp.seg_begin[b + 1];
+		}
 		DecodeParams p;
 		p.src = src;
 		p.src_bytes = src_bytes;
@@ -408,6 +415,21 @@ xa_emul_decode(const bjxa_stream_desc_t *descs, size_t n, const uint8_t *src,
 		p.fault = &fault;
 		p.carry_timeout_ns = 0;
 		p.epoch = 7;
+		if (seg) {
+			/* xa_seg_kernel: tiles in ticket order, the lanes of a pass in any */
+			for (uint32_t t = 0; t < p.n_tiles; t++) {
+				auto v = [&](uint32_t i) { return visit(i, 32, order); };
+				switch (b) {
+				case 0: walk_seg_tile_serial<4, 1>(p, p.tiles[t], v); break;
+				case 1: walk_seg_tile_serial<4, 2>(p, p.tiles[t], v); break;
+				case 2: walk_seg_tile_serial<6, 1>(p, p.tiles[t], v); break;
+				case 3: walk_seg_tile_serial<6, 2>(p, p.tiles[t], v); break;
+				case 4: walk_seg_tile_serial<8, 1>(p, p.tiles[t], v); break;
+				default: walk_seg_tile_serial<8, 2>(p, p.tiles[t], v); break;
+				}
+			}
+			continue;
+		}
 		switch (b) {
 		case 0: emul_decode_bucket<4, 1>(p, ns, order); break;
 		case 1: emul_decode_bucket<4, 2>(p, ns, order); break;
@@ -513,6 +535,11 @@ void xa_emul_use_alt(int on) { g_use_alt = on; }
 void xa_emul_pool(int on) { g_pool = on; }
 void xa_emul_split(int on) { g_split = on; }
 void xa_emul_relay(int on) { g_relay = on; }
+void xa_emul_seg(int on) { g_seg = on; }
+int xa_emul_seg_items(void) { return (int)kSegItems; }
+int xa_emul_seg_back(void) { return (int)kSegBack; }
+int xa_emul_seg_min_streams(void) { return (int)kSegMinStreams; }
+int xa_emul_seg_long_items(void) { return (int)kSegLongItems; }
 int xa_emul_strip_blocks(int ns, int ch) { return (int)strip_blocks(ns, ch); }
 int xa_emul_wide(void) { return kDecWide; }
 int xa_emul_enc_tile_blocks(void) { return kEncTBE; }

@@ -34,6 +34,11 @@ class Emul:
         self.use_alt = d.xa_emul_use_alt                # (0|1): step the alternative tile lists
         self.pool = d.xa_emul_pool                      # (0|1): direct forms walk as the pooled kernel does
         self.relay = d.xa_emul_relay                    # (0|1): long-strip tiles walk their chains but hand stragglers on (relay form)
+        self.seg = d.xa_emul_seg                        # (0|1): classes of enough streams go through the segment form (xa_walk.h)
+        self.seg_items = d.xa_emul_seg_items()
+        self.seg_back = d.xa_emul_seg_back()
+        self.seg_min_streams = d.xa_emul_seg_min_streams()
+        self.seg_long_items = d.xa_emul_seg_long_items()
         self.split = d.xa_emul_split                    # (0|1): long-strip tiles go through the split form (xa_walk.h)
 
     def dec_tile_blocks(self, ch):

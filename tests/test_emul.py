@@ -257,3 +257,86 @@ def test_plan_order_and_validation(emul):
     sb2 = emul.strip_blocks(w, 2)
     assert (tc[ab[1]:ab[2]] == w).all() and ab[2] - ab[1] == (20000 // w) * -(-3 // sb2)
     assert slots == 20000 * -(-3 // sb2)
+
+
+# ---- the segment form (xa_walk.h: walk_seg_serial, the semantics of xa_seg_kernel) ----
+
+@pytest.fixture()
+def seg_emul():
+    e = Emul()
+    e.seg(1)
+    yield e
+    e.seg(0)
+
+
+@pytest.mark.parametrize("order", [0, 1, 2])
+@pytest.mark.parametrize("bits,ch", [(4, 1), (6, 1), (8, 1), (4, 2), (6, 2), (8, 2)])
+def test_seg_form_class(seg_emul, oracle, bits, ch, order):
+    """One class large enough for the segment list; lengths from one item to several
+    segments (ragged last blocks), every mix: P0/P1 find a cut block right in front
+    of a segment, P2 a few items back, P3 never -- those lanes take the state from
+    the mailbox of the lane in front; streams shorter than the look-back start from
+    their own state."""
+    e = seg_emul
+    seg, n = e.seg_items, e.seg_min_streams + 9
+    specs = [dict(bits=bits, channels=ch,
+                  samples=32 * (1 + (i * 37) % (3 * seg + 5)) - (i % 32 if i % 3 else 0),
+                  mix=("P2", "P3", "P1", "P0", "P2")[i % 5], key=9000 + 100 * bits + 10 * ch + i,
+                  prev=((i, -i), (7 * i, -3))) for i in range(n)]
+    specs[0]["samples"] = 32 * (4 * seg + 3) + 5        # the longest: five segments
+    specs[1]["samples"] = 32 * (4 * seg) + 32           # P3, mailbox hand-overs all the way
+    _run_decode(e, oracle, specs, order=order, xa_gap=3)
+
+
+@pytest.mark.parametrize("bits,ch", [(4, 1), (8, 1), (6, 2), (8, 2)])
+def test_seg_form_look_back_limits(seg_emul, oracle, bits, ch):
+    """Chains that reach just inside and just outside the look-back in front of a
+    segment's first item, per channel: a cut block exactly kSegBack items back is
+    found, one item further is not (the state then comes through the mailbox); an
+    invalid profile counts as a cut and is reported once, by the lane whose segment
+    holds it."""
+    e = seg_emul
+    seg, back, n = e.seg_items, e.seg_back, e.seg_min_streams
+    specs = []
+    for i in range(n):
+        blocks = 2 * seg + 17
+        patch = {}
+        # all chain blocks (mix P3) but for the patched ones; item m, channel c = m * ch + c
+        m0 = seg - back - 1 + (i % 3)                    # back + 1, back, back - 1 items in front
+        patch[m0 * ch] = 0x03                            # channel 0: a cut block, range 3
+        if ch == 2:
+            patch[(seg - 1 - (i % 5)) * ch + 1] = 0x00   # channel 1: a cut close by
+            if i % 4 == 0:
+                patch[(2 * seg - 1 - back - (i % 8)) * ch + 1] = 0x0f
+        if i % 7 == 0:
+            patch[(seg + 5) * ch + (ch - 1)] = 0x5a      # invalid filter inside segment 1
+        if i % 11 == 0:
+            patch[(seg - 2) * ch] = 0xf1                 # ... and as the "cut" in front of it
+        specs.append(dict(bits=bits, channels=ch, samples=32 * blocks - 3 * (i % 9),
+                          mix="P3", key=9900 + i, patch=patch, prev=((11, -12), (13, -14))))
+    _run_decode(e, oracle, specs, xa_gap=1)
+
+
+@pytest.mark.parametrize("order", [0, 2])
+@pytest.mark.parametrize("bits,ch", [(8, 1), (4, 2), (6, 1)])
+def test_seg_form_long_streams(seg_emul, oracle, bits, ch, order):
+    """Streams long enough for a warp of their own (32 lanes = 32 consecutive segments
+    of one stream) next to short ones that share warps.  P2: every lane finds its
+    state a few items back; P3: every lane but the first waits for the lane in front
+    of it -- 32 passes over the tile -- and the first for the mailbox of the stream's
+    previous tile; a P3 stream with a few cut blocks: some lanes wait, some do not."""
+    e = seg_emul
+    seg, long_items = e.seg_items, e.seg_long_items
+    specs = [
+        dict(bits=bits, channels=ch, samples=32 * (long_items + 3 * seg + 7) - 5, mix="P2", key=31000,
+             prev=((100, -100), (7, 8))),
+        dict(bits=bits, channels=ch, samples=32 * (long_items + 1), mix="P3", key=31001,
+             prev=((-5, 6), (70, -80))),
+        dict(bits=bits, channels=ch, samples=32 * (long_items + 40 * seg) - 31, mix="P3", key=31002,
+             patch={(5 * seg - 3) * ch: 0x02, (9 * seg - 50) * ch + (ch - 1): 0x0c,
+                    (33 * seg + 1) * ch: 0x60, (36 * seg - 1) * ch: 0x00, (36 * seg - 1) * ch + ch - 1: 0x04}),
+        dict(bits=bits, channels=ch, samples=32 * long_items, mix="P1", key=31003),
+    ]
+    specs += [dict(bits=bits, channels=ch, samples=32 * (1 + (i * 53) % (2 * seg)) - i % 32,
+                   mix=("P2", "P3", "P0")[i % 3], key=31100 + i, prev=((i, -i), (2 * i, 3))) for i in range(40)]
+    _run_decode(e, oracle, specs, order=order, xa_gap=2)

@@ -37,6 +37,8 @@ def main():
     ap.add_argument("--search", action="store_true",
                     help="also run the searching encoder (BJXA_PLAN_ENCODE_SEARCH) on the decoded PCM")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--padx", type=int, default=0, help="bytes between consecutive streams' XA payloads")
+    ap.add_argument("--padp", type=int, default=0, help="extra bytes (x16) between consecutive streams' PCM")
     a = ap.parse_args()
 
     lib = Bjxa(os.environ["BJXA_LIB"]) if os.environ.get("BJXA_LIB") else bjxa_b200.load()
@@ -47,20 +49,23 @@ def main():
     bs = (4 * bits + 1) * ch
     xa_bytes = blocks * bs
     pcm_bytes = samples * 2 * ch
-    pitch = (blocks * 64 * ch + 15) & ~15
-    xa = torch.empty((S, blocks * ch, 4 * bits + 1), dtype=torch.uint8, device=dev)
+    pitch = ((blocks * 64 * ch + 15) & ~15) + 16 * a.padp
+    xrow = xa_bytes + a.padx
+    xa_flat = torch.zeros((S, xrow), dtype=torch.uint8, device=dev)
+    xa = xa_flat[:, :xa_bytes].view(S, blocks * ch, 4 * bits + 1)
     g = torch.Generator(device=dev)
     g.manual_seed(1)
     for s0 in range(0, S, 128):
         xa[s0:s0 + 128].random_(0, 256, generator=g)
     pcm = torch.empty(S * pitch, dtype=torch.uint8, device=dev)
     descs = make_descs(S)
-    descs["xa_off"] = np.arange(S, dtype=np.uint64) * xa_bytes
+    descs["xa_off"] = np.arange(S, dtype=np.uint64) * xrow
     descs["pcm_off"] = np.arange(S, dtype=np.uint64) * pitch
     descs["blocks"], descs["pcm_len"] = blocks, pcm_bytes
     descs["bits"], descs["channels"] = bits, ch
     stream = torch.cuda.current_stream().cuda_stream
     algo = S * (xa_bytes + pcm_bytes)
+    assert not (a.encode or a.search) or a.padx == 0
 
     for mix in a.mix.split(","):
         for s0 in range(0, S, 256):
@@ -72,7 +77,7 @@ def main():
         plan = lib.plan_create(PLAN_DECODE, descs)
 
         def step():
-            lib.plan_run(plan, pcm.data_ptr(), pcm.numel(), xa.data_ptr(), xa.numel(), stream)
+            lib.plan_run(plan, pcm.data_ptr(), pcm.numel(), xa_flat.data_ptr(), xa_flat.numel(), stream)
         for _ in range(a.warmup):
             step()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]

@@ -1238,11 +1238,37 @@ xa_seg_kernel(const DecodeParams p)
 		ticket = __shfl_sync(FULL, ticket, 0);
 		if (ticket >= p.n_tiles)
 			break;
-		const uint4 te = ldg_u128(&p.tiles[ticket]);	/* first, count, j, lanes per stream */
-		/* lane L: segment j * P + L % P of stream L / P of the tile (xa_walk.h: seg_lane) */
-		const uint32_t lps = te.w, sidx = lane / lps, sub = lane & (lps - 1u);
-		bool valid = sidx < te.y;
-		uint32_t stream = 0, n = 0, n0 = 0, slot = 0;
+		const uint4 te = ldg_u128(&p.tiles[ticket]);	/* first stream, its segment, lanes, streams */
+		/* lane L: the L-th segment from segment te.y of stream order[te.x] on (xa_walk.h:
+		 * seg_lane); lane k looks up how many segments the tile's k-th stream has */
+		bool valid = lane < te.z;
+		uint32_t stream = 0, seg = 0, n = 0, n0 = 0, slot = 0;
+		{
+			uint32_t mine = lane < te.w ? p.order[te.x + lane] : 0u;
+			uint32_t ns = lane < te.w ? (p.streams[mine].blocks + kSegItems - 1u) / kSegItems : 0u;
+			if (lane == 0)
+				ns -= te.y;		/* the first stream's segments in front of the tile */
+			uint32_t incl = ns;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t t = __shfl_up_sync(FULL, incl, d);
+				if (lane >= (uint32_t)d)
+					incl += t;
+			}
+			/* streams whose segments all lie in front of this lane's */
+			uint32_t k = 0;
+#pragma unroll 4
+			for (uint32_t q = 0; q < 32u; q++) {
+				if (q >= te.w)
+					break;
+				k += __shfl_sync(FULL, incl, q) <= lane;
+			}
+			k = k < te.w ? k : te.w - 1u;
+			stream = __shfl_sync(FULL, mine, k);
+			const uint32_t excl = __shfl_sync(FULL, incl - ns, k);
+			seg = lane - excl + (k == 0 ? te.y : 0u);
+			n0 = seg * kSegItems;
+		}
 		uint64_t a0 = 0, o0 = 0;
 		bool ends = false;		/* the segment is its stream's last */
 		bool pending = false;		/* the state comes from lane - 1, after a pass */
@@ -1252,20 +1278,13 @@ xa_seg_kernel(const DecodeParams p)
 		for (int c = 0; c < CH; c++)
 			p0[c] = p1[c] = 0;
 		if (valid) {
-			stream = p.order[te.x + sidx];
-			const StreamDev &sd0 = p.streams[stream];
-			const uint64_t at = ((uint64_t)te.z * lps + sub) * kSegItems;
-			valid = at < sd0.blocks;
-			n0 = (uint32_t)at;
-		}
-		if (valid) {
 			const StreamDev &sd = p.streams[stream];
 			const uint32_t blocks = sd.blocks;
 			n = blocks - n0 < kSegItems ? blocks - n0 : kSegItems;
 			ends = n0 + n == blocks;
 			a0 = sd.xa_off + (uint64_t)n0 * STEP;
 			o0 = sd.pcm_off + (uint64_t)n0 * OUT;
-			slot = sd.slot_base + te.z;
+			slot = sd.slot_base + seg;
 
 			/* ---- the state in front of the segment (seg_front) ---- */
 			bool own = n0 == 0, mail = false;
@@ -1312,11 +1331,11 @@ xa_seg_kernel(const DecodeParams p)
 					p1[c] = sd.prev[c][1];
 				}
 			}
-			if (mail && sub == 0) {
-				/* the stream's previous tile holds a lower ticket: running or done */
+			if (mail && lane == 0) {
+				/* the tile before holds a lower ticket: running or done */
 #pragma unroll
 				for (int c = 0; c < CH; c++)
-					seg_wait_front(p, slot, te.z >= 2u, (uint32_t)c, p0[c], p1[c]);
+					seg_wait_front(p, slot, seg >= 2u, (uint32_t)c, p0[c], p1[c]);
 			} else if (mail) {
 				pending = true;		/* lane - 1 decodes the segment in front */
 			}
@@ -1486,8 +1505,8 @@ xa_seg_kernel(const DecodeParams p)
 			printf("seg prof ticket %u turns %d: wait %lld read %lld request %lld decode %lld out %lld loop %lld\n",
 			    ticket, nmax + maxback, pc[0], pc[1], pc[2], pc[3], pc[4], pc[5]);
 #endif
-		if (run && !ends && sub == lps - 1u) {
-			/* the state behind the tile, for its stream's next tile's first lane */
+		if (run && !ends && lane == 31u) {
+			/* the state behind the tile, for the next tile's first lane */
 #pragma unroll
 			for (int c = 0; c < CH; c++)
 				mailbox_put(&p.carry[(uint64_t)slot * 2 + c],

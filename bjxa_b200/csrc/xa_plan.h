@@ -117,12 +117,9 @@ struct HostPlan {
  * override.
  */
 constexpr size_t kDecWideMinStreams = 1024;
-/* the segment form (xa_walk.h) puts one stream on every lane of a warp: classes
- * of at least this many streams get its list as well */
-constexpr size_t kSegMinStreams = 64;
-/* ... or that have streams long enough for a warp of their own; and in either case
- * enough items for the form's tiles (32 lanes x kSegItems) to fill the device.
- * (BJXA_B200_SEG=on lifts the latter: tests force the form on small batches.) */
+/* the segment form (xa_walk.h): classes with enough items for its tiles (32 lanes x
+ * kSegItems) to fill the device get its list as well.  (BJXA_B200_SEG=on lifts
+ * that: tests force the form on small batches.) */
 constexpr uint64_t kSegMinItems = 1ull << 22;
 
 /* effective blocks per strip */
@@ -154,64 +151,55 @@ inline void emit_decode_tiles(HostPlan &hp, const std::vector<uint32_t> &o, uint
 }
 
 /*
- * The segment form's list (xa_walk.h).  Streams of at least kSegLongItems items get
- * a warp to themselves: tiles of 32 consecutive segments of ONE stream (te.pad = 32
- * lanes per stream), time-major over those streams.  The shorter ones share warps,
- * a stream per lane (te.pad = 1): tiles of 32 streams x one segment.  A tile may
- * wait for the one in front of it in its streams (data without cut blocks), so that
- * one must hold a lower ticket -- but strictly time-major order would hand the
- * tiles of one step, the ones that can run at the same time, to the warps of the
- * same few CTAs (a CTA's warps draw consecutive tickets).  So the steps go in
- * groups of kSegStepGroup: within a group, the group's steps of one 32-stream
- * column, then the next column's.
+ * The segment form's list (xa_walk.h): all segments (kSegItems items) of all streams
+ * of the class, the streams in the order they lie in the XA arena, dealt out 32 to a
+ * tile -- a lane each.  A long stream fills many tiles by itself, short ones share
+ * a tile; either way the lanes of a warp, and the warps that run at the same time,
+ * read and write next to each other (a warp's turn touches a handful of pages of the
+ * arenas; with one stream per lane it was 32 + 32, and on long streams the address
+ * translation, not the arithmetic, then set the pace: profiles/history_r2.md).
+ *   te.first  index into order[] of the stream of lane 0 (the class's streams in
+ *             arena order are appended to order[] for this list)
+ *   te.count  segment of that stream lane 0 decodes
+ *   te.j      lanes in use
+ *   te.pad    streams the tile touches
+ * The segment in front of a lane's is the lane before it, or -- lane 0 -- the last
+ * lane of the tile before: a lower ticket.
  */
-#ifndef XA_SEG_STEP_GROUP
-#define XA_SEG_STEP_GROUP 8
-#endif
-#ifndef XA_SEG_LONG
-#define XA_SEG_LONG (2 * 32 * XA_SEG_ITEMS)
-#endif
-constexpr uint32_t kSegStepGroup = XA_SEG_STEP_GROUP;
-constexpr uint32_t kSegLongItems = XA_SEG_LONG;
-inline void emit_seg_tiles(HostPlan &hp, const std::vector<uint32_t> &o, uint32_t order0)
+inline uint32_t seg_count(uint32_t blocks)
 {
-	/* longest first: the long streams are a prefix */
-	size_t n_long = 0;
-	while (n_long < o.size() && hp.streams[o[n_long]].blocks >= kSegLongItems)
-		n_long++;
-	const uint32_t per_tile = 32u * kSegItems;
-	size_t active = n_long;
-	for (uint32_t j = 0; active > 0; j++) {
-		while (active > 0 && (uint64_t)j * per_tile >= hp.streams[o[active - 1]].blocks)
-			active--;
-		for (size_t k = 0; k < active; k++) {
-			TileEnt te = { order0 + (uint32_t)k, 1u, j, 32u };
-			hp.tiles.push_back(te);
-		}
-	}
-	auto active_at = [&](uint32_t j, size_t from) {
-		size_t a = from;
-		while (a > n_long && (uint64_t)j * kSegItems >= hp.streams[o[a - 1]].blocks)
-			a--;
-		return a;
-	};
-	active = o.size();
-	for (uint32_t j0 = 0;; j0 += kSegStepGroup) {
-		active = active_at(j0, active);
-		if (active == n_long)
-			break;
-		for (size_t base = n_long; base < active; base += 32) {
-			size_t act = active;
-			for (uint32_t j = j0; j < j0 + kSegStepGroup; j++) {
-				act = active_at(j, act);
-				if (base >= act)
-					break;
-				TileEnt te = { order0 + (uint32_t)base,
-				    (uint32_t)std::min(act - base, (size_t)32), j, 1u };
+	return (blocks + kSegItems - 1) / kSegItems;
+}
+
+inline void emit_seg_tiles(HostPlan &hp, const std::vector<uint32_t> &members)
+{
+	std::vector<uint32_t> o(members);
+	std::stable_sort(o.begin(), o.end(), [&](uint32_t x, uint32_t y) {
+		return hp.streams[x].xa_off < hp.streams[y].xa_off;
+	});
+	const uint32_t order0 = (uint32_t)hp.order.size();
+	hp.order.insert(hp.order.end(), o.begin(), o.end());
+	TileEnt te = { 0u, 0u, 0u, 0u };
+	for (size_t k = 0; k < o.size(); k++) {
+		const uint32_t ns = seg_count(hp.streams[o[k]].blocks);
+		for (uint32_t sg = 0; sg < ns; ) {
+			if (te.j == 0) {
+				te.first = order0 + (uint32_t)k;
+				te.count = sg;
+				te.pad = 0;
+			}
+			const uint32_t take = std::min(ns - sg, 32u - te.j);
+			te.j += take;
+			te.pad++;
+			sg += take;
+			if (te.j == 32) {
 				hp.tiles.push_back(te);
+				te.j = 0;
 			}
 		}
 	}
+	if (te.j != 0)
+		hp.tiles.push_back(te);
 }
 
 /*
@@ -308,8 +296,7 @@ inline int build_plan(HostPlan &hp, int kind, const Desc *d, size_t n,
 		uint64_t items = 0;
 		for (size_t k = 0; k < o.size(); k++)
 			items += hp.streams[o[k]].blocks;
-		const bool seg = (o.size() >= kSegMinStreams || hp.streams[o[0]].blocks >= kSegLongItems) &&
-		    items >= seg_min_items;
+		const bool seg = items >= seg_min_items;
 		has_seg[b] = seg;
 		const uint32_t fine = std::min(strip_blocks(std::max(hp.ns[b], hp.alt_ns[b]), bucket_ch(b)),
 		    seg ? kSegItems : ~0u);
@@ -331,7 +318,7 @@ inline int build_plan(HostPlan &hp, int kind, const Desc *d, size_t n,
 	for (int b = 0; b < 6; b++) {
 		hp.seg_begin[b] = (uint32_t)hp.tiles.size();
 		if (kind == kKindDecode && has_seg[b])
-			emit_seg_tiles(hp, members[b], hp.order_begin[b]);
+			emit_seg_tiles(hp, members[b]);
 	}
 	hp.seg_begin[6] = (uint32_t)hp.tiles.size();
 	return 0;

@@ -414,51 +414,46 @@ XA_HD SegFront<BITS, CH> seg_front(uint32_t n0, Prof prof)
 }
 
 /*
- * Lanes and streams.  A tile's 32 lanes are te.pad = P lanes per stream (a power of
- * two) times te.count streams: lane L decodes segment te.j * P + L % P of stream
- * L / P of the tile.
- *   P = 32  one long stream per warp: the lanes read and write next to each other
- *           (a warp's turn touches two or three pages of the arenas -- with a stream
- *           per lane it is 32 + 32, and on long streams the address translation,
- *           not the arithmetic, then sets the pace: profiles/history_r2.md);
- *   P = 1   32 short streams per warp, which alone would leave most lanes idle.
- * A lane that cannot recompute its state waits for the segment in front: lane
- * L - 1 of its own warp if L % P != 0 -- the warp then makes another pass over the
- * tile for the lanes that had to wait -- else the mailbox its stream's previous
- * tile (a lower ticket) leaves.
+ * Lanes and streams (xa_plan.h: emit_seg_tiles).  The class's segments, streams in
+ * arena order, are dealt out 32 to a tile: lane L of a tile decodes the L-th segment
+ * counted from segment te.count of stream order[te.first].  A lane that cannot
+ * recompute its state waits for the segment in front: the lane before it -- the
+ * warp then makes another pass over the tile for the lanes that had to wait -- or,
+ * lane 0, the mailbox that the last lane of the tile before leaves (a lower ticket).
  */
 template <int BITS, int CH>
 struct SegLane {
-	uint32_t stream, n0, n, slot, sub;
+	uint32_t stream, seg, n0, n, slot;
 	uint64_t a0, o0;
 	bool valid, ends;
 };
 
 template <int BITS, int CH>
-XA_HD SegLane<BITS, CH> seg_lane(const DecodeParams &p, uint32_t first, uint32_t count, uint32_t j,
-    uint32_t lanes_per_stream, uint32_t lane)
+XA_HD SegLane<BITS, CH> seg_lane(const DecodeParams &p, const TileEnt &te, uint32_t lane)
 {
 	typedef Walk<BITS, CH> W;
 	SegLane<BITS, CH> l;
-	const uint32_t sidx = lane / lanes_per_stream;
-	l.sub = lane % lanes_per_stream;
-	l.valid = sidx < count;
-	l.stream = 0; l.n0 = 0; l.n = 0; l.slot = 0; l.a0 = 0; l.o0 = 0; l.ends = false;
+	l.valid = lane < te.j;
+	l.stream = 0; l.seg = 0; l.n0 = 0; l.n = 0; l.slot = 0; l.a0 = 0; l.o0 = 0; l.ends = false;
 	if (!l.valid)
 		return l;
-	l.stream = p.order[first + sidx];
-	const StreamDev &sd = p.streams[l.stream];
-	const uint64_t n0 = ((uint64_t)j * lanes_per_stream + l.sub) * kSegItems;
-	if (n0 >= sd.blocks) {
-		l.valid = false;
-		return l;
+	uint32_t k = te.first, at = te.count + lane;
+	for (;;) {
+		const uint32_t ns = (p.streams[p.order[k]].blocks + kSegItems - 1u) / kSegItems;
+		if (at < ns)
+			break;
+		at -= ns;
+		k++;
 	}
-	l.n0 = (uint32_t)n0;
+	l.stream = p.order[k];
+	l.seg = at;
+	const StreamDev &sd = p.streams[l.stream];
+	l.n0 = at * kSegItems;
 	l.n = sd.blocks - l.n0 < kSegItems ? sd.blocks - l.n0 : kSegItems;
 	l.ends = l.n0 + l.n == sd.blocks;
 	l.a0 = sd.xa_off + (uint64_t)l.n0 * W::STEP;
 	l.o0 = sd.pcm_off + (uint64_t)l.n0 * W::OUT;
-	l.slot = sd.slot_base + j;
+	l.slot = sd.slot_base + at;
 	return l;
 }
 
@@ -514,14 +509,13 @@ template <int BITS, int CH, class Visit>
 XA_HD void walk_seg_tile_serial(const DecodeParams &p, const TileEnt &te, Visit visit)
 {
 	typedef Walk<BITS, CH> W;
-	const uint32_t P = te.pad;
 	SegLane<BITS, CH> ln[32];
 	int st0[32][CH], st1[32][CH];
 	uint32_t back[32];
 	enum { kIdle, kReady, kPending, kDone } state[32];
 	for (uint32_t lane = 0; lane < 32; lane++) {
 		SegLane<BITS, CH> &l = ln[lane];
-		l = seg_lane<BITS, CH>(p, te.first, te.count, te.j, P, lane);
+		l = seg_lane<BITS, CH>(p, te, lane);
 		state[lane] = kIdle;
 		back[lane] = 0;
 		if (!l.valid)
@@ -538,7 +532,7 @@ XA_HD void walk_seg_tile_serial(const DecodeParams &p, const TileEnt &te, Visit 
 			if (f.own) {
 				st0[lane][c] = sd.prev[c][0];
 				st1[lane][c] = sd.prev[c][1];
-			} else if (f.mail && l.sub == 0) {
+			} else if (f.mail && lane == 0) {
 				const unsigned long long v = mailbox_get(
 				    &p.carry[(uint64_t)(l.slot - 1u) * 2 + c], p.epoch, p.fault,
 				    p.carry_timeout_ns);
@@ -565,7 +559,7 @@ XA_HD void walk_seg_tile_serial(const DecodeParams &p, const TileEnt &te, Visit 
 			if (state[lane] == kReady) {
 				state[lane] = kDone;
 				const SegLane<BITS, CH> &l = ln[lane];
-				if (!l.ends && l.sub == P - 1u) {
+				if (!l.ends && lane == 31u) {
 #pragma unroll
 					for (int c = 0; c < CH; c++)
 						mailbox_put(&p.carry[(uint64_t)l.slot * 2 + c],

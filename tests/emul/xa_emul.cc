@@ -396,7 +396,7 @@ xa_emul_decode(const bjxa_stream_desc_t *descs, size_t n, const uint8_t *src,
 		}
 		const bool seg = g_seg && hp.seg_begin[b + 1] > hp.seg_begin[b];
 		if (seg) {
-			/* the segment form's list (classes of at least kSegMinStreams streams) */
+			/* the segment form's list */
 			t0 = hp.seg_begin[b];
 			t1 = hp.seg_begin[b + 1];
 		}
@@ -538,8 +538,6 @@ void xa_emul_relay(int on) { g_relay = on; }
 void xa_emul_seg(int on) { g_seg = on; }
 int xa_emul_seg_items(void) { return (int)kSegItems; }
 int xa_emul_seg_back(void) { return (int)kSegBack; }
-int xa_emul_seg_min_streams(void) { return (int)kSegMinStreams; }
-int xa_emul_seg_long_items(void) { return (int)kSegLongItems; }
 int xa_emul_strip_blocks(int ns, int ch) { return (int)strip_blocks(ns, ch); }
 int xa_emul_wide(void) { return kDecWide; }
 int xa_emul_enc_tile_blocks(void) { return kEncTBE; }

@@ -37,8 +37,6 @@ class Emul:
         self.seg = d.xa_emul_seg                        # (0|1): classes of enough streams go through the segment form (xa_walk.h)
         self.seg_items = d.xa_emul_seg_items()
         self.seg_back = d.xa_emul_seg_back()
-        self.seg_min_streams = d.xa_emul_seg_min_streams()
-        self.seg_long_items = d.xa_emul_seg_long_items()
         self.split = d.xa_emul_split                    # (0|1): long-strip tiles go through the split form (xa_walk.h)
 
     def dec_tile_blocks(self, ch):

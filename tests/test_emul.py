@@ -272,13 +272,13 @@ def seg_emul():
 @pytest.mark.parametrize("order", [0, 1, 2])
 @pytest.mark.parametrize("bits,ch", [(4, 1), (6, 1), (8, 1), (4, 2), (6, 2), (8, 2)])
 def test_seg_form_class(seg_emul, oracle, bits, ch, order):
-    """One class large enough for the segment list; lengths from one item to several
-    segments (ragged last blocks), every mix: P0/P1 find a cut block right in front
-    of a segment, P2 a few items back, P3 never -- those lanes take the state from
-    the mailbox of the lane in front; streams shorter than the look-back start from
-    their own state."""
+    """One class, lengths from one item to several segments (ragged last blocks), so
+    that a tile's 32 lanes belong to many streams; every mix: P0/P1 find a cut block
+    right in front of a segment, P2 a few items back, P3 never -- those lanes wait
+    for the lane in front (another pass over the tile) or, lane 0, for the mailbox of
+    the tile before; streams shorter than the look-back start from their own state."""
     e = seg_emul
-    seg, n = e.seg_items, e.seg_min_streams + 9
+    seg, n = e.seg_items, 73
     specs = [dict(bits=bits, channels=ch,
                   samples=32 * (1 + (i * 37) % (3 * seg + 5)) - (i % 32 if i % 3 else 0),
                   mix=("P2", "P3", "P1", "P0", "P2")[i % 5], key=9000 + 100 * bits + 10 * ch + i,
@@ -296,7 +296,7 @@ def test_seg_form_look_back_limits(seg_emul, oracle, bits, ch):
     invalid profile counts as a cut and is reported once, by the lane whose segment
     holds it."""
     e = seg_emul
-    seg, back, n = e.seg_items, e.seg_back, e.seg_min_streams
+    seg, back, n = e.seg_items, e.seg_back, 64
     specs = []
     for i in range(n):
         blocks = 2 * seg + 17
@@ -320,13 +320,13 @@ def test_seg_form_look_back_limits(seg_emul, oracle, bits, ch):
 @pytest.mark.parametrize("order", [0, 2])
 @pytest.mark.parametrize("bits,ch", [(8, 1), (4, 2), (6, 1)])
 def test_seg_form_long_streams(seg_emul, oracle, bits, ch, order):
-    """Streams long enough for a warp of their own (32 lanes = 32 consecutive segments
-    of one stream) next to short ones that share warps.  P2: every lane finds its
-    state a few items back; P3: every lane but the first waits for the lane in front
-    of it -- 32 passes over the tile -- and the first for the mailbox of the stream's
-    previous tile; a P3 stream with a few cut blocks: some lanes wait, some do not."""
+    """Streams that fill several tiles by themselves (32 lanes = 32 consecutive
+    segments of one stream) next to short ones that share tiles.  P2: every lane
+    finds its state a few items back; P3: every lane but the first waits for the lane
+    in front of it -- 32 passes over the tile -- and the first for the mailbox of the
+    tile before; a P3 stream with a few cut blocks: some lanes wait, some do not."""
     e = seg_emul
-    seg, long_items = e.seg_items, e.seg_long_items
+    seg, long_items = e.seg_items, 64 * e.seg_items
     specs = [
         dict(bits=bits, channels=ch, samples=32 * (long_items + 3 * seg + 7) - 5, mix="P2", key=31000,
              prev=((100, -100), (7, 8))),

@@ -33,21 +33,32 @@ E="tools/prof_decode.py --mix P0 --streams 1024 --seconds 4 --bits 4 --ch 2 --st
 timeout 300 python $E > gpurun_out/prof_search_$tag.json 2>/dev/null && \
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:xa_search_kernel -c 1 \
     -f -o gpurun_out/search_stereo4_$tag python $E > gpurun_out/ncu_search_$tag.log 2>&1
-# the two-pass forms on chain-rich data: the relay form's first pass (tile walkers
-# that hand their stragglers on) and second pass, mono 8-bit mix P2; the split
-# form's dense walkers, stereo 4-bit mix P2
-F="tools/prof_decode.py --mix P2 --streams 2048 --seconds 30 --bits 8 --ch 1 --steps 1 --warmup 0"
-timeout 300 python $F > gpurun_out/prof_relay_$tag.json 2>/dev/null && \
-timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-    -k "regex:xa_decode_kernel<.*true" -c 1 \
-    -f -o gpurun_out/relay_pass1_mono8_p2_$tag python $F > gpurun_out/ncu_relay1_$tag.log 2>&1
-timeout 300 python $F > /dev/null 2>&1 && \
+# chain-rich data: the segment form (xa_seg_kernel), mono 8-bit and stereo 4-bit, mix P2;
+# the relay form's two passes where the census still picks it (mono 8-bit, a fifth of
+# chain blocks)
+F="tools/prof_decode.py --mix P2 --streams 2048 --seconds 30 --bits 8 --ch 1 --steps 1 --warmup 1"
+timeout 300 python $F > gpurun_out/prof_seg_mono8_$tag.json 2>/dev/null && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:xa_seg_kernel -c 1 \
+    -f -o gpurun_out/seg_mono8_p2_$tag python $F > gpurun_out/ncu_seg1_$tag.log 2>&1
+G="tools/prof_decode.py --mix P2 --streams 2048 --seconds 30 --bits 4 --ch 2 --steps 1 --warmup 1"
+timeout 300 python $G > gpurun_out/prof_seg_stereo4_$tag.json 2>/dev/null && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:xa_seg_kernel -c 1 \
+    -f -o gpurun_out/seg_stereo4_p2_$tag python $G > gpurun_out/ncu_seg2_$tag.log 2>&1
+H="tools/prof_decode.py --mix C20 --streams 2048 --seconds 30 --bits 8 --ch 1 --steps 1 --warmup 1"
+timeout 300 python $H > gpurun_out/prof_relay_$tag.json 2>/dev/null && \
+timeout 600 ncu --set full --clock-control none --import-source on \
+    -k "regex:xa_decode_kernel.*true" -c 1 \
+    -f -o gpurun_out/relay_pass1_mono8_c20_$tag python $H > gpurun_out/ncu_relay1_$tag.log 2>&1
+timeout 300 python $H > /dev/null 2>&1 && \
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:xa_walk_kernel -c 1 \
-    -f -o gpurun_out/relay_pass2_mono8_p2_$tag python $F > gpurun_out/ncu_relay2_$tag.log 2>&1
-G="tools/prof_decode.py --mix P2 --streams 2048 --seconds 30 --bits 4 --ch 2 --steps 1 --warmup 0"
-timeout 300 python $G > gpurun_out/prof_split_$tag.json 2>/dev/null && \
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:xa_walk_kernel -c 1 \
-    -f -o gpurun_out/split_walk_stereo4_p2_$tag python $G > gpurun_out/ncu_split_$tag.log 2>&1
+    -f -o gpurun_out/relay_pass2_mono8_c20_$tag python $H > gpurun_out/ncu_relay2_$tag.log 2>&1
+# by shape and mix, whatever the census picks (the table of DESIGN.md)
+: > gpurun_out/auto_sweep_$tag.log
+for shape in "8 1" "6 1" "4 1" "8 2" "6 2" "4 2"; do
+    set -- $shape
+    timeout 600 python tools/prof_decode.py --mix P0,P1,C10,C20,C50,P2,P3 --streams 4096 --seconds 30 \
+        --bits $1 --ch $2 --steps 3 --warmup 1 --tag auto >> gpurun_out/auto_sweep_$tag.log 2>/dev/null
+done
 timeout 300 python tools/pcie_probe.py > gpurun_out/pcie_$tag.json 2> gpurun_out/pcie_$tag.err
 # gpurun brings back at most 64 MiB: the raw metric page of every capture as CSV
 # (what tools/summarize_profiles.py reads), the SASS page of the walkers, and only
@@ -55,11 +66,11 @@ timeout 300 python tools/pcie_probe.py > gpurun_out/pcie_$tag.json 2> gpurun_out
 for r in gpurun_out/*_$tag.ncu-rep; do
     ncu -i $r --page raw --csv > ${r%.ncu-rep}.raw.csv 2>/dev/null
 done
-for k in relay_pass1_mono8_p2 relay_pass2_mono8_p2 split_walk_stereo4_p2; do
+for k in seg_mono8_p2 seg_stereo4_p2 relay_pass1_mono8_c20 relay_pass2_mono8_c20; do
     ncu -i gpurun_out/${k}_$tag.ncu-rep --page source --csv > gpurun_out/${k}_$tag.source.csv 2>/dev/null
 done
 for r in gpurun_out/*_$tag.ncu-rep; do
-    case $r in *decode_p1_4096_*|*relay_pass1_*) ;; *) rm -f $r ;; esac
+    case $r in *decode_p1_4096_*|*seg_mono8_p2_*) ;; *) rm -f $r ;; esac
 done
 du -sh gpurun_out
 echo done

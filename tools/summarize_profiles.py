@@ -96,7 +96,7 @@ def launches(tag):
           "One step = one `bjxa_plan_run()` = one `cudaMemsetAsync` (arms first_bad[], the ticket "
           "counters and the census words; a memset node, not a kernel) + the launches below. The "
           "4096-stream class has several candidate forms (long strips, wide tiles, the relay form's "
-          "two passes), so the census kernel runs and the forms it does not pick return at once:", "",
+          "two passes, the segment form), so the census kernel runs and the forms it does not pick return at once:", "",
           "| launch | kernel | ms under ncu |", "|---|---|---:|"]
     per_step = len(ours) // 5 if len(ours) % 5 == 0 else None
     for i, (k, ms) in enumerate(ours):
@@ -212,19 +212,23 @@ def main():
     secondary(tag, "search_stereo4",
               "tools/prof_decode.py --mix P0 --streams 1024 --seconds 4 --bits 4 --ch 2 --steps 1 --warmup 0 --search",
               "searching encoder (extension), 1024 stereo streams x 4 s -> 4-bit XA, 65 candidates per block")
-    secondary(tag, "relay_pass1_mono8_p2",
-              "tools/prof_decode.py --mix P2 --streams 2048 --seconds 30 --bits 8 --ch 1 --steps 1 --warmup 0",
+    secondary(tag, "seg_mono8_p2",
+              "tools/prof_decode.py --mix P2 --streams 2048 --seconds 30 --bits 8 --ch 1 --steps 1 --warmup 1",
+              "segment form (xa_seg_kernel): every lane a fixed segment of one stream, all blocks through "
+              "the chain step; 2048 mono 8-bit streams x 30 s, mix P2 (80 % chain blocks)")
+    secondary(tag, "seg_stereo4_p2",
+              "tools/prof_decode.py --mix P2 --streams 2048 --seconds 30 --bits 4 --ch 2 --steps 1 --warmup 1",
+              "segment form, stereo: both channels side by side in every lane; 2048 stereo 4-bit streams x 30 s, mix P2")
+    secondary(tag, "relay_pass1_mono8_c20",
+              "tools/prof_decode.py --mix C20 --streams 2048 --seconds 30 --bits 8 --ch 1 --steps 1 --warmup 1",
               "relay form, first pass: the direct form whose walker warps hand their stragglers on; "
-              "2048 mono 8-bit streams x 30 s, mix P2 (80 % chain blocks)")
-    secondary(tag, "relay_pass2_mono8_p2",
-              "tools/prof_decode.py --mix P2 --streams 2048 --seconds 30 --bits 8 --ch 1 --steps 1 --warmup 0",
+              "2048 mono 8-bit streams x 30 s, 20 % chain blocks")
+    secondary(tag, "relay_pass2_mono8_c20",
+              "tools/prof_decode.py --mix C20 --streams 2048 --seconds 30 --bits 8 --ch 1 --steps 1 --warmup 1",
               "relay form, second pass: the dense walkers finishing the handed-on chains; same launch")
-    secondary(tag, "split_walk_stereo4_p2",
-              "tools/prof_decode.py --mix P2 --streams 2048 --seconds 30 --bits 4 --ch 2 --steps 1 --warmup 0",
-              "split form, second pass: the dense walkers, every lane a run of effective blocks; "
-              "2048 stereo 4-bit streams x 30 s, mix P2")
     for n in (f"bench_{tag}.json", f"bench_ref_{tag}.json", f"extras_{tag}.json", f"pcie_{tag}.json",
-              f"latency_{tag}.json", f"prof_relay_{tag}.json", f"prof_split_{tag}.json"):
+              f"latency_{tag}.json", f"prof_relay_{tag}.json", f"prof_seg_mono8_{tag}.json",
+              f"prof_seg_stereo4_{tag}.json", f"auto_sweep_{tag}.log"):
         copy(n)
     launches(tag)
     full(tag)

@@ -1432,15 +1432,35 @@ xa_seg_kernel(const DecodeParams p)
 				for (int c = 0; c < CH; c++) {
 					const uint32_t at = at32 + (uint32_t)(c * BS);
 					it.prof[c] = ringp[at & (RING - 1)];
-					const uint32_t pay = at + 1u, w0 = pay & ~3u, sh = (pay & 3u) * 8u;
-					uint32_t prev = *reinterpret_cast<const uint32_t *>(ringp + (w0 & (RING - 1)));
+					/*
+					 * The payload out of the ring as whole 16-byte chunks: 32 lanes, each
+					 * with a 16-byte aligned ring of its own, read 4-byte words 4-way bank
+					 * conflicted whatever the lane stride, but 16-byte words at full rate
+					 * (a quarter warp covers all 32 banks).  So: the NW chunks from the
+					 * one that holds payload byte 0, then the word the payload starts in
+					 * selected in two steps (by 2 words, by 1), then the byte shift.
+					 */
+					constexpr int NW = (15 + 4 * BITS + 15) / 16;
+					const uint32_t pay = at + 1u, cb = pay & ~15u, sh = (pay & 3u) * 8u;
+					uint32_t w[4 * NW + 2];
 #pragma unroll
-					for (int i = 0; i < BITS; i++) {
-						const uint32_t nx = *reinterpret_cast<const uint32_t *>(
-						    ringp + ((w0 + 4u * (i + 1)) & (RING - 1)));
-						it.pw[c][i] = __funnelshift_r(prev, nx, sh);
-						prev = nx;
+					for (int k = 0; k < NW; k++) {
+						const uint4 q = *reinterpret_cast<const uint4 *>(
+						    ringp + ((cb + 16u * k) & (RING - 1)));
+						w[4 * k] = q.x; w[4 * k + 1] = q.y; w[4 * k + 2] = q.z; w[4 * k + 3] = q.w;
 					}
+					w[4 * NW] = w[4 * NW + 1] = 0u;
+					const bool by2 = (pay & 8u) != 0, by1 = (pay & 4u) != 0;
+					uint32_t v[BITS + 2], u[BITS + 1];
+#pragma unroll
+					for (int k = 0; k < BITS + 2; k++)
+						v[k] = by2 ? w[k + 2] : w[k];
+#pragma unroll
+					for (int k = 0; k < BITS + 1; k++)
+						u[k] = by1 ? v[k + 1] : v[k];
+#pragma unroll
+					for (int k = 0; k < BITS; k++)
+						it.pw[c][k] = __funnelshift_r(u[k], u[k + 1], sh);
 				}
 				if (t >= 0) {
 #pragma unroll
@@ -2425,8 +2445,8 @@ seg_mode(void)
  * From this share of chain blocks (permille) the census sends a class to the
  * segment form, and from seg_below() on to whatever the other thresholds say.
  * Measured crossovers at 4096 streams x 30 s (profiles/history_r2.md): the form's
- * rate hardly depends on the mix (every block goes through the chain step: 58-62 %
- * of the HBM peak for mono, 47-49 % for 6/8-bit stereo, 59-66 % for 4-bit stereo),
+ * rate hardly depends on the mix (every block goes through the chain step: 61-70 %
+ * of the HBM peak for mono, 51-53 % for 6/8-bit stereo, 65-71 % for 4-bit stereo),
  * so it takes over where the tile forms, which get slower with every chain block,
  * fall below it.
  */
@@ -2439,8 +2459,8 @@ seg_mode(void)
 constexpr uint32_t seg_permille(int bits, int ch)
 {
 	return XA_SEG_PERMILLE != 0 ? XA_SEG_PERMILLE :
-	    ch == 2 ? (bits == 4 ? 100u : bits == 6 ? 380u : 440u) :
-	    (bits == 4 ? 420u : bits == 6 ? 380u : 450u);
+	    ch == 2 ? (bits == 4 ? 80u : bits == 6 ? 310u : 360u) :
+	    (bits == 4 ? 350u : bits == 6 ? 300u : 350u);
 }
 /* above this share lanes too often find no cut block within kSegBack items and wait
  * for their neighbours (0.93^48 = 3 % of the lanes, a second pass for most tiles) */

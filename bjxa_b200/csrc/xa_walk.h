@@ -354,9 +354,8 @@ XA_HD void walk_relay_serial(const DecodeParams &p, const RelayRec &r)
 
 /*
  * The SEGMENT form: no chains, no heads, one pass.  A stream is cut into segments
- * of kSegItems items; lane L of a warp decodes segment j of stream L of the tile
- * (tiles as in the wide shape, time-major) from its first item to its last with
- * the chain step throughout -- a cut or invalid block is the step with
+ * of kSegItems items; a lane decodes one segment from its first item to its last
+ * with the chain step throughout -- a cut or invalid block is the step with
  * k0 = k1 = 0 (libbjxa.c:526), which forgets the state by itself.  So the only
  * thing a lane has to find is the state in front of its segment (seg_front):
  *   - the stream's own, in front of item 0 (libbjxa.c:417-420);
@@ -365,11 +364,9 @@ XA_HD void walk_relay_serial(const DecodeParams &p, const RelayRec &r)
  *     until it reaches its segment: whatever state it starts with is forgotten
  *     at that block.  On data that has cut blocks at all this costs a few items
  *     per segment, and nothing is ever waited for;
- *   - if a channel has no such block within reach, the state comes through the
- *     carry mailbox from the lane that decodes the segment in front -- every lane
- *     leaves its final state there.  That lane holds a lower ticket, so the wait
- *     cannot deadlock; on data without cut blocks this is the serial walk such
- *     data demands, one stream per lane.
+ *   - if a channel has no such block within reach, the state comes from whoever
+ *     decodes the segment in front (see "Lanes and streams" below).  On data
+ *     without cut blocks this is the serial walk such data demands.
  * All 32 lanes of a warp decode a block in every turn but the few at either end.
  */
 template <int BITS, int CH>

@@ -46,8 +46,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:xa_s
     -f -o gpurun_out/seg_stereo4_p2_$tag python $G > gpurun_out/ncu_seg2_$tag.log 2>&1
 H="tools/prof_decode.py --mix C20 --streams 2048 --seconds 30 --bits 8 --ch 1 --steps 1 --warmup 1"
 timeout 300 python $H > gpurun_out/prof_relay_$tag.json 2>/dev/null && \
-timeout 600 ncu --set full --clock-control none --import-source on \
-    -k "regex:xa_decode_kernel.*true" -c 1 \
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
+    -k 'regex:xa_decode_kernel.*bool.1' -c 1 \
     -f -o gpurun_out/relay_pass1_mono8_c20_$tag python $H > gpurun_out/ncu_relay1_$tag.log 2>&1
 timeout 300 python $H > /dev/null 2>&1 && \
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:xa_walk_kernel -c 1 \

@@ -68,6 +68,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 	    "}\n" :: "r"(bar), "r"(parity) : "memory");
 }
 
+/* the same for a warp that has time: it sleeps between looks, so that its polling
+ * does not take shared-memory pipe cycles from a warp on the critical path (the
+ * chain form's stepper ran 1.7 x slower next to two tightly polling warps) */
+__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity, uint32_t ns)
+{
+	for (;;) {
+		uint32_t done;
+		asm volatile(
+		    "{\n"
+		    ".reg .pred p;\n"
+		    "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+		    "selp.u32 %0, 1, 0, p;\n"
+		    "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+		if (done)
+			return;
+		if (ns != 0)
+			__nanosleep(ns);
+	}
+}
+
 /* global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned;
  * completion is signalled on the mbarrier as transaction bytes */
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src,
@@ -124,6 +144,8 @@ constexpr int kDecBlock = kDecThreads + 64;	/* consumers + loader warp + scanner
  *          stragglers to xa_walk_kernel                       (relay <= share < split)
  *   bit 5  (alone) the segment form, xa_seg_kernel            (seg <= share < seg_below;
  *          asked first)
+ *   bit 6  (alone) the chain form, xa_chain_kernel: mono data (all but) without cut
+ *          blocks                                             (chain <= share; asked second)
  * A threshold above 1000 permille switches that choice off.  One CTA, no
  * atomics, nothing to clear; all of a thread's loads in flight together.  Measured crossovers:
  * profiles/history_r1.md.
@@ -136,7 +158,7 @@ constexpr uint32_t staged_permille(int bits) { return bits == 4 ? 300u : bits ==
 constexpr uint32_t kWideManyStreams = 8192;
 constexpr uint32_t kWidePermilleMono[2] = { 985, 930 }, kWidePermilleStereo[2] = { 920, 700 };
 constexpr uint32_t kNever = 1001;
-enum { kFormStaged = 1, kFormWide = 2, kFormPool = 4, kFormSplit = 8, kFormRelay = 16, kFormSeg = 32 };
+enum { kFormStaged = 1, kFormWide = 2, kFormPool = 4, kFormSplit = 8, kFormRelay = 16, kFormSeg = 32, kFormChain = 64 };
 /* pooled walkers instead of one walker warp per tile: from this share of chain
  * blocks (measured crossovers: profiles/history_r1.md), for classes of at least
  * kPoolMinTiles tiles -- below that the launch is too short to care */
@@ -153,7 +175,8 @@ __global__ void __launch_bounds__(kCensusThreads)
 xa_census_kernel(const uint8_t *src, const StreamDev *streams, const uint32_t *order,
     uint32_t n_streams, uint32_t block_bytes_one, uint32_t ch, uint32_t staged_permille,
     uint32_t wide_permille, uint32_t pool_permille, uint32_t split_permille,
-    uint32_t relay_permille, uint32_t seg_permille, uint32_t seg_below, uint32_t *choice)
+    uint32_t relay_permille, uint32_t seg_permille, uint32_t seg_below, uint32_t chain_permille,
+    uint32_t *choice)
 {
 	__shared__ uint32_t warp_sum[kCensusThreads / 32];
 	const uint32_t tid = threadIdx.x;
@@ -189,6 +212,7 @@ xa_census_kernel(const uint8_t *src, const StreamDev *streams, const uint32_t *o
 		const uint32_t permille = total * 1000u / (kCensusThreads * kCensusPerThread);
 		const uint32_t staged = permille >= staged_permille ? kFormStaged : 0u;
 		*choice = permille >= seg_permille && permille < seg_below ? (uint32_t)kFormSeg :
+		    permille >= chain_permille ? (uint32_t)kFormChain :
 		    permille >= wide_permille ? kFormWide | staged :
 		    permille >= split_permille ? (uint32_t)kFormSplit :
 		    permille >= relay_permille ? (uint32_t)kFormRelay :
@@ -1561,6 +1585,284 @@ xa_seg_kernel(const DecodeParams p)
 	}
 }
 
+/* ---- chain form: mono data without cut blocks --------------------------------------- */
+/*
+ * A stream without cut blocks is one dependent chain from its first sample to its
+ * last: nothing but more streams makes such data faster, and what a stream costs is
+ * the latency of the step -- 31 cycles a sample for a warp that does nothing else
+ * (tools/step_bench.cu).  In the tile forms and the segment form a lone warp's turn
+ * takes twice that: it also feeds itself (ring, payload, ranged codes) and takes
+ * its samples away (rows, stores) in between.  Here a CTA owns 32 streams from
+ * their first block to their last, a stream per lane, and three warps share the
+ * work:
+ *   loader   keeps the lanes' rings filled (the segment form's data path) and puts
+ *            every block's payload, word-aligned, and profile byte into shared
+ *            memory [word][lane];
+ *   stepper  does nothing but the block step (xa_core.h: decode_block_chain -- the
+ *            ranged codes and the packing ride in the gaps of the dependent chain),
+ *            BITS + 1 loads and 16 stores a block beside it, the state in registers
+ *            for the whole stream -- no hand-overs, no carries;
+ *   storer   takes the packed samples, a 64-byte row per lane, and stores them 16
+ *            bytes a lane.
+ * Stages of kChainK blocks go round between them on mbarriers.  The census sends
+ * mono classes here from 98.5 % chain blocks (where the wide tiles used to go).
+ */
+#ifndef XA_CHAIN_K
+#define XA_CHAIN_K 8
+#endif
+constexpr int kChainK = XA_CHAIN_K, kChainS = 2, kChainThreads = 96, kChainRing = 256;
+
+template <int BITS>
+struct ChainSmem {
+	uint32_t pw[kChainS][kChainK][BITS + 1][32];	/* payload words and the profile byte, [word][lane] */
+	__align__(16) uint32_t out[kChainS][kChainK][32][20];	/* a row of 16 packed pairs per lane;
+							 * 20: rows 80 bytes apart, so that eight lanes'
+							 * 16-byte accesses hit all 32 banks */
+	__align__(16) unsigned char ring[32][kChainRing + 16];
+	unsigned long long bar[4][kChainS];		/* xs full / empty, out full / empty */
+	uint32_t blocks[32];
+	uint32_t maxblocks;
+};
+
+template <int BITS>
+__global__ void __launch_bounds__(kChainThreads)
+xa_chain_kernel(const DecodeParams p, const uint32_t *order, uint32_t n_streams)
+{
+	typedef Walk<BITS, 1> W;
+	typedef SegCfg<BITS, 1> C;
+	/* the loader alone hides the arena's latency here: four items ahead */
+	constexpr int STEP = W::STEP, RING = kChainRing, K = kChainK, S = kChainS;
+	constexpr int D = (RING - 30) / STEP - 1 > 4 ? 4 : (RING - 30) / STEP - 1;
+	static_assert(D >= 1, "ring");
+	constexpr uint32_t FULL = 0xffffffffu;
+	enum { kXsFull, kXsEmpty, kOutFull, kOutEmpty };
+
+	if (p.choice != NULL && *p.choice != p.want)
+		return;		/* the census picked another form */
+
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	ChainSmem<BITS> &sm = *reinterpret_cast<ChainSmem<BITS> *>(smem_raw);
+	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	const uint32_t first = blockIdx.x * 32u;
+	const bool have = first + lane < n_streams;
+	const uint32_t stream = have ? order[first + lane] : 0u;
+	const uint32_t nblk = have ? p.streams[stream].blocks : 0u;
+	if (warp == 0) {
+		sm.blocks[lane] = nblk;
+		const uint32_t mx = __reduce_max_sync(FULL, nblk);
+		if (lane == 0)
+			sm.maxblocks = mx;
+	}
+	if (tid == 0)
+		for (int b = 0; b < 4; b++)
+			for (int s = 0; s < S; s++)
+				mbar_init(smem_u32(&sm.bar[b][s]), 1);
+	__syncthreads();
+	const uint32_t nst = (sm.maxblocks + K - 1) / K;
+#ifdef XA_CHAIN_PROF
+	long long wt = 0, t_begin = clock64(), g_begin;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_begin));
+#define XA_CHAIN_WAIT(b, ph) do { long long w0_ = clock64(); mbar_wait(b, ph); wt += clock64() - w0_; } while (0)
+#else
+#define XA_CHAIN_WAIT(b, ph) mbar_wait_idle(b, ph, 0)
+#endif
+	/* loader and storer have time to spare: they sleep between looks */
+#define XA_CHAIN_IDLE(b, ph) mbar_wait_idle(b, ph, 64)
+
+	if (warp == 0) {
+		/* ---- loader ---- */
+		const uint64_t a0 = have ? p.streams[stream].xa_off : 0;
+		uint8_t *const ringp = sm.ring[lane];
+		const uint32_t ring = smem_u32(ringp);
+		const uint64_t safe = p.src_bytes & ~(uint64_t)15;
+		const uint32_t a32 = (uint32_t)a0 & 15u;
+		const int nn = (int)nblk;
+		int fe = -(int)a32;
+		const uint8_t *gq = p.src + a0 + (int64_t)fe;
+		const uint64_t room = safe > a0 ? safe - a0 : 0;
+		const int fe_safe = have ? (room > 0x40000000ULL ? 0x40000000 : (int)room) : 0;
+		const bool tail = __any_sync(FULL, have && nn * STEP > fe_safe);
+		auto request = [&](int u) {
+			if (u < nn) {
+				const int want = (u + 1) * STEP < fe_safe ? (u + 1) * STEP : fe_safe;
+				const uint32_t r32 = a32 + (uint32_t)fe;
+				int k = 0;
+#pragma unroll
+				for (int i = 0; i < C::KMAX; i++)
+					if (fe + 16 * i < want) {
+						cp_async16(ring + ((r32 + 16u * i) & (RING - 1)), gq + 16 * i);
+						k = i + 1;
+					}
+				fe += 16 * k;
+				gq += 16 * k;
+			}
+			asm volatile("cp.async.commit_group;" ::: "memory");
+			if (tail && u < nn && (u + 1) * STEP > fe_safe) {
+				const int from = u * STEP > fe_safe ? u * STEP : fe_safe < 0 ? 0 : fe_safe;
+				for (int b = from; b < (u + 1) * STEP; b++)
+					if (a0 + (uint64_t)(int64_t)b < p.src_bytes)
+						ringp[(a32 + (uint32_t)b) & (RING - 1)] = p.src[a0 + (uint64_t)(int64_t)b];
+			}
+		};
+#pragma unroll
+		for (int d = 0; d < D; d++)
+			request(d);
+		uint32_t at = a32;
+#pragma unroll 1
+		for (uint32_t st = 0; st < nst; st++) {
+			const uint32_t s = st % S;
+			if (st >= (uint32_t)S)
+				XA_CHAIN_IDLE(smem_u32(&sm.bar[kXsEmpty][s]), (st / S - 1u) & 1u);
+#pragma unroll 1
+			for (int k = 0; k < K; k++) {
+				const int t = (int)st * K + k;
+				asm volatile("cp.async.wait_group %0;" :: "n"(D - 1) : "memory");
+				uint32_t prof = 0, pw[BITS];
+				if (t < nn) {
+					prof = ringp[at & (RING - 1)];
+					constexpr int NW = (15 + 4 * BITS + 15) / 16;
+					const uint32_t pay = at + 1u, cb = pay & ~15u, sh = (pay & 3u) * 8u;
+					uint32_t w[4 * NW];
+#pragma unroll
+					for (int i = 0; i < NW; i++) {
+						const uint4 q = *reinterpret_cast<const uint4 *>(
+						    ringp + ((cb + 16u * i) & (RING - 1)));
+						w[4 * i] = q.x; w[4 * i + 1] = q.y; w[4 * i + 2] = q.z; w[4 * i + 3] = q.w;
+					}
+					const bool by2 = (pay & 8u) != 0, by1 = (pay & 4u) != 0;
+					uint32_t v[BITS + 2], u[BITS + 1];
+#pragma unroll
+					for (int i = 0; i < BITS + 2; i++)
+						v[i] = by2 ? w[i + 2] : w[i];
+#pragma unroll
+					for (int i = 0; i < BITS + 1; i++)
+						u[i] = by1 ? v[i + 1] : v[i];
+#pragma unroll
+					for (int i = 0; i < BITS; i++)
+						pw[i] = __funnelshift_r(u[i], u[i + 1], sh);
+				}
+				request(t + D);
+				if (t < nn) {
+					if (prof >> 4 >= 5u)
+						global_min_u32(&p.first_bad[stream], (uint32_t)t);
+#pragma unroll
+					for (int i = 0; i < BITS; i++)
+						sm.pw[s][k][i][lane] = pw[i];
+				}
+				/* a lane whose stream is through: filter 0, whatever the payload */
+				sm.pw[s][k][BITS][lane] = t < nn ? prof : 0u;
+				at += (uint32_t)STEP;
+			}
+			__syncwarp();
+			if (lane == 0)
+				mbar_arrive(smem_u32(&sm.bar[kXsFull][s]));
+		}
+	} else if (warp == 1) {
+		/* ---- stepper ---- */
+		/*
+		 * One block a turn: its words out of shared memory, then the production block
+		 * step (xa_core.h: decode_block_chain -- ranged codes and packing ride in the
+		 * gaps of the dependent chain).  (Fetching block t + 1's words while block t
+		 * steps, or ranging it in the same turn, measured 3-12 % slower: ptxas keeps
+		 * neither early, profiles/history_r2.md.)
+		 */
+		int p0 = 0, p1 = 0;		/* the state, n-1 and n-2 */
+		if (have) {
+			p0 = p.streams[stream].prev[0][0];
+			p1 = p.streams[stream].prev[0][1];
+		}
+#pragma unroll 1
+		for (uint32_t st = 0; st < nst; st++) {
+			const uint32_t s = st % S;
+			XA_CHAIN_WAIT(smem_u32(&sm.bar[kXsFull][s]), (st / S) & 1u);
+			if (st >= (uint32_t)S)
+				XA_CHAIN_WAIT(smem_u32(&sm.bar[kOutEmpty][s]), (st / S - 1u) & 1u);
+#pragma unroll 1
+			for (int k = 0; k < K; k++) {
+				uint32_t pw[BITS], o[16];
+#pragma unroll
+				for (int i = 0; i < BITS; i++)
+					pw[i] = sm.pw[s][k][i][lane];
+				const uint32_t prof = sm.pw[s][k][BITS][lane];
+				decode_block_chain<BITS, true>(o, pw, prof, p0, p1);
+#pragma unroll
+				for (int i = 0; i < 4; i++)
+					*reinterpret_cast<uint4 *>(&sm.out[s][k][lane][4 * i]) =
+					    make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+				if (st * K + k + 1u == nblk) {
+					p.results[stream].prev[0][0] = (int16_t)p0;
+					p.results[stream].prev[0][1] = (int16_t)p1;
+				}
+			}
+			__syncwarp();
+			if (lane == 0) {
+				mbar_arrive(smem_u32(&sm.bar[kXsEmpty][s]));
+				mbar_arrive(smem_u32(&sm.bar[kOutFull][s]));
+			}
+		}
+	} else {
+		/* ---- storer: lane = 16-byte unit `unit` of the rows of streams 8q + lane % 8 ----
+		 * (a quarter warp reads one unit of eight rows: all 32 banks) */
+		const uint32_t unit = lane >> 3, r0 = lane & 7u;
+		uint32_t nb[4], owed[4];
+		uint8_t *base[4];
+#pragma unroll
+		for (int q = 0; q < 4; q++) {
+			const uint32_t r = 8u * q + r0;
+			nb[q] = sm.blocks[r];
+			owed[q] = 0;
+			base[q] = NULL;
+			if (nb[q] != 0) {
+				const StreamDev &sd = p.streams[order[first + r]];
+				base[q] = p.dst + sd.pcm_off + unit * 16u;
+				owed[q] = W::last_valid(sd);
+			}
+		}
+#pragma unroll 1
+		for (uint32_t st = 0; st < nst; st++) {
+			const uint32_t s = st % S;
+			XA_CHAIN_IDLE(smem_u32(&sm.bar[kOutFull][s]), (st / S) & 1u);
+#pragma unroll 1
+			for (int k = 0; k < K; k++) {
+				const uint32_t t = st * K + k;
+				uint4 v[4];
+#pragma unroll
+				for (int q = 0; q < 4; q++)
+					v[q] = *reinterpret_cast<const uint4 *>(&sm.out[s][k][8 * q + r0][4 * unit]);
+#pragma unroll
+				for (int q = 0; q < 4; q++) {
+					if (t < nb[q]) {
+						uint8_t *d = base[q] + (uint64_t)t * 64u;
+						if (t + 1u < nb[q] || unit * 16u + 16u <= owed[q]) {
+							*reinterpret_cast<uint4 *>(d) = v[q];
+						} else if (unit * 16u < owed[q]) {
+							/* the stream's last block owes less than this unit */
+							const uint32_t n16 = (owed[q] - unit * 16u) / 2u;
+#pragma unroll
+							for (uint32_t h = 0; h < 8u; h++) {
+								const uint32_t w4 = h < 2 ? v[q].x : h < 4 ? v[q].y : h < 6 ? v[q].z : v[q].w;
+								if (h < n16)
+									reinterpret_cast<uint16_t *>(d)[h] = (uint16_t)(w4 >> (16u * (h & 1u)));
+							}
+						}
+					}
+				}
+			}
+			__syncwarp();
+			if (lane == 0)
+				mbar_arrive(smem_u32(&sm.bar[kOutEmpty][s]));
+		}
+	}
+#ifdef XA_CHAIN_PROF
+	if (lane == 0 && blockIdx.x == 1) {
+		long long g_end;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
+		printf("chain prof warp %u: %lld cycles in %lld ns, waited %lld, %u stages\n", warp, clock64() - t_begin,
+		    g_end - g_begin, wt, nst);
+	}
+#endif
+}
+
 template <int BITS, int CH>
 __global__ void __launch_bounds__(kEncThreads)
 xa_encode_kernel(const EncodeParams p)
@@ -1948,8 +2250,10 @@ static int split_candidate(int split, int bits, int ch, int stereo, int ns, uint
 static int relay_mode(void);
 static int relay_candidate(int relay, int bits, int ch, int stereo, int ns, uint32_t n_tiles);
 static int seg_mode(void);
+static int chain_mode(void);
+static int chain_candidate(int chain, int ch, uint32_t n_streams);
 static int seg_candidate(int seg, uint32_t n_seg_tiles);
-static int decode_class_launches(int ch, int stereo, bool alt, int poolc, int splitc, int relayc, int segc);
+static int decode_class_launches(int ch, int stereo, bool alt, int poolc, int splitc, int relayc, int segc, int chainc);
 
 struct bjxa_plan {
 	uint32_t magic;
@@ -1978,6 +2282,7 @@ struct bjxa_plan {
 	int split;			/* split_mode() likewise */
 	int relay;			/* relay_mode() likewise */
 	int seg;			/* seg_mode() likewise */
+	int chain;			/* chain_mode() likewise */
 	/* a plan with several classes runs them side by side (bjxa_plan_run) */
 	cudaStream_t cls_stream[6];
 	cudaEvent_t ev_start, ev_done[6];
@@ -2035,6 +2340,9 @@ set_attrs_one(void)
 		return e;
 	if ((e = cudaFuncSetAttribute(xa_seg_kernel<BITS, CH>,
 	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SegCfg<BITS, CH>::kSmem)) != cudaSuccess)
+		return e;
+	if (CH == 1 && (e = cudaFuncSetAttribute(xa_chain_kernel<BITS>,
+	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainSmem<BITS>))) != cudaSuccess)
 		return e;
 	return cudaFuncSetAttribute(xa_encode_kernel<BITS, CH>,
 	    cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2134,6 +2442,7 @@ plan_build(bjxa_plan *pl, int kind, const bjxa_stream_desc_t *descs, size_t n)
 	pl->split = split_mode();
 	pl->relay = relay_mode();
 	pl->seg = seg_mode();
+	pl->chain = chain_mode();
 	for (int b = 0; b < 6; b++)
 		if (pl->hp.order_begin[b + 1] > pl->hp.order_begin[b]) {
 			const uint32_t nt = pl->hp.tile_begin[b + 1] - pl->hp.tile_begin[b];
@@ -2141,7 +2450,8 @@ plan_build(bjxa_plan *pl, int kind, const bjxa_stream_desc_t *descs, size_t n)
 			    pl->stereo, pl->hp.alt_ns[b] != 0, pool_candidate(pl->pool, pl->hp.ns[b], nt),
 			    split_candidate(pl->split, bucket_bits(b), bucket_ch(b), pl->stereo, pl->hp.ns[b], nt),
 			    relay_candidate(pl->relay, bucket_bits(b), bucket_ch(b), pl->stereo, pl->hp.ns[b], nt),
-			    seg_candidate(pl->seg, pl->hp.seg_begin[b + 1] - pl->hp.seg_begin[b])) : 1;
+			    seg_candidate(pl->seg, pl->hp.seg_begin[b + 1] - pl->hp.seg_begin[b]),
+			    chain_candidate(pl->chain, bucket_ch(b), pl->hp.order_begin[b + 1] - pl->hp.order_begin[b])) : 1;
 		}
 	return (plan_upload(pl));
 }
@@ -2314,6 +2624,7 @@ struct DecodeClass {
 	int split;			/* likewise */
 	int relay;			/* likewise */
 	int seg;			/* likewise */
+	int chain;			/* likewise */
 	const TileEnt *seg_tiles;	/* the segment form's list, or NULL */
 	uint32_t seg_n;
 	uint32_t *d_choice;
@@ -2506,16 +2817,49 @@ launch_seg(const DecodeParams &p, cudaStream_t st)
 	return cudaGetLastError();
 }
 
+/*
+ * chain form (xa_chain_kernel): 0 = never, 1 = always, 2 = let the census decide
+ * (BJXA_B200_CHAIN=on|off|auto, default auto).  Mono classes of at least
+ * kChainMinStreams streams (fewer chains than that are not worth a kernel).
+ */
+static int
+chain_mode(void)
+{
+	const char *e = getenv("BJXA_B200_CHAIN");
+	return e == NULL ? 2 : strcmp(e, "on") == 0 ? 1 : strcmp(e, "off") == 0 ? 0 : 2;
+}
+
+constexpr uint32_t kChainMinStreams = 128;
+/* from this share of chain blocks (permille): where the mono wide tiles used to take over */
+constexpr uint32_t kChainPermille = 985;
+
+static int
+chain_candidate(int chain, int ch, uint32_t n_streams)
+{
+	if (ch != 1 || chain == 0)
+		return 0;
+	return chain == 1 ? 1 : n_streams >= kChainMinStreams ? 2 : 0;
+}
+
+template <int BITS>
+static cudaError_t
+launch_chain(const DecodeParams &p, const uint32_t *d_order, uint32_t n_streams, cudaStream_t st)
+{
+	xa_chain_kernel<BITS><<<(n_streams + 31u) / 32u, kChainThreads, sizeof(ChainSmem<BITS>), st>>>(
+	    p, d_order, n_streams);
+	return cudaGetLastError();
+}
+
 /* how many kernels decode_class() launches */
 static int
-decode_class_launches(int ch, int stereo, bool alt, int poolc, int splitc, int relayc, int segc)
+decode_class_launches(int ch, int stereo, bool alt, int poolc, int splitc, int relayc, int segc, int chainc)
 {
-	if (poolc == 1 || segc == 1)
+	if (poolc == 1 || segc == 1 || chainc == 1)
 		return 1;
 	if (splitc == 1 || relayc == 1)
 		return 2;
 	const int forms = (ch == 2 && stereo == 2 ? 2 : 1) + (alt ? 1 : 0) + (poolc == 2 ? 1 : 0) +
-	    (splitc == 2 ? 2 : 0) + (relayc == 2 ? 2 : 0) + (segc == 2 ? 1 : 0);
+	    (splitc == 2 ? 2 : 0) + (relayc == 2 ? 2 : 0) + (segc == 2 ? 1 : 0) + (chainc == 2 ? 1 : 0);
 	return forms == 1 ? 1 : forms + 1;
 }
 
@@ -2560,8 +2904,11 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 	const int splitc = split_candidate(c.split, BITS, CH, c.stereo, c.ns, c.p.n_tiles);
 	const int relayc = relay_candidate(c.relay, BITS, CH, c.stereo, c.ns, c.p.n_tiles);
 	const int segc = seg_candidate(c.seg, c.seg_tiles != NULL ? c.seg_n : 0u);
+	const int chainc = chain_candidate(c.chain, CH, c.n_streams);
 	DecodeParams p = c.p;
 	cudaError_t e;
+	if (chainc == 1)
+		return launch_chain<BITS>(p, c.d_order, c.n_streams, st);
 	if (segc == 1) {
 		p.tiles = c.seg_tiles;
 		p.n_tiles = c.seg_n;
@@ -2583,7 +2930,7 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 			return e;
 		return launch_walk<BITS, CH, true>(p, st);
 	}
-	if (!alt && !pick_form && poolc == 0 && splitc == 0 && relayc == 0 && segc == 0) {
+	if (!alt && !pick_form && poolc == 0 && splitc == 0 && relayc == 0 && segc == 0 && chainc == 0) {
 		const bool staged = CH == 2 && c.stereo == 1;
 		return c.ns == 1 ? launch_form<BITS, CH, 1>(p, staged, st) :
 		    launch_form<BITS, CH, kDecWide>(p, staged, st);
@@ -2597,7 +2944,7 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 	    splitc == 2 ? split_permille(BITS, CH) : kNever,
 	    relayc == 2 ? relay_permille(BITS, CH) : kNever,
 	    segc == 2 ? seg_permille(BITS, CH) : kNever, seg_below(BITS, CH),
-	    c.d_choice);
+	    chainc == 2 ? kChainPermille : kNever, c.d_choice);
 	if ((e = cudaGetLastError()) != cudaSuccess)
 		return e;
 	p.choice = c.d_choice;
@@ -2631,6 +2978,12 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 	if (poolc == 2) {
 		p.want = kFormPool;
 		if ((e = launch_pool<typename PoolTile<BITS, CH>::type>(p, st)) != cudaSuccess)
+			return e;
+	}
+	if (chainc == 2) {
+		DecodeParams q = p;
+		q.want = kFormChain;
+		if ((e = launch_chain<BITS>(q, c.d_order, c.n_streams, st)) != cudaSuccess)
 			return e;
 	}
 	if (segc == 2) {
@@ -2804,6 +3157,7 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 			c.split = pl->d_live.p != NULL ? pl->split : 0;
 			c.relay = pl->d_relay.p != NULL ? pl->relay : 0;
 			c.seg = pl->seg;
+			c.chain = pl->chain;
 			c.seg_tiles = hp.seg_begin[b + 1] > hp.seg_begin[b] ? pl->d_tiles.p + hp.seg_begin[b] : NULL;
 			c.seg_n = hp.seg_begin[b + 1] - hp.seg_begin[b];
 			c.d_choice = pl->d_first_bad.p + ((n + 3) & ~(size_t)3) + 12 + b;

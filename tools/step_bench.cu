@@ -17,6 +17,8 @@ __global__ void run(const uint32_t *in, uint32_t *out, long long *cyc, int block
 		pw[i] = in[threadIdx.x * BITS + i];
 	int p0 = threadIdx.x, p1 = -3;
 	uint32_t acc = 0;
+	long long g0, g1;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
 	long long t0 = clock64();
 #pragma unroll 1
 	for (int b = 0; b < blocks; b++) {
@@ -66,15 +68,18 @@ __global__ void run(const uint32_t *in, uint32_t *out, long long *cyc, int block
 		pw[b & (BITS - 1)] ^= acc & 0x01010101u;
 	}
 	long long t1 = clock64();
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
 	out[threadIdx.x] = acc ^ (uint32_t)p0;
-	if (threadIdx.x == 0)
+	if (threadIdx.x == 0 && blockIdx.x == 0) {
 		cyc[0] = t1 - t0;
+		cyc[1] = g1 - g0;
+	}
 }
 
 int main()
 {
-	uint32_t *d_in, *d_out; long long *d_c, h;
-	cudaMalloc(&d_in, 4096); cudaMalloc(&d_out, 4096); cudaMalloc(&d_c, 8);
+	uint32_t *d_in, *d_out; long long *d_c, h, hh[2];
+	cudaMalloc(&d_in, 4096); cudaMalloc(&d_out, 4096); cudaMalloc(&d_c, 16);
 	cudaMemset(d_in, 0x5a, 4096);
 	const int blocks = 2048;
 #define RUN(BITS, VAR, WARPS, name) \
@@ -92,6 +97,14 @@ int main()
 	RUN(6, 1, 24, "ranged codes hoisted, mad bias")
 	RUN(6, 0, 24, "decode_block_chain (production)")
 	RUN(8, 0, 24, "decode_block_chain (production)")
+	/* the SM clock a lone warp sees, and a full device: cycles / elapsed ns */
+	for (int grid = 1; grid <= 148; grid *= 148) {
+		for (int rep = 0; rep < 3; rep++) {
+			run<8, 1><<<grid, grid == 1 ? 32 : 1024>>>(d_in, d_out, d_c, 65536, 0x23);
+			cudaMemcpy(hh, d_c, 16, cudaMemcpyDeviceToHost);
+			printf("grid %3d: %lld cycles in %lld ns = %.0f MHz\n", grid, hh[0], hh[1], 1e3 * hh[0] / hh[1]);
+		}
+	}
 	cudaError_t e = cudaDeviceSynchronize();
 	printf("status %s\n", cudaGetErrorString(e));
 	return 0;

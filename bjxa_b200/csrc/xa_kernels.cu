@@ -1610,11 +1610,16 @@ xa_seg_kernel(const DecodeParams p)
 #ifndef XA_CHAIN_K
 #define XA_CHAIN_K 8
 #endif
+#ifndef XA_CHAIN_UNROLL
+#define XA_CHAIN_UNROLL 8
+#endif
+constexpr int kChainUnroll = XA_CHAIN_UNROLL;
 constexpr int kChainK = XA_CHAIN_K, kChainS = 2, kChainThreads = 96, kChainRing = 256;
 
 template <int BITS>
 struct ChainSmem {
-	uint32_t pw[kChainS][kChainK][BITS + 1][32];	/* payload words and the profile byte, [word][lane] */
+	uint32_t pw[kChainS][kChainK][BITS + 4][32];	/* payload words, the range shift, k0, k1 and c
+							 * (xa_core.h: chain_bias_c), [word][lane] */
 	__align__(16) uint32_t out[kChainS][kChainK][32][20];	/* a row of 16 packed pairs per lane;
 							 * 20: rows 80 bytes apart, so that eight lanes'
 							 * 16-byte accesses hit all 32 banks */
@@ -1749,8 +1754,15 @@ xa_chain_kernel(const DecodeParams p, const uint32_t *order, uint32_t n_streams)
 					for (int i = 0; i < BITS; i++)
 						sm.pw[s][k][i][lane] = pw[i];
 				}
-				/* a lane whose stream is through: filter 0, whatever the payload */
-				sm.pw[s][k][BITS][lane] = t < nn ? prof : 0u;
+				{
+					/* a lane whose stream is through: filter 0, whatever the payload */
+					const uint32_t pf = t < nn ? prof : 0u;
+					const int k0 = gain_k0(pf >> 4), k1 = gain_k1(pf >> 4);
+					sm.pw[s][k][BITS][lane] = 16u + (pf & 15u);
+					sm.pw[s][k][BITS + 1][lane] = (uint32_t)k0;
+					sm.pw[s][k][BITS + 2][lane] = (uint32_t)k1;
+					sm.pw[s][k][BITS + 3][lane] = (uint32_t)chain_bias_c(k0, k1);
+				}
 				at += (uint32_t)STEP;
 			}
 			__syncwarp();
@@ -1766,10 +1778,10 @@ xa_chain_kernel(const DecodeParams p, const uint32_t *order, uint32_t n_streams)
 		 * steps, or ranging it in the same turn, measured 3-12 % slower: ptxas keeps
 		 * neither early, profiles/history_r2.md.)
 		 */
-		int p0 = 0, p1 = 0;		/* the state, n-1 and n-2 */
+		int b0 = 32768, b1 = 32768;	/* the state, n-1 and n-2, biased (xa_core.h: sample_chain_r) */
 		if (have) {
-			p0 = p.streams[stream].prev[0][0];
-			p1 = p.streams[stream].prev[0][1];
+			b0 += p.streams[stream].prev[0][0];
+			b1 += p.streams[stream].prev[0][1];
 		}
 #pragma unroll 1
 		for (uint32_t st = 0; st < nst; st++) {
@@ -1777,21 +1789,28 @@ xa_chain_kernel(const DecodeParams p, const uint32_t *order, uint32_t n_streams)
 			XA_CHAIN_WAIT(smem_u32(&sm.bar[kXsFull][s]), (st / S) & 1u);
 			if (st >= (uint32_t)S)
 				XA_CHAIN_WAIT(smem_u32(&sm.bar[kOutEmpty][s]), (st / S - 1u) & 1u);
-#pragma unroll 1
+#pragma unroll kChainUnroll
 			for (int k = 0; k < K; k++) {
 				uint32_t pw[BITS], o[16];
 #pragma unroll
 				for (int i = 0; i < BITS; i++)
 					pw[i] = sm.pw[s][k][i][lane];
-				const uint32_t prof = sm.pw[s][k][BITS][lane];
-				decode_block_chain<BITS, true>(o, pw, prof, p0, p1);
+				const int sh = (int)sm.pw[s][k][BITS][lane];
+				const int k0 = (int)sm.pw[s][k][BITS + 1][lane], k1 = (int)sm.pw[s][k][BITS + 2][lane];
+				const int c = (int)sm.pw[s][k][BITS + 3][lane];
+#pragma unroll
+				for (int i = 0; i < 16; i++) {
+					const int a = sample_chain_r(top_code<BITS>(pw, 2 * i), sh, k0, k1, c, b0, b1);
+					const int b = sample_chain_r(top_code<BITS>(pw, 2 * i + 1), sh, k0, k1, c, b0, b1);
+					o[i] = pack2_biased(a, b);
+				}
 #pragma unroll
 				for (int i = 0; i < 4; i++)
 					*reinterpret_cast<uint4 *>(&sm.out[s][k][lane][4 * i]) =
 					    make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
 				if (st * K + k + 1u == nblk) {
-					p.results[stream].prev[0][0] = (int16_t)p0;
-					p.results[stream].prev[0][1] = (int16_t)p1;
+					p.results[stream].prev[0][0] = (int16_t)(b0 - 32768);
+					p.results[stream].prev[0][1] = (int16_t)(b1 - 32768);
 				}
 			}
 			__syncwarp();

@@ -1614,29 +1614,38 @@ xa_seg_kernel(const DecodeParams p)
 #define XA_CHAIN_UNROLL 8
 #endif
 constexpr int kChainUnroll = XA_CHAIN_UNROLL;
+#ifndef XA_CHAIN_LOADER_UNROLL
+#define XA_CHAIN_LOADER_UNROLL 1
+#endif
+constexpr int kChainLoaderUnroll = XA_CHAIN_LOADER_UNROLL;
 constexpr int kChainK = XA_CHAIN_K, kChainS = 2, kChainThreads = 96, kChainRing = 256;
 
-template <int BITS>
+/* blocks (stereo: pairs) per stage: what lets three CTAs share an SM's shared memory for
+ * mono; stereo rows are twice as long */
+template <int CH> struct ChainK { static constexpr int K = CH == 1 ? kChainK : kChainK / 2; };
+
+template <int BITS, int CH>
 struct ChainSmem {
-	uint32_t pw[kChainS][kChainK][BITS + 4][32];	/* payload words, the range shift, k0, k1 and c
-							 * (xa_core.h: chain_bias_c), [word][lane] */
-	__align__(16) uint32_t out[kChainS][kChainK][32][20];	/* a row of 16 packed pairs per lane;
-							 * 20: rows 80 bytes apart, so that eight lanes'
-							 * 16-byte accesses hit all 32 banks */
+	static constexpr int K = ChainK<CH>::K;
+	static constexpr int ROW = 16 * CH + 4;		/* words: rows 80 (144) bytes apart, so that eight
+							 * lanes' 16-byte accesses hit all 32 banks */
+	uint32_t pw[kChainS][K][CH][BITS + 4][32];	/* per channel: payload words, the range shift,
+							 * k0, k1 and c (xa_core.h: chain_bias_c), [word][lane] */
+	__align__(16) uint32_t out[kChainS][K][32][ROW];	/* a row of PCM per lane */
 	__align__(16) unsigned char ring[32][kChainRing + 16];
 	unsigned long long bar[4][kChainS];		/* xs full / empty, out full / empty */
 	uint32_t blocks[32];
 	uint32_t maxblocks;
 };
 
-template <int BITS>
+template <int BITS, int CH>
 __global__ void __launch_bounds__(kChainThreads)
 xa_chain_kernel(const DecodeParams p, const uint32_t *order, uint32_t n_streams)
 {
-	typedef Walk<BITS, 1> W;
-	typedef SegCfg<BITS, 1> C;
-	/* the loader alone hides the arena's latency here: four items ahead */
-	constexpr int STEP = W::STEP, RING = kChainRing, K = kChainK, S = kChainS;
+	typedef Walk<BITS, CH> W;
+	typedef SegCfg<BITS, CH> C;
+	/* the loader alone hides the arena's latency here: up to four items ahead */
+	constexpr int BS = W::BS, STEP = W::STEP, OUT = W::OUT, RING = kChainRing, K = ChainK<CH>::K, S = kChainS;
 	constexpr int D = (RING - 30) / STEP - 1 > 4 ? 4 : (RING - 30) / STEP - 1;
 	static_assert(D >= 1, "ring");
 	constexpr uint32_t FULL = 0xffffffffu;
@@ -1646,7 +1655,7 @@ xa_chain_kernel(const DecodeParams p, const uint32_t *order, uint32_t n_streams)
 		return;		/* the census picked another form */
 
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	ChainSmem<BITS> &sm = *reinterpret_cast<ChainSmem<BITS> *>(smem_raw);
+	ChainSmem<BITS, CH> &sm = *reinterpret_cast<ChainSmem<BITS, CH> *>(smem_raw);
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	const uint32_t first = blockIdx.x * 32u;
 	const bool have = first + lane < n_streams;
@@ -1712,58 +1721,64 @@ xa_chain_kernel(const DecodeParams p, const uint32_t *order, uint32_t n_streams)
 #pragma unroll
 		for (int d = 0; d < D; d++)
 			request(d);
-		uint32_t at = a32;
+		uint32_t at0 = a32;
 #pragma unroll 1
 		for (uint32_t st = 0; st < nst; st++) {
 			const uint32_t s = st % S;
 			if (st >= (uint32_t)S)
 				XA_CHAIN_IDLE(smem_u32(&sm.bar[kXsEmpty][s]), (st / S - 1u) & 1u);
-#pragma unroll 1
+#pragma unroll kChainLoaderUnroll
 			for (int k = 0; k < K; k++) {
 				const int t = (int)st * K + k;
 				asm volatile("cp.async.wait_group %0;" :: "n"(D - 1) : "memory");
-				uint32_t prof = 0, pw[BITS];
-				if (t < nn) {
-					prof = ringp[at & (RING - 1)];
-					constexpr int NW = (15 + 4 * BITS + 15) / 16;
-					const uint32_t pay = at + 1u, cb = pay & ~15u, sh = (pay & 3u) * 8u;
-					uint32_t w[4 * NW];
+				uint32_t prof[CH], pw[CH][BITS];
 #pragma unroll
-					for (int i = 0; i < NW; i++) {
-						const uint4 q = *reinterpret_cast<const uint4 *>(
-						    ringp + ((cb + 16u * i) & (RING - 1)));
-						w[4 * i] = q.x; w[4 * i + 1] = q.y; w[4 * i + 2] = q.z; w[4 * i + 3] = q.w;
+				for (int c = 0; c < CH; c++) {
+					prof[c] = 0;
+					if (t < nn) {
+						const uint32_t at = at0 + (uint32_t)(c * BS);
+						prof[c] = ringp[at & (RING - 1)];
+						constexpr int NW = (15 + 4 * BITS + 15) / 16;
+						const uint32_t pay = at + 1u, cb = pay & ~15u, sh = (pay & 3u) * 8u;
+						uint32_t w[4 * NW];
+#pragma unroll
+						for (int i = 0; i < NW; i++) {
+							const uint4 q = *reinterpret_cast<const uint4 *>(
+							    ringp + ((cb + 16u * i) & (RING - 1)));
+							w[4 * i] = q.x; w[4 * i + 1] = q.y; w[4 * i + 2] = q.z; w[4 * i + 3] = q.w;
+						}
+						const bool by2 = (pay & 8u) != 0, by1 = (pay & 4u) != 0;
+						uint32_t v[BITS + 2], u[BITS + 1];
+#pragma unroll
+						for (int i = 0; i < BITS + 2; i++)
+							v[i] = by2 ? w[i + 2] : w[i];
+#pragma unroll
+						for (int i = 0; i < BITS + 1; i++)
+							u[i] = by1 ? v[i + 1] : v[i];
+#pragma unroll
+						for (int i = 0; i < BITS; i++)
+							pw[c][i] = __funnelshift_r(u[i], u[i + 1], sh);
 					}
-					const bool by2 = (pay & 8u) != 0, by1 = (pay & 4u) != 0;
-					uint32_t v[BITS + 2], u[BITS + 1];
-#pragma unroll
-					for (int i = 0; i < BITS + 2; i++)
-						v[i] = by2 ? w[i + 2] : w[i];
-#pragma unroll
-					for (int i = 0; i < BITS + 1; i++)
-						u[i] = by1 ? v[i + 1] : v[i];
-#pragma unroll
-					for (int i = 0; i < BITS; i++)
-						pw[i] = __funnelshift_r(u[i], u[i + 1], sh);
 				}
 				request(t + D);
-				if (t < nn) {
-					if (prof >> 4 >= 5u)
-						global_min_u32(&p.first_bad[stream], (uint32_t)t);
 #pragma unroll
-					for (int i = 0; i < BITS; i++)
-						sm.pw[s][k][i][lane] = pw[i];
-				}
-				{
+				for (int c = 0; c < CH; c++) {
+					if (t < nn) {
+						if (prof[c] >> 4 >= 5u)
+							global_min_u32(&p.first_bad[stream], (uint32_t)t * CH + c);
+#pragma unroll
+						for (int i = 0; i < BITS; i++)
+							sm.pw[s][k][c][i][lane] = pw[c][i];
+					}
 					/* a lane whose stream is through: filter 0, whatever the payload */
-					const uint32_t pf = t < nn ? prof : 0u;
+					const uint32_t pf = prof[c];
 					const int k0 = gain_k0(pf >> 4), k1 = gain_k1(pf >> 4);
-					sm.pw[s][k][BITS][lane] = 16u + (pf & 15u);
-					sm.pw[s][k][BITS + 1][lane] = (uint32_t)k0;
-					sm.pw[s][k][BITS + 2][lane] = (uint32_t)k1;
-					sm.pw[s][k][BITS + 3][lane] = (uint32_t)chain_bias_c(k0, k1);
+					sm.pw[s][k][c][BITS][lane] = 16u + (pf & 15u);
+					sm.pw[s][k][c][BITS + 1][lane] = (uint32_t)k0;
+					sm.pw[s][k][c][BITS + 2][lane] = (uint32_t)k1;
+					sm.pw[s][k][c][BITS + 3][lane] = (uint32_t)chain_bias_c(k0, k1);
 				}
-				at += (uint32_t)STEP;
+				at0 += (uint32_t)STEP;
 			}
 			__syncwarp();
 			if (lane == 0)
@@ -1772,16 +1787,21 @@ xa_chain_kernel(const DecodeParams p, const uint32_t *order, uint32_t n_streams)
 	} else if (warp == 1) {
 		/* ---- stepper ---- */
 		/*
-		 * One block a turn: its words out of shared memory, then the production block
-		 * step (xa_core.h: decode_block_chain -- ranged codes and packing ride in the
-		 * gaps of the dependent chain).  (Fetching block t + 1's words while block t
-		 * steps, or ranging it in the same turn, measured 3-12 % slower: ptxas keeps
-		 * neither early, profiles/history_r2.md.)
+		 * One block (stereo: one pair, the two chains side by side) a turn: its words
+		 * and constants out of shared memory, then nothing but the step -- ranged
+		 * codes and packing ride in the gaps of the dependent chain; the state stays
+		 * biased from block to block (xa_core.h: sample_chain_r).  (Fetching block
+		 * t + 1's words while block t steps, or ranging it in the same turn, measured
+		 * 3-12 % slower: ptxas keeps neither early, profiles/history_r2.md.)
 		 */
-		int b0 = 32768, b1 = 32768;	/* the state, n-1 and n-2, biased (xa_core.h: sample_chain_r) */
-		if (have) {
-			b0 += p.streams[stream].prev[0][0];
-			b1 += p.streams[stream].prev[0][1];
+		int b0[CH], b1[CH];		/* the state, n-1 and n-2, biased */
+#pragma unroll
+		for (int c = 0; c < CH; c++) {
+			b0[c] = b1[c] = 32768;
+			if (have) {
+				b0[c] += p.streams[stream].prev[c][0];
+				b1[c] += p.streams[stream].prev[c][1];
+			}
 		}
 #pragma unroll 1
 		for (uint32_t st = 0; st < nst; st++) {
@@ -1789,28 +1809,46 @@ xa_chain_kernel(const DecodeParams p, const uint32_t *order, uint32_t n_streams)
 			XA_CHAIN_WAIT(smem_u32(&sm.bar[kXsFull][s]), (st / S) & 1u);
 			if (st >= (uint32_t)S)
 				XA_CHAIN_WAIT(smem_u32(&sm.bar[kOutEmpty][s]), (st / S - 1u) & 1u);
-#pragma unroll kChainUnroll
+#pragma unroll (CH == 1 ? kChainUnroll : kChainUnroll / 2)
 			for (int k = 0; k < K; k++) {
-				uint32_t pw[BITS], o[16];
+				uint32_t pw[CH][BITS], o[16 * CH];
+				int sh[CH], k0[CH], k1[CH], cc[CH];
 #pragma unroll
-				for (int i = 0; i < BITS; i++)
-					pw[i] = sm.pw[s][k][i][lane];
-				const int sh = (int)sm.pw[s][k][BITS][lane];
-				const int k0 = (int)sm.pw[s][k][BITS + 1][lane], k1 = (int)sm.pw[s][k][BITS + 2][lane];
-				const int c = (int)sm.pw[s][k][BITS + 3][lane];
+				for (int c = 0; c < CH; c++) {
 #pragma unroll
-				for (int i = 0; i < 16; i++) {
-					const int a = sample_chain_r(top_code<BITS>(pw, 2 * i), sh, k0, k1, c, b0, b1);
-					const int b = sample_chain_r(top_code<BITS>(pw, 2 * i + 1), sh, k0, k1, c, b0, b1);
-					o[i] = pack2_biased(a, b);
+					for (int i = 0; i < BITS; i++)
+						pw[c][i] = sm.pw[s][k][c][i][lane];
+					sh[c] = (int)sm.pw[s][k][c][BITS][lane];
+					k0[c] = (int)sm.pw[s][k][c][BITS + 1][lane];
+					k1[c] = (int)sm.pw[s][k][c][BITS + 2][lane];
+					cc[c] = (int)sm.pw[s][k][c][BITS + 3][lane];
 				}
 #pragma unroll
-				for (int i = 0; i < 4; i++)
+				for (int i = 0; i < 16; i++) {
+					int a[CH], b[CH];
+#pragma unroll
+					for (int c = 0; c < CH; c++)
+						a[c] = sample_chain_r(top_code<BITS>(pw[c], 2 * i), sh[c], k0[c], k1[c], cc[c], b0[c], b1[c]);
+#pragma unroll
+					for (int c = 0; c < CH; c++)
+						b[c] = sample_chain_r(top_code<BITS>(pw[c], 2 * i + 1), sh[c], k0[c], k1[c], cc[c], b0[c], b1[c]);
+					if (CH == 1) {
+						o[i] = pack2_biased(a[0], b[0]);
+					} else {
+						o[2 * i] = pack2_biased(a[0], a[CH - 1]);	/* a frame: left | right << 16 */
+						o[2 * i + 1] = pack2_biased(b[0], b[CH - 1]);
+					}
+				}
+#pragma unroll
+				for (int i = 0; i < 4 * CH; i++)
 					*reinterpret_cast<uint4 *>(&sm.out[s][k][lane][4 * i]) =
 					    make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
 				if (st * K + k + 1u == nblk) {
-					p.results[stream].prev[0][0] = (int16_t)(b0 - 32768);
-					p.results[stream].prev[0][1] = (int16_t)(b1 - 32768);
+#pragma unroll
+					for (int c = 0; c < CH; c++) {
+						p.results[stream].prev[c][0] = (int16_t)(b0[c] - 32768);
+						p.results[stream].prev[c][1] = (int16_t)(b1[c] - 32768);
+					}
 				}
 			}
 			__syncwarp();
@@ -1820,8 +1858,8 @@ xa_chain_kernel(const DecodeParams p, const uint32_t *order, uint32_t n_streams)
 			}
 		}
 	} else {
-		/* ---- storer: lane = 16-byte unit `unit` of the rows of streams 8q + lane % 8 ----
-		 * (a quarter warp reads one unit of eight rows: all 32 banks) */
+		/* ---- storer: lane = 16-byte units `unit` (+ 4 for stereo) of the rows of streams
+		 * 8q + lane % 8 (a quarter warp reads one unit of eight rows: all 32 banks) ---- */
 		const uint32_t unit = lane >> 3, r0 = lane & 7u;
 		uint32_t nb[4], owed[4];
 		uint8_t *base[4];
@@ -1844,24 +1882,28 @@ xa_chain_kernel(const DecodeParams p, const uint32_t *order, uint32_t n_streams)
 #pragma unroll 1
 			for (int k = 0; k < K; k++) {
 				const uint32_t t = st * K + k;
-				uint4 v[4];
 #pragma unroll
-				for (int q = 0; q < 4; q++)
-					v[q] = *reinterpret_cast<const uint4 *>(&sm.out[s][k][8 * q + r0][4 * unit]);
+				for (int uh = 0; uh < CH; uh++) {
+					const uint32_t un = unit + 4u * uh;	/* this lane's unit of the row */
+					uint4 v[4];
 #pragma unroll
-				for (int q = 0; q < 4; q++) {
-					if (t < nb[q]) {
-						uint8_t *d = base[q] + (uint64_t)t * 64u;
-						if (t + 1u < nb[q] || unit * 16u + 16u <= owed[q]) {
-							*reinterpret_cast<uint4 *>(d) = v[q];
-						} else if (unit * 16u < owed[q]) {
-							/* the stream's last block owes less than this unit */
-							const uint32_t n16 = (owed[q] - unit * 16u) / 2u;
+					for (int q = 0; q < 4; q++)
+						v[q] = *reinterpret_cast<const uint4 *>(&sm.out[s][k][8 * q + r0][4 * un]);
 #pragma unroll
-							for (uint32_t h = 0; h < 8u; h++) {
-								const uint32_t w4 = h < 2 ? v[q].x : h < 4 ? v[q].y : h < 6 ? v[q].z : v[q].w;
-								if (h < n16)
-									reinterpret_cast<uint16_t *>(d)[h] = (uint16_t)(w4 >> (16u * (h & 1u)));
+					for (int q = 0; q < 4; q++) {
+						if (t < nb[q]) {
+							uint8_t *d = base[q] + (uint64_t)t * OUT + 64u * uh;
+							if (t + 1u < nb[q] || un * 16u + 16u <= owed[q]) {
+								*reinterpret_cast<uint4 *>(d) = v[q];
+							} else if (un * 16u < owed[q]) {
+								/* the stream's last block owes less than this unit */
+								const uint32_t n16 = (owed[q] - un * 16u) / 2u;
+#pragma unroll
+								for (uint32_t h = 0; h < 8u; h++) {
+									const uint32_t w4 = h < 2 ? v[q].x : h < 4 ? v[q].y : h < 6 ? v[q].z : v[q].w;
+									if (h < n16)
+										reinterpret_cast<uint16_t *>(d)[h] = (uint16_t)(w4 >> (16u * (h & 1u)));
+								}
 							}
 						}
 					}
@@ -2360,8 +2402,8 @@ set_attrs_one(void)
 	if ((e = cudaFuncSetAttribute(xa_seg_kernel<BITS, CH>,
 	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SegCfg<BITS, CH>::kSmem)) != cudaSuccess)
 		return e;
-	if (CH == 1 && (e = cudaFuncSetAttribute(xa_chain_kernel<BITS>,
-	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainSmem<BITS>))) != cudaSuccess)
+	if ((e = cudaFuncSetAttribute(xa_chain_kernel<BITS, CH>,
+	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainSmem<BITS, CH>))) != cudaSuccess)
 		return e;
 	return cudaFuncSetAttribute(xa_encode_kernel<BITS, CH>,
 	    cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2850,21 +2892,22 @@ chain_mode(void)
 
 constexpr uint32_t kChainMinStreams = 128;
 /* from this share of chain blocks (permille): where the mono wide tiles used to take over */
-constexpr uint32_t kChainPermille = 985;
+constexpr uint32_t kChainPermille = 985, kChainPermilleStereo = 930;
 
 static int
 chain_candidate(int chain, int ch, uint32_t n_streams)
 {
-	if (ch != 1 || chain == 0)
+	(void)ch;
+	if (chain == 0)
 		return 0;
 	return chain == 1 ? 1 : n_streams >= kChainMinStreams ? 2 : 0;
 }
 
-template <int BITS>
+template <int BITS, int CH>
 static cudaError_t
 launch_chain(const DecodeParams &p, const uint32_t *d_order, uint32_t n_streams, cudaStream_t st)
 {
-	xa_chain_kernel<BITS><<<(n_streams + 31u) / 32u, kChainThreads, sizeof(ChainSmem<BITS>), st>>>(
+	xa_chain_kernel<BITS, CH><<<(n_streams + 31u) / 32u, kChainThreads, sizeof(ChainSmem<BITS, CH>), st>>>(
 	    p, d_order, n_streams);
 	return cudaGetLastError();
 }
@@ -2927,7 +2970,7 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 	DecodeParams p = c.p;
 	cudaError_t e;
 	if (chainc == 1)
-		return launch_chain<BITS>(p, c.d_order, c.n_streams, st);
+		return launch_chain<BITS, CH>(p, c.d_order, c.n_streams, st);
 	if (segc == 1) {
 		p.tiles = c.seg_tiles;
 		p.n_tiles = c.seg_n;
@@ -2963,7 +3006,7 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 	    splitc == 2 ? split_permille(BITS, CH) : kNever,
 	    relayc == 2 ? relay_permille(BITS, CH) : kNever,
 	    segc == 2 ? seg_permille(BITS, CH) : kNever, seg_below(BITS, CH),
-	    chainc == 2 ? kChainPermille : kNever, c.d_choice);
+	    chainc == 2 ? (CH == 2 ? kChainPermilleStereo : kChainPermille) : kNever, c.d_choice);
 	if ((e = cudaGetLastError()) != cudaSuccess)
 		return e;
 	p.choice = c.d_choice;
@@ -3002,7 +3045,7 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 	if (chainc == 2) {
 		DecodeParams q = p;
 		q.want = kFormChain;
-		if ((e = launch_chain<BITS>(q, c.d_order, c.n_streams, st)) != cudaSuccess)
+		if ((e = launch_chain<BITS, CH>(q, c.d_order, c.n_streams, st)) != cudaSuccess)
 			return e;
 	}
 	if (segc == 2) {

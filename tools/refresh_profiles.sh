@@ -52,6 +52,11 @@ timeout 600 ncu --set full --clock-control none --import-source on --kernel-name
 timeout 300 python $H > /dev/null 2>&1 && \
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:xa_walk_kernel -c 1 \
     -f -o gpurun_out/relay_pass2_mono8_c20_$tag python $H > gpurun_out/ncu_relay2_$tag.log 2>&1
+# data without cut blocks, mono: the chain form (a CTA per 32 streams, loader / stepper / storer)
+I="tools/prof_decode.py --mix P3 --streams 4096 --seconds 4 --bits 8 --ch 1 --steps 1 --warmup 1"
+timeout 300 python $I > gpurun_out/prof_chain_mono8_$tag.json 2>/dev/null && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:xa_chain_kernel -c 1 \
+    -f -o gpurun_out/chain_mono8_p3_$tag python $I > gpurun_out/ncu_chain_$tag.log 2>&1
 # by shape and mix, whatever the census picks (the table of DESIGN.md)
 : > gpurun_out/auto_sweep_$tag.log
 for shape in "8 1" "6 1" "4 1" "8 2" "6 2" "4 2"; do
@@ -66,7 +71,7 @@ timeout 300 python tools/pcie_probe.py > gpurun_out/pcie_$tag.json 2> gpurun_out
 for r in gpurun_out/*_$tag.ncu-rep; do
     ncu -i $r --page raw --csv > ${r%.ncu-rep}.raw.csv 2>/dev/null
 done
-for k in seg_mono8_p2 seg_stereo4_p2 relay_pass1_mono8_c20 relay_pass2_mono8_c20; do
+for k in seg_mono8_p2 seg_stereo4_p2 relay_pass1_mono8_c20 relay_pass2_mono8_c20 chain_mono8_p3; do
     ncu -i gpurun_out/${k}_$tag.ncu-rep --page source --csv > gpurun_out/${k}_$tag.source.csv 2>/dev/null
 done
 for r in gpurun_out/*_$tag.ncu-rep; do

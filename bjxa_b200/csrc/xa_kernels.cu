@@ -2920,7 +2920,7 @@ decode_class_launches(int ch, int stereo, bool alt, int poolc, int splitc, int r
 		return 1;
 	if (splitc == 1 || relayc == 1)
 		return 2;
-	const int forms = (ch == 2 && stereo == 2 ? 2 : 1) + (alt ? 1 : 0) + (poolc == 2 ? 1 : 0) +
+	const int forms = (ch == 2 && stereo == 2 ? 2 : 1) + (alt && chainc != 2 ? 1 : 0) + (poolc == 2 ? 1 : 0) +
 	    (splitc == 2 ? 2 : 0) + (relayc == 2 ? 2 : 0) + (segc == 2 ? 1 : 0) + (chainc == 2 ? 1 : 0);
 	return forms == 1 ? 1 : forms + 1;
 }
@@ -2960,13 +2960,15 @@ template <int BITS, int CH>
 static cudaError_t
 decode_class(const DecodeClass &c, cudaStream_t st)
 {
-	const bool alt = c.alt_tiles != NULL;
 	const bool pick_form = CH == 2 && c.stereo == 2;
 	const int poolc = pool_candidate(c.pool, c.ns, c.p.n_tiles);
 	const int splitc = split_candidate(c.split, BITS, CH, c.stereo, c.ns, c.p.n_tiles);
 	const int relayc = relay_candidate(c.relay, BITS, CH, c.stereo, c.ns, c.p.n_tiles);
 	const int segc = seg_candidate(c.seg, c.seg_tiles != NULL ? c.seg_n : 0u);
 	const int chainc = chain_candidate(c.chain, CH, c.n_streams);
+	/* where the chain form is a candidate, the wide tiles (data without cut blocks was
+	 * all they were for) are never picked: not launched */
+	const bool alt = c.alt_tiles != NULL && chainc != 2;
 	DecodeParams p = c.p;
 	cudaError_t e;
 	if (chainc == 1)

@@ -514,7 +514,6 @@ def main():
     descs["pcm_len"] = PCM_BYTES
     descs["bits"], descs["channels"] = BITS, CH
     plan = lib.plan_create(PLAN_DECODE, descs)
-    launches_per_step = lib.plan_launches(plan)
 
     def step():
         lib.plan_run(plan, pcm.data_ptr(), pcm.numel(), xa.data_ptr(), xa.numel(), stream)
@@ -523,7 +522,9 @@ def main():
     set_mix(HEADLINE_MIX)
     for _ in range(warm):
         step()
+    launched0 = lib.plan_launched(plan)
     total_ms, per_launch, window, _ = timed(step, args.steps)
+    gpu_launches = lib.plan_launched(plan) - launched0     # counted by the library, launch by launch
     ms_per_step = total_ms / args.steps
     samples_per_step = world * S * SAMPLES * CH
     value = samples_per_step / (ms_per_step * 1e-3) / 1e6
@@ -551,7 +552,7 @@ def main():
         "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": workload_config(S), "roofline": roofline,
-        "gpu_launches": args.steps * launches_per_step, "clocks": clocks, "parity": parity,
+        "gpu_launches": gpu_launches, "clocks": clocks, "parity": parity,
     }
 
     if not args.no_extras:
@@ -687,14 +688,16 @@ def main():
             lib.plan_run(vplan, vpcm.data_ptr(), vpcm.numel(), vxa.data_ptr(), vxa.numel(), stream)
         vstep()
         vstep()
+        vl0 = lib.plan_launched(vplan)
         tms, _, _, _ = timed(vstep, 3)
+        vlaunches = (lib.plan_launched(vplan) - vl0) / 3
         ms = tms / 3
         tot_samples = sum_over_ranks(nsamp)
         par = parity_decode(lib, vplan, d, vxa, pick_streams(tab.n, args.full_parity, 7), "configs[2]")
         configs["configs[2]"] = {
             "what": "mixed batch decode: 4096 stereo streams per GPU, 4/6/8 bit, 0.5-120 s "
                     "log-uniform, mix P2, random header state",
-            "ms_per_step": round(ms, 3), "launches_per_step": lib.plan_launches(vplan),
+            "ms_per_step": round(ms, 3), "launches_per_step": round(vlaunches, 1),
             "Msamples_per_s": round(tot_samples / ms / 1e3, 1),
             "hbm_frac": round(algo / (ms * 1e-3) / 1e9 / peak, 4), "parity": par}
         lib.plan_free(vplan)
@@ -761,12 +764,13 @@ def main():
                 lib.plan_run(dplan, cpcm.data_ptr(), cpcm.numel(), cxa.data_ptr(), cxa.numel(), stream)
             dstep()
             dstep()
+            dl0 = lib.plan_launched(dplan)
             tms, _, _, own = timed(dstep, 3)
+            launches = round((lib.plan_launched(dplan) - dl0) / 3, 1)
             dms = tms / 3
             per_rank = gather(own / 3)
             par_d = parity_decode(lib, dplan, d, cxa, pick_streams(cnt, args.full_parity, 11 + rank),
                                   f"configs[4] {tag} decode")
-            launches = lib.plan_launches(dplan)
             lib.plan_free(dplan)
             # ... then encode the PCM just produced back to XA (same shapes)
             cxa2 = torch.empty(cxa.numel(), dtype=torch.uint8, device=dev)

@@ -65,6 +65,7 @@ BATCH_SYMBOLS = {
     "bjxa_plan_run": (C.c_int, [_VP, _VP, _SZ, _VP, _SZ, _VP]),
     "bjxa_plan_fetch": (C.c_int, [_VP, _VP, _SZ]),
     "bjxa_plan_launches": (C.c_int, [_VP]),
+    "bjxa_plan_launched": (C.c_uint64, [_VP]),
     "bjxa_plan_checksum": (C.c_int, [_VP, _VP, _SZ]),
     "bjxa_thread_release": (None, []),
     "bjxa_plan_extent": (C.c_int, [_VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
@@ -164,6 +165,10 @@ class Bjxa(BjxaLib):
 
     def plan_launches(self, plan: int) -> int:
         return self._bjxa_plan_launches(plan)
+
+    def plan_launched(self, plan: int) -> int:
+        """kernels bjxa_plan_run has launched for this plan so far"""
+        return int(self._bjxa_plan_launched(plan))
 
     def plan_checksum(self, plan: int, n: int) -> np.ndarray:
         """Per-stream checksums of the last run's output, computed on the device

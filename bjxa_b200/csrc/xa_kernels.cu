@@ -2347,9 +2347,25 @@ struct bjxa_plan {
 	/* a plan with several classes runs them side by side (bjxa_plan_run) */
 	cudaStream_t cls_stream[6];
 	cudaEvent_t ev_start, ev_done[6];
+	/* BJXA_B200_CENSUS_EVERY=n > 1 (off by default): what the census chose is read back
+	 * without waiting, the next runs launch that form alone (any form decodes any data;
+	 * the census only picks the fastest) and every n-th run asks again.  For callers
+	 * that run one plan over and over on data of one kind: a batch of another kind
+	 * in the same arenas runs through the old choice until the census is asked again */
+	uint32_t *h_choice;		/* pinned, 6 words */
+	cudaEvent_t ev_choice;
+	bool choice_pending;
+	bool choice_asked[6];
+	int cached[6];			/* -1: not known */
+	uint32_t cached_age[6];
+	uint32_t census_every;
+	unsigned long long n_launched;
 };
 
 #include <atomic>
+/* kernels launched by this thread (bjxa_plan_launched sums them per plan) */
+static thread_local unsigned long long tls_launched = 0;
+
 /* devices whose kernels have their shared-memory attributes set (bit = device) */
 static std::atomic<unsigned long long> g_attr_devices(0);
 
@@ -2498,6 +2514,16 @@ plan_build(bjxa_plan *pl, int kind, const bjxa_stream_desc_t *descs, size_t n)
 	}
 	pl->ran = false;
 	pl->launches = 0;
+	pl->choice_pending = false;
+	for (int b = 0; b < 6; b++) {
+		pl->cached[b] = -1;
+		pl->cached_age[b] = 0;
+		pl->choice_asked[b] = false;
+	}
+	{
+		const char *e = getenv("BJXA_B200_CENSUS_EVERY");
+		pl->census_every = e != NULL && atoi(e) > 0 ? (uint32_t)atoi(e) : 1u;
+	}
 	pl->stereo = stereo_mode();
 	pl->pool = pool_mode();
 	pl->split = split_mode();
@@ -2532,6 +2558,9 @@ bjxa_plan_create(int kind, const bjxa_stream_desc_t *descs, size_t n)
 	pl->magic = BJXA_PLAN_MAGIC;
 	pl->epoch = 0;
 	pl->ran = false;
+	pl->h_choice = NULL;
+	pl->ev_choice = NULL;
+	pl->n_launched = 0;
 	if (plan_build(pl, kind, descs, n) < 0) {
 		int e = errno;
 		bjxa_plan_free(&pl);
@@ -2585,6 +2614,10 @@ bjxa_plan_free(bjxa_plan_t **planp)
 	}
 	if (pl->ev_start != NULL)
 		(void)cudaEventDestroy(pl->ev_start);
+	if (pl->ev_choice != NULL)
+		(void)cudaEventDestroy(pl->ev_choice);
+	if (pl->h_choice != NULL)
+		(void)cudaFreeHost(pl->h_choice);
 	pl->magic = 0;
 	delete pl;
 	*planp = NULL;
@@ -2596,6 +2629,16 @@ bjxa_plan_launches(const bjxa_plan_t *pl)
 {
 	CHECK_PLAN(pl);
 	return (pl->launches);
+}
+
+extern "C" unsigned long long
+bjxa_plan_launched(const bjxa_plan_t *pl)
+{
+	if (pl == NULL || pl->magic != BJXA_PLAN_MAGIC) {
+		errno = pl == NULL ? EFAULT : EINVAL;
+		return (0);
+	}
+	return (pl->n_launched);
 }
 
 extern "C" int
@@ -2636,6 +2679,7 @@ launch_persistent(const DecodeParams &p, cudaStream_t st)
 	if (grid > p.n_tiles)
 		grid = p.n_tiles;
 	xa_decode_kernel<Tile, MODE><<<grid, kDecBlock, smem, st>>>(p);
+	tls_launched++;
 	return cudaGetLastError();
 }
 
@@ -2665,6 +2709,7 @@ launch_pool(const DecodeParams &p, cudaStream_t st)
 	if (grid > p.n_tiles)
 		grid = p.n_tiles;
 	xa_decode_pool_kernel<Tile><<<grid, kPoolBlock, smem, st>>>(p);
+	tls_launched++;
 	return cudaGetLastError();
 }
 
@@ -2689,6 +2734,7 @@ struct DecodeClass {
 	const TileEnt *seg_tiles;	/* the segment form's list, or NULL */
 	uint32_t seg_n;
 	uint32_t *d_choice;
+	bool *censused;			/* set when the census kernel was launched */
 	const uint32_t *d_order;	/* the class's streams */
 	uint32_t n_streams;
 };
@@ -2875,6 +2921,7 @@ launch_seg(const DecodeParams &p, cudaStream_t st)
 	if (grid > need)
 		grid = need;
 	xa_seg_kernel<BITS, CH><<<grid, C::kThreads, C::kSmem, st>>>(p);
+	tls_launched++;
 	return cudaGetLastError();
 }
 
@@ -2909,6 +2956,7 @@ launch_chain(const DecodeParams &p, const uint32_t *d_order, uint32_t n_streams,
 {
 	xa_chain_kernel<BITS, CH><<<(n_streams + 31u) / 32u, kChainThreads, sizeof(ChainSmem<BITS, CH>), st>>>(
 	    p, d_order, n_streams);
+	tls_launched++;
 	return cudaGetLastError();
 }
 
@@ -2953,7 +3001,40 @@ launch_walk(const DecodeParams &p, cudaStream_t st)
 	if (grid > need)
 		grid = need;
 	xa_walk_kernel<BITS, CH, RELAY><<<grid, C::kThreads, C::kSmem, st>>>(p);
+	tls_launched++;
 	return cudaGetLastError();
+}
+
+/* the class with every choice made: the form the census picked in an earlier run */
+static DecodeClass
+chosen_class(const DecodeClass &c, uint32_t choice)
+{
+	DecodeClass f = c;
+	f.pool = f.split = f.relay = f.seg = f.chain = 0;
+	f.censused = NULL;
+	if (choice & kFormSeg) {
+		f.seg = 1;
+	} else if (choice & kFormChain) {
+		f.chain = 1;
+	} else if (choice & kFormRelay) {
+		f.relay = 1;
+		f.stereo = 0;
+	} else if (choice & kFormSplit) {
+		f.split = 1;
+		f.stereo = 0;
+	} else if (choice & kFormPool) {
+		f.pool = 1;
+	} else if ((choice & kFormWide) && c.alt_tiles != NULL) {
+		f.p.tiles = c.alt_tiles;
+		f.p.n_tiles = c.alt_n;
+		f.ns = kDecWide;
+		f.stereo = (choice & kFormStaged) ? 1 : 0;
+	} else {
+		f.stereo = (choice & kFormStaged) ? 1 : 0;
+	}
+	f.alt_tiles = NULL;
+	f.alt_n = 0;
+	return f;
 }
 
 template <int BITS, int CH>
@@ -3009,6 +3090,9 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 	    relayc == 2 ? relay_permille(BITS, CH) : kNever,
 	    segc == 2 ? seg_permille(BITS, CH) : kNever, seg_below(BITS, CH),
 	    chainc == 2 ? (CH == 2 ? kChainPermilleStereo : kChainPermille) : kNever, c.d_choice);
+	tls_launched++;
+	if (c.censused != NULL)
+		*c.censused = true;
 	if ((e = cudaGetLastError()) != cudaSuccess)
 		return e;
 	p.choice = c.d_choice;
@@ -3076,6 +3160,7 @@ launch_encode(const EncodeParams &p, cudaStream_t st)
 {
 	xa_encode_kernel<BITS, CH><<<p.n_tiles, kEncThreads,
 	    sizeof(EncSmem<BITS, CH, kEncTBE>), st>>>(p);
+	tls_launched++;
 	return cudaGetLastError();
 }
 
@@ -3108,6 +3193,17 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 		return (-1);
 	}
 	XA_CUDA(set_attrs());
+	const unsigned long long launched0 = tls_launched;
+	if (pl->choice_pending && cudaEventQuery(pl->ev_choice) == cudaSuccess) {
+		for (int b = 0; b < 6; b++)
+			if (pl->choice_asked[b]) {
+				pl->cached[b] = (int)pl->h_choice[b];
+				pl->cached_age[b] = 0;
+				pl->choice_asked[b] = false;
+			}
+		pl->choice_pending = false;
+	}
+	bool asked_now = false;
 
 	size_t n = hp.streams.size();
 	pl->epoch++;
@@ -3181,6 +3277,7 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 			case 4: xa_search_kernel<8, 1><<<grid, kSearchThreads, 0, st>>>(p); break;
 			default: xa_search_kernel<8, 2><<<grid, kSearchThreads, 0, st>>>(p); break;
 			}
+			tls_launched++;
 			e = cudaGetLastError();
 		} else if (hp.kind == kKindDecode) {
 			DecodeParams p;
@@ -3227,6 +3324,12 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 			c.d_choice = pl->d_first_bad.p + ((n + 3) & ~(size_t)3) + 12 + b;
 			c.d_order = pl->d_order.p + hp.order_begin[b];
 			c.n_streams = hp.order_begin[b + 1] - hp.order_begin[b];
+			bool censused = false;
+			c.censused = &censused;
+			if (pl->cached[b] >= 0 && pl->cached_age[b] + 1u < pl->census_every && !pl->choice_pending) {
+				c = chosen_class(c, (uint32_t)pl->cached[b]);
+				pl->cached_age[b]++;
+			}
 			switch (b) {
 			case 0: e = decode_class<4, 1>(c, st); break;
 			case 1: e = decode_class<4, 2>(c, st); break;
@@ -3234,6 +3337,17 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 			case 3: e = decode_class<6, 2>(c, st); break;
 			case 4: e = decode_class<8, 1>(c, st); break;
 			default: e = decode_class<8, 2>(c, st); break;
+			}
+			if (e == cudaSuccess && censused && !pl->choice_pending) {
+				/* the choice comes back behind the class's kernels; nobody waits for it */
+				if (pl->h_choice == NULL) {
+					XA_CUDA(cudaHostAlloc((void **)&pl->h_choice, 8 * sizeof(uint32_t), cudaHostAllocDefault));
+					XA_CUDA(cudaEventCreateWithFlags(&pl->ev_choice, cudaEventDisableTiming));
+				}
+				e = cudaMemcpyAsync(&pl->h_choice[b], c.d_choice, sizeof(uint32_t),
+				    cudaMemcpyDeviceToHost, st);
+				pl->choice_asked[b] = true;
+				asked_now = true;
 			}
 		} else {
 			EncodeParams p;
@@ -3263,6 +3377,11 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 		}
 	}
 	st = user_st;
+	if (asked_now) {
+		XA_CUDA(cudaEventRecord(pl->ev_choice, st));
+		pl->choice_pending = true;
+	}
+	pl->n_launched += tls_launched - launched0;
 	pl->ran = true;
 	pl->last_stream = st;
 	pl->last_dst = (uint8_t *)dst;

@@ -125,6 +125,15 @@ int bjxa_plan_checksum(bjxa_plan_t *plan, uint64_t *sums, size_t n);
 
 /* Kernel launches one bjxa_plan_run() issues (for launch accounting). */
 int bjxa_plan_launches(const bjxa_plan_t *plan);
+/*
+ * Kernels bjxa_plan_run() has launched for this plan so far (counted launch by
+ * launch).  With BJXA_B200_CENSUS_EVERY=n > 1 in the environment when the plan is
+ * built, a decode plan asks the census -- and launches every candidate form -- only
+ * in every n-th run; the runs in between launch the form chosen last alone.  Every
+ * form decodes every batch, the census only picks the fastest: meant for callers
+ * that run one plan over and over on data of one kind.  Default: every run.
+ */
+unsigned long long bjxa_plan_launched(const bjxa_plan_t *plan);
 
 /* Arena bytes the plan reads / writes (so callers can size allocations). */
 int bjxa_plan_extent(const bjxa_plan_t *plan, uint64_t *src_bytes, uint64_t *dst_bytes);

@@ -1143,9 +1143,10 @@ xa_walk_kernel(const DecodeParams p)
 
 /* ---- segment form (xa_walk.h) ---------------------------------------------------- */
 /*
- * One warp per tile of the segment list, one stream per lane, kSegItems items per
- * lane, every item decoded with the chain step (walk_seg_serial in xa_walk.h is the
- * same thing in plain loops).  The data path is the dense walkers': a lane reads
+ * One warp per tile of the segment list (32 segments, streams in arena order: xa_plan.h
+ * emit_seg_tiles), a segment of kSegItems items per lane, every item decoded with
+ * the chain step (walk_seg_tile_serial in xa_walk.h is the same thing in plain
+ * loops).  The data path is the dense walkers': a lane reads
  * its items straight from the arena, 16-byte cp.async chunks into a private ring in
  * shared memory, one item ahead of the decode; the PCM goes to a row of shared
  * memory and leaves the warp eight (stereo: four) rows per store instruction.

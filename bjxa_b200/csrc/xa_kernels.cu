@@ -783,6 +783,14 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
 }
 
+/* the same past the L1: for kernels whose shared memory leaves the L1 too small to
+ * hold a chunk's neighbour until it is asked for (the segment form's 6/8-bit stereo
+ * classes: +19-30 %; with a larger L1 it costs 1-6 %, profiles/history_r2.md) */
+__device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void *src)
+{
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+
 /* loads whose results must not be asked for before the turn's decode is over: as
  * PTX, so that the compiler neither re-extends the byte nor moves its first use up */
 __device__ __forceinline__ uint32_t ldg_u8(const uint8_t *p)
@@ -1178,6 +1186,8 @@ struct SegCfg {
 	static constexpr int RING = ahead_of(64) >= XA_SEG_AHEAD ? 64 : ahead_of(128) >= XA_SEG_AHEAD ? 128 : 256;
 	static constexpr int D = XA_SEG_AHEAD;
 	static constexpr int SLOT = RING + 16;	/* lane stride: spreads equal offsets over the banks */
+	/* the big rings leave the L1 some 20 KB: their copies go past it (cp_async16_cg) */
+	static constexpr bool kPastL1 = RING > 128;
 	/* chunks a lane asks for in one turn at most: one item's worth */
 	static constexpr int KMAX = (15 + W::STEP + 15) / 16;
 	/* mono: 2 CTAs of 10 warps (96 registers a thread) measured 3-6 % faster than 3 of 8
@@ -1403,7 +1413,10 @@ xa_seg_kernel(const DecodeParams p)
 #pragma unroll
 				for (int i = 0; i < C::KMAX; i++)
 					if (fe + 16 * i < want) {
-						cp_async16(ring + ((r32 + 16u * i) & (RING - 1)), gq + 16 * i);
+						if (C::kPastL1)
+							cp_async16_cg(ring + ((r32 + 16u * i) & (RING - 1)), gq + 16 * i);
+						else
+							cp_async16(ring + ((r32 + 16u * i) & (RING - 1)), gq + 16 * i);
 						k = i + 1;
 					}
 				fe += 16 * k;
@@ -2865,7 +2878,7 @@ seg_mode(void)
  * segment form, and from seg_below() on to whatever the other thresholds say.
  * Measured crossovers at 4096 streams x 30 s (profiles/history_r2.md): the form's
  * rate hardly depends on the mix (every block goes through the chain step: 61-70 %
- * of the HBM peak for mono, 51-53 % for 6/8-bit stereo, 65-71 % for 4-bit stereo),
+ * of the HBM peak for mono, 60-68 % for 6/8-bit stereo, 65-71 % for 4-bit stereo),
  * so it takes over where the tile forms, which get slower with every chain block,
  * fall below it.
  */
@@ -2878,7 +2891,7 @@ seg_mode(void)
 constexpr uint32_t seg_permille(int bits, int ch)
 {
 	return XA_SEG_PERMILLE != 0 ? XA_SEG_PERMILLE :
-	    ch == 2 ? (bits == 4 ? 80u : bits == 6 ? 310u : 360u) :
+	    ch == 2 ? (bits == 4 ? 80u : bits == 6 ? 110u : 210u) :
 	    (bits == 4 ? 350u : bits == 6 ? 300u : 350u);
 }
 /* above this share lanes too often find no cut block within kSegBack items and wait

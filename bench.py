@@ -564,7 +564,8 @@ def main():
                 continue
             set_mix(mix)
             step()
-            k = 3
+            step()
+            k = 5
             tms, _, _, _ = timed(step, k)
             v = samples_per_step / (tms / k * 1e-3) / 1e6
             by_mix[mix] = {"Msamples_per_s": round(v, 1),

@@ -1641,11 +1641,12 @@ template <int CH> struct ChainK { static constexpr int K = CH == 1 ? kChainK : k
 template <int BITS, int CH>
 struct ChainSmem {
 	static constexpr int K = ChainK<CH>::K;
-	static constexpr int ROW = 16 * CH + 4;		/* words: rows 80 (144) bytes apart, so that eight
-							 * lanes' 16-byte accesses hit all 32 banks */
+	static constexpr int ROW = 20;			/* words: rows 80 bytes apart, so that eight lanes'
+							 * 16-byte accesses hit all 32 banks */
 	uint32_t pw[kChainS][K][CH][BITS + 4][32];	/* per channel: payload words, the range shift,
 							 * k0, k1 and c (xa_core.h: chain_bias_c), [word][lane] */
-	__align__(16) uint32_t out[kChainS][K][32][ROW];	/* a row of PCM per lane */
+	__align__(16) uint32_t out[kChainS][K][CH][32][ROW];	/* per channel: a row of 16 packed pairs
+							 * of its samples per lane */
 	__align__(16) unsigned char ring[32][kChainRing + 16];
 	unsigned long long bar[4][kChainS];		/* xs full / empty, out full / empty */
 	uint32_t blocks[32];
@@ -1653,7 +1654,7 @@ struct ChainSmem {
 };
 
 template <int BITS, int CH>
-__global__ void __launch_bounds__(kChainThreads)
+__global__ void __launch_bounds__(kChainThreads + 32 * (CH - 1))
 xa_chain_kernel(const DecodeParams p, const uint32_t *order, uint32_t n_streams)
 {
 	typedef Walk<BITS, CH> W;
@@ -1683,8 +1684,8 @@ xa_chain_kernel(const DecodeParams p, const uint32_t *order, uint32_t n_streams)
 	}
 	if (tid == 0)
 		for (int b = 0; b < 4; b++)
-			for (int s = 0; s < S; s++)
-				mbar_init(smem_u32(&sm.bar[b][s]), 1);
+			for (int s = 0; s < S; s++)	/* a stepper per channel arrives on "xs empty" and "out full" */
+				mbar_init(smem_u32(&sm.bar[b][s]), b == kXsEmpty || b == kOutFull ? CH : 1);
 	__syncthreads();
 	const uint32_t nst = (sm.maxblocks + K - 1) / K;
 #ifdef XA_CHAIN_PROF
@@ -1798,24 +1799,23 @@ xa_chain_kernel(const DecodeParams p, const uint32_t *order, uint32_t n_streams)
 			if (lane == 0)
 				mbar_arrive(smem_u32(&sm.bar[kXsFull][s]));
 		}
-	} else if (warp == 1) {
-		/* ---- stepper ---- */
+	} else if (warp != 2) {
+		/* ---- stepper: warp 1 the left (or only) channel, warp 3 the right ---- */
 		/*
-		 * One block (stereo: one pair, the two chains side by side) a turn: its words
-		 * and constants out of shared memory, then nothing but the step -- ranged
-		 * codes and packing ride in the gaps of the dependent chain; the state stays
-		 * biased from block to block (xa_core.h: sample_chain_r).  (Fetching block
+		 * One block a turn: its words and constants out of shared memory, then nothing
+		 * but the step -- ranged codes and packing ride in the gaps of the dependent
+		 * chain; the state stays biased from block to block (xa_core.h:
+		 * sample_chain_r).  Stereo: a warp per channel -- both chains of a pair side
+		 * by side in one warp took 63 cycles a frame, a lone warp issuing one
+		 * instruction every three cycles (profiles/history_r2.md).  (Fetching block
 		 * t + 1's words while block t steps, or ranging it in the same turn, measured
-		 * 3-12 % slower: ptxas keeps neither early, profiles/history_r2.md.)
+		 * 3-12 % slower: ptxas keeps neither early.)
 		 */
-		int b0[CH], b1[CH];		/* the state, n-1 and n-2, biased */
-#pragma unroll
-		for (int c = 0; c < CH; c++) {
-			b0[c] = b1[c] = 32768;
-			if (have) {
-				b0[c] += p.streams[stream].prev[c][0];
-				b1[c] += p.streams[stream].prev[c][1];
-			}
+		const int c = warp == 1 ? 0 : CH - 1;
+		int b0 = 32768, b1 = 32768;	/* the state, n-1 and n-2, biased */
+		if (have) {
+			b0 += p.streams[stream].prev[c][0];
+			b1 += p.streams[stream].prev[c][1];
 		}
 #pragma unroll 1
 		for (uint32_t st = 0; st < nst; st++) {
@@ -1825,44 +1825,26 @@ xa_chain_kernel(const DecodeParams p, const uint32_t *order, uint32_t n_streams)
 				XA_CHAIN_WAIT(smem_u32(&sm.bar[kOutEmpty][s]), (st / S - 1u) & 1u);
 #pragma unroll (CH == 1 ? kChainUnroll : kChainUnroll / 2)
 			for (int k = 0; k < K; k++) {
-				uint32_t pw[CH][BITS], o[16 * CH];
-				int sh[CH], k0[CH], k1[CH], cc[CH];
+				uint32_t pw[BITS], o[16];
 #pragma unroll
-				for (int c = 0; c < CH; c++) {
-#pragma unroll
-					for (int i = 0; i < BITS; i++)
-						pw[c][i] = sm.pw[s][k][c][i][lane];
-					sh[c] = (int)sm.pw[s][k][c][BITS][lane];
-					k0[c] = (int)sm.pw[s][k][c][BITS + 1][lane];
-					k1[c] = (int)sm.pw[s][k][c][BITS + 2][lane];
-					cc[c] = (int)sm.pw[s][k][c][BITS + 3][lane];
-				}
+				for (int i = 0; i < BITS; i++)
+					pw[i] = sm.pw[s][k][c][i][lane];
+				const int sh = (int)sm.pw[s][k][c][BITS][lane];
+				const int k0 = (int)sm.pw[s][k][c][BITS + 1][lane], k1 = (int)sm.pw[s][k][c][BITS + 2][lane];
+				const int cc = (int)sm.pw[s][k][c][BITS + 3][lane];
 #pragma unroll
 				for (int i = 0; i < 16; i++) {
-					int a[CH], b[CH];
-#pragma unroll
-					for (int c = 0; c < CH; c++)
-						a[c] = sample_chain_r(top_code<BITS>(pw[c], 2 * i), sh[c], k0[c], k1[c], cc[c], b0[c], b1[c]);
-#pragma unroll
-					for (int c = 0; c < CH; c++)
-						b[c] = sample_chain_r(top_code<BITS>(pw[c], 2 * i + 1), sh[c], k0[c], k1[c], cc[c], b0[c], b1[c]);
-					if (CH == 1) {
-						o[i] = pack2_biased(a[0], b[0]);
-					} else {
-						o[2 * i] = pack2_biased(a[0], a[CH - 1]);	/* a frame: left | right << 16 */
-						o[2 * i + 1] = pack2_biased(b[0], b[CH - 1]);
-					}
+					const int x0 = sample_chain_r(top_code<BITS>(pw, 2 * i), sh, k0, k1, cc, b0, b1);
+					const int x1 = sample_chain_r(top_code<BITS>(pw, 2 * i + 1), sh, k0, k1, cc, b0, b1);
+					o[i] = pack2_biased(x0, x1);
 				}
 #pragma unroll
-				for (int i = 0; i < 4 * CH; i++)
-					*reinterpret_cast<uint4 *>(&sm.out[s][k][lane][4 * i]) =
+				for (int i = 0; i < 4; i++)
+					*reinterpret_cast<uint4 *>(&sm.out[s][k][c][lane][4 * i]) =
 					    make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
 				if (st * K + k + 1u == nblk) {
-#pragma unroll
-					for (int c = 0; c < CH; c++) {
-						p.results[stream].prev[c][0] = (int16_t)(b0[c] - 32768);
-						p.results[stream].prev[c][1] = (int16_t)(b1[c] - 32768);
-					}
+					p.results[stream].prev[c][0] = (int16_t)(b0 - 32768);
+					p.results[stream].prev[c][1] = (int16_t)(b1 - 32768);
 				}
 			}
 			__syncwarp();
@@ -1901,8 +1883,19 @@ xa_chain_kernel(const DecodeParams p, const uint32_t *order, uint32_t n_streams)
 					const uint32_t un = unit + 4u * uh;	/* this lane's unit of the row */
 					uint4 v[4];
 #pragma unroll
-					for (int q = 0; q < 4; q++)
-						v[q] = *reinterpret_cast<const uint4 *>(&sm.out[s][k][8 * q + r0][4 * un]);
+					for (int q = 0; q < 4; q++) {
+						if (CH == 1) {
+							v[q] = *reinterpret_cast<const uint4 *>(&sm.out[s][k][0][8 * q + r0][4 * un]);
+						} else {
+							/* four frames = two packed pairs of either channel, interleaved */
+							const uint2 l = *reinterpret_cast<const uint2 *>(&sm.out[s][k][0][8 * q + r0][2 * un]);
+							const uint2 r = *reinterpret_cast<const uint2 *>(&sm.out[s][k][CH - 1][8 * q + r0][2 * un]);
+							v[q].x = __byte_perm(l.x, r.x, 0x5410);
+							v[q].y = __byte_perm(l.x, r.x, 0x7632);
+							v[q].z = __byte_perm(l.y, r.y, 0x5410);
+							v[q].w = __byte_perm(l.y, r.y, 0x7632);
+						}
+					}
 #pragma unroll
 					for (int q = 0; q < 4; q++) {
 						if (t < nb[q]) {
@@ -2968,7 +2961,7 @@ template <int BITS, int CH>
 static cudaError_t
 launch_chain(const DecodeParams &p, const uint32_t *d_order, uint32_t n_streams, cudaStream_t st)
 {
-	xa_chain_kernel<BITS, CH><<<(n_streams + 31u) / 32u, kChainThreads, sizeof(ChainSmem<BITS, CH>), st>>>(
+	xa_chain_kernel<BITS, CH><<<(n_streams + 31u) / 32u, kChainThreads + 32 * (CH - 1), sizeof(ChainSmem<BITS, CH>), st>>>(
 	    p, d_order, n_streams);
 	tls_launched++;
 	return cudaGetLastError();

@@ -57,6 +57,10 @@ I="tools/prof_decode.py --mix P3 --streams 4096 --seconds 4 --bits 8 --ch 1 --st
 timeout 300 python $I > gpurun_out/prof_chain_mono8_$tag.json 2>/dev/null && \
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:xa_chain_kernel -c 1 \
     -f -o gpurun_out/chain_mono8_p3_$tag python $I > gpurun_out/ncu_chain_$tag.log 2>&1
+J="tools/prof_decode.py --mix P3 --streams 4096 --seconds 4 --bits 8 --ch 2 --steps 1 --warmup 1"
+timeout 300 python $J > gpurun_out/prof_chain_stereo8_$tag.json 2>/dev/null && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:xa_chain_kernel -c 1 \
+    -f -o gpurun_out/chain_stereo8_p3_$tag python $J > gpurun_out/ncu_chain2_$tag.log 2>&1
 # by shape and mix, whatever the census picks (the table of DESIGN.md)
 : > gpurun_out/auto_sweep_$tag.log
 for shape in "8 1" "6 1" "4 1" "8 2" "6 2" "4 2"; do

@@ -224,6 +224,10 @@ def main():
               "tools/prof_decode.py --mix P3 --streams 4096 --seconds 4 --bits 8 --ch 1 --steps 1 --warmup 1",
               "chain form (xa_chain_kernel): a CTA per 32 streams, loader / stepper / storer warps; "
               "4096 mono 8-bit streams x 4 s without any cut block (latency-bound by design: one chain per stream)")
+    secondary(tag, "chain_stereo8_p3",
+              "tools/prof_decode.py --mix P3 --streams 4096 --seconds 4 --bits 8 --ch 2 --steps 1 --warmup 1",
+              "chain form, stereo: a stepper warp per channel, the storer interleaves; "
+              "4096 stereo 8-bit streams x 4 s without any cut block")
     secondary(tag, "relay_pass1_mono8_c20",
               "tools/prof_decode.py --mix C20 --streams 2048 --seconds 30 --bits 8 --ch 1 --steps 1 --warmup 1",
               "relay form, first pass: the direct form whose walker warps hand their stragglers on; "
@@ -233,7 +237,7 @@ def main():
               "relay form, second pass: the dense walkers finishing the handed-on chains; same launch")
     for n in (f"bench_{tag}.json", f"bench_ref_{tag}.json", f"extras_{tag}.json", f"pcie_{tag}.json",
               f"latency_{tag}.json", f"prof_relay_{tag}.json", f"prof_seg_mono8_{tag}.json",
-              f"prof_seg_stereo4_{tag}.json", f"prof_chain_mono8_{tag}.json", f"auto_sweep_{tag}.log"):
+              f"prof_seg_stereo4_{tag}.json", f"prof_chain_mono8_{tag}.json", f"prof_chain_stereo8_{tag}.json", f"auto_sweep_{tag}.log"):
         copy(n)
     launches(tag)
     full(tag)

@@ -1647,14 +1647,15 @@ struct ChainSmem {
 							 * k0, k1 and c (xa_core.h: chain_bias_c), [word][lane] */
 	__align__(16) uint32_t out[kChainS][K][CH][32][ROW];	/* per channel: a row of 16 packed pairs
 							 * of its samples per lane */
-	__align__(16) unsigned char ring[32][kChainRing + 16];
+	__align__(16) unsigned char ring[CH][32][kChainRing + 16];	/* a loader warp per channel, each with
+							 * rings of its own */
 	unsigned long long bar[4][kChainS];		/* xs full / empty, out full / empty */
 	uint32_t blocks[32];
 	uint32_t maxblocks;
 };
 
 template <int BITS, int CH>
-__global__ void __launch_bounds__(kChainThreads + 32 * (CH - 1))
+__global__ void __launch_bounds__(kChainThreads + 64 * (CH - 1))
 xa_chain_kernel(const DecodeParams p, const uint32_t *order, uint32_t n_streams)
 {
 	typedef Walk<BITS, CH> W;
@@ -1684,8 +1685,8 @@ xa_chain_kernel(const DecodeParams p, const uint32_t *order, uint32_t n_streams)
 	}
 	if (tid == 0)
 		for (int b = 0; b < 4; b++)
-			for (int s = 0; s < S; s++)	/* a stepper per channel arrives on "xs empty" and "out full" */
-				mbar_init(smem_u32(&sm.bar[b][s]), b == kXsEmpty || b == kOutFull ? CH : 1);
+			for (int s = 0; s < S; s++)	/* a loader and a stepper per channel; one storer */
+				mbar_init(smem_u32(&sm.bar[b][s]), b == kOutEmpty ? 1 : CH);
 	__syncthreads();
 	const uint32_t nst = (sm.maxblocks + K - 1) / K;
 #ifdef XA_CHAIN_PROF
@@ -1698,10 +1699,12 @@ xa_chain_kernel(const DecodeParams p, const uint32_t *order, uint32_t n_streams)
 	/* loader and storer have time to spare: they sleep between looks */
 #define XA_CHAIN_IDLE(b, ph) mbar_wait_idle(b, ph, 64)
 
-	if (warp == 0) {
-		/* ---- loader ---- */
+	if (warp == 0 || warp == 4) {
+		/* ---- loader: warp 0 the left (or only) channel, warp 4 the right -- each reads the
+		 * whole stream through rings of its own and aligns its channel's words ---- */
+		const int lc = warp == 0 ? 0 : CH - 1;
 		const uint64_t a0 = have ? p.streams[stream].xa_off : 0;
-		uint8_t *const ringp = sm.ring[lane];
+		uint8_t *const ringp = sm.ring[lc][lane];
 		const uint32_t ring = smem_u32(ringp);
 		const uint64_t safe = p.src_bytes & ~(uint64_t)15;
 		const uint32_t a32 = (uint32_t)a0 & 15u;
@@ -1746,52 +1749,46 @@ xa_chain_kernel(const DecodeParams p, const uint32_t *order, uint32_t n_streams)
 			for (int k = 0; k < K; k++) {
 				const int t = (int)st * K + k;
 				asm volatile("cp.async.wait_group %0;" :: "n"(D - 1) : "memory");
-				uint32_t prof[CH], pw[CH][BITS];
+				uint32_t prof = 0, pw[BITS];
+				if (t < nn) {
+					const uint32_t at = at0 + (uint32_t)(lc * BS);
+					prof = ringp[at & (RING - 1)];
+					constexpr int NW = (15 + 4 * BITS + 15) / 16;
+					const uint32_t pay = at + 1u, cb = pay & ~15u, sh = (pay & 3u) * 8u;
+					uint32_t w[4 * NW];
 #pragma unroll
-				for (int c = 0; c < CH; c++) {
-					prof[c] = 0;
-					if (t < nn) {
-						const uint32_t at = at0 + (uint32_t)(c * BS);
-						prof[c] = ringp[at & (RING - 1)];
-						constexpr int NW = (15 + 4 * BITS + 15) / 16;
-						const uint32_t pay = at + 1u, cb = pay & ~15u, sh = (pay & 3u) * 8u;
-						uint32_t w[4 * NW];
-#pragma unroll
-						for (int i = 0; i < NW; i++) {
-							const uint4 q = *reinterpret_cast<const uint4 *>(
-							    ringp + ((cb + 16u * i) & (RING - 1)));
-							w[4 * i] = q.x; w[4 * i + 1] = q.y; w[4 * i + 2] = q.z; w[4 * i + 3] = q.w;
-						}
-						const bool by2 = (pay & 8u) != 0, by1 = (pay & 4u) != 0;
-						uint32_t v[BITS + 2], u[BITS + 1];
-#pragma unroll
-						for (int i = 0; i < BITS + 2; i++)
-							v[i] = by2 ? w[i + 2] : w[i];
-#pragma unroll
-						for (int i = 0; i < BITS + 1; i++)
-							u[i] = by1 ? v[i + 1] : v[i];
-#pragma unroll
-						for (int i = 0; i < BITS; i++)
-							pw[c][i] = __funnelshift_r(u[i], u[i + 1], sh);
+					for (int i = 0; i < NW; i++) {
+						const uint4 q = *reinterpret_cast<const uint4 *>(
+						    ringp + ((cb + 16u * i) & (RING - 1)));
+						w[4 * i] = q.x; w[4 * i + 1] = q.y; w[4 * i + 2] = q.z; w[4 * i + 3] = q.w;
 					}
+					const bool by2 = (pay & 8u) != 0, by1 = (pay & 4u) != 0;
+					uint32_t v[BITS + 2], u[BITS + 1];
+#pragma unroll
+					for (int i = 0; i < BITS + 2; i++)
+						v[i] = by2 ? w[i + 2] : w[i];
+#pragma unroll
+					for (int i = 0; i < BITS + 1; i++)
+						u[i] = by1 ? v[i + 1] : v[i];
+#pragma unroll
+					for (int i = 0; i < BITS; i++)
+						pw[i] = __funnelshift_r(u[i], u[i + 1], sh);
 				}
 				request(t + D);
+				if (t < nn) {
+					if (prof >> 4 >= 5u)
+						global_min_u32(&p.first_bad[stream], (uint32_t)t * CH + lc);
 #pragma unroll
-				for (int c = 0; c < CH; c++) {
-					if (t < nn) {
-						if (prof[c] >> 4 >= 5u)
-							global_min_u32(&p.first_bad[stream], (uint32_t)t * CH + c);
-#pragma unroll
-						for (int i = 0; i < BITS; i++)
-							sm.pw[s][k][c][i][lane] = pw[c][i];
-					}
+					for (int i = 0; i < BITS; i++)
+						sm.pw[s][k][lc][i][lane] = pw[i];
+				}
+				{
 					/* a lane whose stream is through: filter 0, whatever the payload */
-					const uint32_t pf = prof[c];
-					const int k0 = gain_k0(pf >> 4), k1 = gain_k1(pf >> 4);
-					sm.pw[s][k][c][BITS][lane] = 16u + (pf & 15u);
-					sm.pw[s][k][c][BITS + 1][lane] = (uint32_t)k0;
-					sm.pw[s][k][c][BITS + 2][lane] = (uint32_t)k1;
-					sm.pw[s][k][c][BITS + 3][lane] = (uint32_t)chain_bias_c(k0, k1);
+					const int k0 = gain_k0(prof >> 4), k1 = gain_k1(prof >> 4);
+					sm.pw[s][k][lc][BITS][lane] = 16u + (prof & 15u);
+					sm.pw[s][k][lc][BITS + 1][lane] = (uint32_t)k0;
+					sm.pw[s][k][lc][BITS + 2][lane] = (uint32_t)k1;
+					sm.pw[s][k][lc][BITS + 3][lane] = (uint32_t)chain_bias_c(k0, k1);
 				}
 				at0 += (uint32_t)STEP;
 			}
@@ -2961,7 +2958,7 @@ template <int BITS, int CH>
 static cudaError_t
 launch_chain(const DecodeParams &p, const uint32_t *d_order, uint32_t n_streams, cudaStream_t st)
 {
-	xa_chain_kernel<BITS, CH><<<(n_streams + 31u) / 32u, kChainThreads + 32 * (CH - 1), sizeof(ChainSmem<BITS, CH>), st>>>(
+	xa_chain_kernel<BITS, CH><<<(n_streams + 31u) / 32u, kChainThreads + 64 * (CH - 1), sizeof(ChainSmem<BITS, CH>), st>>>(
 	    p, d_order, n_streams);
 	tls_launched++;
 	return cudaGetLastError();

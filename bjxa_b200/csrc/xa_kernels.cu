@@ -2315,6 +2315,7 @@ static int split_candidate(int split, int bits, int ch, int stereo, int ns, uint
 static int relay_mode(void);
 static int relay_candidate(int relay, int bits, int ch, int stereo, int ns, uint32_t n_tiles);
 static int seg_mode(void);
+static int stereo_effective(int stereo, int ch, int segc, int chainc);
 static int chain_mode(void);
 static int chain_candidate(int chain, int ch, uint32_t n_streams);
 static int seg_candidate(int seg, uint32_t n_seg_tiles);
@@ -2537,12 +2538,15 @@ plan_build(bjxa_plan *pl, int kind, const bjxa_stream_desc_t *descs, size_t n)
 	for (int b = 0; b < 6; b++)
 		if (pl->hp.order_begin[b + 1] > pl->hp.order_begin[b]) {
 			const uint32_t nt = pl->hp.tile_begin[b + 1] - pl->hp.tile_begin[b];
+			const int segc = seg_candidate(pl->seg, pl->hp.seg_begin[b + 1] - pl->hp.seg_begin[b]);
+			const int chainc = chain_candidate(pl->chain, bucket_ch(b),
+			    pl->hp.order_begin[b + 1] - pl->hp.order_begin[b]);
+			const int stereo = stereo_effective(pl->stereo, bucket_ch(b), segc, chainc);
 			pl->launches += kind == kKindDecode ? decode_class_launches(bucket_ch(b),
-			    pl->stereo, pl->hp.alt_ns[b] != 0, pool_candidate(pl->pool, pl->hp.ns[b], nt),
-			    split_candidate(pl->split, bucket_bits(b), bucket_ch(b), pl->stereo, pl->hp.ns[b], nt),
-			    relay_candidate(pl->relay, bucket_bits(b), bucket_ch(b), pl->stereo, pl->hp.ns[b], nt),
-			    seg_candidate(pl->seg, pl->hp.seg_begin[b + 1] - pl->hp.seg_begin[b]),
-			    chain_candidate(pl->chain, bucket_ch(b), pl->hp.order_begin[b + 1] - pl->hp.order_begin[b])) : 1;
+			    stereo, pl->hp.alt_ns[b] != 0, pool_candidate(pl->pool, pl->hp.ns[b], nt),
+			    split_candidate(pl->split, bucket_bits(b), bucket_ch(b), stereo, pl->hp.ns[b], nt),
+			    relay_candidate(pl->relay, bucket_bits(b), bucket_ch(b), stereo, pl->hp.ns[b], nt),
+			    segc, chainc) : 1;
 		}
 	return (plan_upload(pl));
 }
@@ -2837,9 +2841,11 @@ relay_mode(void)
  * form (below it the plain direct form; above split_permille the split form) */
 constexpr uint32_t relay_permille(int bits, int ch)
 {
-	/* 4-bit stereo goes straight to the split form: its pair walkers' tiles are
-	 * the slowest to turn over, and the dense walkers the cheapest per sample */
-	return ch == 2 ? (bits == 4 ? 1001u : 80u) : 150u;
+	/* Since the segment form takes chain-rich data, the relay form's band is narrow,
+	 * and in it it beats the direct form only for 4/6-bit mono (by 1.5 points at 20 %
+	 * chain blocks; 8-bit mono and stereo: nothing, profiles/auto_sweep_r2.log against
+	 * round 1's table): elsewhere its two launches are not even candidates */
+	return ch == 2 || bits == 8 ? 1001u : 150u;
 }
 
 static int
@@ -2881,7 +2887,7 @@ seg_mode(void)
 constexpr uint32_t seg_permille(int bits, int ch)
 {
 	return XA_SEG_PERMILLE != 0 ? XA_SEG_PERMILLE :
-	    ch == 2 ? (bits == 4 ? 80u : bits == 6 ? 110u : 210u) :
+	    ch == 2 ? (bits == 4 ? 80u : bits == 6 ? 110u : 190u) :
 	    (bits == 4 ? 350u : bits == 6 ? 300u : 350u);
 }
 /* above this share lanes too often find no cut block within kSegBack items and wait
@@ -2962,6 +2968,12 @@ launch_chain(const DecodeParams &p, const uint32_t *d_order, uint32_t n_streams,
 	    p, d_order, n_streams);
 	tls_launched++;
 	return cudaGetLastError();
+}
+
+static int
+stereo_effective(int stereo, int ch, int segc, int chainc)
+{
+	return ch == 2 && stereo == 2 && segc == 2 && chainc == 2 ? 0 : stereo;
 }
 
 /* how many kernels decode_class() launches */
@@ -3045,12 +3057,15 @@ template <int BITS, int CH>
 static cudaError_t
 decode_class(const DecodeClass &c, cudaStream_t st)
 {
-	const bool pick_form = CH == 2 && c.stereo == 2;
-	const int poolc = pool_candidate(c.pool, c.ns, c.p.n_tiles);
-	const int splitc = split_candidate(c.split, BITS, CH, c.stereo, c.ns, c.p.n_tiles);
-	const int relayc = relay_candidate(c.relay, BITS, CH, c.stereo, c.ns, c.p.n_tiles);
 	const int segc = seg_candidate(c.seg, c.seg_tiles != NULL ? c.seg_n : 0u);
 	const int chainc = chain_candidate(c.chain, CH, c.n_streams);
+	/* where the segment and chain forms are candidates they take everything the staged
+	 * stereo form used to be chosen for: it is not launched */
+	const int stereo = stereo_effective(c.stereo, CH, segc, chainc);
+	const bool pick_form = CH == 2 && stereo == 2;
+	const int poolc = pool_candidate(c.pool, c.ns, c.p.n_tiles);
+	const int splitc = split_candidate(c.split, BITS, CH, stereo, c.ns, c.p.n_tiles);
+	const int relayc = relay_candidate(c.relay, BITS, CH, stereo, c.ns, c.p.n_tiles);
 	/* where the chain form is a candidate, the wide tiles (data without cut blocks was
 	 * all they were for) are never picked: not launched */
 	const bool alt = c.alt_tiles != NULL && chainc != 2;
@@ -3080,13 +3095,13 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 		return launch_walk<BITS, CH, true>(p, st);
 	}
 	if (!alt && !pick_form && poolc == 0 && splitc == 0 && relayc == 0 && segc == 0 && chainc == 0) {
-		const bool staged = CH == 2 && c.stereo == 1;
+		const bool staged = CH == 2 && stereo == 1;
 		return c.ns == 1 ? launch_form<BITS, CH, 1>(p, staged, st) :
 		    launch_form<BITS, CH, kDecWide>(p, staged, st);
 	}
 	xa_census_kernel<<<1, kCensusThreads, 0, st>>>(p.src, p.streams, c.d_order, c.n_streams,
 	    (uint32_t)block_bytes(BITS), (uint32_t)CH,
-	    pick_form ? staged_permille(BITS) : c.stereo == 1 && CH == 2 ? 0u : kNever,
+	    pick_form ? staged_permille(BITS) : stereo == 1 && CH == 2 ? 0u : kNever,
 	    /* with the split form at hand, wide tiles are for all-chain data only */
 	    alt ? (CH == 2 ? kWidePermilleStereo : kWidePermilleMono)[splitc != 2 && c.n_streams >= kWideManyStreams] :
 	    kNever, poolc == 2 ? (CH == 2 ? kPoolPermilleStereo : kPoolPermilleMono) : kNever,
@@ -3102,7 +3117,7 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 	p.choice = c.d_choice;
 	/* long strips: direct and/or staged */
 	for (int staged = 0; staged < 2; staged++) {
-		if (CH == 1 ? staged == 1 : !pick_form && staged != c.stereo)
+		if (CH == 1 ? staged == 1 : !pick_form && staged != stereo)
 			continue;
 		/* with a wide list, chain-heavy stereo data goes to its staged form
 		 * only: "staged, long strips" then means bit 0 without bit 1 */
@@ -3151,7 +3166,7 @@ decode_class(const DecodeClass &c, cudaStream_t st)
 		 * wide tiles is far above the one that selects the staged form) */
 		p.tiles = c.alt_tiles;
 		p.n_tiles = c.alt_n;
-		const bool staged = CH == 2 && c.stereo != 0;
+		const bool staged = CH == 2 && stereo != 0;
 		p.want = kFormWide | (staged ? kFormStaged : 0u);
 		e = launch_form<BITS, CH, kDecWide>(p, staged, st);
 	}

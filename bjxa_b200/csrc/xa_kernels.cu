@@ -1187,7 +1187,8 @@ struct SegCfg {
 	static constexpr int D = XA_SEG_AHEAD;
 	static constexpr int SLOT = RING + 16;	/* lane stride: spreads equal offsets over the banks */
 	/* the big rings leave the L1 some 20 KB: their copies go past it (cp_async16_cg) */
-	static constexpr bool kPastL1 = RING > 128;
+	static constexpr bool kPastL1 = RING > 128 || CH == 2;	/* 4-bit stereo: the same either way alone,
+							 * but it often shares an SM with a big-ring class */
 	/* chunks a lane asks for in one turn at most: one item's worth */
 	static constexpr int KMAX = (15 + W::STEP + 15) / 16;
 	/* mono: 2 CTAs of 10 warps (96 registers a thread) measured 3-6 % faster than 3 of 8

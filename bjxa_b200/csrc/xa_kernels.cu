@@ -3358,7 +3358,7 @@ bjxa_plan_run(bjxa_plan_t *pl, void *dst, size_t dst_bytes, const void *src,
 			case 4: e = decode_class<8, 1>(c, st); break;
 			default: e = decode_class<8, 2>(c, st); break;
 			}
-			if (e == cudaSuccess && censused && !pl->choice_pending) {
+			if (e == cudaSuccess && censused && !pl->choice_pending && pl->census_every > 1u) {
 				/* the choice comes back behind the class's kernels; nobody waits for it */
 				if (pl->h_choice == NULL) {
 					XA_CUDA(cudaHostAlloc((void **)&pl->h_choice, 8 * sizeof(uint32_t), cudaHostAllocDefault));

@@ -1,5 +1,7 @@
 /*
- * xa_walk.h -- the second pass of the SPLIT decode form: dense chain walkers.
+ * xa_walk.h -- decode forms that do not walk chains tile by tile: the dense chain
+ * walkers (second pass of the SPLIT and RELAY forms) and, further down, the SEGMENT
+ * form (a fixed segment per lane, every block through the chain step).
  *
  * The tile forms of xa_tile.h walk a tile's chains (runs of filter-1..4 blocks,
  * /root/reference/src/libbjxa.c:556-575) while the tile sits in shared memory,
